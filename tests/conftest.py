@@ -1,0 +1,34 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def small():
+    return np.load(os.path.join(GOLDEN, "small.npz"))
+
+
+@pytest.fixture(scope="session")
+def configs():
+    return np.load(os.path.join(GOLDEN, "configs.npz"))
+
+
+def randn(seed, *shape):
+    """Input generator shared with tests/golden/make_golden.py."""
+    return np.random.default_rng(seed).standard_normal(shape, dtype=np.float32)
+
+
+def none_if_neg(case):
+    return [None if v < 0 else int(v) for v in case]

@@ -1,0 +1,224 @@
+"""The oracle (oracle/panorama_oracle.py) against outputs of the imported reference
+(tests/golden/*.npz, made by tests/golden/make_golden.py).  CPU only."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import none_if_neg, randn
+from oracle import panorama_oracle as po
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+def test_ring_segments_and_index(small):
+    for i, (b, e, s) in enumerate(small["slices/cases"]):
+        want = small[f"slices/{i}"]
+        assert np.array_equal(po.ring_index(b, e, s), want)
+        segs = po.ring_segments(int(b), int(e), int(s))
+        assert np.array_equal(np.concatenate([np.arange(st, st + ln) for st, ln in segs]), want)
+
+
+def test_ring_get_set(small):
+    lat0 = randn(11, *small["ring/shape"])
+    for i, c in enumerate(small["ring/get_cases"]):
+        assert np.array_equal(po.ring_get(lat0, *none_if_neg(c)), small[f"ring/get/{i}"])
+    for i, c in enumerate(small["ring/set_cases"]):
+        lat = lat0.copy()
+        po.ring_set(lat, randn(100 + i, *po.ring_get(lat0, *none_if_neg(c)).shape), *none_if_neg(c))
+        assert np.array_equal(lat, small[f"ring/set/{i}"])
+
+
+def test_ring_illegal_windows():
+    lat = np.zeros((1, 1, 4, 8, 16), np.float32)
+    with pytest.raises(AssertionError):
+        po.ring_get(lat, 20, 20)            # left < right
+    with pytest.raises(AssertionError):
+        po.ring_get(lat, 0, 33)             # right <= 2W
+    with pytest.raises(AssertionError):
+        po.ring_set(lat, np.zeros((1, 1, 4, 8, 17), np.float32), 0, 17)   # wrap onto itself
+
+
+def test_image_ring(small):
+    img0 = randn(12, 3, 8, 12)
+    for i, c in enumerate(small["img/cases"]):
+        assert np.array_equal(po.image_ring_get(img0, *none_if_neg(c)), small[f"img/get/{i}"])
+
+
+def test_uv_map_bit_exact(small):
+    for i, (fov, th, ph, w, h, H, W) in enumerate(small["uv/cases"]):
+        u, v = po.uv_map(fov, th, ph, int(w), int(h), int(H), int(W))
+        if f"uv/{i}/u" in small:
+            assert np.array_equal(u, small[f"uv/{i}/u"]) and np.array_equal(v, small[f"uv/{i}/v"])
+        else:
+            assert np.array_equal(sha(u), small[f"uv/{i}/u_sha"]) and np.array_equal(sha(v), small[f"uv/{i}/v_sha"])
+
+
+def test_sphere_small(small):
+    pano5 = randn(21, 1, 2, 3, 16, 32)
+    for i, (fov, th, ph) in enumerate(small["sph/views"]):
+        view_in = randn(300 + i, 1, 2, 3, 6, 10)
+        vw, m = po.proxy_get_nearest(pano5, fov, th, ph, 10, 6)
+        assert np.array_equal(vw, small[f"sph/get_nearest/{i}"])
+        assert np.array_equal(m, small[f"sph/get_nearest_mask/{i}"])
+        got = po.proxy_get_bilinear(pano5, fov, th, ph, 10, 6)
+        assert np.abs(got - small[f"sph/get_bilinear/{i}"]).max() <= 1e-6
+        assert np.abs(po.sphere_get_bilinear_torch(pano5, fov, th, ph, 10, 6) - small[f"sph/get_bilinear/{i}"]).max() == 0
+        for name, fn in (("set_nearest", po.proxy_set_nearest), ("set_bilinear", po.proxy_set_bilinear),
+                         ("set_round", po.proxy_set_round)):
+            lat = pano5.copy()
+            fn(lat, view_in, fov, th, ph)
+            assert np.array_equal(lat, small[f"sph/{name}/{i}"]), (name, i)
+
+
+def test_sphere_image_and_mask(small):
+    img = randn(22, 3, 16, 32)
+    for i, (fov, th, ph) in enumerate(small["sph/views"][:3]):
+        assert np.array_equal(po.sphere_get_nearest(img, fov, th, ph, 10, 6)[0], small[f"sph/img_get/{i}"])
+        assert np.abs(po.sphere_get_bilinear(img, fov, th, ph, 10, 6) - small[f"sph/img_get_bilinear/{i}"]).max() <= 1e-6
+        for name, fn in (("img_set", po.sphere_set_nearest), ("img_set_round", po.sphere_set_round),
+                         ("img_set_bilinear", po.sphere_set_bilinear)):
+            a = img.copy()
+            fn(a, randn(400 + i, 3, 6, 10), fov, th, ph)
+            assert np.array_equal(a, small[f"sph/{name}/{i}"]), (name, i)
+        m = np.zeros((1, 16, 32), np.float32)
+        po.sphere_set_nearest(m, np.ones((1, 6, 10), np.float32), fov, th, ph)
+        assert np.array_equal(m, small[f"sph/mask_set/{i}"])
+
+
+def test_frame_ring_sphere(small):
+    rp5 = randn(31, 1, 2, 7, 16, 32)
+    for i, (fov, th, ph, fb, fe) in enumerate(small["rsph/cases"]):
+        fb, fe = int(fb), int(fe)
+        view_in = randn(500 + i, 1, 2, fe - fb, 6, 10)
+        assert np.array_equal(po.proxy_get_nearest(rp5, fov, th, ph, 10, 6, fb, fe)[0], small[f"rsph/get_nearest/{i}"])
+        assert np.abs(po.proxy_get_bilinear(rp5, fov, th, ph, 10, 6, fb, fe) - small[f"rsph/get_bilinear/{i}"]).max() <= 1e-6
+        for name, fn in (("set_nearest", po.proxy_set_nearest), ("set_bilinear", po.proxy_set_bilinear),
+                         ("set_round", po.proxy_set_round)):
+            if f"rsph/{name}/{i}" not in small:
+                continue
+            lat = rp5.copy()
+            fn(lat, view_in, fov, th, ph, fb, fe)
+            assert np.array_equal(lat, small[f"rsph/{name}/{i}"]), (name, i)
+
+
+def test_mix_mask(small):
+    l1, add = randn(41, 1, 4, 5, 6, 10), randn(42, 1, 4, 5, 6, 10)
+    m3 = (randn(43, 1, 6, 10) > 0).astype(np.float32)
+    m5 = (randn(44, 1, 4, 5, 6, 10) > 0).astype(np.float32)
+    for i, (m, r) in enumerate([(m3, 0.5), (m3, 0.3), (m5, 0.8), (m5, 1.0), (m3, 0.0)]):
+        assert np.array_equal(po.mix_mask(l1, add, m, r), small[f"mix/{i}"])
+    with pytest.raises(NotImplementedError):
+        po.mix_mask(l1, add, m3[0], 0.5)
+
+
+def test_last_writer_flags():
+    p = np.array([5, 3, 5, 7, 3, 3, 9])
+    assert po.last_writer_flags(p).tolist() == [False, False, True, True, False, True, True]
+
+
+def _payload(n, win):
+    return (win * np.float32(0.5) + randn(700 + n, *win.shape), win * np.float32(0.25) - randn(800 + n, *win.shape))
+
+
+def test_step_sequential_small(small):
+    """The reference's own window-after-window order (t2v_sphere_panorama_pipeline.py:176-291)."""
+    lat = randn(51, 1, 2, 3, 16, 32)
+    den = np.zeros_like(lat)
+    msk = np.zeros((1, 16, 32), np.float32)
+    for n, (ph, th) in enumerate(small["step/views"]):
+        vw, _ = po.proxy_get_nearest(lat, 120, th, ph, 10, 6)
+        mk, _ = po.sphere_get_nearest(msk, 120, th, ph, 10, 6)
+        noised = vw * np.float32(0.9) + randn(600 + n, 1, 2, 3, 6, 10) * np.float32(0.4359)
+        vw = po.mix_mask(vw, noised, mk, 0.6)
+        x_prev, x0 = _payload(n, vw)
+        po.proxy_set_nearest(lat, x_prev, 120, th, ph)
+        po.proxy_set_nearest(den, x0, 120, th, ph)
+        po.sphere_set_nearest(msk, np.ones((1, 6, 10), np.float32), 120, th, ph)
+    assert np.array_equal(lat, small["step/seq/latent"])
+    assert np.array_equal(den, small["step/seq/denoised"])
+    assert np.array_equal(msk, small["step/seq/mask"])
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+def test_step_batched_small(small, mode):
+    lat = randn(51, 1, 2, 3, 16, 32)
+    den = np.zeros_like(lat)
+    views = [(ph, th) for ph, th in small["step/views"]]
+    wins, mask = po.sphere_step_batched(lat, den, views, _payload, fov=120, width=10, height=6, mode=mode)
+    tol = 0 if mode == "nearest" else 1e-6
+    assert np.abs(np.stack(wins) - small[f"step/batched_{mode}/windows"]).max() <= tol
+    assert np.abs(lat - small[f"step/batched_{mode}/latent"]).max() <= tol * 10
+    assert np.abs(den - small[f"step/batched_{mode}/denoised"]).max() <= tol * 10
+    assert np.array_equal(mask[0, 0, 0][None] if mode == "nearest" else mask[0, 0, 0][None],
+                          small[f"step/batched_{mode}/mask"])
+
+
+def test_config1_ring_digest(configs):
+    lat = randn(0, 1, 4, 16, 64, 128)
+    den = np.zeros_like(lat)
+    windows = [(int(l), int(t), 0) for l, t in configs["cfg1/windows"]]
+    assert windows[:9] == [(l, t, 0) for l, t in
+                           [(12 + 8 * a, 3 + 8 * b) for a in range(16) for b in range(8)][:9]]
+    pay = lambda n, w: (randn(1000 + n, *w.shape), randn(2000 + n, *w.shape))
+    wins, mask = po.ring_step_batched(lat, den, windows, pay)
+    assert np.array_equal(sha(np.stack(wins)), configs["cfg1/windows_sha"])
+    assert np.array_equal(sha(lat), configs["cfg1/latent_sha"])
+    assert np.array_equal(sha(den), configs["cfg1/denoised_sha"])
+    assert np.array_equal(sha(np.broadcast_to(mask, lat.shape)), configs["cfg1/mask_sha"])
+
+
+def test_config2_views_and_index_maps(configs):
+    views = po.default_sphere_views(1)
+    assert len(views) == 44
+    assert np.array_equal(np.array(views, dtype=np.float64), configs["cfg2/views"])
+    for n, (ph, th) in enumerate(views):
+        u, v = po.uv_map(120, th, ph, 64, 40, 128, 256)
+        assert np.array_equal(po.nearest_read_index(u, v, 128, 256), configs["cfg2/idx_read"][n])
+        assert np.array_equal(po.nearest_write_index(u, v, 128, 256)[0], configs["cfg2/idx_write"][n])
+
+
+def test_config2_nearest_digest(configs):
+    lat = randn(0, 1, 4, 16, 128, 256)
+    den = np.zeros_like(lat)
+    pay = lambda n, w: (randn(1000 + n, *w.shape), randn(2000 + n, *w.shape))
+    wins, mask = po.sphere_step_batched(lat, den, po.default_sphere_views(1), pay, mode="nearest")
+    assert np.array_equal(sha(np.stack(wins)), configs["cfg2/nearest/windows_sha"])
+    assert np.array_equal(sha(lat), configs["cfg2/nearest/latent_sha"])
+    assert np.array_equal(sha(den), configs["cfg2/nearest/denoised_sha"])
+    assert np.array_equal(sha(mask[0, 0, 0][None]), configs["cfg2/nearest/mask_sha"])
+
+
+def test_config2_bilinear(configs):
+    lat = randn(0, 1, 4, 16, 128, 256)
+    den = np.zeros_like(lat)
+    pay = lambda n, w: (randn(1000 + n, *w.shape), randn(2000 + n, *w.shape))
+    wins, mask = po.sphere_step_batched(lat, den, po.default_sphere_views(1), pay, mode="bilinear")
+    s = lambda a: a.reshape(-1)[::4099]
+    assert np.abs(s(np.stack(wins)) - configs["cfg2/bilinear/windows_sample"]).max() <= 1e-6
+    assert np.array_equal(sha(lat), configs["cfg2/bilinear/latent_sha"])
+    assert np.array_equal(sha(den), configs["cfg2/bilinear/denoised_sha"])
+
+
+def test_config4_frame_ring_digest(configs):
+    lat = randn(4, 1, 4, 64, 128, 256)
+    jobs = [(int(fb), ph, th) for fb, ph, th in configs["cfg4/jobs"]]
+    wins = [po.proxy_get_nearest(lat, 120, th, ph, 64, 40, fb, fb + 16)[0] for fb, ph, th in jobs]
+    for n, (fb, ph, th) in enumerate(jobs):
+        po.proxy_set_nearest(lat, randn(1000 + n, 1, 4, 16, 40, 64), 120, th, ph, fb, fb + 16)
+    assert np.array_equal(sha(np.stack(wins)), configs["cfg4/windows_sha"])
+    assert np.array_equal(sha(lat), configs["cfg4/latent_sha"])
+
+
+def test_geometry_helpers():
+    # SURVEY A.9
+    assert po.ring_window_grid(0, 2, 2, 1024, 512) == [(0, 0), (0, 24), (64, 0), (64, 24)]
+    g3 = po.ring_window_grid(0, 4, 4, 2048, 1024)
+    assert sorted({l for l, _ in g3}) == [0, 64, 128, 192] and sorted({t for _, t in g3}) == [0, 29, 59, 88]
+    g5 = po.ring_window_grid(1, 16, 16, 8192, 4096)
+    assert g5[0] == (4, 1) and len(g5) == 256
+    assert po.frame_window_begins(0) == [(4 * s) % 64 for s in range(13)]
+    assert po.frame_window_begins(3)[0] == 3
+    assert len(po.frame_window_begins(0, overlap=0.5)) == 7
