@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- panorama denoise-step blends/s on B200 (driver contract in the task spec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (torch port)
+
+Workload (BASELINE.json configs[1]): T2V sphere panorama, latent [1,4,16,128,256] fp32,
+44 default views (gen_pano_360.py:444-455) of 40x64 at fov 120, longitude offset
+(i % 10) * 12 per step.  One STEP = gather_all (every window cut from the step-start
+panorama) -> injected payloads (x_prev, pred_x0; stand-ins for UNet + ddim_step) ->
+merge_all (latent <- x_prev, denoised <- pred_x0, mask <- 1).  value = steps/s * 44.
+The headline mode is "bilinear" (bilinear resample + weighted splat/normalise, the
+"window resample + weighted blend" the config names); "nearest" (the variant the reference
+pipelines call) is measured in the same run and reported under "variants".
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+WORKLOADS = {
+    # name: (C, F, H, W, view_w, view_h, fov)
+    "cfg2_sphere_128x256": dict(C=4, F=16, H=128, W=256, w=64, h=40, fov=120, views=44),
+}
+L2_BYTES = 126 * 1024 * 1024
+
+
+def default_views(i):
+    thetas = [360 * t // 6 for t in range(6)]
+    table = [(90, [0]), (-90, [0])] + [(p, thetas) for p in (75, -75, 60, -60, 45, -45, 0)]
+    off = (i % 10) * 12
+    return [(phi, th + off) for phi, ths in table for th in ths]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ clock sampler ----
+class ClockSampler(threading.Thread):
+    """NVML samples of SM clock + throttle reasons while ``self.load`` is set."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.load, self.stop_flag = [], set(), False, False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while self.nv is not None and not self.stop_flag:
+            if self.load:
+                try:
+                    self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    self.reasons |= {n for bit, n in self.REASONS.items() if mask & bit}
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------ reference arm ----
+def cpu_step_time(wl, mode, reps):
+    """Times oracle/torch_port.sphere_step (the reference's per-call torch op sequence) on
+    the host cores.  Returns (seconds per step, cores, sample description)."""
+    from oracle import torch_port as tp
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
+    vshape = (1, wl["C"], wl["F"], wl["h"], wl["w"])
+    lat = torch.randn(shape, generator=g)
+    xp = [torch.randn(vshape, generator=g) for _ in range(wl["views"])]
+    x0 = [torch.randn(vshape, generator=g) for _ in range(wl["views"])]
+    ts = []
+    for i in range(reps + 1):
+        t = time.perf_counter()
+        tp.sphere_step(lat, torch.zeros_like(lat), default_views(i), xp, x0, fov=wl["fov"], width=wl["w"],
+                       height=wl["h"], mode=mode)
+        ts.append(time.perf_counter() - t)
+    return statistics.mean(ts[1:]), torch.get_num_threads(), f"{reps} full steps ({wl['views']} windows each) after 1 warm-up"
+
+
+def run_reference(args, wl, wl_name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    reps = max(1, min(args.steps, 3 if args.mode == "bilinear" else 20))
+    sec, cores, sample = cpu_step_time(wl, args.mode, reps)
+    value = wl["views"] / sec
+    print(json.dumps({
+        "impl": "reference", "metric": "panorama denoise-step window-blends/sec", "value": value, "unit": "blends/s",
+        "n_gpus": args.gpus, "steps": reps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl_name, "mode": args.mode, "latent": [1, wl["C"], wl["F"], wl["H"], wl["W"]],
+                   "windows_per_step": wl["views"], "window": [wl["h"], wl["w"]]},
+        "cpu_baseline": {"value": value, "unit": "blends/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "blends/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------ our arm ----
+class Workset:
+    """One rotating buffer set (panoramas + windows + payloads), so consecutive steps touch
+    different memory and the aggregate footprint exceeds L2."""
+
+    def __init__(self, wl, n_local, dev, gen):
+        shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
+        vshape = (n_local, 1, wl["C"], wl["F"], wl["h"], wl["w"])
+        self.lat = torch.randn(shape, device=dev, generator=gen)
+        self.den = torch.zeros(shape, device=dev)
+        self.mask = torch.zeros(1, wl["H"], wl["W"], device=dev)
+        self.wins = torch.empty(vshape, device=dev)
+        self.x_prev = torch.randn(vshape, device=dev, generator=gen)
+        self.x0 = torch.randn(vshape, device=dev, generator=gen)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.lat, self.den, self.mask, self.wins, self.x_prev, self.x0))
+
+
+def time_graph(graphs, iters, dist_on):
+    """CUDA-event time (ms) of ``iters`` replays cycling through ``graphs``."""
+    if dist_on:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(iters):
+        graphs[i % len(graphs)]()
+    b.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        torch.distributed.barrier()
+    return a.elapsed_time(b)
+
+
+def capture(fn, use_graph):
+    """Returns a zero-arg callable replaying ``fn`` (as a CUDA graph when possible)."""
+    if not use_graph:
+        return fn
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g.replay
+
+
+def run_ours(args, wl, wl_name):
+    import torch.distributed as dist
+    from dynamicscaler_b200 import lib
+    from dynamicscaler_b200.step import PanoramaStepper
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_on = world > 1
+    if dist_on:
+        dist.init_process_group("nccl", device_id=dev)
+    assert lib.ds_abi_version() == 1                     # fails loudly if the .so is missing
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    st = PanoramaStepper(wl["H"], wl["W"], wl["F"], device=dev, rank=rank, world=world)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    plans = {m: [st.plan_sphere(default_views(i), wl["w"], wl["h"], fov=wl["fov"], mode=m) for i in range(10)]
+             for m in ("bilinear", "nearest")}
+    n_local = st.local_jobs(plans["nearest"][0])[1]
+    one = Workset(wl, n_local, dev, gen)
+    n_sets = max(4, -(-3 * L2_BYTES // one.nbytes()))    # aggregate footprint >= 3x L2
+    sets = [one] + [Workset(wl, n_local, dev, gen) for _ in range(n_sets - 1)]
+    combos = [(i % 10, i % n_sets) for i in range(10 * n_sets // np.gcd(10, n_sets))]
+
+    def make_step(mode, off, s):
+        ws, plan = sets[s], plans[mode][off]
+
+        def step():
+            st.gather_all(ws.lat, plan, out=ws.wins)
+            st.merge_all([ws.lat, ws.den], [ws.x_prev, ws.x0], plan, mask=ws.mask)
+        return step
+
+    def make_gather(mode, off, s):
+        ws, plan = sets[s], plans[mode][off]
+        return lambda: st.gather_all(ws.lat, plan, out=ws.wins)
+
+    def make_merge(mode, off, s):
+        ws, plan = sets[s], plans[mode][off]
+        return lambda: st.merge_all([ws.lat, ws.den], [ws.x_prev, ws.x0], plan, mask=ws.mask)
+
+    # warm-up outside graphs (module load, NCCL communicator setup)
+    side = torch.cuda.Stream()
+    for mode in ("bilinear", "nearest"):
+        for c in combos[:3]:
+            make_step(mode, *c)()
+    torch.cuda.synchronize()
+    use_graph = not args.no_graph
+    launches_before = lib.launches
+
+    def build(maker, mode):
+        try:
+            with torch.cuda.stream(side):
+                return [capture(maker(mode, *c), use_graph) for c in combos], use_graph
+        except Exception as e:                             # e.g. a collective that cannot be captured
+            torch.cuda.synchronize()
+            print(f"[bench] graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            return [maker(mode, *c) for c in combos], False
+
+    results = {}
+    K, Wm = args.steps, max(args.warmup, 3)
+    for mode in ("bilinear", "nearest"):
+        steps, graphed = build(make_step, mode)
+        launches_per_step = (lib.launches - launches_before) // max(len(combos), 1) if graphed else None
+        launches_before = lib.launches
+        for i in range(Wm):
+            steps[i % len(steps)]()
+        sampler.load = True
+        ms = time_graph(steps, K, dist_on)
+        sampler.load = False
+        if dist_on:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        results[mode] = {"ms_total": ms, "ms_per_step": ms / K, "graph": graphed,
+                         "launches_per_step": launches_per_step}
+        # per-kernel pass (same rotation) for the roofline
+        if not dist_on:
+            for name, maker in (("gather", make_gather), ("merge", make_merge)):
+                gs, _ = build(maker, mode)
+                for i in range(3):
+                    gs[i % len(gs)]()
+                iters = max(K, 5 * len(gs))
+                sampler.load = True
+                results[mode][name + "_us"] = time_graph(gs, iters, False) / iters * 1e3
+                sampler.load = False
+    # make sure the clock sampler saw the load: replay the headline step for ~0.3 s
+    steps, _ = build(make_step, args.mode)
+    sampler.load = True
+    t_end = time.perf_counter() + 0.3
+    while time.perf_counter() < t_end:
+        for i in range(50):
+            steps[i % len(steps)]()
+        torch.cuda.synchronize()
+    sampler.load = False
+
+    # ---- e2e: host buffers in, host buffers out, through the public API ---------------
+    mode = args.mode
+    ws = sets[0]
+    h_xp = torch.randn(ws.x_prev.shape).pin_memory()
+    h_x0 = torch.randn(ws.x0.shape).pin_memory()
+    h_wins = torch.empty(ws.wins.shape).pin_memory()
+    copy_stream = torch.cuda.Stream()
+    e2e_steps = max(3, min(K, 30))
+
+    def e2e_step(i):
+        plan = plans[mode][i % 10]
+        up = torch.cuda.Event()
+        with torch.cuda.stream(copy_stream):               # this step's inputs: pinned host -> device
+            ws.x_prev.copy_(h_xp, non_blocking=True)
+            ws.x0.copy_(h_x0, non_blocking=True)
+            up.record()
+        st.gather_all(ws.lat, plan, out=ws.wins)
+        h_wins.copy_(ws.wins, non_blocking=True)           # this step's result: device -> pinned host
+        torch.cuda.current_stream().wait_event(up)
+        st.merge_all([ws.lat, ws.den], [ws.x_prev, ws.x0], plan, mask=ws.mask)
+        copy_stream.wait_stream(torch.cuda.current_stream())
+
+    for i in range(3):
+        e2e_step(i)
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(b) / e2e_steps
+    if dist_on:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    sampler.stop_flag = True
+
+    if rank == 0:
+        head = results[args.mode]
+        n_win = wl["views"]
+        value = n_win / (head["ms_per_step"] * 1e-3)
+        peak, peak_src = peaks()
+        line = {
+            "metric": "panorama denoise-step window-blends/sec", "value": value, "unit": "blends/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": head["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl_name, "mode": args.mode, "latent": [1, wl["C"], wl["F"], wl["H"], wl["W"]],
+                       "windows_per_step": n_win, "window": [wl["h"], wl["w"]], "payloads": 2,
+                       "l2_policy": f"inputs larger than L2: {n_sets} rotating buffer sets, {n_sets * one.nbytes() / 2**20:.0f} MiB",
+                       "cuda_graph": head["graph"], "maps": "precomputed on host (static geometry), cached on device",
+                       "sharding": "windows split over ranks, 1 NCCL all-reduce/step" if dist_on else "none"},
+            "steps_per_s": 1e3 / head["ms_per_step"],
+            "gpu_launches": (head["launches_per_step"] or (2 if not dist_on else 6)) * K,
+            "clocks": sampler.summary(),
+            "e2e": {"value": n_win / (e2e_ms * 1e-3), "unit": "blends/s",
+                    "h2d_bytes_per_step": int(h_xp.numel() * 4 + h_x0.numel() * 4),
+                    "d2h_bytes_per_step": int(h_wins.numel() * 4), "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "variants": {m: {"ms_per_step": r["ms_per_step"], "blends_per_s": n_win / (r["ms_per_step"] * 1e-3),
+                             **{k: v for k, v in r.items() if k.endswith("_us")}} for m, r in results.items()},
+        }
+        if not dist_on:
+            P = wl["C"]
+            gb, mb = st.algorithmic_bytes(plans[args.mode][0], P, 4, k=2)
+            kern = "merge" if head["merge_us"] >= head["gather_us"] else "gather"
+            bytes_launch = mb if kern == "merge" else gb
+            dur = head[kern + "_us"] * 1e-6
+            line["roofline"] = {
+                "bound": "hbm", "kernel": f"{kern}_{args.mode}", "achieved": bytes_launch / dur / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": bytes_launch / dur / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": {"gather": gb, "merge": mb, "coverage": plans[args.mode][0].coverage},
+                "step_frac": (gb + mb) / (head["ms_per_step"] * 1e-3) / 1e9 / peak,
+                "all": {m: {kn: (st.algorithmic_bytes(plans[m][0], P, 4)[0 if kn == "gather" else 1]
+                                 / (results[m][kn + "_us"] * 1e-6) / 1e9) for kn in ("gather", "merge")}
+                        for m in results},
+            }
+            reps = 2 if args.mode == "bilinear" else 10
+            if not args.no_cpu:
+                sec, cores, sample = cpu_step_time(wl, args.mode, reps)
+                line["cpu_baseline"] = {"value": n_win / sec, "unit": "blends/s", "cores": cores, "kind": "port",
+                                        "sample": sample, "ms_per_step": sec * 1e3}
+        print(json.dumps(line))
+    if dist_on:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="bilinear", choices=["bilinear", "nearest"])
+    ap.add_argument("--workload", default="cfg2_sphere_128x256", choices=list(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, args.workload)
+    else:
+        run_ours(args, wl, args.workload)
+
+
+if __name__ == "__main__":
+    main()

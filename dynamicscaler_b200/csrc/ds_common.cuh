@@ -1,0 +1,66 @@
+// Shared device helpers for libdynscaler_sm100 (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dynscaler.h"
+
+namespace ds {
+
+constexpr int kBlock = 256;          // threads per CTA for every kernel of the path
+constexpr int kSMs = 148;            // B200: grids for grid-stride kernels are multiples of this
+
+// ---- element types ---------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  using vec4 = float4;                                    // 16-byte vector of 4 elements
+  static __device__ __forceinline__ float to_f(float v) { return v; }
+  static __device__ __forceinline__ float from_f(float v) { return v; }
+  static __device__ __forceinline__ float one() { return 1.0f; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  using vec4 = uint2;                                     // 8-byte vector of 4 elements
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ __nv_bfloat16 one() { return __float2bfloat16_rn(1.0f); }
+};
+
+// read-only (LDG.NC) scalar / vector loads
+template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
+template <> __device__ __forceinline__ __nv_bfloat16 ldg(const __nv_bfloat16* p) {
+  return __ushort_as_bfloat16(__ldg(reinterpret_cast<const unsigned short*>(p)));
+}
+
+__device__ __forceinline__ int pos_mod(int a, int m) {   // a in [0, 2m)
+  return a >= m ? a - m : a;
+}
+
+// Host-side launch helpers ----------------------------------------------------------
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? DS_OK : static_cast<int>(e);
+}
+
+inline unsigned div_up(long long a, long long b) { return static_cast<unsigned>((a + b - 1) / b); }
+
+}  // namespace ds
+
+#define DS_REQUIRE(cond, code) \
+  do {                         \
+    if (!(cond)) return (code); \
+  } while (0)
+
+#define DS_DISPATCH_DTYPE(dtype, ...)                   \
+  do {                                                  \
+    if ((dtype) == DS_F32) {                            \
+      using ET = float;                                  \
+      __VA_ARGS__                                       \
+    } else if ((dtype) == DS_BF16) {                    \
+      using ET = __nv_bfloat16;                          \
+      __VA_ARGS__                                       \
+    } else {                                            \
+      return DS_ERR_DTYPE;                              \
+    }                                                   \
+  } while (0)

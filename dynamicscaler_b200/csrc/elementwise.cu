@@ -1,0 +1,143 @@
+// Elementwise steps either side of the tiling path: mix_latents_with_mask
+// (reference utils/tensor_utils.py:19-39) and the final select of the sharded merge
+// (SURVEY §8e).  Grid-stride, 16-byte vectors when everything is aligned.
+#include "ds_common.cuh"
+
+namespace ds {
+
+// out = l1*(1-m) + (l1*(1-r) + add*r)*m with every product / sum rounded on its own,
+// exactly like the reference's chain of torch elementwise ops.
+__device__ __forceinline__ float mix_one(float l1, float add, float m, float r, float omr) {
+  const float mixed = __fadd_rn(__fmul_rn(l1, omr), __fmul_rn(add, r));
+  return __fadd_rn(__fmul_rn(l1, __fsub_rn(1.0f, m)), __fmul_rn(mixed, m));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+mix_mask_kernel(const T* __restrict__ l1, const T* __restrict__ add, const T* __restrict__ mask,
+                T* __restrict__ out, float r, float omr, long long n, int mask_hw) {
+  const long long stride = static_cast<long long>(gridDim.x) * kBlock;
+  for (long long i = static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
+    const long long mi = mask_hw > 0 ? i % mask_hw : i;
+    out[i] = Elem<T>::from_f(mix_one(Elem<T>::to_f(ldg(l1 + i)), Elem<T>::to_f(ldg(add + i)),
+                                     Elem<T>::to_f(ldg(mask + mi)), r, omr));
+  }
+}
+
+// fp32, n % 4 == 0, mask_hw % 4 == 0, all pointers 16-byte aligned
+__global__ void __launch_bounds__(kBlock)
+mix_mask_f32x4_kernel(const float4* __restrict__ l1, const float4* __restrict__ add,
+                      const float4* __restrict__ mask, float4* __restrict__ out, float r, float omr,
+                      long long n4, int mask_hw4) {
+  const long long stride = static_cast<long long>(gridDim.x) * kBlock;
+  for (long long i = static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x; i < n4; i += stride) {
+    const float4 a = __ldg(l1 + i), b = __ldg(add + i);
+    const float4 m = __ldg(mask + (mask_hw4 > 0 ? i % mask_hw4 : i));
+    float4 o;
+    o.x = mix_one(a.x, b.x, m.x, r, omr);
+    o.y = mix_one(a.y, b.y, m.y, r, omr);
+    o.z = mix_one(a.z, b.z, m.z, r, omr);
+    o.w = mix_one(a.w, b.w, m.w, r, omr);
+    out[i] = o;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+select_merged_kernel(T* __restrict__ pano, const T* __restrict__ sum, const T* __restrict__ weight,
+                     long long n, long long period) {
+  const long long stride = static_cast<long long>(gridDim.x) * kBlock;
+  for (long long i = static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
+    const float w = Elem<T>::to_f(ldg(weight + i % period));
+    if (w > 0.0f) pano[i] = ldg(sum + i);
+  }
+}
+
+// fp32, n % 4 == 0, period % 4 == 0, 16-byte aligned: whole float4 groups
+__global__ void __launch_bounds__(kBlock)
+select_merged_f32x4_kernel(float4* __restrict__ pano, const float4* __restrict__ sum,
+                           const float4* __restrict__ weight, long long n4, long long period4) {
+  const long long stride = static_cast<long long>(gridDim.x) * kBlock;
+  for (long long i = static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x; i < n4; i += stride) {
+    const float4 w = __ldg(weight + i % period4);
+    if (w.x > 0.0f || w.y > 0.0f || w.z > 0.0f || w.w > 0.0f) {
+      const float4 s = __ldg(sum + i);
+      float4 p = pano[i];
+      p.x = w.x > 0.0f ? s.x : p.x;
+      p.y = w.y > 0.0f ? s.y : p.y;
+      p.z = w.z > 0.0f ? s.z : p.z;
+      p.w = w.w > 0.0f ? s.w : p.w;
+      pano[i] = p;
+    }
+  }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+static unsigned stride_grid(long long work_items) {
+  // enough CTAs for 8 resident per SM, in multiples of the SM count
+  const long long want = (work_items + kBlock - 1) / kBlock;
+  const long long cap = static_cast<long long>(kSMs) * 8;
+  if (want >= cap) return static_cast<unsigned>(cap);
+  return static_cast<unsigned>(want > 0 ? want : 1);
+}
+
+}  // namespace ds
+
+extern "C" int ds_mix_mask(const void* l1, const void* add, const void* mask, void* out,
+                           float ratio, float one_minus_ratio, long long n, int mask_hw, int dtype,
+                           void* stream) {
+  using namespace ds;
+  DS_REQUIRE(l1 != nullptr && add != nullptr && mask != nullptr && out != nullptr, DS_ERR_NULL);
+  DS_REQUIRE(n > 0 && mask_hw >= 0, DS_ERR_DIM);
+  DS_REQUIRE(mask_hw == 0 || n % mask_hw == 0, DS_ERR_DIM);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == DS_F32 && n % 4 == 0 && mask_hw % 4 == 0 && aligned16(l1) && aligned16(add) &&
+      aligned16(mask) && aligned16(out)) {
+    mix_mask_f32x4_kernel<<<stride_grid(n / 4), kBlock, 0, st>>>(
+        static_cast<const float4*>(l1), static_cast<const float4*>(add), static_cast<const float4*>(mask),
+        static_cast<float4*>(out), ratio, one_minus_ratio, n / 4, mask_hw / 4);
+    return check_launch();
+  }
+  DS_DISPATCH_DTYPE(dtype, {
+    mix_mask_kernel<ET><<<stride_grid(n), kBlock, 0, st>>>(static_cast<const ET*>(l1), static_cast<const ET*>(add),
+                                                            static_cast<const ET*>(mask), static_cast<ET*>(out),
+                                                            ratio, one_minus_ratio, n, mask_hw);
+  });
+  return check_launch();
+}
+
+extern "C" int ds_select_merged(void* pano, const void* sum, const void* weight, long long n,
+                                long long weight_period, int dtype, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(pano != nullptr && sum != nullptr && weight != nullptr, DS_ERR_NULL);
+  DS_REQUIRE(n > 0 && weight_period > 0 && n % weight_period == 0, DS_ERR_DIM);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == DS_F32 && n % 4 == 0 && weight_period % 4 == 0 && aligned16(pano) && aligned16(sum) &&
+      aligned16(weight)) {
+    select_merged_f32x4_kernel<<<stride_grid(n / 4), kBlock, 0, st>>>(
+        static_cast<float4*>(pano), static_cast<const float4*>(sum), static_cast<const float4*>(weight),
+        n / 4, weight_period / 4);
+    return check_launch();
+  }
+  DS_DISPATCH_DTYPE(dtype, {
+    select_merged_kernel<ET><<<stride_grid(n), kBlock, 0, st>>>(static_cast<ET*>(pano), static_cast<const ET*>(sum),
+                                                                 static_cast<const ET*>(weight), n, weight_period);
+  });
+  return check_launch();
+}
+
+extern "C" int ds_abi_version(void) { return DS_ABI_VERSION; }
+
+extern "C" const char* ds_error_string(int code) {
+  switch (code) {
+    case DS_OK: return "ok";
+    case DS_ERR_NULL: return "dynscaler: required pointer is NULL";
+    case DS_ERR_DIM: return "dynscaler: bad or inconsistent dimension";
+    case DS_ERR_DTYPE: return "dynscaler: unknown dtype";
+    case DS_ERR_WINDOW: return "dynscaler: illegal ring window";
+    case DS_ERR_COUNT: return "dynscaler: bad payload count";
+    case DS_ERR_ALIGN: return "dynscaler: vectorised variant on unaligned data";
+    default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "dynscaler: unknown error";
+  }
+}

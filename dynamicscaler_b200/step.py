@@ -1,0 +1,271 @@
+"""Batched per-denoising-step driver (additive API).
+
+The reference walks the windows of a step one by one (get -> UNet -> set; window k+1
+reads what window k wrote).  The batched order used here -- and by the window-sharded
+multi-GPU path BASELINE.json names -- is
+
+    gather_all  : every window of the step is cut from the step-start panorama (1 launch)
+    denoise     : the caller's UNet + ddim_step over the stacked windows
+    merge_all   : all windows written back "in window order, last writer wins" or
+                  "weighted splat + normalise" (1 launch, gather form)
+
+which equals the reference's own get_*/set_* functions composed in that order
+(oracle.panorama_oracle.sphere_step_batched / ring_step_batched).  With world_size > 1
+the ordered job list is split contiguously over the ranks; each rank merges only the
+pixels its own windows win into zeroed sum / weight buffers, one NCCL all-reduce adds the
+(disjoint-support) buffers, and a final select produces the next step-start replica on
+every rank.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, maps
+from ._lib import lib
+from .panorama_tensor_utils import (_launch_gather_bilinear, _launch_gather_nearest, _launch_merge_bilinear,
+                                    _launch_merge_nearest)
+
+
+def shard_range(n_jobs: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of the ordered job list: (begin, count) of ``rank``."""
+    base, rem = divmod(n_jobs, world)
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+@dataclass
+class StepPlan:
+    kind: str                       # "sphere_nearest" | "sphere_bilinear" | "ring"
+    n_jobs: int
+    vpf: int                        # spatial windows (views) per frame window
+    f_len: int
+    F: int
+    H: int
+    W: int
+    h: int
+    w: int
+    d_jobs: Optional[torch.Tensor] = None      # [n_jobs, 2] (map row, frame_begin) / ring: [n_jobs, 3]
+    d_idx: Optional[torch.Tensor] = None       # nearest gather maps [vpf, hw]
+    d_taps: Optional[tuple] = None             # bilinear gather (idx4, wt4)
+    d_dst: Optional[torch.Tensor] = None       # nearest merge plan (None: dense)
+    d_src: Optional[torch.Tensor] = None
+    T: int = 0
+    vec: int = 1
+    d_csr: Optional[tuple] = None              # bilinear merge plan
+    d_ftab: Optional[torch.Tensor] = None
+    coverage: float = 0.0                      # touched fraction of H*W (bytes accounting)
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def hw(self):
+        return self.h * self.w
+
+
+class PanoramaStepper:
+    """Plans and runs gather_all / merge_all for one panorama geometry on one device."""
+
+    def __init__(self, H: int, W: int, F: int, device=None, rank: int = 0, world: int = 1, group=None):
+        self.H, self.W, self.F = int(H), int(W), int(F)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.rank, self.world, self.group = rank, world, group
+        self._plans = {}
+        self._xbuf = {}
+
+    # ------------------------------------------------------------------ planning ----
+    def _frames(self, frame_begins, frames):
+        if frame_begins is None:
+            return [0], self.F
+        assert frames is not None and 0 < frames <= self.F, "warp should not occur"
+        for fb in frame_begins:
+            assert 0 <= fb < fb + frames <= 2 * self.F, f"Invalid frame_begin {fb} and frame_end {fb + frames}"
+        return [int(fb) for fb in frame_begins], int(frames)
+
+    def _ftab(self, fbs, f_len):
+        if len(fbs) == 1 and fbs[0] == 0 and f_len == self.F:
+            return None
+        return maps.on_device(("ftab", self.F, tuple(fbs), f_len), self.device,
+                              lambda: maps.frame_table(self.F, fbs, f_len))
+
+    def plan_sphere(self, views: Sequence[Tuple[float, float]], width: int, height: int, fov=120,
+                    mode: str = "nearest", frame_begins=None, frames=None) -> StepPlan:
+        """``views``: ordered (phi, theta) list of the step (pipeline loop order); with
+        ``frame_begins`` the job order is frame-window-major, like the reference's loops
+        (i2v_sphere_panorama_pipeline.py:284-325)."""
+        assert self.W == 2 * self.H
+        assert mode in ("nearest", "bilinear")
+        fbs, f_len = self._frames(frame_begins, frames)
+        key = ("sphere", mode, tuple(views), width, height, fov, tuple(fbs), f_len)
+        if key in self._plans:
+            return self._plans[key]
+        vms = [maps.view_map(fov, th, ph, width, height, self.H, self.W) for (ph, th) in views]
+        nv = len(vms)
+        plan = StepPlan(kind="sphere_" + mode, n_jobs=nv * len(fbs), vpf=nv, f_len=f_len, F=self.F,
+                        H=self.H, W=self.W, h=height, w=width)
+        vkey = tuple(vm.key for vm in vms)
+        jobs = np.array([[v, fb] for fb in fbs for v in range(nv)], dtype=np.int32)
+        plan.d_jobs = maps.on_device(("jobs", nv, tuple(fbs)), self.device, lambda: jobs)
+        plan.d_ftab = self._ftab(fbs, f_len)
+        if mode == "nearest":
+            plan.d_idx = maps.on_device(("idx_all", vkey), self.device, lambda: np.stack([vm.idx_read for vm in vms]))
+            plan.d_dst, plan.d_src = maps.on_device(("nplan", vkey), self.device, lambda: maps.nearest_merge_plan(vms))
+            plan.T = plan.d_dst.numel()
+        else:
+            plan.d_taps = maps.on_device(
+                ("taps_all", vkey), self.device,
+                lambda: (np.stack([vm.read_taps()[0] for vm in vms]), np.stack([vm.read_taps()[1] for vm in vms])))
+            plan.d_csr = maps.on_device(("bplan", vkey), self.device, lambda: maps.bilinear_merge_plan(vms))
+            plan.T = plan.d_csr[0].numel()
+        plan.coverage = plan.T / float(self.H * self.W)
+        self._plans[key] = plan
+        return plan
+
+    def plan_ring(self, windows: Sequence[Tuple[int, int]], w: int, h: int,
+                  frame_begins=None, frames=None) -> StepPlan:
+        """``windows``: ordered (left, top) list of the step's planar shift windows
+        (t2v_sphere_panorama_pipeline.py:537-560 loop order)."""
+        fbs, f_len = self._frames(frame_begins, frames)
+        assert w <= self.W and h <= self.H, "warp should not occur"
+        for (l, t) in windows:
+            assert 0 <= l < l + w <= 2 * self.W, f"Invalid pos_left {l} and pos_right {l + w}"
+            assert 0 <= t < t + h <= 2 * self.H, f"Invalid pos_top {t} and pos_down {t + h}"
+        key = ("ring", tuple(windows), w, h, tuple(fbs), f_len)
+        if key in self._plans:
+            return self._plans[key]
+        nv = len(windows)
+        plan = StepPlan(kind="ring", n_jobs=nv * len(fbs), vpf=nv, f_len=f_len, F=self.F, H=self.H, W=self.W, h=h, w=w)
+        jobs3 = np.array([[l, t, fb] for fb in fbs for (l, t) in windows], dtype=np.int32)
+        plan.d_jobs = torch.from_numpy(jobs3).to(self.device)
+        d_wins2 = torch.from_numpy(np.array(windows, dtype=np.int32).reshape(-1, 2)).to(self.device)
+        plan.d_src = torch.empty(self.H * self.W, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            lib.check(lib.ds_ring_merge_plan(plan.d_src.data_ptr(), d_wins2.data_ptr(), nv, self.H, self.W, h, w,
+                                             _lib.stream_ptr(self.device)), "ds_ring_merge_plan")
+        aligned = self.W % 4 == 0 and w % 4 == 0 and all(l % 4 == 0 for l, _ in windows)
+        plan.vec = 4 if aligned else 1
+        plan.T = self.H * self.W // plan.vec
+        plan.d_ftab = self._ftab(fbs, f_len)
+        plan.coverage = float((plan.d_src >= 0).float().mean().item())
+        plan.extra["d_wins2"] = d_wins2
+        self._plans[key] = plan
+        return plan
+
+    # --------------------------------------------------------------------- gather ----
+    def local_jobs(self, plan: StepPlan) -> Tuple[int, int]:
+        return shard_range(plan.n_jobs, self.rank, self.world)
+
+    def gather_all(self, latent: torch.Tensor, plan: StepPlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """latent [B, C, F, H, W] -> windows [n_local_jobs, B, C, f_len, h, w] (this rank's
+        slice of the ordered job list)."""
+        _lib.require_cuda(latent, "latent")
+        assert latent.is_contiguous() and latent.dim() == 5
+        B, C, F, H, W = latent.shape
+        assert (F, H, W) == (plan.F, plan.H, plan.W)
+        j0, nj = self.local_jobs(plan)
+        shape = (nj, B, C, plan.f_len, plan.h, plan.w)
+        if out is None:
+            out = torch.empty(shape, dtype=latent.dtype, device=latent.device)
+        assert tuple(out.shape) == shape and out.is_contiguous()
+        if nj == 0:
+            return out
+        if plan.kind == "ring":
+            d_jobs = plan.d_jobs[j0:j0 + nj]
+            with torch.cuda.device(latent.device):
+                lib.check(lib.ds_ring_gather(latent.data_ptr(), out.data_ptr(), d_jobs.data_ptr(), nj, 0, 0, 0,
+                                             B * C, F, H, W, plan.f_len, plan.h, plan.w,
+                                             _lib.dtype_code(latent.dtype), _lib.stream_ptr(latent.device)),
+                          "ds_ring_gather")
+        elif plan.kind == "sphere_nearest":
+            _launch_gather_nearest(latent, out, plan.d_idx, plan.d_jobs[j0:j0 + nj], 0, nj, B * C, F, H * W,
+                                   plan.f_len, plan.hw)
+        else:
+            _launch_gather_bilinear(latent, out, plan.d_taps[0], plan.d_taps[1], plan.d_jobs[j0:j0 + nj], 0, nj,
+                                    B * C, F, H * W, plan.f_len, plan.hw)
+        return out
+
+    # ---------------------------------------------------------------------- merge ----
+    def _merge_into(self, panos, payloads, mask, mask_mode, mask_planes, plan, P, j0, nj):
+        HW = plan.H * plan.W
+        if plan.kind == "sphere_bilinear":
+            _launch_merge_bilinear(panos, payloads, mask, mask_mode, mask_planes, plan.d_csr, plan.d_ftab, plan.vpf,
+                                   P, plan.F, HW, plan.f_len, plan.hw, job_begin=j0, job_count=nj)
+        else:
+            _launch_merge_nearest(panos, payloads, mask, mask_mode, mask_planes, plan.d_dst, plan.d_src, plan.T,
+                                  plan.d_ftab, plan.vpf, P, plan.F, HW, plan.f_len, plan.hw, vec=plan.vec,
+                                  job_begin=j0, job_count=nj)
+
+    def merge_all(self, panos: List[torch.Tensor], payloads: List[torch.Tensor], plan: StepPlan,
+                  mask: Optional[torch.Tensor] = None):
+        """In-place merge of this step's payloads into the panoramas.
+
+        panos[q]: [B, C, F, H, W]; payloads[q]: [n_local_jobs, B, C, f_len, h, w] (x_prev ->
+        latent panorama, pred_x0 -> denoised panorama, ...).  ``mask``: optional [1, H, W]
+        (T2V, t2v_sphere_panorama_pipeline.py:159) or [B, C, F, H, W] (I2V, i2v_sphere_
+        panorama_pipeline.py:220) denoised-mask panorama that receives 1 where written.
+        With world_size > 1 every rank ends up with the identical merged replica."""
+        assert len(panos) == len(payloads) and 0 < len(panos) <= _lib.DS_MAX_PAYLOADS
+        B, C, F, H, W = panos[0].shape
+        P = B * C
+        for p_, y in zip(panos, payloads):
+            _lib.require_cuda(p_, "panorama")
+            assert p_.is_contiguous() and y.is_contiguous() and p_.shape == panos[0].shape and y.dtype == p_.dtype
+        j0, nj = self.local_jobs(plan)
+        mask_mode, mask_planes = _lib.DS_MASK_NONE, 0
+        if mask is not None:
+            assert mask.is_contiguous() and mask.dtype == panos[0].dtype
+            if mask.numel() == H * W:
+                assert plan.d_ftab is None, "a [1, H, W] mask panorama has no frame axis"
+                mask_mode = _lib.DS_MASK_PLANE
+            else:
+                assert mask.numel() % (F * H * W) == 0
+                mask_mode, mask_planes = _lib.DS_MASK_FULL, mask.numel() // (F * H * W)
+        if self.world == 1:
+            self._merge_into(panos, payloads, mask, mask_mode, mask_planes, plan, P, 0, plan.n_jobs)
+            return
+        self._merge_sharded(panos, payloads, mask, plan, P, j0, nj)
+
+    def _merge_sharded(self, panos, payloads, mask, plan, P, j0, nj):
+        """disjoint-support partial merge -> one all-reduce -> select."""
+        import torch.distributed as dist
+        Q = len(panos)
+        n = panos[0].numel()
+        per_frame = plan.d_ftab is not None
+        wlen = plan.F * plan.H * plan.W if per_frame else plan.H * plan.W
+        key = (Q, n, wlen, panos[0].dtype)
+        buf = self._xbuf.get(key)
+        if buf is None:
+            buf = self._xbuf[key] = torch.empty(Q * n + wlen, dtype=panos[0].dtype, device=panos[0].device)
+        buf.zero_()
+        sums = [buf[q * n:(q + 1) * n] for q in range(Q)]
+        weight = buf[Q * n:]
+        if nj > 0:
+            self._merge_into(sums, payloads, weight, _lib.DS_MASK_FULL if per_frame else _lib.DS_MASK_PLANE,
+                             1 if per_frame else 0, plan, P, j0, nj)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        with torch.cuda.device(buf.device):
+            for q in range(Q):
+                lib.check(lib.ds_select_merged(panos[q].data_ptr(), sums[q].data_ptr(), weight.data_ptr(), n, wlen,
+                                               _lib.dtype_code(buf.dtype), _lib.stream_ptr(buf.device)),
+                          "ds_select_merged")
+            if mask is not None:
+                okey = ("one", mask.numel(), mask.dtype)
+                if okey not in self._xbuf:
+                    self._xbuf[okey] = torch.ones(mask.numel(), dtype=mask.dtype, device=mask.device)
+                one = self._xbuf[okey]
+                lib.check(lib.ds_select_merged(mask.data_ptr(), one.data_ptr(), weight.data_ptr(), mask.numel(),
+                                               wlen, _lib.dtype_code(buf.dtype), _lib.stream_ptr(buf.device)),
+                          "ds_select_merged")
+
+    # ------------------------------------------------------------- bytes accounting ----
+    def algorithmic_bytes(self, plan: StepPlan, P: int, elem_size: int, k: int = 2):
+        """N*V*s [gather out] + cov*P*s [pano read once] + k*N*V*s [payloads in]
+        + k*cov*P*s [pano written once] (+ mask).  Returns (gather_bytes, merge_bytes)."""
+        V = P * plan.f_len * plan.hw * elem_size
+        frames_touched = plan.F if plan.d_ftab is None else int((plan.d_ftab >= 0).sum().item())
+        pano = plan.coverage * P * frames_touched * plan.H * plan.W * elem_size
+        gather = plan.n_jobs * V + pano
+        merge = k * plan.n_jobs * V + k * pano
+        return gather, merge

@@ -1,0 +1,163 @@
+/*
+ * dynscaler.h -- C ABI of libdynscaler_sm100.so: the B200 (sm_100a) implementation of
+ * DynamicScaler's per-denoising-step panorama tiling path.
+ *
+ * This is the drop-in boundary ("interface level 2").  The reference is
+ * pure Python/PyTorch and has no FFI; each entry point below names the reference
+ * function (file:line under the reference checkout) whose tensor arithmetic it replaces.
+ * The Python shims in dynamicscaler_b200/ keep the reference's class/method signatures
+ * ("interface level 1") and call these through ctypes with tensor.data_ptr().
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer unless its name starts with h_ (host).
+ *   - The library allocates nothing, keeps no global state, and is stream-ordered and
+ *     re-entrant: every call only enqueues kernels on `stream` (a cudaStream_t).
+ *   - Return value: 0 = ok; < 0 = argument error (DS_ERR_*); > 0 = a cudaError_t.
+ *   - dtype: DS_F32 or DS_BF16 for every latent/payload/window buffer of one call.
+ *   - A panorama latent is addressed as planes [P][F][H*W] (P = B*C, frame-major, W
+ *     fastest) -- the reference's own [B,C,F,H,W] memory order
+ *     (shift_window_utils.py:42).  A window/view batch is [n_jobs][P][f_len][h*w].
+ *   - k = y*w + x is a view pixel, p = r*W + c a panorama pixel.  Index maps are int32.
+ *   - "job" j reads/writes frames (frame_begin_j + fo) mod F, fo in [0, f_len): the
+ *     frame-axis ring of shift_window_utils.py:97,181 / ring_panorama_tensor_utils.py:61.
+ */
+#ifndef DYNSCALER_H_
+#define DYNSCALER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DS_ABI_VERSION 1
+
+enum { DS_F32 = 0, DS_BF16 = 1 };
+
+enum {
+  DS_OK = 0,
+  DS_ERR_NULL = -1,      /* a required pointer is NULL          */
+  DS_ERR_DIM = -2,       /* a dimension is <= 0 or inconsistent */
+  DS_ERR_DTYPE = -3,     /* unknown dtype                       */
+  DS_ERR_WINDOW = -4,    /* window outside 0 <= begin < end <= 2*size, or larger than the axis on a write */
+  DS_ERR_COUNT = -5,     /* too many payloads (> DS_MAX_PAYLOADS) */
+  DS_ERR_ALIGN = -6      /* vectorised variant requested on unaligned data */
+};
+
+#define DS_MAX_PAYLOADS 4
+
+/* mask_mode of the merge calls */
+enum { DS_MASK_NONE = 0, DS_MASK_PLANE = 1 /* one [H*W] plane */, DS_MASK_FULL = 2 /* [mask_planes][F][H*W] */ };
+
+int ds_abi_version(void);
+/* Static string for a return code of this library (never NULL). */
+const char* ds_error_string(int code);
+
+/* ---------------------------------------------------------------- ring windows ---- */
+
+/* RingLatent.get_window_latent (utils/shift_window_utils.py:48-114) for n windows at once:
+ *   out[j][pl][fo][y][x] = pano[pl][(f0_j+fo) mod F][(top_j+y) mod H][(left_j+x) mod W]
+ * d_wins: [n][3] int32 (left, top, frame_begin).  If d_wins is NULL, n must be 1 and the
+ * window is (h_left, h_top, h_f0) (no device descriptor needed for the per-call API).
+ * Also serves RingImageTensor.get_window_tensor (:232-263) with P=3, F=f_len=1. */
+int ds_ring_gather(const void* pano, void* out, const int32_t* d_wins, int n,
+                   int h_left, int h_top, int h_f0,
+                   int P, int F, int H, int W, int f_len, int h, int w, int dtype, void* stream);
+
+/* RingLatent.set_window_latent (utils/shift_window_utils.py:116-206), one window:
+ *   pano[pl][(f0+fo) mod F][(top+y) mod H][(left+x) mod W] = in[pl][fo][y][x]
+ * requires f_len <= F, h <= H, w <= W (":145-147 warp should not occur"). */
+int ds_ring_scatter(void* pano, const void* in, int left, int top, int f0,
+                    int P, int F, int H, int W, int f_len, int h, int w, int dtype, void* stream);
+
+/* Merge plan of an ordered list of planar ring windows (the sequential
+ * set_window_latent loop of pipeline/t2v_sphere_panorama_pipeline.py:609-632 collapsed
+ * to "last window in order wins"): for every panorama pixel p covered by any window,
+ *   plan_src[p] = j*h*w + y*w + x  of the LAST window j covering it, else -1.
+ * d_wins: [n][2] int32 (left, top).  plan_src: [H*W] int32 out. */
+int ds_ring_merge_plan(int32_t* plan_src, const int32_t* d_wins, int n,
+                       int H, int W, int h, int w, void* stream);
+
+/* ------------------------------------------------- sphere (equirect <-> view) ---- */
+
+/* PanoramaTensor.get_view_tensor_no_interpolate (utils/panorama_tensor_utils.py:53-70,
+ * 185-202) and its frame-ring twin (utils/ring_panorama_tensor_utils.py:59-78), batched:
+ *   out[j][pl][fo][k] = pano[pl][(f0_j+fo) mod F][ idx[map_j][k] ]
+ * d_idx:  [n_maps][hw] int32 panorama pixel per view pixel (column wrapped, row clamped).
+ * d_jobs: [n_jobs][2] int32 (map row, frame_begin), or NULL => job j = (j, h_f0). */
+int ds_gather_nearest(const void* pano, void* out, const int32_t* d_idx, const int32_t* d_jobs,
+                      int h_f0, int n_jobs, int P, int F, int HW, int f_len, int hw, int dtype,
+                      void* stream);
+
+/* PanoramaTensor.get_view_tensor_interpolate (utils/panorama_tensor_utils.py:28-51;
+ * ring twin ring_panorama_tensor_utils.py:31-57): F.grid_sample(bilinear, border).
+ *   out = fma(t3,w3, fma(t2,w2, fma(t1,w1, t0*w0)))   (ATen's CPU summation order)
+ * d_idx4: [n_maps][4][hw] int32 tap pixels (nw, ne, sw, se; clamped in bounds),
+ * d_wt4:  [n_maps][4][hw] float32 tap weights. */
+int ds_gather_bilinear(const void* pano, void* out, const int32_t* d_idx4, const float* d_wt4,
+                       const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
+                       int hw, int dtype, void* stream);
+
+/* Nearest merge in gather form.  Replaces the forward scatters
+ * PanoramaTensor.set_view_tensor_no_interpolation (utils/panorama_tensor_utils.py:154-183),
+ * its ring twin (ring_panorama_tensor_utils.py:170-198), set_view_tensor (:72-96) and --
+ * with a plan from ds_ring_merge_plan -- RingLatent.set_window_latent, for one view or
+ * for a whole ordered list of views/windows ("last writer wins"):
+ *   for t < T, q < Q, every plane pl and panorama frame f with d_ftab[f] >= 0:
+ *     panos[q][pl][f][dst[t]] = payloads[q][(s*views_per_fwin + v)][pl][fo][k]
+ *   where src[t] = v*hw + k and d_ftab[f] = s*f_len + fo.
+ * d_dst/d_src: [T] int32.  If d_dst is NULL the plan is dense: T = HW, dst[t] = t and
+ *   entries with src[t] < 0 are skipped.
+ * d_ftab: [F] int32 or NULL (=> identity: f_len == F, s = 0, fo = f).
+ * mask: optional panorama that receives 1.0 at every written location
+ *   (DS_MASK_PLANE: mask[dst]; DS_MASK_FULL: mask[mpl][f][dst] for mpl < mask_planes).
+ * h_panos / h_payloads: HOST arrays of Q device pointers.
+ * vec: 1, or 4 when every dst/src entry addresses 4 consecutive, 16-byte aligned
+ *   elements (planar ring windows on multiples of 4); then T counts groups of 4.
+ * job_begin/job_count: window sharding.  Only entries whose job
+ *   s*views_per_fwin + v lies in [job_begin, job_begin + job_count) are applied and the
+ *   payloads hold just those jobs ([job_count][P][f_len][hw]); everything else is left
+ *   untouched (mask included), so per-rank outputs have disjoint support. */
+int ds_merge_nearest(void* const* h_panos, const void* const* h_payloads, int Q,
+                     void* mask, int mask_mode, int mask_planes,
+                     const int32_t* d_dst, const int32_t* d_src, int T, const int32_t* d_ftab,
+                     int views_per_fwin, int job_begin, int job_count,
+                     int P, int F, int HW, int f_len, int hw, int vec, int dtype, void* stream);
+
+/* Weighted scatter-accumulate + per-pixel weight normalisation in gather form:
+ * PanoramaTensor.set_view_tensor_bilinear (utils/panorama_tensor_utils.py:98-152; ring twin
+ * ring_panorama_tensor_utils.py:107-166).  Row t owns panorama pixel d_row_dst[t] and
+ * the CSR entries e in [d_row_ptr[t], d_row_ptr[t+1]), listed tap-major then k ascending
+ * (the order index_add_ applies them):
+ *     acc = 0; ws = 0;  for e: acc = acc + (payload[src_e] * w_e);  ws = ws + w_e
+ *     if ws > 0: pano[...][dst] = acc / ws            (mul, add, div individually rounded)
+ * Frame/plane/payload addressing, the mask and job_begin/job_count as in
+ * ds_merge_nearest (all entries of one row come from one view). */
+int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q,
+                      void* mask, int mask_mode, int mask_planes,
+                      const int32_t* d_row_dst, const int32_t* d_row_ptr, int T,
+                      const int32_t* d_ent_src, const float* d_ent_w, const int32_t* d_ftab,
+                      int views_per_fwin, int job_begin, int job_count,
+                      int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
+
+/* ------------------------------------------------------------------ elementwise ---- */
+
+/* mix_latents_with_mask (utils/tensor_utils.py:19-39):
+ *   mixed = l1*(1-r) + add*r;  out = l1*(1-m) + mixed*m     (no FMA contraction)
+ * one_minus_ratio is passed separately because the reference forms (1 - mix_ratio) in
+ * Python double precision before the tensor multiply.
+ * mask_hw > 0: mask is one [mask_hw] plane broadcast over n/mask_hw planes (the [1,h,w]
+ * case, :21-23); mask_hw == 0: mask has n elements (the 5-D case, :24-25). */
+int ds_mix_mask(const void* l1, const void* add, const void* mask, void* out,
+                float ratio, float one_minus_ratio, long long n, int mask_hw, int dtype, void* stream);
+
+/* Final select of the sharded merge: pano[i] = weight[i mod period] > 0 ?
+ * sum[i] : pano[i] for i < n.  weight has the panorama's dtype; weight_period is H*W (one
+ * plane), F*H*W (one plane per frame) or n. */
+int ds_select_merged(void* pano, const void* sum, const void* weight,
+                     long long n, long long weight_period, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYNSCALER_H_ */

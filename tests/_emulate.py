@@ -1,0 +1,107 @@
+"""numpy emulation of the kernels' contracts (include/dynscaler.h), used by the CPU test
+suite to validate the host-built maps / plans without a GPU.  Test-only."""
+import numpy as np
+
+F32 = np.float32
+
+
+def gather_nearest(pano, idx, jobs, f_len):
+    """pano [P, F, HW]; idx [n_maps, hw]; jobs [(map, f0)] -> [n_jobs, P, f_len, hw]"""
+    P, F, HW = pano.shape
+    out = np.empty((len(jobs), P, f_len, idx.shape[1]), pano.dtype)
+    for j, (m, f0) in enumerate(jobs):
+        fi = (f0 + np.arange(f_len)) % F
+        out[j] = pano[:, fi][:, :, idx[m]]
+    return out
+
+
+def gather_bilinear(pano, idx4, wt4, jobs, f_len):
+    P, F, HW = pano.shape
+    out = np.empty((len(jobs), P, f_len, idx4.shape[2]), pano.dtype)
+    fma = lambda a, b, c: (a.astype(np.float64) * b.astype(np.float64) + c.astype(np.float64)).astype(F32)
+    for j, (m, f0) in enumerate(jobs):
+        fi = (f0 + np.arange(f_len)) % F
+        src = pano[:, fi]
+        r = src[:, :, idx4[m, 0]] * wt4[m, 0]
+        for t in (1, 2, 3):
+            r = fma(src[:, :, idx4[m, t]], wt4[m, t][None, None], r)
+        out[j] = r
+    return out
+
+
+def _sources(ftab, F, f_len, vpf, v, job_begin, job_count):
+    """per panorama frame f: (local job, fo) or None"""
+    res = []
+    for f in range(F):
+        sfo = f if ftab is None else int(ftab[f])
+        if sfo < 0:
+            res.append(None)
+            continue
+        s, fo = divmod(sfo, f_len)
+        job = s * vpf + v - job_begin
+        res.append((job, fo) if 0 <= job < job_count else None)
+    return res
+
+
+def merge_nearest(panos, payloads, dst, src, ftab, vpf, f_len, hw, mask=None, mask_mode=0,
+                  job_begin=0, job_count=1 << 30):
+    """panos[q] [P, F, HW] in place; payloads[q] [n_local_jobs, P, f_len, hw]"""
+    P, F, HW = panos[0].shape if panos else (0, len(ftab) if ftab is not None else 0, 0)
+    if dst is None:
+        keep = src >= 0
+        dst, src = np.nonzero(keep)[0], src[keep]
+    v_all, k_all = src // hw, src % hw
+    for v in np.unique(v_all):
+        sel = v_all == v
+        d, k = dst[sel], k_all[sel]
+        for f, sf in enumerate(_sources(ftab, F, f_len, vpf, int(v), job_begin, job_count)):
+            if sf is None:
+                continue
+            job, fo = sf
+            for q in range(len(panos)):
+                panos[q][:, f, d] = payloads[q][job][:, fo][:, k]
+            if mask_mode == 2:
+                mask[:, f, d] = 1
+            if mask_mode == 1 and f == 0:
+                mask[d] = 1
+
+
+def merge_bilinear(panos, payloads, plan, ftab, vpf, f_len, hw, mask=None, mask_mode=0,
+                   job_begin=0, job_count=1 << 30):
+    row_dst, row_ptr, ent_src, ent_w = plan
+    P, F, HW = panos[0].shape
+    for t in range(row_dst.shape[0]):
+        e0, e1 = row_ptr[t], row_ptr[t + 1]
+        if e1 <= e0:
+            continue
+        v = int(ent_src[e0]) // hw
+        ks = ent_src[e0:e1] - v * hw
+        ws_ = F32(0)
+        for w in ent_w[e0:e1]:
+            ws_ = F32(ws_ + w)
+        if not ws_ > 0:
+            continue
+        for f, sf in enumerate(_sources(ftab, F, f_len, vpf, v, job_begin, job_count)):
+            if sf is None:
+                continue
+            job, fo = sf
+            for q in range(len(panos)):
+                acc = np.zeros(P, F32)
+                x = payloads[q][job][:, fo]                       # [P, hw]
+                for k, w in zip(ks, ent_w[e0:e1]):
+                    acc = acc + x[:, k] * w
+                panos[q][:, f, row_dst[t]] = acc / ws_
+            if mask_mode == 2:
+                mask[:, f, row_dst[t]] = 1
+            if mask_mode == 1 and f == 0:
+                mask[row_dst[t]] = 1
+
+
+def ring_merge_plan(windows, H, W, h, w):
+    """dense plan_src [H*W] of ds_ring_merge_plan"""
+    plan = np.full((H, W), -1, np.int32)
+    for j, (l, t) in enumerate(windows):
+        ys = (t + np.arange(h)) % H
+        xs = (l + np.arange(w)) % W
+        plan[np.ix_(ys, xs)] = (j * h + np.arange(h))[:, None] * w + np.arange(w)[None, :]
+    return plan.reshape(-1)

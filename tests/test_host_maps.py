@@ -1,0 +1,160 @@
+"""Host-side geometry of the product (dynamicscaler_b200/maps.py, step planning) against
+the reference's golden vectors, by emulating the kernel contracts in numpy.  CPU only:
+no kernels run here, the oracle is only the checker."""
+import numpy as np
+import pytest
+
+from _emulate import gather_bilinear, gather_nearest, merge_bilinear, merge_nearest, ring_merge_plan
+from conftest import randn
+from dynamicscaler_b200 import maps
+from dynamicscaler_b200.shift_window_utils import get_dimension_slices_and_sizes
+from dynamicscaler_b200.step import shard_range
+from oracle import panorama_oracle as po
+
+
+def test_uv_maps_bit_exact_vs_reference(small):
+    for i, (fov, th, ph, w, h, H, W) in enumerate(small["uv/cases"]):
+        if f"uv/{i}/u" not in small:
+            continue
+        vm = maps.view_map(fov, th, ph, int(w), int(h), int(H), int(W))
+        assert np.array_equal(vm.u, small[f"uv/{i}/u"]) and np.array_equal(vm.v, small[f"uv/{i}/v"])
+
+
+def test_index_maps_bit_exact_config2(configs):
+    """north_star: 'window index/wrap maps bit-exact'."""
+    for n, (ph, th) in enumerate(configs["cfg2/views"]):
+        vm = maps.view_map(120, th, ph, 64, 40, 128, 256)
+        assert vm.idx_read.dtype == np.int32
+        assert np.array_equal(vm.idx_read, configs["cfg2/idx_read"][n])
+        dst, src = vm.write_plan
+        tgt = configs["cfg2/idx_write"][n]
+        win = po.last_writer_flags(tgt.astype(np.int64))
+        assert np.array_equal(np.sort(tgt[win]), dst) and np.array_equal(tgt[src], dst)
+        assert win[src].all()
+
+
+def test_angles_not_reduced_mod_360():
+    a = maps.view_map(120, 48, 45, 64, 40, 128, 256)
+    b = maps.view_map(120, 408, 45, 64, 40, 128, 256)
+    assert a is not b and (a.idx_read != b.idx_read).any()
+
+
+def test_slices_helper(small):
+    for i, (b, e, s) in enumerate(small["slices/cases"]):
+        sl, sz = get_dimension_slices_and_sizes(int(b), int(e), int(s))
+        assert [x.stop - x.start for x in sl] == sz
+        assert np.array_equal(np.concatenate([np.arange(x.start, x.stop) for x in sl]), small[f"slices/{i}"])
+
+
+def _planes(a):   # [B, C, F, H, W] -> [P, F, HW]
+    B, C, F, H, W = a.shape
+    return a.reshape(B * C, F, H * W).copy()
+
+
+def test_per_view_plans_small(small):
+    pano5 = randn(21, 1, 2, 3, 16, 32)
+    for i, (fov, th, ph) in enumerate(small["sph/views"]):
+        vm = maps.view_map(fov, th, ph, 10, 6, 16, 32)
+        view_in = randn(300 + i, 1, 2, 3, 6, 10).reshape(1, 2, 3, 60)
+        got = gather_nearest(_planes(pano5), vm.idx_read[None], [(0, 0)], 3)
+        assert np.array_equal(got.reshape(1, 2, 3, 6, 10), small[f"sph/get_nearest/{i}"])
+        idx4, wt4 = vm.read_taps()
+        got = gather_bilinear(_planes(pano5), idx4[None], wt4[None], [(0, 0)], 3)
+        assert np.abs(got.reshape(1, 2, 3, 6, 10) - small[f"sph/get_bilinear/{i}"]).max() <= 1e-6
+        lat = _planes(pano5)
+        merge_nearest([lat], [view_in], *vm.write_plan, None, 1, 3, 60)
+        assert np.array_equal(lat.reshape(pano5.shape), small[f"sph/set_nearest/{i}"])
+        lat = _planes(pano5)
+        merge_bilinear([lat], [view_in], maps.bilinear_merge_plan([vm]), None, 1, 3, 60)
+        assert np.array_equal(lat.reshape(pano5.shape), small[f"sph/set_bilinear/{i}"])
+        # quirk Q3 of set_view_tensor: L = B*F = 3 images
+        lat = pano5.copy()
+        for b in range(3):
+            dst, src = maps.round_merge_plan(vm, 3, b)
+            img = lat[0, :, b].reshape(2, -1).copy()
+            img[:, dst] = view_in[0, :, b][:, src]
+            lat[0, :, b] = img.reshape(2, 16, 32)
+        assert np.array_equal(lat, small[f"sph/set_round/{i}"])
+
+
+def test_frame_ring_plans_small(small):
+    rp5 = randn(31, 1, 2, 7, 16, 32)
+    for i, (fov, th, ph, fb, fe) in enumerate(small["rsph/cases"]):
+        fb, fe = int(fb), int(fe)
+        nf = fe - fb
+        vm = maps.view_map(fov, th, ph, 10, 6, 16, 32)
+        got = gather_nearest(_planes(rp5), vm.idx_read[None], [(0, fb)], nf)
+        assert np.array_equal(got.reshape(1, 2, nf, 6, 10), small[f"rsph/get_nearest/{i}"])
+        view_in = randn(500 + i, 1, 2, nf, 6, 10).reshape(1, 2, nf, 60)
+        ftab = maps.frame_table(7, [fb], nf)
+        lat = _planes(rp5)
+        merge_nearest([lat], [view_in], *vm.write_plan, ftab, 1, nf, 60)
+        assert np.array_equal(lat.reshape(rp5.shape), small[f"rsph/set_nearest/{i}"])
+        lat = _planes(rp5)
+        merge_bilinear([lat], [view_in], maps.bilinear_merge_plan([vm]), ftab, 1, nf, 60)
+        assert np.array_equal(lat.reshape(rp5.shape), small[f"rsph/set_bilinear/{i}"])
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_batched_plan_equals_reference_order(small, mode, world):
+    """merge_all plan == the reference sets applied view after view, also when
+    the job list is sharded over ranks and the disjoint partial results are summed."""
+    lat0 = randn(51, 1, 2, 3, 16, 32)
+    views = [(ph, th) for ph, th in small["step/views"]]
+    vms = [maps.view_map(120, th, ph, 10, 6, 16, 32) for ph, th in views]
+    wins = small[f"step/batched_{mode}/windows"]                     # [n, 1, 2, 3, 6, 10]
+    x_prev = np.stack([wins[n] * np.float32(0.5) + randn(700 + n, 1, 2, 3, 6, 10) for n in range(len(views))])
+    x0 = np.stack([wins[n] * np.float32(0.25) - randn(800 + n, 1, 2, 3, 6, 10) for n in range(len(views))])
+    pay = [x_prev.reshape(len(views), 2, 3, 60), x0.reshape(len(views), 2, 3, 60)]
+    plan = maps.nearest_merge_plan(vms) if mode == "nearest" else maps.bilinear_merge_plan(vms)
+    sums = [np.zeros((2, 3, 512), np.float32) for _ in range(2)]
+    weight = np.zeros(512, np.float32)
+    for r in range(world):
+        j0, nj = shard_range(len(views), r, world)
+        part = [np.zeros((2, 3, 512), np.float32) for _ in range(2)]
+        wpart = np.zeros(512, np.float32)
+        local = [p[j0:j0 + nj] for p in pay]
+        if mode == "nearest":
+            merge_nearest(part, local, plan[0], plan[1], None, len(views), 3, 60, wpart, 1, j0, nj)
+        else:
+            merge_bilinear(part, local, plan, None, len(views), 3, 60, wpart, 1, j0, nj)
+        for q in range(2):
+            sums[q] += part[q]
+        weight += wpart
+    assert weight.max() == 1.0                                        # exactly one owner per pixel
+    lat, den = _planes(lat0), np.zeros((2, 3, 512), np.float32)
+    lat[:, :, weight > 0] = sums[0][:, :, weight > 0]
+    den[:, :, weight > 0] = sums[1][:, :, weight > 0]
+    tol = 0 if mode == "nearest" else 1e-5
+    assert np.abs(lat.reshape(lat0.shape) - small[f"step/batched_{mode}/latent"]).max() <= tol
+    assert np.abs(den.reshape(lat0.shape) - small[f"step/batched_{mode}/denoised"]).max() <= tol
+    assert np.array_equal(weight.reshape(1, 16, 32), small[f"step/batched_{mode}/mask"])
+
+
+def test_ring_merge_plan_emulation_matches_oracle():
+    H, W, h, w = 16, 32, 6, 12
+    windows = [(4 * a + 2, 3 * b + 1) for a in range(8) for b in range(5)]
+    lat = randn(1, 1, 2, 3, H, W)
+    pays = [randn(100 + n, 1, 2, 3, h, w) for n in range(len(windows))]
+    ref = lat.copy()
+    for n, (l, t) in enumerate(windows):
+        po.ring_set(ref, pays[n], l, l + w, t, t + h)
+    plan = ring_merge_plan(windows, H, W, h, w)
+    got = _planes(lat)
+    merge_nearest([got], [np.stack(pays).reshape(len(windows), 2, 3, h * w)], None, plan, None, len(windows), 3, h * w)
+    assert np.array_equal(got.reshape(lat.shape), ref)
+
+
+def test_frame_table_last_window_wins():
+    ftab = maps.frame_table(8, [6, 1], 4)            # windows [6,7,0,1] then [1,2,3,4]
+    assert ftab.tolist() == [2, 4, 5, 6, 7, -1, 0, 1]
+
+
+def test_shard_range_partitions():
+    for n in (1, 5, 44, 88, 572):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            assert all(spans[r][0] + spans[r][1] == spans[r + 1][0] for r in range(world - 1))
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
