@@ -1,0 +1,8 @@
+#!/bin/bash
+# Round check on a B200 box (run through gpurun): smoke, GPU parity tests, bench.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
+python -m pytest tests -m gpu -x -q 2>&1 | tail -30
+python bench.py --steps 200 --warmup 20 2>gpurun_out/bench_err.log | tee gpurun_out/bench_latest.json
+tail -5 gpurun_out/bench_err.log
