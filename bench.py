@@ -127,7 +127,7 @@ class Workset:
     """One rotating buffer set (panoramas + windows + payloads), so consecutive steps touch
     different memory and the aggregate footprint exceeds L2."""
 
-    def __init__(self, wl, n_local, dev, gen):
+    def __init__(self, wl, n_local, dev, gen, st=None):
         shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
         vshape = (n_local, 1, wl["C"], wl["F"], wl["h"], wl["w"])
         self.lat = torch.randn(shape, device=dev, generator=gen)
@@ -136,6 +136,15 @@ class Workset:
         self.wins = torch.empty(vshape, device=dev)
         self.x_prev = torch.randn(vshape, device=dev, generator=gen)
         self.x0 = torch.randn(vshape, device=dev, generator=gen)
+        # resident pixel-major state (layout "pm"): gather/merge work on it in place
+        self.state = st.make_state([self.lat, self.den], mask=self.mask) if st is not None else None
+        self.pano = self.state if self.state is not None else self.lat
+
+    def merge(self, st, plan):
+        if self.state is not None:
+            st.merge_all(self.state, [self.x_prev, self.x0], plan)
+        else:
+            st.merge_all([self.lat, self.den], [self.x_prev, self.x0], plan, mask=self.mask)
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.lat, self.den, self.mask, self.wins, self.x_prev, self.x0))
@@ -181,7 +190,7 @@ def run_ours(args, wl, wl_name):
     dist_on = world > 1
     if dist_on:
         dist.init_process_group("nccl", device_id=dev)
-    assert lib.ds_abi_version() == 1                     # fails loudly if the .so is missing
+    assert lib.ds_abi_version() == 2                     # fails loudly if the .so is missing
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -190,26 +199,27 @@ def run_ours(args, wl, wl_name):
     plans = {m: [st.plan_sphere(default_views(i), wl["w"], wl["h"], fov=wl["fov"], mode=m) for i in range(10)]
              for m in ("bilinear", "nearest")}
     n_local = st.local_jobs(plans["nearest"][0])[1]
-    one = Workset(wl, n_local, dev, gen)
+    st_pm = st if args.layout == "pm" else None
+    one = Workset(wl, n_local, dev, gen, st_pm)
     n_sets = max(4, -(-3 * L2_BYTES // one.nbytes()))    # aggregate footprint >= 3x L2
-    sets = [one] + [Workset(wl, n_local, dev, gen) for _ in range(n_sets - 1)]
+    sets = [one] + [Workset(wl, n_local, dev, gen, st_pm) for _ in range(n_sets - 1)]
     combos = [(i % 10, i % n_sets) for i in range(10 * n_sets // np.gcd(10, n_sets))]
 
     def make_step(mode, off, s):
         ws, plan = sets[s], plans[mode][off]
 
         def step():
-            st.gather_all(ws.lat, plan, out=ws.wins)
-            st.merge_all([ws.lat, ws.den], [ws.x_prev, ws.x0], plan, mask=ws.mask)
+            st.gather_all(ws.pano, plan, out=ws.wins)
+            ws.merge(st, plan)
         return step
 
     def make_gather(mode, off, s):
         ws, plan = sets[s], plans[mode][off]
-        return lambda: st.gather_all(ws.lat, plan, out=ws.wins)
+        return lambda: st.gather_all(ws.pano, plan, out=ws.wins)
 
     def make_merge(mode, off, s):
         ws, plan = sets[s], plans[mode][off]
-        return lambda: st.merge_all([ws.lat, ws.den], [ws.x_prev, ws.x0], plan, mask=ws.mask)
+        return lambda: ws.merge(st, plan)
 
     # warm-up outside graphs (module load, NCCL communicator setup)
     side = torch.cuda.Stream()
@@ -282,10 +292,10 @@ def run_ours(args, wl, wl_name):
             ws.x_prev.copy_(h_xp, non_blocking=True)
             ws.x0.copy_(h_x0, non_blocking=True)
             up.record()
-        st.gather_all(ws.lat, plan, out=ws.wins)
+        st.gather_all(ws.pano, plan, out=ws.wins)
         h_wins.copy_(ws.wins, non_blocking=True)           # this step's result: device -> pinned host
         torch.cuda.current_stream().wait_event(up)
-        st.merge_all([ws.lat, ws.den], [ws.x_prev, ws.x0], plan, mask=ws.mask)
+        ws.merge(st, plan)
         copy_stream.wait_stream(torch.cuda.current_stream())
 
     for i in range(3):
@@ -318,7 +328,10 @@ def run_ours(args, wl, wl_name):
             "config": {"workload": wl_name, "mode": args.mode, "latent": [1, wl["C"], wl["F"], wl["H"], wl["W"]],
                        "windows_per_step": n_win, "window": [wl["h"], wl["w"]], "payloads": 2,
                        "l2_policy": f"inputs larger than L2: {n_sets} rotating buffer sets, {n_sets * one.nbytes() / 2**20:.0f} MiB",
-                       "cuda_graph": head["graph"], "maps": "precomputed on host (static geometry), cached on device",
+                       "cuda_graph": head["graph"],
+                       "layout": "resident pixel-major [H*W][F][4] (csrc/pm.cu)" if args.layout == "pm"
+                                 else "reference [B,C,F,H,W] (csrc/sphere.cu)",
+                       "maps": "precomputed on host (static geometry), cached on device",
                        "sharding": "windows split over ranks, 1 NCCL all-reduce/step" if dist_on else "none"},
             "steps_per_s": 1e3 / head["ms_per_step"],
             "gpu_launches": (head["launches_per_step"] or (2 if not dist_on else 6)) * K,
@@ -362,6 +375,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bilinear", choices=["bilinear", "nearest"])
+    ap.add_argument("--layout", default="pm", choices=["pm", "ref"],
+                    help="pm: panoramas resident in pixel-major order (PanoramaState); ref: reference order")
     ap.add_argument("--workload", default="cfg2_sphere_128x256", choices=list(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

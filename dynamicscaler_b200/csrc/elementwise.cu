@@ -45,15 +45,15 @@ mix_mask_f32x4_kernel(const float4* __restrict__ l1, const float4* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
 select_merged_kernel(T* __restrict__ pano, const T* __restrict__ sum, const T* __restrict__ weight,
-                     long long n, long long period) {
+                     long long n, long long period, long long group) {
   const long long stride = static_cast<long long>(gridDim.x) * kBlock;
   for (long long i = static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
-    const float w = Elem<T>::to_f(ldg(weight + i % period));
+    const float w = Elem<T>::to_f(ldg(weight + (i / group) % period));
     if (w > 0.0f) pano[i] = ldg(sum + i);
   }
 }
 
-// fp32, n % 4 == 0, period % 4 == 0, 16-byte aligned: whole float4 groups
+// fp32, n % 4 == 0, 16-byte aligned, group == 1 and period % 4 == 0: whole float4 groups
 __global__ void __launch_bounds__(kBlock)
 select_merged_f32x4_kernel(float4* __restrict__ pano, const float4* __restrict__ sum,
                            const float4* __restrict__ weight, long long n4, long long period4) {
@@ -69,6 +69,17 @@ select_merged_f32x4_kernel(float4* __restrict__ pano, const float4* __restrict__
       p.w = w.w > 0.0f ? s.w : p.w;
       pano[i] = p;
     }
+  }
+}
+
+// fp32, n % 4 == 0, 16-byte aligned, group % 4 == 0: one weight per float4 (pixel-major rows)
+__global__ void __launch_bounds__(kBlock)
+select_merged_f32x4_grouped_kernel(float4* __restrict__ pano, const float4* __restrict__ sum,
+                                   const float* __restrict__ weight, long long n4, long long period,
+                                   long long group4) {
+  const long long stride = static_cast<long long>(gridDim.x) * kBlock;
+  for (long long i = static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x; i < n4; i += stride) {
+    if (__ldg(weight + (i / group4) % period) > 0.0f) pano[i] = __ldg(sum + i);
   }
 }
 
@@ -108,21 +119,29 @@ extern "C" int ds_mix_mask(const void* l1, const void* add, const void* mask, vo
 }
 
 extern "C" int ds_select_merged(void* pano, const void* sum, const void* weight, long long n,
-                                long long weight_period, int dtype, void* stream) {
+                                long long weight_period, long long weight_group, int dtype, void* stream) {
   using namespace ds;
   DS_REQUIRE(pano != nullptr && sum != nullptr && weight != nullptr, DS_ERR_NULL);
-  DS_REQUIRE(n > 0 && weight_period > 0 && n % weight_period == 0, DS_ERR_DIM);
+  DS_REQUIRE(n > 0 && weight_period > 0 && weight_group > 0, DS_ERR_DIM);
+  DS_REQUIRE(n % (weight_period * weight_group) == 0, DS_ERR_DIM);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (dtype == DS_F32 && n % 4 == 0 && weight_period % 4 == 0 && aligned16(pano) && aligned16(sum) &&
-      aligned16(weight)) {
+  const bool vec_ok = dtype == DS_F32 && n % 4 == 0 && aligned16(pano) && aligned16(sum);
+  if (vec_ok && weight_group == 1 && weight_period % 4 == 0 && aligned16(weight)) {
     select_merged_f32x4_kernel<<<stride_grid(n / 4), kBlock, 0, st>>>(
         static_cast<float4*>(pano), static_cast<const float4*>(sum), static_cast<const float4*>(weight),
         n / 4, weight_period / 4);
     return check_launch();
   }
+  if (vec_ok && weight_group % 4 == 0) {
+    select_merged_f32x4_grouped_kernel<<<stride_grid(n / 4), kBlock, 0, st>>>(
+        static_cast<float4*>(pano), static_cast<const float4*>(sum), static_cast<const float*>(weight),
+        n / 4, weight_period, weight_group / 4);
+    return check_launch();
+  }
   DS_DISPATCH_DTYPE(dtype, {
     select_merged_kernel<ET><<<stride_grid(n), kBlock, 0, st>>>(static_cast<ET*>(pano), static_cast<const ET*>(sum),
-                                                                 static_cast<const ET*>(weight), n, weight_period);
+                                                                 static_cast<const ET*>(weight), n, weight_period,
+                                                                 weight_group);
   });
   return check_launch();
 }

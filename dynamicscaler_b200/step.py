@@ -57,12 +57,60 @@ class StepPlan:
     vec: int = 1
     d_csr: Optional[tuple] = None              # bilinear merge plan
     d_ftab: Optional[torch.Tensor] = None
+    d_fbegin: Optional[torch.Tensor] = None    # [n_fwin] frame_begin per frame window (pixel-major merges)
+    pm_merge: Optional[tuple] = None           # scatter-form plan of the pixel-major merge (maps.pm_*_plan)
     coverage: float = 0.0                      # touched fraction of H*W (bytes accounting)
     extra: dict = field(default_factory=dict)
 
     @property
     def hw(self):
         return self.h * self.w
+
+    @property
+    def n_fwin(self):
+        return self.n_jobs // self.vpf
+
+
+class PanoramaState:
+    """Panoramas of one denoising stage, resident on the device in the pixel-major
+    ``pm[H*W][F][P]`` order of csrc/pm.cu (P = B*C = 4).  Created by
+    ``PanoramaStepper.make_state`` from reference-order [B, C, F, H, W] tensors and turned
+    back by ``export()``; between the two, ``gather_all`` / ``merge_all`` work on it in place.
+
+    ``mask``: optional denoised-mask panorama -- a [1, H, W] plane (T2V,
+    t2v_sphere_panorama_pipeline.py:159; kept as is) or a latent-shaped tensor (I2V,
+    i2v_sphere_panorama_pipeline.py:220; kept pixel-major)."""
+
+    def __init__(self, stepper, tensors, mask=None):
+        t0 = tensors[0]
+        _lib.require_cuda(t0, "panorama")
+        B, C, F, H, W = t0.shape
+        assert B * C == 4, "the pixel-major path needs B*C == 4 planes (use reference-order tensors otherwise)"
+        assert (F, H, W) == (stepper.F, stepper.H, stepper.W)
+        self.stepper, self.shape, self.dtype, self.device = stepper, tuple(t0.shape), t0.dtype, t0.device
+        self.pms = [stepper._pack(t) for t in tensors]
+        self.mask_plane, self.mask_pm = None, None
+        if mask is not None:
+            assert mask.dtype == t0.dtype
+            if mask.numel() == H * W:
+                self.mask_plane = mask.contiguous().clone()
+            else:
+                assert tuple(mask.shape) == self.shape
+                self.mask_pm = stepper._pack(mask)
+        self._mask_shape = None if mask is None else tuple(mask.shape)
+
+    def export(self, index=None):
+        """Reference-order [B, C, F, H, W] copies of the resident panoramas (all, or one)."""
+        if index is not None:
+            return self.stepper._unpack(self.pms[index], self.shape)
+        return [self.stepper._unpack(pm, self.shape) for pm in self.pms]
+
+    def export_mask(self):
+        if self.mask_plane is not None:
+            return self.mask_plane.view(self._mask_shape).clone()
+        if self.mask_pm is not None:
+            return self.stepper._unpack(self.mask_pm, self.shape)
+        return None
 
 
 class PanoramaStepper:
@@ -109,6 +157,9 @@ class PanoramaStepper:
         jobs = np.array([[v, fb] for fb in fbs for v in range(nv)], dtype=np.int32)
         plan.d_jobs = maps.on_device(("jobs", nv, tuple(fbs)), self.device, lambda: jobs)
         plan.d_ftab = self._ftab(fbs, f_len)
+        if plan.d_ftab is not None:
+            plan.d_fbegin = maps.on_device(("fbegin", tuple(fbs)), self.device, lambda: np.array(fbs, dtype=np.int32))
+        plan.extra["vms"] = vms
         if mode == "nearest":
             plan.d_idx = maps.on_device(("idx_all", vkey), self.device, lambda: np.stack([vm.idx_read for vm in vms]))
             plan.d_dst, plan.d_src = maps.on_device(("nplan", vkey), self.device, lambda: maps.nearest_merge_plan(vms))
@@ -120,6 +171,7 @@ class PanoramaStepper:
             plan.d_csr = maps.on_device(("bplan", vkey), self.device, lambda: maps.bilinear_merge_plan(vms))
             plan.T = plan.d_csr[0].numel()
         plan.coverage = plan.T / float(self.H * self.W)
+        self._pm_merge_plan(plan)          # uploaded now, so later launches are capturable in a CUDA graph
         self._plans[key] = plan
         return plan
 
@@ -157,9 +209,92 @@ class PanoramaStepper:
     def local_jobs(self, plan: StepPlan) -> Tuple[int, int]:
         return shard_range(plan.n_jobs, self.rank, self.world)
 
-    def gather_all(self, latent: torch.Tensor, plan: StepPlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """latent [B, C, F, H, W] -> windows [n_local_jobs, B, C, f_len, h, w] (this rank's
-        slice of the ordered job list)."""
+    # ------------------------------------------------------- pixel-major residency ----
+    def make_state(self, tensors: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None) -> PanoramaState:
+        """Pack reference-order panoramas (latent, denoised, ...) into a resident
+        :class:`PanoramaState`; one pack kernel per tensor, once per stage."""
+        return PanoramaState(self, list(tensors), mask)
+
+    def _pack(self, t: torch.Tensor) -> torch.Tensor:
+        """[B, C, F, H, W] (B*C == 4) -> pm [H*W, F, 4]: ds_pm_merge_nearest with the identity plan."""
+        B, C, F, H, W = t.shape
+        t = t.contiguous()
+        pm = torch.empty((H * W, F, 4), dtype=t.dtype, device=t.device)
+        with torch.cuda.device(t.device):
+            lib.check(lib.ds_pm_merge_nearest(_lib.ptr_array([pm]), _lib.ptr_array([t]), 1, None, _lib.DS_MASK_NONE,
+                                              None, 0, None, None, H * W, None, None, 1, 1, 0, 1,
+                                              4, F, H * W, F, H * W, _lib.dtype_code(t.dtype),
+                                              _lib.stream_ptr(t.device)), "ds_pm_merge_nearest(pack)")
+        return pm
+
+    def _unpack(self, pm: torch.Tensor, shape) -> torch.Tensor:
+        """pm [H*W, F, 4] -> [B, C, F, H, W]: ds_pm_gather with the identity map."""
+        B, C, F, H, W = shape
+        out = torch.empty(shape, dtype=pm.dtype, device=pm.device)
+        with torch.cuda.device(pm.device):
+            lib.check(lib.ds_pm_gather(pm.data_ptr(), out.data_ptr(), None, None, 1, None, 0, 1, 4, F, H * W, F,
+                                       H * W, _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)),
+                      "ds_pm_gather(unpack)")
+        return out
+
+    def _pm_merge_plan(self, plan: StepPlan):
+        if plan.pm_merge is None:
+            vms = plan.extra["vms"]
+            vkey = tuple(vm.key for vm in vms)
+            if plan.kind == "sphere_nearest":
+                plan.pm_merge = maps.on_device(("pm_nplan", vkey), self.device, lambda: maps.pm_nearest_plan(vms))
+            else:
+                plan.pm_merge = maps.on_device(("pm_bplan", vkey), self.device, lambda: maps.pm_bilinear_plan(vms))
+        return plan.pm_merge
+
+    def _pm_gather(self, pm, plan, out, j0, nj):
+        F, HW = plan.F, plan.H * plan.W
+        d_jobs = plan.d_jobs[j0:j0 + nj]
+        if plan.kind == "sphere_nearest":
+            d_idx, d_wt, taps = plan.d_idx, None, 1
+        else:
+            (d_idx, d_wt), taps = plan.d_taps, 4
+        with torch.cuda.device(pm.device):
+            lib.check(lib.ds_pm_gather(pm.data_ptr(), out.data_ptr(), d_idx.data_ptr(), _lib.ptr(d_wt), taps,
+                                       d_jobs.data_ptr(), 0, nj, 4, F, HW, plan.f_len, plan.hw,
+                                       _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)), "ds_pm_gather")
+
+    def _pm_merge_into(self, pms, payloads, mask, mask_mode, plan, j0, nj):
+        mp = self._pm_merge_plan(plan)
+        F, HW = plan.F, plan.H * plan.W
+        ref = pms[0] if pms else mask
+        common = (_lib.ptr(plan.d_ftab), _lib.ptr(plan.d_fbegin), plan.n_fwin, plan.vpf, j0, nj,
+                  4, F, HW, plan.f_len, plan.hw, _lib.dtype_code(ref.dtype), _lib.stream_ptr(ref.device))
+        with torch.cuda.device(ref.device):
+            if plan.kind == "sphere_nearest":
+                tiles, ent_k, ent_dst = mp
+                lib.check(lib.ds_pm_merge_nearest(_lib.ptr_array(pms), _lib.ptr_array(payloads), len(pms),
+                                                  _lib.ptr(mask), mask_mode, tiles.data_ptr(), tiles.shape[0],
+                                                  ent_k.data_ptr(), ent_dst.data_ptr(), ent_k.numel(), *common),
+                          "ds_pm_merge_nearest")
+            else:
+                tiles, row_dst, row_ptr, ent_k, ent_w = mp
+                lib.check(lib.ds_pm_merge_bilinear(_lib.ptr_array(pms), _lib.ptr_array(payloads), len(pms),
+                                                   _lib.ptr(mask), mask_mode, tiles.data_ptr(), tiles.shape[0],
+                                                   row_dst.data_ptr(), row_ptr.data_ptr(), row_dst.numel(),
+                                                   ent_k.data_ptr(), ent_w.data_ptr(), *common),
+                          "ds_pm_merge_bilinear")
+
+    def gather_all(self, latent, plan: StepPlan, out: Optional[torch.Tensor] = None, index: int = 0) -> torch.Tensor:
+        """latent [B, C, F, H, W] -- or a :class:`PanoramaState` (panorama ``index``) -- ->
+        windows [n_local_jobs, B, C, f_len, h, w] (this rank's slice of the ordered job list)."""
+        if isinstance(latent, PanoramaState):
+            assert plan.kind != "ring", "planar ring windows run on reference-order tensors"
+            st = latent
+            B, C = st.shape[0], st.shape[1]
+            j0, nj = self.local_jobs(plan)
+            shape = (nj, B, C, plan.f_len, plan.h, plan.w)
+            if out is None:
+                out = torch.empty(shape, dtype=st.dtype, device=st.device)
+            assert tuple(out.shape) == shape and out.is_contiguous()
+            if nj > 0:
+                self._pm_gather(st.pms[index], plan, out, j0, nj)
+            return out
         _lib.require_cuda(latent, "latent")
         assert latent.is_contiguous() and latent.dim() == 5
         B, C, F, H, W = latent.shape
@@ -206,6 +341,8 @@ class PanoramaStepper:
         (T2V, t2v_sphere_panorama_pipeline.py:159) or [B, C, F, H, W] (I2V, i2v_sphere_
         panorama_pipeline.py:220) denoised-mask panorama that receives 1 where written.
         With world_size > 1 every rank ends up with the identical merged replica."""
+        if isinstance(panos, PanoramaState):
+            return self._merge_state(panos, payloads, plan)
         assert len(panos) == len(payloads) and 0 < len(panos) <= _lib.DS_MAX_PAYLOADS
         B, C, F, H, W = panos[0].shape
         P = B * C
@@ -227,6 +364,57 @@ class PanoramaStepper:
             return
         self._merge_sharded(panos, payloads, mask, plan, P, j0, nj)
 
+    def _merge_state(self, st: PanoramaState, payloads, plan: StepPlan):
+        """merge_all on a resident state: payloads[q] -> st.pms[q]; the state's mask receives 1."""
+        assert plan.kind != "ring", "planar ring windows run on reference-order tensors"
+        assert 0 < len(payloads) <= len(st.pms)
+        pms = st.pms[:len(payloads)]
+        for y in payloads:
+            assert y.is_contiguous() and y.dtype == st.dtype
+        j0, nj = self.local_jobs(plan)
+        mask, mask_mode = None, _lib.DS_MASK_NONE
+        if st.mask_plane is not None:
+            assert plan.d_ftab is None, "a [1, H, W] mask panorama has no frame axis"
+            mask, mask_mode = st.mask_plane, _lib.DS_MASK_PLANE
+        elif st.mask_pm is not None:
+            mask, mask_mode = st.mask_pm, _lib.DS_MASK_FULL
+        if self.world == 1:
+            self._pm_merge_into(pms, payloads, mask, mask_mode, plan, 0, plan.n_jobs)
+            return
+        # sharded: disjoint-support partial merge into zeroed buffers -> all-reduce -> select
+        import torch.distributed as dist
+        Q, n = len(pms), pms[0].numel()
+        per_frame = plan.d_ftab is not None
+        HW = plan.H * plan.W
+        wlen = n if per_frame else HW
+        key = ("pm", Q, n, wlen, st.dtype)
+        buf = self._xbuf.get(key)
+        if buf is None:
+            buf = self._xbuf[key] = torch.empty(Q * n + wlen, dtype=st.dtype, device=st.device)
+        buf.zero_()
+        sums = [buf[q * n:(q + 1) * n] for q in range(Q)]
+        weight = buf[Q * n:]
+        if nj > 0:
+            self._pm_merge_into(sums, payloads, weight, _lib.DS_MASK_FULL if per_frame else _lib.DS_MASK_PLANE,
+                                plan, j0, nj)
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        group, period = (1, n) if per_frame else (n // HW, HW)
+        code, sp = _lib.dtype_code(st.dtype), _lib.stream_ptr(st.device)
+        with torch.cuda.device(st.device):
+            for q in range(Q):
+                lib.check(lib.ds_select_merged(pms[q].data_ptr(), sums[q].data_ptr(), weight.data_ptr(), n, period,
+                                               group, code, sp), "ds_select_merged")
+            if mask is not None:
+                okey = ("one", mask.numel(), mask.dtype)
+                if okey not in self._xbuf:
+                    self._xbuf[okey] = torch.ones(mask.numel(), dtype=mask.dtype, device=mask.device)
+                if mask_mode == _lib.DS_MASK_PLANE:
+                    lib.check(lib.ds_select_merged(mask.data_ptr(), self._xbuf[okey].data_ptr(), weight.data_ptr(),
+                                                   HW, HW, 1, code, sp), "ds_select_merged")
+                else:
+                    lib.check(lib.ds_select_merged(mask.data_ptr(), self._xbuf[okey].data_ptr(), weight.data_ptr(),
+                                                   n, period, group, code, sp), "ds_select_merged")
+
     def _merge_sharded(self, panos, payloads, mask, plan, P, j0, nj):
         """disjoint-support partial merge -> one all-reduce -> select."""
         import torch.distributed as dist
@@ -247,7 +435,7 @@ class PanoramaStepper:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
         with torch.cuda.device(buf.device):
             for q in range(Q):
-                lib.check(lib.ds_select_merged(panos[q].data_ptr(), sums[q].data_ptr(), weight.data_ptr(), n, wlen,
+                lib.check(lib.ds_select_merged(panos[q].data_ptr(), sums[q].data_ptr(), weight.data_ptr(), n, wlen, 1,
                                                _lib.dtype_code(buf.dtype), _lib.stream_ptr(buf.device)),
                           "ds_select_merged")
             if mask is not None:
@@ -256,7 +444,7 @@ class PanoramaStepper:
                     self._xbuf[okey] = torch.ones(mask.numel(), dtype=mask.dtype, device=mask.device)
                 one = self._xbuf[okey]
                 lib.check(lib.ds_select_merged(mask.data_ptr(), one.data_ptr(), weight.data_ptr(), mask.numel(),
-                                               wlen, _lib.dtype_code(buf.dtype), _lib.stream_ptr(buf.device)),
+                                               wlen, 1, _lib.dtype_code(buf.dtype), _lib.stream_ptr(buf.device)),
                           "ds_select_merged")
 
     # ------------------------------------------------------------- bytes accounting ----

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DS_ABI_VERSION 1
+#define DS_ABI_VERSION 2
 
 enum { DS_F32 = 0, DS_BF16 = 1 };
 
@@ -140,6 +140,56 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
                       int views_per_fwin, int job_begin, int job_count,
                       int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
 
+/* ------------------------------------------- pixel-major resident panorama path ---- */
+/* The batched step driver keeps the panorama of a stage resident as pm[pixel][frame][plane]
+ * (H*W pixels, F frames, P == 4 planes; element (pl, f, p) of the reference's [P][F][H*W]
+ * order lives at (p*F + f)*4 + pl).  Window tensors keep the reference's
+ * [job][plane][frame][h*w] order.  Same reference functions as the plane-major entry
+ * points above; only the resident layout differs. */
+
+/* get_view_tensor_no_interpolate (taps == 1; panorama_tensor_utils.py:53-70,185-202) or
+ * get_view_tensor_interpolate (taps == 4; :28-51) for all jobs of a step:
+ *   out[j][pl][fo][k] = sum_t wt[map_j][t][k] * pm[idx[map_j][t][k]][(f0_j+fo) mod F][pl]
+ * d_idx: [n_maps][taps][hw] int32; d_wt: [n_maps][4][hw] float32 (taps == 4 only).
+ * d_idx == NULL (taps == 1): identity map, i.e. the unpack pm -> [P][F][hw], hw <= H*W.
+ * d_jobs as in ds_gather_nearest.  Requires hw % (16 / elem_size) == 0. */
+int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d_wt, int taps,
+                 const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
+                 int hw, int dtype, void* stream);
+
+/* Ordered sequence of set_view_tensor_no_interpolation calls (panorama_tensor_utils.py:
+ * 154-183; ring twin ring_panorama_tensor_utils.py:170-198), scatter form over the surviving
+ * view pixels only.  Entry e of tile t (view v_t, entries [begin_t, begin_t + count_t),
+ * count_t <= 32) is the view pixel d_ent_k[e] of view v_t that wins panorama pixel
+ * d_ent_dst[e] ("last writer wins"):
+ *   pms[q][dst][(fb_s+fo) mod F][pl] = payloads[q][s*views_per_fwin + v_t - job_begin][pl][fo][k]
+ * for every frame window s < n_fwin whose job is in [job_begin, job_begin + job_count) and
+ * every fo with d_ftab[(fb_s+fo) mod F] == s*f_len + fo (d_ftab/d_fbegin NULL: one window,
+ * identity).  d_tiles: [n_tiles][3] int32 (v, begin, count).  All three plan arrays NULL:
+ * identity plan over n_ent pixels, i.e. the pack [P][F][hw] -> pm.
+ * mask: DS_MASK_PLANE -> mask[dst] = 1 ([H*W] plane); DS_MASK_FULL -> a pixel-major
+ * panorama that receives 1 in every written atom. */
+int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payloads, int Q,
+                        void* mask, int mask_mode, const int32_t* d_tiles, int n_tiles,
+                        const int32_t* d_ent_k, const int32_t* d_ent_dst, int n_ent,
+                        const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
+                        int views_per_fwin, int job_begin, int job_count,
+                        int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
+
+/* Ordered sequence of set_view_tensor_bilinear calls (panorama_tensor_utils.py:98-152; ring
+ * twin ring_panorama_tensor_utils.py:107-166).  Row r of tile t is panorama pixel
+ * d_row_dst[r], owned by view v_t, with CSR entries [d_row_ptr[r], d_row_ptr[r+1]) of
+ * (view pixel d_ent_k, weight d_ent_w) in index_add_ order (tap-major, k ascending):
+ *   acc = acc + (payload * w); ws = ws + w; pm[...][dst] = acc / ws  if ws > 0
+ * Frame windows, sharding and mask as in ds_pm_merge_nearest. */
+int ds_pm_merge_bilinear(void* const* h_pms, const void* const* h_payloads, int Q,
+                         void* mask, int mask_mode, const int32_t* d_tiles, int n_tiles,
+                         const int32_t* d_row_dst, const int32_t* d_row_ptr, int n_rows,
+                         const int32_t* d_ent_k, const float* d_ent_w,
+                         const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
+                         int views_per_fwin, int job_begin, int job_count,
+                         int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
+
 /* ------------------------------------------------------------------ elementwise ---- */
 
 /* mix_latents_with_mask (utils/tensor_utils.py:19-39):
@@ -151,11 +201,13 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
 int ds_mix_mask(const void* l1, const void* add, const void* mask, void* out,
                 float ratio, float one_minus_ratio, long long n, int mask_hw, int dtype, void* stream);
 
-/* Final select of the sharded merge: pano[i] = weight[i mod period] > 0 ?
- * sum[i] : pano[i] for i < n.  weight has the panorama's dtype; weight_period is H*W (one
- * plane), F*H*W (one plane per frame) or n. */
+/* Final select of the sharded merge:
+ *   pano[i] = weight[(i / weight_group) mod weight_period] > 0 ? sum[i] : pano[i]   for i < n.
+ * weight has the panorama's dtype.  Reference layout: weight_group = 1 and weight_period =
+ * H*W (one plane), F*H*W (one plane per frame) or n.  Pixel-major layout: weight_group =
+ * F*P with weight_period = H*W (one weight per pixel), or group 1 / period n. */
 int ds_select_merged(void* pano, const void* sum, const void* weight,
-                     long long n, long long weight_period, int dtype, void* stream);
+                     long long n, long long weight_period, long long weight_group, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -105,3 +105,72 @@ def ring_merge_plan(windows, H, W, h, w):
         xs = (l + np.arange(w)) % W
         plan[np.ix_(ys, xs)] = (j * h + np.arange(h))[:, None] * w + np.arange(w)[None, :]
     return plan.reshape(-1)
+
+
+# ------------------------------------------------ pixel-major kernels (csrc/pm.cu) ----
+def pm_pack(pano):
+    """[P, F, HW] -> pm [HW, F, P]"""
+    return np.ascontiguousarray(pano.transpose(2, 1, 0))
+
+
+def pm_unpack(pm):
+    return np.ascontiguousarray(pm.transpose(2, 1, 0))
+
+
+def pm_merge_nearest(pms, payloads, plan, ftab, fbegin, vpf, f_len, mask=None, mask_mode=0,
+                     job_begin=0, job_count=1 << 30):
+    """Scatter form, CTA by CTA like ds_pm_merge_nearest: pms[q] [HW, F, P] in place."""
+    tiles, ent_k, ent_dst = plan
+    F = pms[0].shape[1] if pms else mask.shape[1]
+    n_fwin = 1 if fbegin is None else len(fbegin)
+    for (v, b, c) in tiles:
+        for s in range(n_fwin):
+            job = s * vpf + v - job_begin
+            if not (0 <= job < job_count):
+                continue
+            fb = 0 if fbegin is None else fbegin[s]
+            k, d = ent_k[b:b + c], ent_dst[b:b + c]
+            if mask_mode == 1:
+                mask[d] = 1
+            for fo in range(f_len):
+                f = (fb + fo) % F
+                if ftab is not None and ftab[f] != s * f_len + fo:
+                    continue
+                for q in range(len(pms)):
+                    pms[q][d, f, :] = payloads[q][job][:, fo][:, k].T
+                if mask_mode == 2:
+                    mask[d, f, :] = 1
+
+
+def pm_merge_bilinear(pms, payloads, plan, ftab, fbegin, vpf, f_len, mask=None, mask_mode=0,
+                      job_begin=0, job_count=1 << 30):
+    tiles, row_dst, row_ptr, ent_k, ent_w = plan
+    F = pms[0].shape[1]
+    n_fwin = 1 if fbegin is None else len(fbegin)
+    for (v, b, c) in tiles:
+        for s in range(n_fwin):
+            job = s * vpf + v - job_begin
+            if not (0 <= job < job_count):
+                continue
+            fb = 0 if fbegin is None else fbegin[s]
+            for r in range(b, b + c):
+                e0, e1 = row_ptr[r], row_ptr[r + 1]
+                ws_ = F32(0)
+                for w in ent_w[e0:e1]:
+                    ws_ = F32(ws_ + w)
+                if not ws_ > 0:
+                    continue
+                if mask_mode == 1:
+                    mask[row_dst[r]] = 1
+                for fo in range(f_len):
+                    f = (fb + fo) % F
+                    if ftab is not None and ftab[f] != s * f_len + fo:
+                        continue
+                    for q in range(len(pms)):
+                        x = payloads[q][job][:, fo]
+                        acc = np.zeros(x.shape[0], F32)
+                        for k, w in zip(ent_k[e0:e1], ent_w[e0:e1]):
+                            acc = acc + x[:, k] * w
+                        pms[q][row_dst[r], f, :] = acc / ws_
+                    if mask_mode == 2:
+                        mask[row_dst[r], f, :] = 1

@@ -132,6 +132,43 @@ def test_batched_plan_equals_reference_order(small, mode, world):
     assert np.array_equal(weight.reshape(1, 16, 32), small[f"step/batched_{mode}/mask"])
 
 
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+@pytest.mark.parametrize("world", [1, 2])
+def test_pixel_major_plan_equals_plane_major(mode, world):
+    """The scatter-form plans of the pixel-major kernels (maps.pm_*_plan) give the same
+    panorama as the plane-major plans (pinned to the golden above), with wrapping frame
+    windows and a sharded job list; tiles hold <= 32 entries of one view."""
+    from _emulate import pm_merge_bilinear, pm_merge_nearest, pm_pack, pm_unpack
+    H, W, F, h, w, f_len = 16, 32, 6, 6, 10, 4
+    views = po.default_sphere_views(3)[:9]
+    fbs = [0, 2, 4]                                                    # last window wraps: frames 4,5,0,1
+    vms = [maps.view_map(120, th, ph, w, h, H, W) for ph, th in views]
+    nj = len(views) * len(fbs)
+    pay = [randn(900 + q, nj, 4, f_len, h * w) for q in range(2)]
+    ftab = maps.frame_table(F, fbs, f_len)
+    base = randn(5, 4, F, H * W)
+    want = [base.copy(), base.copy()]
+    wmask = np.zeros((4, F, H * W), np.float32)
+    got = [pm_pack(base), pm_pack(base)]
+    gmask = np.zeros((H * W, F, 4), np.float32)
+    pm_plan = maps.pm_nearest_plan(vms) if mode == "nearest" else maps.pm_bilinear_plan(vms)
+    assert pm_plan[0][:, 2].max() <= maps.PM_TILE and pm_plan[0][:, 2].min() >= 1
+    for r in range(world):
+        j0, n = shard_range(nj, r, world)
+        local = [p[j0:j0 + n] for p in pay]
+        if mode == "nearest":
+            d, s_ = maps.nearest_merge_plan(vms)
+            merge_nearest(want, local, d, s_, ftab, len(views), f_len, h * w, wmask, 2, j0, n)
+            pm_merge_nearest(got, local, pm_plan, ftab, fbs, len(views), f_len, gmask, 2, j0, n)
+        else:
+            merge_bilinear(want, local, maps.bilinear_merge_plan(vms), ftab, len(views), f_len, h * w, wmask, 2, j0, n)
+            pm_merge_bilinear(got, local, pm_plan, ftab, fbs, len(views), f_len, gmask, 2, j0, n)
+    for q in range(2):
+        assert np.array_equal(pm_unpack(got[q]), want[q])
+    assert np.array_equal(pm_unpack(gmask), wmask)
+    assert 0 < wmask.mean() < 1
+
+
 def test_ring_merge_plan_emulation_matches_oracle():
     H, W, h, w = 16, 32, 6, 12
     windows = [(4 * a + 2, 3 * b + 1) for a in range(8) for b in range(5)]
