@@ -150,15 +150,14 @@ class Workset:
         return sum(t.numel() * t.element_size() for t in (self.lat, self.den, self.mask, self.wins, self.x_prev, self.x0))
 
 
-def time_graph(graphs, iters, dist_on):
-    """CUDA-event time (ms) of ``iters`` replays cycling through ``graphs``."""
+def timed(run, dist_on):
+    """CUDA-event time (ms) of one call of ``run`` bracketed by barrier + synchronize."""
     if dist_on:
         torch.distributed.barrier()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    for i in range(iters):
-        graphs[i % len(graphs)]()
+    run()
     b.record()
     torch.cuda.synchronize()
     if dist_on:
@@ -166,14 +165,35 @@ def time_graph(graphs, iters, dist_on):
     return a.elapsed_time(b)
 
 
-def capture(fn, use_graph):
-    """Returns a zero-arg callable replaying ``fn`` (as a CUDA graph when possible)."""
+def make_runner(fns, K, use_graph, stream):
+    """``run()`` executes exactly K steps, step i = fns[i % len(fns)].  With graphs, whole
+    cycles of len(fns) consecutive steps are captured into ONE CUDA graph (plus one graph for
+    the remainder), so the launch-bound inner loop costs one graph launch per cycle."""
+    n = len(fns)
     if not use_graph:
-        return fn
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        fn()
-    return g.replay
+        def run():
+            for i in range(K):
+                fns[i % n]()
+        return run
+
+    def cap(count):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(count):
+                fns[i % n]()
+        return g
+
+    with torch.cuda.stream(stream):
+        full, rem = divmod(K, n)
+        g_full = cap(n) if full else None
+        g_rem = cap(rem) if rem else None
+
+    def run():
+        for _ in range(full):
+            g_full.replay()
+        if g_rem is not None:
+            g_rem.replay()
+    return run
 
 
 def run_ours(args, wl, wl_name):
@@ -230,25 +250,25 @@ def run_ours(args, wl, wl_name):
     use_graph = not args.no_graph
     launches_before = lib.launches
 
-    def build(maker, mode):
+    def runner(maker, mode, count):
+        fns = [maker(mode, *c) for c in combos]
         try:
-            with torch.cuda.stream(side):
-                return [capture(maker(mode, *c), use_graph) for c in combos], use_graph
+            return make_runner(fns, count, use_graph, side), use_graph
         except Exception as e:                             # e.g. a collective that cannot be captured
             torch.cuda.synchronize()
             print(f"[bench] graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
-            return [maker(mode, *c) for c in combos], False
+            return make_runner(fns, count, False, side), False
 
     results = {}
     K, Wm = args.steps, max(args.warmup, 3)
     for mode in ("bilinear", "nearest"):
-        steps, graphed = build(make_step, mode)
-        launches_per_step = (lib.launches - launches_before) // max(len(combos), 1) if graphed else None
         launches_before = lib.launches
-        for i in range(Wm):
-            steps[i % len(steps)]()
+        run, graphed = runner(make_step, mode, K)
+        launches_per_step = (lib.launches - launches_before) / K if graphed else None
+        warm, _ = runner(make_step, mode, Wm)
+        warm()
         sampler.load = True
-        ms = time_graph(steps, K, dist_on)
+        ms = timed(run, dist_on)
         sampler.load = False
         if dist_on:
             t = torch.tensor([ms], device=dev)
@@ -258,21 +278,19 @@ def run_ours(args, wl, wl_name):
                          "launches_per_step": launches_per_step}
         # per-kernel pass (same rotation) for the roofline
         if not dist_on:
+            iters = max(K, 5 * len(combos))
             for name, maker in (("gather", make_gather), ("merge", make_merge)):
-                gs, _ = build(maker, mode)
-                for i in range(3):
-                    gs[i % len(gs)]()
-                iters = max(K, 5 * len(gs))
+                krun, _ = runner(maker, mode, iters)
+                krun()
                 sampler.load = True
-                results[mode][name + "_us"] = time_graph(gs, iters, False) / iters * 1e3
+                results[mode][name + "_us"] = timed(krun, False) / iters * 1e3
                 sampler.load = False
     # make sure the clock sampler saw the load: replay the headline step for ~0.3 s
-    steps, _ = build(make_step, args.mode)
+    run, _ = runner(make_step, args.mode, 20 * len(combos))
     sampler.load = True
     t_end = time.perf_counter() + 0.3
     while time.perf_counter() < t_end:
-        for i in range(50):
-            steps[i % len(steps)]()
+        run()
         torch.cuda.synchronize()
     sampler.load = False
 
@@ -328,13 +346,13 @@ def run_ours(args, wl, wl_name):
             "config": {"workload": wl_name, "mode": args.mode, "latent": [1, wl["C"], wl["F"], wl["H"], wl["W"]],
                        "windows_per_step": n_win, "window": [wl["h"], wl["w"]], "payloads": 2,
                        "l2_policy": f"inputs larger than L2: {n_sets} rotating buffer sets, {n_sets * one.nbytes() / 2**20:.0f} MiB",
-                       "cuda_graph": head["graph"],
+                       "cuda_graph": head["graph"], "steps_per_graph": len(combos) if head["graph"] else 0,
                        "layout": "resident pixel-major [H*W][F][4] (csrc/pm.cu)" if args.layout == "pm"
                                  else "reference [B,C,F,H,W] (csrc/sphere.cu)",
                        "maps": "precomputed on host (static geometry), cached on device",
                        "sharding": "windows split over ranks, 1 NCCL all-reduce/step" if dist_on else "none"},
             "steps_per_s": 1e3 / head["ms_per_step"],
-            "gpu_launches": (head["launches_per_step"] or (2 if not dist_on else 6)) * K,
+            "gpu_launches": int(round((head["launches_per_step"] or (2 if not dist_on else 6)) * K)),
             "clocks": sampler.summary(),
             "e2e": {"value": n_win / (e2e_ms * 1e-3), "unit": "blends/s",
                     "h2d_bytes_per_step": int(h_xp.numel() * 4 + h_x0.numel() * 4),

@@ -25,6 +25,7 @@ _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 PROTOTYPES = {
     "ds_abi_version": [],
     "ds_error_string": [_i],
+    "ds_tune": [_i, _i],
     "ds_ring_gather": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_ring_scatter": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_ring_merge_plan": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
@@ -33,8 +34,8 @@ PROTOTYPES = {
     "ds_merge_nearest": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_merge_bilinear": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_pm_gather": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "ds_pm_merge_nearest": [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "ds_pm_merge_bilinear": [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "ds_pm_merge_nearest": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "ds_pm_merge_bilinear": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_mix_mask": [_vp, _vp, _vp, _vp, _f, _f, _ll, _i, _i, _vp],
     "ds_select_merged": [_vp, _vp, _vp, _ll, _ll, _ll, _i, _vp],
 }

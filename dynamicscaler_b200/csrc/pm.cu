@@ -18,19 +18,28 @@
 //   pm_merge_bilinear_kernel set_view_tensor_bilinear, all views (weighted splat + normalise)
 // and, with identity maps, the pack / unpack between the two layouts.
 //
-// Merges are in SCATTER form over a host-built, per-view compacted list of the view pixels
+// Merges are in SCATTER form over a host-built list, sorted by view, of the view pixels
 // (nearest) / panorama rows (bilinear) that survive the ordered sequence of writes, so no
 // two threads ever write the same panorama atom: race-free without atomics, bit-identical
 // to the reference's sequential order, and per-rank outputs have disjoint support when the
 // job list is sharded.
+//
+// Scheduling: these kernels run for 10-20 us, so wave quantisation and tails matter as much
+// as bandwidth.  Every kernel is launched with at most (SMs x resident CTAs) CTAs and
+// splits its work list evenly over them (persistent CTAs, static balanced partition).
 #include "ds_common.cuh"
 
 namespace ds {
 
 constexpr int kPmPlanes = 4;     // planes per atom (B*C of the latent); other counts use sphere.cu
 constexpr int kPmKT = 64;        // view pixels per gather CTA
-constexpr int kPmET = 32;        // compacted entries (panorama pixels) per merge CTA
+constexpr int kPmET = 32;        // panorama rows per pass of the weighted merge
 constexpr int kWarps = kBlock / 32;
+
+// Launch-shape knobs (ds_tune): defaults are the measured best on B200 for the bench workload.
+static int g_gather_ctas_per_sm = 0;   // 0: occupancy limit
+static int g_merge_persistent = 0;     // 0: one <= 32-entry tile per CTA (hardware CTA scheduling); 1: persistent balanced split
+static int g_merge_ctas_per_sm = 0;    // persistent scheme only; 0: occupancy limit
 
 template <typename T> struct Atom;
 template <> struct Atom<float> {
@@ -70,15 +79,37 @@ template <> __device__ __forceinline__ uint2 atom_ones<__nv_bfloat16>() { return
 
 template <typename A> __device__ __forceinline__ A ldg_atom(const A* p) { return __ldg(p); }
 
+// ------------------------------------------------- async-proxy (TMA bulk) helpers ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// Make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA).
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 1-D bulk copy shared -> global (SASS UBLKCP): bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------- gather ----
 struct PmGatherArgs {
-  int F, HW, f_len, hw, n_fblk;     // n_fblk = ceil(f_len / 8)
+  int F, HW, f_len, hw;
+  int n_tiles, tiles_per_job;
 };
 
-// CTA = (tile of kPmKT view pixels, job).  Phase 1: warp lanes = 4 pixels x 8 frames, each
-// lane one 16-byte atom per tap (4 rows x 128 B per request).  Phase 2: the transposed
-// tile [plane*f_len + fo][k] leaves shared memory as 16-byte vectors along k.
-template <typename T, int TAPS>
+// Persistent CTAs; work item = (tile of kPmKT view pixels, job).
+// Load: warp lanes = 4 pixel groups x 8 frames; a lane loads the atoms of 4 CONSECUTIVE view
+// pixels of one window frame (each request: 4 panorama rows x 128 B), transposes them in
+// registers and stores, per plane, the 4 pixels as one 16-byte vector into the shared tile
+// [plane*f_len + fo][k] (row stride kPmKT + 16 B: conflict-free).
+// Store: every tile row is 256 contiguous bytes of the window tensor and leaves through one
+// TMA bulk copy (cp.async.bulk shared -> global), issued by one thread per row.
+// FL > 0: f_len known at compile time; FL == 0: runtime f_len.
+template <typename T, int TAPS, int FL>
 __global__ void __launch_bounds__(kBlock)
 pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ out,
                  const int32_t* __restrict__ d_idx, const float* __restrict__ d_wt,
@@ -87,93 +118,104 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
   constexpr int VE = 16 / sizeof(T);            // elements per 16-byte vector
   constexpr int S = kPmKT + VE;                 // padded row stride (elements): 4 banks mod 32
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int R = kPmPlanes * a.f_len;
+  const int f_len = FL > 0 ? FL : a.f_len;
+  const int R = kPmPlanes * f_len;
   T* tile = reinterpret_cast<T*>(smem_raw);                                   // [R][S]
-  int32_t* s_idx = reinterpret_cast<int32_t*>(tile + static_cast<size_t>(R) * S);   // [TAPS][KT]
+  int32_t* s_idx = reinterpret_cast<int32_t*>(tile + R * S);                  // [TAPS][KT]
   float* s_wt = reinterpret_cast<float*>(s_idx + TAPS * kPmKT);               // [TAPS][KT] (bilinear)
 
-  const int job = blockIdx.y;
-  const int k0 = blockIdx.x * kPmKT;
-  int map = job, f0 = h_f0;
-  if (d_jobs != nullptr) {
-    map = __ldg(d_jobs + 2 * job);
-    f0 = __ldg(d_jobs + 2 * job + 1);
-  }
-  for (int t = threadIdx.x; t < TAPS * kPmKT; t += kBlock) {
-    const int tap = t / kPmKT, kl = t - tap * kPmKT;
-    const int k = k0 + kl;
-    int idx = 0;
-    float w = 0.f;
-    if (k < a.hw) {
-      if (d_idx != nullptr) idx = __ldg(d_idx + (static_cast<size_t>(map) * TAPS + tap) * a.hw + k);
-      else idx = k;                                                  // identity map: unpack
-      if (TAPS > 1) w = __ldg(d_wt + (static_cast<size_t>(map) * TAPS + tap) * a.hw + k);
-    }
-    s_idx[t] = idx;
-    if (TAPS > 1) s_wt[t] = w;
-  }
-  __syncthreads();
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kq = lane >> 3, fl = lane & 7;
-  const int G = (kPmKT / 4) * a.n_fblk;
-  constexpr int U = TAPS > 1 ? 2 : 4;           // groups in flight per warp
-  for (int g0 = warp * U; g0 < G; g0 += kWarps * U) {
-    A v[U][TAPS];
-    int kl[U], fo[U];
-    bool ok[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int g = g0 + u;
-      const int k4 = g / a.n_fblk, fb = g - k4 * a.n_fblk;
-      kl[u] = k4 * 4 + kq;
-      fo[u] = fb * 8 + fl;
-      ok[u] = g < G && fo[u] < a.f_len && k0 + kl[u] < a.hw;
-      if (ok[u]) {
-        int f = f0 + fo[u];
-        f = f % a.F;
-#pragma unroll
-        for (int t = 0; t < TAPS; ++t)
-          v[u][t] = ldg_atom(pm + static_cast<size_t>(s_idx[t * kPmKT + kl[u]]) * a.F + f);
-      }
+  const int kgl = lane >> 3, fl = lane & 7;
+  const int n_fblk = (f_len + 7) >> 3;
+  const int n_it = (kPmKT / 16) * n_fblk;       // warp iterations: 4 pixel groups x 8 frames each
+
+  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int job = t / a.tiles_per_job;
+    const int k0 = (t - job * a.tiles_per_job) * kPmKT;
+    int map = job, f0 = h_f0;
+    if (d_jobs != nullptr) {
+      map = __ldg(d_jobs + 2 * job);
+      f0 = __ldg(d_jobs + 2 * job + 1);
     }
+    f0 %= a.F;
+    for (int i = threadIdx.x; i < TAPS * kPmKT; i += kBlock) {
+      const int tap = i / kPmKT, kl = i % kPmKT;
+      const int k = k0 + kl;
+      int idx = 0;
+      float w = 0.f;
+      if (k < a.hw) {
+        if (d_idx != nullptr) idx = __ldg(d_idx + (map * TAPS + tap) * a.hw + k);
+        else idx = k;                                                  // identity map: unpack
+        if (TAPS > 1) w = __ldg(d_wt + (map * TAPS + tap) * a.hw + k);
+      }
+      s_idx[i] = idx;
+      if (TAPS > 1) s_wt[i] = w;
+    }
+    __syncthreads();        // also orders the previous tile's bulk-store reads before the STS below
+
+    for (int it = warp; it < n_it; it += kWarps) {
+      const int kgb = it / n_fblk, fb = it - kgb * n_fblk;
+      const int kl = (kgb * 4 + kgl) * 4;         // first of this lane's 4 consecutive view pixels
+      const int fo = fb * 8 + fl;
+      if (fo >= f_len || k0 + kl >= a.hw) continue;
+      int f = f0 + fo;
+      f = f >= a.F ? f - a.F : f;
+      A v[TAPS][4];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (!ok[u]) continue;
-      T* dstp = tile + static_cast<size_t>(fo[u]) * S + kl[u];
+      for (int tp = 0; tp < TAPS; ++tp) {
+        const int4 id = *reinterpret_cast<const int4*>(s_idx + tp * kPmKT + kl);
+        v[tp][0] = ldg_atom(pm + static_cast<size_t>(id.x) * a.F + f);
+        v[tp][1] = ldg_atom(pm + static_cast<size_t>(id.y) * a.F + f);
+        v[tp][2] = ldg_atom(pm + static_cast<size_t>(id.z) * a.F + f);
+        v[tp][3] = ldg_atom(pm + static_cast<size_t>(id.w) * a.F + f);
+      }
+      T e[4][4];                                  // [pixel j][plane p]
       if (TAPS == 1) {
-        T e[4];
-        atom_split<T>(v[u][0], e);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) dstp[static_cast<size_t>(p) * a.f_len * S] = e[p];
+        for (int j = 0; j < 4; ++j) atom_split<T>(v[0][j], e[j]);
       } else {
         // ATen grid_sample (CPU) order: nw*w + ne*w + sw*w + se*w contracted to an FMA chain
-        float r[4], x[4];
-        Atom<T>::unpack(v[u][0], x);
-        const float w0 = s_wt[kl[u]];
+        float r[4][4], x[4];
+        float w[4];
+        *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(s_wt + kl);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) r[p] = __fmul_rn(x[p], w0);
+        for (int j = 0; j < 4; ++j) {
+          Atom<T>::unpack(v[0][j], x);
 #pragma unroll
-        for (int t = 1; t < TAPS; ++t) {
-          Atom<T>::unpack(v[u][t], x);
-          const float wt = s_wt[t * kPmKT + kl[u]];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) r[p] = __fmaf_rn(x[p], wt, r[p]);
+          for (int p = 0; p < 4; ++p) r[j][p] = __fmul_rn(x[p], w[j]);
         }
 #pragma unroll
-        for (int p = 0; p < 4; ++p) dstp[static_cast<size_t>(p) * a.f_len * S] = Elem<T>::from_f(r[p]);
+        for (int tp = 1; tp < TAPS; ++tp) {
+          *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(s_wt + tp * kPmKT + kl);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            Atom<T>::unpack(v[tp][j], x);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) r[j][p] = __fmaf_rn(x[p], w[j], r[j][p]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) e[j][p] = Elem<T>::from_f(r[j][p]);
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const T col[4] = {e[0][p], e[1][p], e[2][p], e[3][p]};
+        *reinterpret_cast<A*>(tile + (p * f_len + fo) * S + kl) = atom_join<T>(col);
       }
     }
-  }
-  __syncthreads();
+    fence_proxy_async_smem();
+    __syncthreads();
 
-  constexpr int VPR = kPmKT / VE;                // 16-byte vectors per tile row
-  T* __restrict__ o = out + static_cast<size_t>(job) * R * a.hw + k0;
-  for (int u = threadIdx.x; u < R * VPR; u += kBlock) {
-    const int row = u / VPR, c = u - row * VPR;
-    if (k0 + c * VE < a.hw)
-      *reinterpret_cast<uint4*>(o + static_cast<size_t>(row) * a.hw + c * VE) =
-          *reinterpret_cast<const uint4*>(tile + static_cast<size_t>(row) * S + c * VE);
+    const uint32_t row_bytes = static_cast<uint32_t>(min(kPmKT, a.hw - k0) * sizeof(T));
+    T* __restrict__ o = out + static_cast<size_t>(job) * R * a.hw + k0;
+    bool issued = false;
+    for (int row = threadIdx.x; row < R; row += kBlock) {
+      bulk_store(o + static_cast<size_t>(row) * a.hw, tile + row * S, row_bytes);
+      issued = true;
+    }
+    if (issued) bulk_commit_and_wait_read();    // the tile is reused / freed only after the copy read it
   }
 }
 
@@ -183,7 +225,8 @@ struct PmMergeArgs {
   const void* pay[DS_MAX_PAYLOADS];
   void* mask;
   int mask_mode;
-  int Q, n_tiles, n_ent;
+  int Q, n_ent;
+  int per_cta;                   // > 0: CTA b owns entries [b*per_cta, (b+1)*per_cta) of its slice; 0: even split over the grid
   int vpf, job_begin, job_count;
   int F, HW, f_len, hw;
 };
@@ -196,219 +239,383 @@ template <typename PT> __device__ __forceinline__ PT pm_sel(PT const (&arr)[DS_M
   return r;
 }
 
-struct PmTileCtx {
-  int v, begin, count, s, job, fb;
+struct PmRange {
+  int lo, hi;      // this CTA's slice of the entry (nearest) / row (weighted) list
+  int s, fb;       // frame window and its first panorama frame
 };
 
-// Resolve this CTA's (tile, frame window) to its payload job; false => nothing to do.
-__device__ __forceinline__ bool pm_tile_ctx(const PmMergeArgs& a, const int32_t* __restrict__ d_tiles,
-                                            const int32_t* __restrict__ d_fbegin, PmTileCtx& c) {
-  const int t = blockIdx.x;
-  if (d_tiles != nullptr) {
-    c.v = __ldg(d_tiles + 3 * t);
-    c.begin = __ldg(d_tiles + 3 * t + 1);
-    c.count = __ldg(d_tiles + 3 * t + 2);
-  } else {                                        // implicit identity tiling (pack)
-    c.v = 0;
-    c.begin = t * kPmET;
-    c.count = min(kPmET, a.n_ent - c.begin);
+// The list is sorted by view and d_view_ptr[v] is the first entry of view v, so the jobs of
+// this rank in frame window s = blockIdx.y are one contiguous slice; it is split evenly over
+// the gridDim.x CTAs.  false => nothing to do.
+__device__ __forceinline__ bool pm_range(const PmMergeArgs& a, const int32_t* __restrict__ d_view_ptr,
+                                         const int32_t* __restrict__ d_fbegin, PmRange& r) {
+  r.s = blockIdx.y;
+  r.fb = d_fbegin != nullptr ? __ldg(d_fbegin + r.s) % a.F : 0;
+  int e_lo = 0, e_hi = a.n_ent;
+  if (d_view_ptr != nullptr) {
+    const int v_lo = min(max(a.job_begin - r.s * a.vpf, 0), a.vpf);
+    const int v_hi = min(max(a.job_begin + a.job_count - r.s * a.vpf, 0), a.vpf);
+    e_lo = __ldg(d_view_ptr + v_lo);
+    e_hi = __ldg(d_view_ptr + v_hi);
   }
-  c.s = blockIdx.y;
-  c.job = c.s * a.vpf + c.v - a.job_begin;
-  c.fb = d_fbegin != nullptr ? __ldg(d_fbegin + c.s) : 0;
-  return c.count > 0 && c.job >= 0 && c.job < a.job_count;
+  if (a.per_cta > 0) {
+    r.lo = e_lo + blockIdx.x * a.per_cta;
+    r.hi = min(r.lo + a.per_cta, e_hi);
+  } else {
+    const long long n = e_hi - e_lo;
+    r.lo = e_lo + static_cast<int>(n * blockIdx.x / gridDim.x);
+    r.hi = e_lo + static_cast<int>(n * (blockIdx.x + 1) / gridDim.x);
+  }
+  return r.hi > r.lo;
 }
 
 // Window frame fo of frame window s lands on panorama frame f; it is written only if s is the
 // LAST frame window (in job order) containing f (d_ftab, maps.frame_table).
 __device__ __forceinline__ bool pm_frame_live(const PmMergeArgs& a, const int32_t* __restrict__ d_ftab,
-                                              const PmTileCtx& c, int fo, int& f) {
-  f = (c.fb + fo) % a.F;
-  return d_ftab == nullptr || __ldg(d_ftab + f) == c.s * a.f_len + fo;
+                                              const PmRange& r, int fo, int f_len, int& f) {
+  f = r.fb + fo;                                 // fb already reduced modulo F, f_len <= F
+  f = f >= a.F ? f - a.F : f;
+  return d_ftab == nullptr || __ldg(d_ftab + f) == r.s * f_len + fo;
 }
 
-// CTA = (tile of <= 32 surviving view pixels of one view, frame window).
-// Load: warp <-> (payload q, window frame fo), lane <-> entry: 4 plane loads -> one atom ->
-// shared tile[q][entry][fo].  Store: 16 lanes write one full panorama row (f_len atoms).
-template <typename T>
+// entry -> payload element offset of (job, plane 0, frame 0, k)
+__device__ __forceinline__ int pm_job_offset(const PmMergeArgs& a, int s, int src, int plane_stride) {
+  const int v = src / a.hw, k = src - v * a.hw;
+  return (s * a.vpf + v - a.job_begin) * kPmPlanes * plane_stride + k;
+}
+
+// Persistent CTAs over the surviving view pixels; a pass handles up to kPmCap entries, two per lane.
+// Load: warp <-> (payload q, window frame fo), lane <-> entries: 4 plane loads -> one atom ->
+// shared tile[q][entry][fo].  Store: f_len consecutive lanes write one full panorama row.
+template <typename T, int FL, int EPL>
 __global__ void __launch_bounds__(kBlock)
-pm_merge_nearest_kernel(PmMergeArgs a, const int32_t* __restrict__ d_tiles,
-                        const int32_t* __restrict__ d_ent_k, const int32_t* __restrict__ d_ent_dst,
+pm_merge_nearest_kernel(PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
+                        const int32_t* __restrict__ d_ent_src, const int32_t* __restrict__ d_ent_dst,
                         const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
-  PmTileCtx c;
-  if (!pm_tile_ctx(a, d_tiles, d_fbegin, c)) return;
+  PmRange rg;
+  if (!pm_range(a, d_view_ptr, d_fbegin, rg)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int SA = a.f_len | 1;                                        // odd row stride in atoms
-  A* tile = reinterpret_cast<A*>(smem_raw);                          // [Q][ET][SA]
-  int32_t* s_dst = reinterpret_cast<int32_t*>(tile + static_cast<size_t>(a.Q) * kPmET * SA);
+  const int f_len = FL > 0 ? FL : a.f_len;
+  const int SA = f_len | 1;                                          // odd row stride in atoms
+  constexpr int CAP = 32 * EPL;                                      // entries per pass
+  A* tile = reinterpret_cast<A*>(smem_raw);                          // [Q][CAP][SA]
+  int32_t* s_dst = reinterpret_cast<int32_t*>(tile + a.Q * CAP * SA);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool have = lane < c.count;
-  int k = 0;
-  if (have) k = d_ent_k != nullptr ? __ldg(d_ent_k + c.begin + lane) : c.begin + lane;
-  if (warp == 0 && have) {
-    const int dst = d_ent_dst != nullptr ? __ldg(d_ent_dst + c.begin + lane) : c.begin + lane;
-    s_dst[lane] = dst;
-    if (a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
-  }
-  const size_t plane_stride = static_cast<size_t>(a.f_len) * a.hw;
-  const int n_pairs = a.Q * a.f_len;
-  constexpr int U = 4;
-  for (int p0 = warp * U; p0 < n_pairs; p0 += kWarps * U) {
-    T e[U][4];
-    bool live[U];
-    int q[U], fo[U];
+  const int plane_stride = f_len * a.hw;
+  const int n_pairs = a.Q * f_len;
+  const int n = rg.hi - rg.lo;
+  const int n_pass = (n + CAP - 1) / CAP;
+  const int per = (n + n_pass - 1) / n_pass;
+  for (int t0 = rg.lo; t0 < rg.hi; t0 += per) {
+    const int cnt = min(per, rg.hi - t0);
+    bool have[EPL];
+    int off[EPL];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pr = p0 + u;
-      q[u] = pr / a.f_len;
-      fo[u] = pr - q[u] * a.f_len;
-      int f;
-      live[u] = pr < n_pairs && have && pm_frame_live(a, d_ftab, c, fo[u], f);
-      if (live[u]) {
-        const T* __restrict__ src = static_cast<const T*>(pm_sel(a.pay, q[u])) +
-                                    (static_cast<size_t>(c.job) * kPmPlanes * a.f_len + fo[u]) * a.hw + k;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) e[u][p] = ldg(src + p * plane_stride);
+    for (int j = 0; j < EPL; ++j) {
+      const int el = lane + 32 * j;
+      have[j] = el < cnt;
+      off[j] = 0;
+      if (have[j]) {
+        const int src = d_ent_src != nullptr ? __ldg(d_ent_src + t0 + el) : t0 + el;
+        off[j] = pm_job_offset(a, rg.s, src, plane_stride);
+        if (warp == 0) {
+          const int dst = d_ent_dst != nullptr ? __ldg(d_ent_dst + t0 + el) : t0 + el;
+          s_dst[el] = dst;
+          if (a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
+        }
       }
     }
+    constexpr int U = 4 / EPL;
+    for (int p0 = warp * U; p0 < n_pairs; p0 += kWarps * U) {
+      T e[U][EPL][4];
+      bool live[U];
+      int q[U], fo[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (live[u]) tile[(static_cast<size_t>(q[u]) * kPmET + lane) * SA + fo[u]] = atom_join<T>(e[u]);
-  }
-  __syncthreads();
-
-  const int per_q = kPmET * a.f_len;
-  for (int u = threadIdx.x; u < a.Q * per_q; u += kBlock) {
-    const int q = u / per_q, r = u - q * per_q;
-    const int i = r / a.f_len, fo = r - i * a.f_len;
-    int f;
-    if (i < c.count && pm_frame_live(a, d_ftab, c, fo, f)) {
-      const size_t off = static_cast<size_t>(s_dst[i]) * a.F + f;
-      static_cast<A*>(pm_sel(a.pm, q))[off] = tile[(static_cast<size_t>(q) * kPmET + i) * SA + fo];
-      if (q == 0 && a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[off] = atom_ones<T>();
+      for (int u = 0; u < U; ++u) {
+        const int pr = p0 + u;
+        q[u] = pr / f_len;
+        fo[u] = pr - q[u] * f_len;
+        int f;
+        live[u] = pr < n_pairs && pm_frame_live(a, d_ftab, rg, fo[u], f_len, f);
+        if (live[u]) {
+          const T* __restrict__ src = static_cast<const T*>(pm_sel(a.pay, q[u])) + fo[u] * a.hw;
+#pragma unroll
+          for (int j = 0; j < EPL; ++j)
+            if (have[j]) {
+#pragma unroll
+              for (int p = 0; p < 4; ++p) e[u][j][p] = ldg(src + off[j] + p * plane_stride);
+            }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (live[u]) {
+#pragma unroll
+          for (int j = 0; j < EPL; ++j)
+            if (have[j]) tile[(q[u] * CAP + lane + 32 * j) * SA + fo[u]] = atom_join<T>(e[u][j]);
+        }
     }
+    __syncthreads();
+
+    const int per_q = cnt * f_len;
+    for (int u = threadIdx.x; u < a.Q * per_q; u += kBlock) {
+      const int q = u / per_q, r = u - q * per_q;
+      const int i = r / f_len, fo = r - i * f_len;
+      int f;
+      if (pm_frame_live(a, d_ftab, rg, fo, f_len, f)) {
+        const size_t o = static_cast<size_t>(s_dst[i]) * a.F + f;
+        static_cast<A*>(pm_sel(a.pm, q))[o] = tile[(q * CAP + i) * SA + fo];
+        if (q == 0 && a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[o] = atom_ones<T>();
+      }
+    }
+    if (a.Q == 0 && a.mask_mode == DS_MASK_FULL) {                   // mask-only call
+      for (int u = threadIdx.x; u < per_q; u += kBlock) {
+        const int i = u / f_len, fo = u - i * f_len;
+        int f;
+        if (pm_frame_live(a, d_ftab, rg, fo, f_len, f))
+          static_cast<A*>(a.mask)[static_cast<size_t>(s_dst[i]) * a.F + f] = atom_ones<T>();
+      }
+    }
+    __syncthreads();
   }
 }
 
-// CTA = (tile of <= 32 panorama rows owned by one view, frame window).  Each lane owns a row
-// and walks its CSR entries (tap-major, k ascending -- index_add_'s order) accumulating
+// Two-phase weighted merge for a compile-time window frame count FL.  Persistent CTAs over the
+// panorama rows (one row = one panorama pixel owned by one view); a pass handles <= 32 rows.
+//   phase A  lane <-> CSR ENTRY (dense, no divergence): product atom = payload * w -> shared
+//   phase B  lane <-> (row, window frame): acc = acc + product over the row's entries in CSR
+//            order (tap-major, k ascending: index_add_'s order); row = acc / ws; one full
+//            panorama row per FL consecutive lanes.
+// Entries are processed in chunks of kPmEC so any row length works; acc lives in registers.
+constexpr int kPmEC = 64;
+template <typename T, int FL, int QMAX>
+__global__ void __launch_bounds__(kBlock)
+pm_merge_bilinear_fl_kernel(PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
+                            const int32_t* __restrict__ d_row_dst, const int32_t* __restrict__ d_row_ptr,
+                            const int32_t* __restrict__ d_ent_src, const float* __restrict__ d_ent_w,
+                            const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
+  using A = typename Atom<T>::type;
+  static_assert(kBlock % FL == 0 && (kPmET * FL) % kBlock == 0, "row/lane mapping");
+  constexpr int SA = FL | 1;
+  constexpr int RPP = kBlock / FL;               // rows per sweep of phase B
+  constexpr int NSW = kPmET / RPP;               // sweeps to cover a pass's rows
+  PmRange rg;
+  if (!pm_range(a, d_view_ptr, d_fbegin, rg)) return;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* prod = reinterpret_cast<float4*>(smem_raw);                 // [Q][EC][SA] fp32 products
+  float* s_w = reinterpret_cast<float*>(prod + (a.Q > 0 ? a.Q : 1) * kPmEC * SA);   // [EC]
+  int32_t* s_rp = reinterpret_cast<int32_t*>(s_w + kPmEC);            // [ET + 1]
+  int32_t* s_dst = s_rp + kPmET + 1;                                  // [ET]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int fo_b = threadIdx.x % FL, row_b = threadIdx.x / FL;       // phase-B ownership
+  int fB;
+  const bool liveB = pm_frame_live(a, d_ftab, rg, fo_b, FL, fB);
+  const int plane_stride = FL * a.hw;
+
+  const int n = rg.hi - rg.lo;
+  const int n_pass = (n + kPmET - 1) / kPmET;
+  const int per = (n + n_pass - 1) / n_pass;
+  for (int r0 = rg.lo; r0 < rg.hi; r0 += per) {
+    const int cnt = min(per, rg.hi - r0);
+    if (threadIdx.x <= cnt) s_rp[threadIdx.x] = __ldg(d_row_ptr + r0 + threadIdx.x);
+    if (threadIdx.x < cnt) s_dst[threadIdx.x] = __ldg(d_row_dst + r0 + threadIdx.x);
+    __syncthreads();
+    const int e_begin = s_rp[0], e_end = s_rp[cnt];
+    float acc[NSW][QMAX][4];
+    float ws[NSW];
+#pragma unroll
+    for (int sw = 0; sw < NSW; ++sw) {
+      ws[sw] = 0.f;
+#pragma unroll
+      for (int q = 0; q < QMAX; ++q)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[sw][q][p] = 0.f;
+    }
+    for (int c0 = e_begin; c0 < e_end; c0 += kPmEC) {
+      const int n_e = min(kPmEC, e_end - c0);
+      // ---- phase A: products ----
+#pragma unroll
+      for (int half = 0; half < kPmEC / 32; ++half) {
+        const int el = half * 32 + lane;
+        if (half * 32 >= n_e) break;
+        const bool have = el < n_e;
+        int off = 0;
+        float w = 0.f;
+        if (have) {
+          off = pm_job_offset(a, rg.s, __ldg(d_ent_src + c0 + el), plane_stride);
+          w = __ldg(d_ent_w + c0 + el);
+          if (warp == 0) s_w[el] = w;
+        }
+        constexpr int NF = (FL + kWarps - 1) / kWarps;       // window frames per warp
+        T x[QMAX][NF][4];
+        bool live[NF];
+#pragma unroll
+        for (int j = 0; j < NF; ++j) {
+          const int fo = warp + j * kWarps;
+          int f;
+          live[j] = have && fo < FL && pm_frame_live(a, d_ftab, rg, fo, FL, f);
+#pragma unroll
+          for (int q = 0; q < QMAX; ++q)
+            if (q < a.Q && live[j]) {
+              const T* __restrict__ src = static_cast<const T*>(a.pay[q]) + off + fo * a.hw;
+#pragma unroll
+              for (int p = 0; p < 4; ++p) x[q][j][p] = ldg(src + p * plane_stride);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < NF; ++j)
+#pragma unroll
+          for (int q = 0; q < QMAX; ++q)
+            if (q < a.Q && live[j]) {
+              const int fo = warp + j * kWarps;
+              prod[(q * kPmEC + el) * SA + fo] =
+                  make_float4(__fmul_rn(Elem<T>::to_f(x[q][j][0]), w), __fmul_rn(Elem<T>::to_f(x[q][j][1]), w),
+                              __fmul_rn(Elem<T>::to_f(x[q][j][2]), w), __fmul_rn(Elem<T>::to_f(x[q][j][3]), w));
+            }
+      }
+      __syncthreads();
+      // ---- phase B: ordered accumulation of this chunk ----
+#pragma unroll
+      for (int sw = 0; sw < NSW; ++sw) {
+        const int i = sw * RPP + row_b;
+        if (i < cnt) {
+          const int lo = max(s_rp[i], c0) - c0, hi = min(s_rp[i + 1], c0 + n_e) - c0;
+          for (int e = lo; e < hi; ++e) {
+            ws[sw] = __fadd_rn(ws[sw], s_w[e]);
+            if (liveB) {
+#pragma unroll
+              for (int q = 0; q < QMAX; ++q)
+                if (q < a.Q) {
+                  const float4 t = prod[(q * kPmEC + e) * SA + fo_b];
+                  acc[sw][q][0] = __fadd_rn(acc[sw][q][0], t.x);
+                  acc[sw][q][1] = __fadd_rn(acc[sw][q][1], t.y);
+                  acc[sw][q][2] = __fadd_rn(acc[sw][q][2], t.z);
+                  acc[sw][q][3] = __fadd_rn(acc[sw][q][3], t.w);
+                }
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // ---- normalise + write full panorama rows ----
+#pragma unroll
+    for (int sw = 0; sw < NSW; ++sw) {
+      const int i = sw * RPP + row_b;
+      if (i < cnt && ws[sw] > 0.f) {
+        const int dst = s_dst[i];
+        if (fo_b == 0 && a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
+        if (liveB) {
+          const size_t o = static_cast<size_t>(dst) * a.F + fB;
+#pragma unroll
+          for (int q = 0; q < QMAX; ++q)
+            if (q < a.Q) {
+              float r[4];
+#pragma unroll
+              for (int p = 0; p < 4; ++p) r[p] = __fdiv_rn(acc[sw][q][p], ws[sw]);
+              static_cast<A*>(a.pm[q])[o] = Atom<T>::pack(r);
+            }
+          if (a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[o] = atom_ones<T>();
+        }
+      }
+    }
+    __syncthreads();                              // s_rp / s_dst are rewritten by the next pass
+  }
+}
+
+// Generic (runtime f_len) weighted merge: each lane owns a row and walks its CSR entries
+// (tap-major, k ascending -- index_add_'s order) accumulating
 //   acc = acc + (payload * w);  ws = ws + w;   row = acc / ws     (each op rounded on its own)
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
-pm_merge_bilinear_kernel(PmMergeArgs a, const int32_t* __restrict__ d_tiles,
+pm_merge_bilinear_kernel(PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                          const int32_t* __restrict__ d_row_dst, const int32_t* __restrict__ d_row_ptr,
-                         const int32_t* __restrict__ d_ent_k, const float* __restrict__ d_ent_w,
+                         const int32_t* __restrict__ d_ent_src, const float* __restrict__ d_ent_w,
                          const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
-  PmTileCtx c;
-  if (!pm_tile_ctx(a, d_tiles, d_fbegin, c)) return;
+  PmRange rg;
+  if (!pm_range(a, d_view_ptr, d_fbegin, rg)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int SA = a.f_len | 1;
   A* tile = reinterpret_cast<A*>(smem_raw);                          // [Q][ET][SA]
-  int32_t* s_dst = reinterpret_cast<int32_t*>(tile + static_cast<size_t>(a.Q) * kPmET * SA);   // -1: row not written
+  int32_t* s_dst = reinterpret_cast<int32_t*>(tile + (a.Q > 0 ? a.Q : 1) * kPmET * SA);   // -1: row not written
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool have = lane < c.count;
-  int e0 = 0, e1 = 0;
-  if (have) {
-    e0 = __ldg(d_row_ptr + c.begin + lane);
-    e1 = __ldg(d_row_ptr + c.begin + lane + 1);
-  }
-  const size_t plane_stride = static_cast<size_t>(a.f_len) * a.hw;
+  const int plane_stride = a.f_len * a.hw;
   const int n_pairs = a.Q * a.f_len;
-  constexpr int U = 2;
-  float ws = 0.f;
-  for (int p0 = warp * U; p0 < n_pairs; p0 += kWarps * U) {
-    float acc[U][4];
-    const T* src[U];
-    bool live[U];
-    int q[U], fo[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pr = p0 + u;
-      q[u] = pr / a.f_len;
-      fo[u] = pr - q[u] * a.f_len;
-      int f;
-      live[u] = pr < n_pairs && have && pm_frame_live(a, d_ftab, c, fo[u], f);
-      src[u] = live[u] ? static_cast<const T*>(pm_sel(a.pay, q[u])) +
-                             (static_cast<size_t>(c.job) * kPmPlanes * a.f_len + fo[u]) * a.hw
-                       : nullptr;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) acc[u][p] = 0.f;
+  for (int r0 = rg.lo; r0 < rg.hi; r0 += kPmET) {
+    const int cnt = min(kPmET, rg.hi - r0);
+    const bool have = lane < cnt;
+    int e0 = 0, e1 = 0;
+    if (have) {
+      e0 = __ldg(d_row_ptr + r0 + lane);
+      e1 = __ldg(d_row_ptr + r0 + lane + 1);
     }
-    ws = 0.f;
-    for (int e = e0; e < e1; ++e) {
-      const int k = __ldg(d_ent_k + e);
-      const float w = __ldg(d_ent_w + e);
-      ws = __fadd_rn(ws, w);
-      float x[U][4];
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (live[u]) {
-#pragma unroll
-          for (int p = 0; p < 4; ++p) x[u][p] = Elem<T>::to_f(ldg(src[u] + p * plane_stride + k));
-        }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (live[u]) {
-#pragma unroll
-          for (int p = 0; p < 4; ++p) acc[u][p] = __fadd_rn(acc[u][p], __fmul_rn(x[u][p], w));
-        }
-    }
-    if (ws > 0.f) {
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (live[u]) {
-          float r[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) r[p] = __fdiv_rn(acc[u][p], ws);
-          tile[(static_cast<size_t>(q[u]) * kPmET + lane) * SA + fo[u]] = Atom<T>::pack(r);
-        }
-    }
-  }
-  if (warp == 0) {
-    // every warp walks the same entries, so warp 0's ws is the row's weight sum
-    if (n_pairs <= 0) {                         // mask-only call: weight sum still needed
-      for (int e = e0; e < e1; ++e) ws = __fadd_rn(ws, __ldg(d_ent_w + e));
-    }
+    float ws = 0.f;
+    for (int e = e0; e < e1; ++e) ws = __fadd_rn(ws, __ldg(d_ent_w + e));
     const bool wr = have && ws > 0.f;
-    const int dst = wr ? __ldg(d_row_dst + c.begin + lane) : -1;
-    s_dst[lane] = dst;
-    if (wr && a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
-  }
-  __syncthreads();
-
-  const int per_q = kPmET * a.f_len;
-  const int n_units = (a.Q > 0 ? a.Q : 1) * per_q;
-  for (int u = threadIdx.x; u < n_units; u += kBlock) {
-    const int q = u / per_q, r = u - q * per_q;
-    const int i = r / a.f_len, fo = r - i * a.f_len;
-    int f;
-    if (i < c.count && s_dst[i] >= 0 && pm_frame_live(a, d_ftab, c, fo, f)) {
-      const size_t off = static_cast<size_t>(s_dst[i]) * a.F + f;
-      if (a.Q > 0) static_cast<A*>(pm_sel(a.pm, q))[off] = tile[(static_cast<size_t>(q) * kPmET + i) * SA + fo];
-      if (q == 0 && a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[off] = atom_ones<T>();
+    if (warp == 0) {
+      const int dst = wr ? __ldg(d_row_dst + r0 + lane) : -1;
+      s_dst[lane] = dst;
+      if (wr && a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
     }
+    for (int pr = warp; pr < n_pairs; pr += kWarps) {
+      const int q = pr / a.f_len, fo = pr - q * a.f_len;
+      int f;
+      if (!wr || !pm_frame_live(a, d_ftab, rg, fo, a.f_len, f)) continue;
+      const T* __restrict__ src = static_cast<const T*>(pm_sel(a.pay, q)) + fo * a.hw;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int e = e0; e < e1; ++e) {
+        const int off = pm_job_offset(a, rg.s, __ldg(d_ent_src + e), plane_stride);
+        const float w = __ldg(d_ent_w + e);
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          acc[p] = __fadd_rn(acc[p], __fmul_rn(Elem<T>::to_f(ldg(src + off + p * plane_stride)), w));
+      }
+      float r[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) r[p] = __fdiv_rn(acc[p], ws);
+      tile[(q * kPmET + lane) * SA + fo] = Atom<T>::pack(r);
+    }
+    __syncthreads();
+    const int per_q = cnt * a.f_len;
+    const int n_units = (a.Q > 0 ? a.Q : 1) * per_q;
+    for (int u = threadIdx.x; u < n_units; u += kBlock) {
+      const int q = u / per_q, r = u - q * per_q;
+      const int i = r / a.f_len, fo = r - i * a.f_len;
+      int f;
+      if (s_dst[i] >= 0 && pm_frame_live(a, d_ftab, rg, fo, a.f_len, f)) {
+        const size_t o = static_cast<size_t>(s_dst[i]) * a.F + f;
+        if (a.Q > 0) static_cast<A*>(pm_sel(a.pm, q))[o] = tile[(q * kPmET + i) * SA + fo];
+        if (q == 0 && a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[o] = atom_ones<T>();
+      }
+    }
+    __syncthreads();
   }
 }
 
 static bool pm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* const* h_payloads, int Q,
-                              void* mask, int mask_mode, int n_tiles, int n_ent, const int32_t* d_ftab,
+                              void* mask, int mask_mode, int n_ent, const int32_t* d_ftab,
                               const int32_t* d_fbegin, int n_fwin, int vpf, int job_begin, int job_count,
                               int P, int F, int HW, int f_len, int hw) {
   DS_REQUIRE(Q >= 0 && Q <= DS_MAX_PAYLOADS, DS_ERR_COUNT);
   DS_REQUIRE(Q == 0 || (h_pms != nullptr && h_payloads != nullptr), DS_ERR_NULL);
   DS_REQUIRE(P == kPmPlanes, DS_ERR_DIM);
-  DS_REQUIRE(n_tiles >= 0 && n_ent >= 0 && n_fwin > 0 && vpf > 0 && F > 0 && HW > 0 && f_len > 0 && hw > 0, DS_ERR_DIM);
+  DS_REQUIRE(n_ent >= 0 && n_fwin > 0 && vpf > 0 && F > 0 && HW > 0 && f_len > 0 && hw > 0, DS_ERR_DIM);
   DS_REQUIRE(f_len <= F && n_fwin <= 65535, DS_ERR_DIM);
   DS_REQUIRE(mask_mode == DS_MASK_NONE || mask_mode == DS_MASK_PLANE || mask_mode == DS_MASK_FULL, DS_ERR_DIM);
   DS_REQUIRE(mask_mode == DS_MASK_NONE || mask != nullptr, DS_ERR_NULL);
   DS_REQUIRE(Q > 0 || mask_mode != DS_MASK_NONE, DS_ERR_COUNT);
-  DS_REQUIRE(job_begin >= 0 && job_count > 0, DS_ERR_DIM);
+  DS_REQUIRE(job_begin >= 0 && job_begin < (1 << 30) && job_count > 0 && job_count <= (1 << 30), DS_ERR_DIM);
+  // payload offsets are 32-bit inside the kernels
+  const long long all_jobs = static_cast<long long>(n_fwin) * vpf;
+  const long long jobs_here = job_count < all_jobs ? job_count : all_jobs;
+  DS_REQUIRE(jobs_here * P * f_len * hw < (1ll << 31), DS_ERR_DIM);
   // frame ring: both tables or neither; without them the single frame window is the identity
   DS_REQUIRE((d_ftab == nullptr) == (d_fbegin == nullptr), DS_ERR_NULL);
   DS_REQUIRE(d_ftab != nullptr || (f_len == F && n_fwin == 1), DS_ERR_DIM);
@@ -421,15 +628,32 @@ static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* co
   }
   if (mask_mode == DS_MASK_FULL) DS_REQUIRE(pm_aligned16(mask), DS_ERR_ALIGN);
   a.mask = mask; a.mask_mode = mask_mode;
-  a.Q = Q; a.n_tiles = n_tiles; a.n_ent = n_ent;
+  a.Q = Q; a.n_ent = n_ent; a.per_cta = 0;
   a.vpf = vpf; a.job_begin = job_begin; a.job_count = job_count;
   a.F = F; a.HW = HW; a.f_len = f_len; a.hw = hw;
   return DS_OK;
 }
 
-template <typename T>
-static size_t pm_merge_smem(int Q, int f_len) {
-  return static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(typename Atom<T>::type) + kPmET * sizeof(int32_t);
+// Persistent launch: at most (SMs x resident CTAs) CTAs along x, never more than `items`
+// work items, raising the dynamic shared memory limit when needed.
+// ctas_per_sm: 0 = occupancy limit, > 0 = cap, < 0 = not persistent (one CTA per item).
+template <typename K, typename... Args>
+static int pm_launch(K kernel, long long items, int ctas_per_sm, unsigned grid_y, size_t smem, cudaStream_t st, Args... args) {
+  DS_REQUIRE(smem <= 200 * 1024, DS_ERR_DIM);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  long long gx = items;
+  if (ctas_per_sm >= 0) {
+    int occ = 0, dev = 0, sms = kSMs;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (ctas_per_sm > 0 && ctas_per_sm < occ) occ = ctas_per_sm;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long slots = static_cast<long long>(sms) * occ;
+    gx = items < slots ? items : slots;
+  }
+  if (gx < 1) gx = 1;
+  DS_REQUIRE(gx < (1ll << 31), DS_ERR_DIM);
+  kernel<<<dim3(static_cast<unsigned>(gx), grid_y), kBlock, smem, st>>>(args...);
+  return check_launch();
 }
 
 }  // namespace ds
@@ -442,79 +666,100 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   DS_REQUIRE(taps == 1 || taps == 4, DS_ERR_DIM);
   DS_REQUIRE(taps == 1 || (d_idx != nullptr && d_wt != nullptr), DS_ERR_NULL);
   DS_REQUIRE(P == kPmPlanes, DS_ERR_DIM);
-  DS_REQUIRE(n_jobs > 0 && n_jobs <= 65535 && F > 0 && HW > 0 && f_len > 0 && hw > 0 && h_f0 >= 0, DS_ERR_DIM);
+  DS_REQUIRE(n_jobs > 0 && F > 0 && HW > 0 && f_len > 0 && f_len <= F && hw > 0 && h_f0 >= 0, DS_ERR_DIM);
   DS_REQUIRE(d_idx != nullptr || hw <= HW, DS_ERR_DIM);
   DS_REQUIRE(pm_aligned16(pm) && pm_aligned16(out), DS_ERR_ALIGN);
-  PmGatherArgs a{F, HW, f_len, hw, (f_len + 7) / 8};
+  const int tpj = static_cast<int>(div_up(hw, kPmKT));
+  const long long n_tiles = static_cast<long long>(n_jobs) * tpj;
+  DS_REQUIRE(n_tiles < (1ll << 31) && static_cast<long long>(n_jobs) * P * f_len * hw < (1ll << 40), DS_ERR_DIM);
+  DS_REQUIRE(static_cast<long long>(n_jobs) * taps * hw < (1ll << 31), DS_ERR_DIM);
+  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid(div_up(hw, kPmKT), n_jobs);
   DS_DISPATCH_DTYPE(dtype, {
     constexpr int VE = 16 / sizeof(ET);
     DS_REQUIRE(hw % VE == 0, DS_ERR_ALIGN);
     const size_t smem = static_cast<size_t>(kPmPlanes) * f_len * (kPmKT + VE) * sizeof(ET) + static_cast<size_t>(taps) * kPmKT * 8;
-    DS_REQUIRE(smem <= 200 * 1024, DS_ERR_DIM);
     using AT = typename Atom<ET>::type;
+    const AT* pmp = static_cast<const AT*>(pm);
+    ET* op = static_cast<ET*>(out);
     if (taps == 1) {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(pm_gather_kernel<ET, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      pm_gather_kernel<ET, 1><<<grid, kBlock, smem, st>>>(static_cast<const AT*>(pm), static_cast<ET*>(out), d_idx, d_wt, d_jobs, h_f0, a);
-    } else {
-      if (smem > 48 * 1024) cudaFuncSetAttribute(pm_gather_kernel<ET, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-      pm_gather_kernel<ET, 4><<<grid, kBlock, smem, st>>>(static_cast<const AT*>(pm), static_cast<ET*>(out), d_idx, d_wt, d_jobs, h_f0, a);
+      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+      return pm_launch(pm_gather_kernel<ET, 1, 0>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
     }
+    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+    return pm_launch(pm_gather_kernel<ET, 4, 0>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
   });
-  return check_launch();
+  return DS_OK;
 }
 
 extern "C" int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payloads, int Q,
-                                   void* mask, int mask_mode, const int32_t* d_tiles, int n_tiles,
-                                   const int32_t* d_ent_k, const int32_t* d_ent_dst, int n_ent,
+                                   void* mask, int mask_mode, const int32_t* d_view_ptr,
+                                   const int32_t* d_ent_src, const int32_t* d_ent_dst, int n_ent,
                                    const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
                                    int views_per_fwin, int job_begin, int job_count,
                                    int P, int F, int HW, int f_len, int hw, int dtype, void* stream) {
   using namespace ds;
   PmMergeArgs a;
-  int rc = pm_fill_merge_args(a, h_pms, h_payloads, Q, mask, mask_mode, n_tiles, n_ent, d_ftab, d_fbegin, n_fwin,
+  int rc = pm_fill_merge_args(a, h_pms, h_payloads, Q, mask, mask_mode, n_ent, d_ftab, d_fbegin, n_fwin,
                               views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw);
   if (rc != DS_OK) return rc;
-  DS_REQUIRE((d_tiles == nullptr) == (d_ent_k == nullptr) && (d_tiles == nullptr) == (d_ent_dst == nullptr), DS_ERR_NULL);
-  if (d_tiles == nullptr) {                      // identity plan: entry i = (k = i, dst = i)
-    DS_REQUIRE(n_ent <= HW && n_ent <= hw && views_per_fwin == 1, DS_ERR_DIM);
-    n_tiles = static_cast<int>(div_up(n_ent, kPmET));
-    a.n_tiles = n_tiles;
-  }
-  if (n_tiles == 0) return DS_OK;
+  DS_REQUIRE((d_view_ptr == nullptr) == (d_ent_src == nullptr) && (d_view_ptr == nullptr) == (d_ent_dst == nullptr), DS_ERR_NULL);
+  if (d_view_ptr == nullptr)                     // identity plan: entry i = (k = i, dst = i) of job 0
+    DS_REQUIRE(n_ent <= HW && n_ent <= hw && views_per_fwin == 1 && n_fwin == 1 && job_begin == 0, DS_ERR_DIM);
+  if (n_ent == 0) return DS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid(n_tiles, n_fwin);
+  const long long items = div_up(n_ent, 32);
+  const int cps = g_merge_persistent ? g_merge_ctas_per_sm : -1;
+  if (!g_merge_persistent) a.per_cta = 32;
   DS_DISPATCH_DTYPE(dtype, {
-    const size_t smem = pm_merge_smem<ET>(Q, f_len);
-    DS_REQUIRE(smem <= 200 * 1024, DS_ERR_DIM);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(pm_merge_nearest_kernel<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    pm_merge_nearest_kernel<ET><<<grid, kBlock, smem, st>>>(a, d_tiles, d_ent_k, d_ent_dst, d_ftab, d_fbegin);
+    using AT = typename Atom<ET>::type;
+    const size_t smem1 = static_cast<size_t>(Q > 0 ? Q : 1) * 32 * (f_len | 1) * sizeof(AT) + 32 * sizeof(int32_t);
+    if (!g_merge_persistent) {
+      if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16, 1>, items, cps, n_fwin, smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+      return pm_launch(pm_merge_nearest_kernel<ET, 0, 1>, items, cps, n_fwin, smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    }
+    if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16, 2>, items, cps, n_fwin, 2 * smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    return pm_launch(pm_merge_nearest_kernel<ET, 0, 2>, items, cps, n_fwin, 2 * smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
   });
-  return check_launch();
+  return DS_OK;
 }
 
 extern "C" int ds_pm_merge_bilinear(void* const* h_pms, const void* const* h_payloads, int Q,
-                                    void* mask, int mask_mode, const int32_t* d_tiles, int n_tiles,
+                                    void* mask, int mask_mode, const int32_t* d_view_ptr,
                                     const int32_t* d_row_dst, const int32_t* d_row_ptr, int n_rows,
-                                    const int32_t* d_ent_k, const float* d_ent_w,
+                                    const int32_t* d_ent_src, const float* d_ent_w,
                                     const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
                                     int views_per_fwin, int job_begin, int job_count,
                                     int P, int F, int HW, int f_len, int hw, int dtype, void* stream) {
   using namespace ds;
   PmMergeArgs a;
-  int rc = pm_fill_merge_args(a, h_pms, h_payloads, Q, mask, mask_mode, n_tiles, n_rows, d_ftab, d_fbegin, n_fwin,
+  int rc = pm_fill_merge_args(a, h_pms, h_payloads, Q, mask, mask_mode, n_rows, d_ftab, d_fbegin, n_fwin,
                               views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw);
   if (rc != DS_OK) return rc;
-  DS_REQUIRE(d_tiles != nullptr && d_row_dst != nullptr && d_row_ptr != nullptr && d_ent_k != nullptr && d_ent_w != nullptr, DS_ERR_NULL);
-  if (n_tiles == 0) return DS_OK;
+  DS_REQUIRE(d_view_ptr != nullptr && d_row_dst != nullptr && d_row_ptr != nullptr && d_ent_src != nullptr && d_ent_w != nullptr, DS_ERR_NULL);
+  if (n_rows == 0) return DS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  dim3 grid(n_tiles, n_fwin);
+  const long long items = div_up(n_rows, kPmET);
+  const int cps = g_merge_persistent ? g_merge_ctas_per_sm : -1;
+  if (!g_merge_persistent) a.per_cta = kPmET;
   DS_DISPATCH_DTYPE(dtype, {
-    const size_t smem = pm_merge_smem<ET>(Q, f_len);
-    DS_REQUIRE(smem <= 200 * 1024, DS_ERR_DIM);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(pm_merge_bilinear_kernel<ET>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    pm_merge_bilinear_kernel<ET><<<grid, kBlock, smem, st>>>(a, d_tiles, d_row_dst, d_row_ptr, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+    if (f_len == 16) {
+      const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) +
+                         (2 * kPmET + 1) * sizeof(int32_t);
+      if (Q <= 2) return pm_launch(pm_merge_bilinear_fl_kernel<ET, 16, 2>, items, cps, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin);
+      return pm_launch(pm_merge_bilinear_fl_kernel<ET, 16, 4>, items, cps, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin);
+    }
+    const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(typename Atom<ET>::type) + kPmET * sizeof(int32_t);
+    return pm_launch(pm_merge_bilinear_kernel<ET>, items, cps, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin);
   });
-  return check_launch();
+  return DS_OK;
+}
+
+extern "C" int ds_tune(int knob, int value) {
+  switch (knob) {
+    case DS_TUNE_PM_GATHER_CTAS_PER_SM: ds::g_gather_ctas_per_sm = value; return DS_OK;
+    case DS_TUNE_PM_MERGE_PERSISTENT: ds::g_merge_persistent = value; return DS_OK;
+    case DS_TUNE_PM_MERGE_CTAS_PER_SM: ds::g_merge_ctas_per_sm = value; return DS_OK;
+    default: return DS_ERR_DIM;
+  }
 }

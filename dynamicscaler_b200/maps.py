@@ -250,43 +250,30 @@ def bilinear_merge_plan(vmaps):
 
 
 # ------------------------------------------- pixel-major (scatter-form) merge plans ----
-PM_TILE = 32          # entries per merge CTA (csrc/pm.cu kPmET)
-
-
-def _tiles_by_view(view_of_entry):
-    """Cut the entry list (already sorted by view) into [n_tiles, 3] (view, begin, count)
-    tiles of at most PM_TILE entries that never straddle two views."""
-    n = view_of_entry.size
-    if n == 0:
-        return np.zeros((0, 3), np.int32)
-    cut = np.nonzero(np.diff(view_of_entry))[0] + 1
-    starts = np.concatenate([[0], cut])
-    ends = np.concatenate([cut, [n]])
-    tiles = []
-    for b, e in zip(starts, ends):
-        tb = np.arange(b, e, PM_TILE)
-        tiles.append(np.stack([np.full(tb.size, view_of_entry[b]), tb, np.minimum(PM_TILE, e - tb)], axis=1))
-    return np.concatenate(tiles).astype(np.int32)
+def _view_ptr(view_of_item, n_views):
+    """[n_views + 1] offsets of each view's slice in a list sorted by view."""
+    return np.searchsorted(view_of_item, np.arange(n_views + 1)).astype(np.int32)
 
 
 def pm_nearest_plan(vmaps):
     """``nearest_merge_plan`` regrouped for the scatter-form kernel: the surviving view
-    pixels, sorted by (view, k).  Returns (tiles[n_tiles, 3], ent_k[T], ent_dst[T])."""
+    pixels sorted by (view, k).  Returns (view_ptr[n_views + 1], ent_src[T] = view*hw + k,
+    ent_dst[T])."""
     dst, src = nearest_merge_plan(vmaps)
-    hw = vmaps[0].hw
-    v, k = src // hw, src % hw
-    order = np.lexsort((k, v))
-    return _tiles_by_view(v[order]), k[order].astype(np.int32), dst[order].astype(np.int32)
+    order = np.argsort(src, kind="stable")
+    src, dst = src[order], dst[order]
+    return _view_ptr(src // vmaps[0].hw, len(vmaps)), src.astype(np.int32), dst.astype(np.int32)
 
 
 def pm_bilinear_plan(vmaps):
     """``bilinear_merge_plan`` regrouped by owning view: rows sorted by (view, dst), CSR
-    entries kept in index_add_ order inside each row, view pixel stored relative to its view.
-    Returns (tiles[n_tiles, 3], row_dst[T], row_ptr[T + 1], ent_k[E], ent_w[E])."""
+    entries kept in index_add_ order inside each row.
+    Returns (view_ptr[n_views + 1] over rows, row_dst[T], row_ptr[T + 1], ent_src[E], ent_w[E])."""
     row_dst, row_ptr, ent_src, ent_w = bilinear_merge_plan(vmaps)
     hw = vmaps[0].hw
     if row_dst.size == 0:
-        return (np.zeros((0, 3), np.int32), row_dst, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0, F32))
+        return (np.zeros(len(vmaps) + 1, np.int32), row_dst, np.zeros(1, np.int32), np.zeros(0, np.int32),
+                np.zeros(0, F32))
     row_ptr = row_ptr.astype(np.int64)
     owner = ent_src[row_ptr[:-1]] // hw
     order = np.lexsort((row_dst, owner))
@@ -294,8 +281,8 @@ def pm_bilinear_plan(vmaps):
     new_ptr = np.concatenate([[0], np.cumsum(counts)])
     # entry gather: for new row r, entries row_ptr[order[r]] + [0, counts[r])
     ent_index = np.repeat(row_ptr[:-1][order] - new_ptr[:-1], counts) + np.arange(new_ptr[-1])
-    return (_tiles_by_view(owner[order]), row_dst[order].astype(np.int32), new_ptr.astype(np.int32),
-            (ent_src[ent_index] % hw).astype(np.int32), np.ascontiguousarray(ent_w[ent_index], dtype=F32))
+    return (_view_ptr(owner[order], len(vmaps)), row_dst[order].astype(np.int32), new_ptr.astype(np.int32),
+            ent_src[ent_index].astype(np.int32), np.ascontiguousarray(ent_w[ent_index], dtype=F32))
 
 
 def frame_table(F, frame_begins, f_len):

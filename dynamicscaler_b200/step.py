@@ -222,7 +222,7 @@ class PanoramaStepper:
         pm = torch.empty((H * W, F, 4), dtype=t.dtype, device=t.device)
         with torch.cuda.device(t.device):
             lib.check(lib.ds_pm_merge_nearest(_lib.ptr_array([pm]), _lib.ptr_array([t]), 1, None, _lib.DS_MASK_NONE,
-                                              None, 0, None, None, H * W, None, None, 1, 1, 0, 1,
+                                              None, None, None, H * W, None, None, 1, 1, 0, 1,
                                               4, F, H * W, F, H * W, _lib.dtype_code(t.dtype),
                                               _lib.stream_ptr(t.device)), "ds_pm_merge_nearest(pack)")
         return pm
@@ -267,17 +267,17 @@ class PanoramaStepper:
                   4, F, HW, plan.f_len, plan.hw, _lib.dtype_code(ref.dtype), _lib.stream_ptr(ref.device))
         with torch.cuda.device(ref.device):
             if plan.kind == "sphere_nearest":
-                tiles, ent_k, ent_dst = mp
+                view_ptr, ent_src, ent_dst = mp
                 lib.check(lib.ds_pm_merge_nearest(_lib.ptr_array(pms), _lib.ptr_array(payloads), len(pms),
-                                                  _lib.ptr(mask), mask_mode, tiles.data_ptr(), tiles.shape[0],
-                                                  ent_k.data_ptr(), ent_dst.data_ptr(), ent_k.numel(), *common),
+                                                  _lib.ptr(mask), mask_mode, view_ptr.data_ptr(),
+                                                  ent_src.data_ptr(), ent_dst.data_ptr(), ent_src.numel(), *common),
                           "ds_pm_merge_nearest")
             else:
-                tiles, row_dst, row_ptr, ent_k, ent_w = mp
+                view_ptr, row_dst, row_ptr, ent_src, ent_w = mp
                 lib.check(lib.ds_pm_merge_bilinear(_lib.ptr_array(pms), _lib.ptr_array(payloads), len(pms),
-                                                   _lib.ptr(mask), mask_mode, tiles.data_ptr(), tiles.shape[0],
+                                                   _lib.ptr(mask), mask_mode, view_ptr.data_ptr(),
                                                    row_dst.data_ptr(), row_ptr.data_ptr(), row_dst.numel(),
-                                                   ent_k.data_ptr(), ent_w.data_ptr(), *common),
+                                                   ent_src.data_ptr(), ent_w.data_ptr(), *common),
                           "ds_pm_merge_bilinear")
 
     def gather_all(self, latent, plan: StepPlan, out: Optional[torch.Tensor] = None, index: int = 0) -> torch.Tensor:

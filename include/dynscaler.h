@@ -49,6 +49,15 @@ enum {
 /* mask_mode of the merge calls */
 enum { DS_MASK_NONE = 0, DS_MASK_PLANE = 1 /* one [H*W] plane */, DS_MASK_FULL = 2 /* [mask_planes][F][H*W] */ };
 
+/* Launch-shape knobs of the pixel-major kernels (process-wide; used by the autotuning script
+ * tools/kbench.py -- results never depend on them, only speed). */
+enum {
+  DS_TUNE_PM_GATHER_CTAS_PER_SM = 0,   /* persistent gather: CTAs per SM, 0 = occupancy limit */
+  DS_TUNE_PM_MERGE_PERSISTENT = 1,     /* 0: one <= 32-entry tile per CTA; 1: persistent even split */
+  DS_TUNE_PM_MERGE_CTAS_PER_SM = 2     /* persistent merges: CTAs per SM, 0 = occupancy limit */
+};
+int ds_tune(int knob, int value);
+
 int ds_abi_version(void);
 /* Static string for a return code of this library (never NULL). */
 const char* ds_error_string(int code);
@@ -159,33 +168,34 @@ int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d
 
 /* Ordered sequence of set_view_tensor_no_interpolation calls (panorama_tensor_utils.py:
  * 154-183; ring twin ring_panorama_tensor_utils.py:170-198), scatter form over the surviving
- * view pixels only.  Entry e of tile t (view v_t, entries [begin_t, begin_t + count_t),
- * count_t <= 32) is the view pixel d_ent_k[e] of view v_t that wins panorama pixel
- * d_ent_dst[e] ("last writer wins"):
- *   pms[q][dst][(fb_s+fo) mod F][pl] = payloads[q][s*views_per_fwin + v_t - job_begin][pl][fo][k]
+ * view pixels only ("last writer wins").  Entry e says: view pixel
+ * d_ent_src[e] = v*hw + k wins panorama pixel d_ent_dst[e].  Entries are sorted by view and
+ * d_view_ptr[v] (length views_per_fwin + 1) is the first entry of view v:
+ *   pms[q][dst][(fb_s+fo) mod F][pl] = payloads[q][s*views_per_fwin + v - job_begin][pl][fo][k]
  * for every frame window s < n_fwin whose job is in [job_begin, job_begin + job_count) and
  * every fo with d_ftab[(fb_s+fo) mod F] == s*f_len + fo (d_ftab/d_fbegin NULL: one window,
- * identity).  d_tiles: [n_tiles][3] int32 (v, begin, count).  All three plan arrays NULL:
- * identity plan over n_ent pixels, i.e. the pack [P][F][hw] -> pm.
+ * identity).  All three plan arrays NULL: identity plan over n_ent pixels, i.e. the pack
+ * [P][F][hw] -> pm.
  * mask: DS_MASK_PLANE -> mask[dst] = 1 ([H*W] plane); DS_MASK_FULL -> a pixel-major
  * panorama that receives 1 in every written atom. */
 int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payloads, int Q,
-                        void* mask, int mask_mode, const int32_t* d_tiles, int n_tiles,
-                        const int32_t* d_ent_k, const int32_t* d_ent_dst, int n_ent,
+                        void* mask, int mask_mode, const int32_t* d_view_ptr,
+                        const int32_t* d_ent_src, const int32_t* d_ent_dst, int n_ent,
                         const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
                         int views_per_fwin, int job_begin, int job_count,
                         int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
 
 /* Ordered sequence of set_view_tensor_bilinear calls (panorama_tensor_utils.py:98-152; ring
- * twin ring_panorama_tensor_utils.py:107-166).  Row r of tile t is panorama pixel
- * d_row_dst[r], owned by view v_t, with CSR entries [d_row_ptr[r], d_row_ptr[r+1]) of
- * (view pixel d_ent_k, weight d_ent_w) in index_add_ order (tap-major, k ascending):
+ * twin ring_panorama_tensor_utils.py:107-166).  Row r is panorama pixel d_row_dst[r], owned
+ * by one view, with CSR entries [d_row_ptr[r], d_row_ptr[r+1]) of (view pixel d_ent_src =
+ * v*hw + k, weight d_ent_w) in index_add_ order (tap-major, k ascending); rows are sorted by
+ * view and d_view_ptr[v] is the first row of view v:
  *   acc = acc + (payload * w); ws = ws + w; pm[...][dst] = acc / ws  if ws > 0
  * Frame windows, sharding and mask as in ds_pm_merge_nearest. */
 int ds_pm_merge_bilinear(void* const* h_pms, const void* const* h_payloads, int Q,
-                         void* mask, int mask_mode, const int32_t* d_tiles, int n_tiles,
+                         void* mask, int mask_mode, const int32_t* d_view_ptr,
                          const int32_t* d_row_dst, const int32_t* d_row_ptr, int n_rows,
-                         const int32_t* d_ent_k, const float* d_ent_w,
+                         const int32_t* d_ent_src, const float* d_ent_w,
                          const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
                          int views_per_fwin, int job_begin, int job_count,
                          int P, int F, int HW, int f_len, int hw, int dtype, void* stream);

@@ -117,19 +117,25 @@ def pm_unpack(pm):
     return np.ascontiguousarray(pm.transpose(2, 1, 0))
 
 
-def pm_merge_nearest(pms, payloads, plan, ftab, fbegin, vpf, f_len, mask=None, mask_mode=0,
+def _pm_view_range(view_ptr, vpf, s, job_begin, job_count):
+    v_lo = min(max(job_begin - s * vpf, 0), vpf)
+    v_hi = min(max(job_begin + job_count - s * vpf, 0), vpf)
+    return int(view_ptr[v_lo]), int(view_ptr[v_hi])
+
+
+def pm_merge_nearest(pms, payloads, plan, ftab, fbegin, vpf, f_len, hw, mask=None, mask_mode=0,
                      job_begin=0, job_count=1 << 30):
-    """Scatter form, CTA by CTA like ds_pm_merge_nearest: pms[q] [HW, F, P] in place."""
-    tiles, ent_k, ent_dst = plan
+    """Scatter form like ds_pm_merge_nearest: pms[q] [HW, F, P] in place."""
+    view_ptr, ent_src, ent_dst = plan
     F = pms[0].shape[1] if pms else mask.shape[1]
     n_fwin = 1 if fbegin is None else len(fbegin)
-    for (v, b, c) in tiles:
-        for s in range(n_fwin):
-            job = s * vpf + v - job_begin
-            if not (0 <= job < job_count):
-                continue
-            fb = 0 if fbegin is None else fbegin[s]
-            k, d = ent_k[b:b + c], ent_dst[b:b + c]
+    for s in range(n_fwin):
+        lo, hi = _pm_view_range(view_ptr, vpf, s, job_begin, job_count)
+        fb = 0 if fbegin is None else fbegin[s] % F
+        for e in range(lo, hi):
+            v, k = divmod(int(ent_src[e]), hw)
+            job, d = s * vpf + v - job_begin, ent_dst[e]
+            assert 0 <= job < min(job_count, len(payloads[0]) if payloads else 1 << 30)
             if mask_mode == 1:
                 mask[d] = 1
             for fo in range(f_len):
@@ -137,40 +143,37 @@ def pm_merge_nearest(pms, payloads, plan, ftab, fbegin, vpf, f_len, mask=None, m
                 if ftab is not None and ftab[f] != s * f_len + fo:
                     continue
                 for q in range(len(pms)):
-                    pms[q][d, f, :] = payloads[q][job][:, fo][:, k].T
+                    pms[q][d, f, :] = payloads[q][job][:, fo, k]
                 if mask_mode == 2:
                     mask[d, f, :] = 1
 
 
-def pm_merge_bilinear(pms, payloads, plan, ftab, fbegin, vpf, f_len, mask=None, mask_mode=0,
+def pm_merge_bilinear(pms, payloads, plan, ftab, fbegin, vpf, f_len, hw, mask=None, mask_mode=0,
                       job_begin=0, job_count=1 << 30):
-    tiles, row_dst, row_ptr, ent_k, ent_w = plan
+    view_ptr, row_dst, row_ptr, ent_src, ent_w = plan
     F = pms[0].shape[1]
     n_fwin = 1 if fbegin is None else len(fbegin)
-    for (v, b, c) in tiles:
-        for s in range(n_fwin):
-            job = s * vpf + v - job_begin
-            if not (0 <= job < job_count):
+    for s in range(n_fwin):
+        lo, hi = _pm_view_range(view_ptr, vpf, s, job_begin, job_count)
+        fb = 0 if fbegin is None else fbegin[s] % F
+        for r in range(lo, hi):
+            e0, e1 = row_ptr[r], row_ptr[r + 1]
+            ws_ = F32(0)
+            for w in ent_w[e0:e1]:
+                ws_ = F32(ws_ + w)
+            if not ws_ > 0:
                 continue
-            fb = 0 if fbegin is None else fbegin[s]
-            for r in range(b, b + c):
-                e0, e1 = row_ptr[r], row_ptr[r + 1]
-                ws_ = F32(0)
-                for w in ent_w[e0:e1]:
-                    ws_ = F32(ws_ + w)
-                if not ws_ > 0:
+            if mask_mode == 1:
+                mask[row_dst[r]] = 1
+            for fo in range(f_len):
+                f = (fb + fo) % F
+                if ftab is not None and ftab[f] != s * f_len + fo:
                     continue
-                if mask_mode == 1:
-                    mask[row_dst[r]] = 1
-                for fo in range(f_len):
-                    f = (fb + fo) % F
-                    if ftab is not None and ftab[f] != s * f_len + fo:
-                        continue
-                    for q in range(len(pms)):
-                        x = payloads[q][job][:, fo]
-                        acc = np.zeros(x.shape[0], F32)
-                        for k, w in zip(ent_k[e0:e1], ent_w[e0:e1]):
-                            acc = acc + x[:, k] * w
-                        pms[q][row_dst[r], f, :] = acc / ws_
-                    if mask_mode == 2:
-                        mask[row_dst[r], f, :] = 1
+                for q in range(len(pms)):
+                    acc = np.zeros(pms[q].shape[2], F32)
+                    for src, w in zip(ent_src[e0:e1], ent_w[e0:e1]):
+                        v, k = divmod(int(src), hw)
+                        acc = acc + payloads[q][s * vpf + v - job_begin][:, fo, k] * w
+                    pms[q][row_dst[r], f, :] = acc / ws_
+                if mask_mode == 2:
+                    mask[row_dst[r], f, :] = 1

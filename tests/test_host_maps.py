@@ -137,7 +137,7 @@ def test_batched_plan_equals_reference_order(small, mode, world):
 def test_pixel_major_plan_equals_plane_major(mode, world):
     """The scatter-form plans of the pixel-major kernels (maps.pm_*_plan) give the same
     panorama as the plane-major plans (pinned to the golden above), with wrapping frame
-    windows and a sharded job list; tiles hold <= 32 entries of one view."""
+    windows and a sharded job list; the lists are sorted by view with a view_ptr offset table."""
     from _emulate import pm_merge_bilinear, pm_merge_nearest, pm_pack, pm_unpack
     H, W, F, h, w, f_len = 16, 32, 6, 6, 10, 4
     views = po.default_sphere_views(3)[:9]
@@ -152,17 +152,17 @@ def test_pixel_major_plan_equals_plane_major(mode, world):
     got = [pm_pack(base), pm_pack(base)]
     gmask = np.zeros((H * W, F, 4), np.float32)
     pm_plan = maps.pm_nearest_plan(vms) if mode == "nearest" else maps.pm_bilinear_plan(vms)
-    assert pm_plan[0][:, 2].max() <= maps.PM_TILE and pm_plan[0][:, 2].min() >= 1
+    assert pm_plan[0][0] == 0 and pm_plan[0][-1] == pm_plan[1].size and np.all(np.diff(pm_plan[0]) >= 0)
     for r in range(world):
         j0, n = shard_range(nj, r, world)
         local = [p[j0:j0 + n] for p in pay]
         if mode == "nearest":
             d, s_ = maps.nearest_merge_plan(vms)
             merge_nearest(want, local, d, s_, ftab, len(views), f_len, h * w, wmask, 2, j0, n)
-            pm_merge_nearest(got, local, pm_plan, ftab, fbs, len(views), f_len, gmask, 2, j0, n)
+            pm_merge_nearest(got, local, pm_plan, ftab, fbs, len(views), f_len, h * w, gmask, 2, j0, n)
         else:
             merge_bilinear(want, local, maps.bilinear_merge_plan(vms), ftab, len(views), f_len, h * w, wmask, 2, j0, n)
-            pm_merge_bilinear(got, local, pm_plan, ftab, fbs, len(views), f_len, gmask, 2, j0, n)
+            pm_merge_bilinear(got, local, pm_plan, ftab, fbs, len(views), f_len, h * w, gmask, 2, j0, n)
     for q in range(2):
         assert np.array_equal(pm_unpack(got[q]), want[q])
     assert np.array_equal(pm_unpack(gmask), wmask)

@@ -1,0 +1,64 @@
+"""Kernel-level autotuning bench for the pixel-major path (run on a B200 through gpurun).
+Times each of the four cfg2 kernels alone (CUDA graph of 20 launches on rotating buffer
+sets, cold L2) for a list of ds_tune knob settings and prints one JSON line per setting."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import WORKLOADS, Workset, default_views, make_runner, timed  # noqa: E402
+from dynamicscaler_b200 import lib  # noqa: E402
+from dynamicscaler_b200.step import PanoramaStepper  # noqa: E402
+
+GATHER_CPS, MERGE_PERSIST, MERGE_CPS = 0, 1, 2
+
+
+def main():
+    wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2_sphere_128x256"]
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    st = PanoramaStepper(wl["H"], wl["W"], wl["F"], device=dev)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    plans = {m: [st.plan_sphere(default_views(i), wl["w"], wl["h"], fov=wl["fov"], mode=m) for i in range(10)]
+             for m in ("bilinear", "nearest")}
+    sets = [Workset(wl, 44, dev, gen, st) for _ in range(4)]
+    combos = [(i % 10, i % 4) for i in range(20)]
+    side = torch.cuda.Stream()
+
+    def t_kernel(kind, mode, iters=200):
+        fns = []
+        for off, s in combos:
+            ws, plan = sets[s], plans[mode][off]
+            if kind == "gather":
+                fns.append(lambda ws=ws, plan=plan: st.gather_all(ws.pano, plan, out=ws.wins))
+            else:
+                fns.append(lambda ws=ws, plan=plan: ws.merge(st, plan))
+        run = make_runner(fns, iters, True, side)
+        run()
+        return timed(run, False) / iters * 1e3
+
+    settings = [
+        {"gather_cps": 0, "persist": 0, "merge_cps": 0},
+        {"gather_cps": 4, "persist": 1, "merge_cps": 0},
+        {"gather_cps": 5, "persist": 1, "merge_cps": 3},
+        {"gather_cps": 6, "persist": 1, "merge_cps": 4},
+        {"gather_cps": 8, "persist": 1, "merge_cps": 5},
+        {"gather_cps": 3, "persist": 1, "merge_cps": 6},
+        {"gather_cps": 2, "persist": 1, "merge_cps": 2},
+    ]
+    for cfg in settings:
+        lib.check(lib.ds_tune(GATHER_CPS, cfg["gather_cps"]))
+        lib.check(lib.ds_tune(MERGE_PERSIST, cfg["persist"]))
+        lib.check(lib.ds_tune(MERGE_CPS, cfg["merge_cps"]))
+        res = dict(cfg)
+        for mode in ("nearest", "bilinear"):
+            for kind in ("gather", "merge"):
+                res[f"{kind}_{mode}_us"] = round(t_kernel(kind, mode), 2)
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()
