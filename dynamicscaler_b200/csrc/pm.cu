@@ -108,9 +108,10 @@ struct PmGatherArgs {
 // [plane*f_len + fo][k] (row stride kPmKT + 16 B: conflict-free).
 // Store: every tile row is 256 contiguous bytes of the window tensor and leaves through one
 // TMA bulk copy (cp.async.bulk shared -> global), issued by one thread per row.
-// FL > 0: f_len known at compile time; FL == 0: runtime f_len.
-template <typename T, int TAPS, int FL>
-__global__ void __launch_bounds__(kBlock)
+// FL > 0: f_len known at compile time; FL == 0: runtime f_len.  MINB: min resident CTAs per SM
+// (register budget; measured best on B200: 8 for the copy-only gather, 4 for the 4-tap one).
+template <typename T, int TAPS, int FL, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
 pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ out,
                  const int32_t* __restrict__ d_idx, const float* __restrict__ d_wt,
                  const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a) {
@@ -169,6 +170,9 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
         v[tp][2] = ldg_atom(pm + static_cast<size_t>(id.z) * a.F + f);
         v[tp][3] = ldg_atom(pm + static_cast<size_t>(id.w) * a.F + f);
       }
+      // keep every tap load in flight before the first use (ptxas otherwise interleaves
+      // loads and FMAs to save registers, serialising the L2 round trips)
+      asm volatile("" ::: "memory");
       T e[4][4];                                  // [pixel j][plane p]
       if (TAPS == 1) {
 #pragma unroll
@@ -683,11 +687,11 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
     const AT* pmp = static_cast<const AT*>(pm);
     ET* op = static_cast<ET*>(out);
     if (taps == 1) {
-      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
-      return pm_launch(pm_gather_kernel<ET, 1, 0>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
     }
-    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
-    return pm_launch(pm_gather_kernel<ET, 4, 0>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
   });
   return DS_OK;
 }

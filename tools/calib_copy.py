@@ -1,37 +1,34 @@
-"""Calibration: what a plain device copy achieves at the byte counts of one step's kernels
-(cold L2, CUDA-graph replay, rotating buffers).  Prints GB/s (read+write) per size."""
+"""Calibration on the GPU box: (1) what a plain device copy achieves at the byte counts of one
+step's kernels, (2) the fixed cost of one kernel node.  20 launches per CUDA graph on rotating
+buffers (cold L2), like bench.py.  Prints one JSON object."""
 import json
+import os
+import sys
+
 import torch
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import make_runner, timed  # noqa: E402
+
 dev = torch.device("cuda:0")
+side = torch.cuda.Stream()
 res = {}
-for mb in (4, 9, 18, 36, 72, 144, 512):
+tiny = torch.zeros(32, device=dev)
+run = make_runner([lambda: tiny.add_(1.0)] * 20, 400, True, side)
+run()
+res["tiny_kernel_node_us"] = round(timed(run, False) / 400 * 1e3, 2)
+for mb in (4, 9, 18, 36, 72, 144):
     n = mb * (1 << 20) // 4
     nset = max(4, (3 * 126) // (2 * mb) + 1)
     a = [torch.randn(n, device=dev) for _ in range(nset)]
     b = [torch.empty(n, device=dev) for _ in range(nset)]
-    gs = []
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        for i in range(nset):
-            b[i].copy_(a[i])
-        torch.cuda.synchronize()
-        for i in range(nset):
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                b[i].copy_(a[i])
-            gs.append(g)
-    for i in range(3 * nset):
-        gs[i % nset].replay()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    iters = 40 * nset
-    s.record()
-    for i in range(iters):
-        gs[i % nset].replay()
-    e.record()
-    torch.cuda.synchronize()
-    us = s.elapsed_time(e) / iters * 1e3
-    res[f"{mb}MiB"] = {"us": round(us, 2), "GBps_rw": round(2 * mb * (1 << 20) / us / 1e3, 1)}
-    del a, b, gs
+    fns = [(lambda i=i: b[i].copy_(a[i])) for i in range(nset)]
+    iters = 20 * nset
+    run = make_runner(fns, iters, True, side)
+    run()
+    us = timed(run, False) / iters * 1e3
+    res[f"copy_{mb}MiB"] = {"us": round(us, 2), "traffic_MB": round(2 * mb * 1.048576, 1),
+                            "GBps_rw": round(2 * mb * (1 << 20) / us / 1e3, 1)}
+    del a, b, fns, run
 print(json.dumps(res))

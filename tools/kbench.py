@@ -42,13 +42,12 @@ def main():
 
     settings = [
         {"gather_cps": 0, "persist": 0, "merge_cps": 0},
-        {"gather_cps": 4, "persist": 1, "merge_cps": 0},
-        {"gather_cps": 5, "persist": 1, "merge_cps": 3},
-        {"gather_cps": 6, "persist": 1, "merge_cps": 4},
-        {"gather_cps": 8, "persist": 1, "merge_cps": 5},
-        {"gather_cps": 3, "persist": 1, "merge_cps": 6},
-        {"gather_cps": 2, "persist": 1, "merge_cps": 2},
+        {"gather_cps": 0, "persist": 0, "merge_cps": 0},
+        {"gather_cps": 6, "persist": 1, "merge_cps": 0},
+        {"gather_cps": 4, "persist": 1, "merge_cps": 4},
     ]
+    if os.environ.get("KBENCH_DEFAULT_ONLY"):
+        settings = settings[:1]
     for cfg in settings:
         lib.check(lib.ds_tune(GATHER_CPS, cfg["gather_cps"]))
         lib.check(lib.ds_tune(MERGE_PERSIST, cfg["persist"]))
