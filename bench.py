@@ -383,8 +383,13 @@ def run_ours(args, wl, wl_name):
                                         "sample": sample, "ms_per_step": sec * 1e3}
         print(json.dumps(line))
     if dist_on:
+        # Leave without tearing NCCL down: destroying a communicator whose collectives were
+        # captured in still-alive CUDA graphs can block forever; the JSON line is out, so exit.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
