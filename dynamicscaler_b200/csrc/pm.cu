@@ -40,6 +40,8 @@ constexpr int kWarps = kBlock / 32;
 static int g_gather_ctas_per_sm = 0;   // 0: occupancy limit
 static int g_merge_persistent = 0;     // 0: one <= 32-entry tile per CTA (hardware CTA scheduling); 1: persistent balanced split
 static int g_merge_ctas_per_sm = 0;    // persistent scheme only; 0: occupancy limit
+static int g_merge_qsplit = 0;         // 1: one payload per CTA (gridDim.z = Q)
+static int g_merge_minb = 0;           // experiment: min blocks of the weighted merge
 
 template <typename T> struct Atom;
 template <> struct Atom<float> {
@@ -243,6 +245,18 @@ template <typename PT> __device__ __forceinline__ PT pm_sel(PT const (&arr)[DS_M
   return r;
 }
 
+// gridDim.z > 1: payload q = blockIdx.z only (one payload per CTA: more, lighter CTAs).
+__device__ __forceinline__ PmMergeArgs pm_split_q(const PmMergeArgs& in) {
+  PmMergeArgs a = in;
+  if (gridDim.z > 1) {
+    a.pm[0] = pm_sel(in.pm, blockIdx.z);
+    a.pay[0] = pm_sel(in.pay, blockIdx.z);
+    a.Q = 1;
+    if (blockIdx.z > 0) a.mask_mode = DS_MASK_NONE;
+  }
+  return a;
+}
+
 struct PmRange {
   int lo, hi;      // this CTA's slice of the entry (nearest) / row (weighted) list
   int s, fb;       // frame window and its first panorama frame
@@ -293,10 +307,11 @@ __device__ __forceinline__ int pm_job_offset(const PmMergeArgs& a, int s, int sr
 // shared tile[q][entry][fo].  Store: f_len consecutive lanes write one full panorama row.
 template <typename T, int FL, int EPL>
 __global__ void __launch_bounds__(kBlock)
-pm_merge_nearest_kernel(PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
+pm_merge_nearest_kernel(const PmMergeArgs a_in, const int32_t* __restrict__ d_view_ptr,
                         const int32_t* __restrict__ d_ent_src, const int32_t* __restrict__ d_ent_dst,
                         const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
+  const PmMergeArgs a = pm_split_q(a_in);
   PmRange rg;
   if (!pm_range(a, d_view_ptr, d_fbegin, rg)) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -394,13 +409,14 @@ pm_merge_nearest_kernel(PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
 //            panorama row per FL consecutive lanes.
 // Entries are processed in chunks of kPmEC so any row length works; acc lives in registers.
 constexpr int kPmEC = 64;
-template <typename T, int FL, int QMAX>
-__global__ void __launch_bounds__(kBlock)
-pm_merge_bilinear_fl_kernel(PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
+template <typename T, int FL, int QMAX, int MINB>
+__global__ void __launch_bounds__(kBlock, MINB)
+pm_merge_bilinear_fl_kernel(const PmMergeArgs a_in, const int32_t* __restrict__ d_view_ptr,
                             const int32_t* __restrict__ d_row_dst, const int32_t* __restrict__ d_row_ptr,
                             const int32_t* __restrict__ d_ent_src, const float* __restrict__ d_ent_w,
                             const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
+  const PmMergeArgs a = pm_split_q(a_in);
   static_assert(kBlock % FL == 0 && (kPmET * FL) % kBlock == 0, "row/lane mapping");
   constexpr int SA = FL | 1;
   constexpr int RPP = kBlock / FL;               // rows per sweep of phase B
@@ -530,6 +546,140 @@ pm_merge_bilinear_fl_kernel(PmMergeArgs a, const int32_t* __restrict__ d_view_pt
   }
 }
 
+// Tiled weighted merge (fast path): the host pads the CSR entry list so that tile t owns
+// exactly entries [t*kPmEC, (t+1)*kPmEC) (d_ent_k < 0 = padding), all of one view, and <= 32
+// whole rows: d_tile[t] = (first row, view, rows, entries).  The entry loads therefore depend
+// on nothing but blockIdx: global dependency depth 2 (entries -> payload) instead of 3, and
+// every loop bound of phase A is a compile-time constant.  d_view_ptr[v] = first tile of view
+// v; d_row_start[r] = first (padded) entry of row r, rows of a tile being contiguous.
+template <typename T, int FL, int QN>
+__global__ void __launch_bounds__(kBlock)
+pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
+                               const int4* __restrict__ d_tile, const int32_t* __restrict__ d_row_dst,
+                               const int32_t* __restrict__ d_row_start, const int32_t* __restrict__ d_ent_k,
+                               const float* __restrict__ d_ent_w, const int32_t* __restrict__ d_ftab,
+                               const int32_t* __restrict__ d_fbegin) {
+  using A = typename Atom<T>::type;
+  static_assert(FL == 16 && kBlock == 256, "lane mapping: 8 warps x 2 frames in phase A, 16 rows x 16 frames in phase B");
+  constexpr int SA = FL + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float4* prod = reinterpret_cast<float4*>(smem_raw);                 // [QN][EC][SA] fp32 products
+  float* s_w = reinterpret_cast<float*>(prod + QN * kPmEC * SA);      // [EC]
+  int32_t* s_rp = reinterpret_cast<int32_t*>(s_w + kPmEC);            // [ET + 1] local entry offsets
+  int32_t* s_dst = s_rp + kPmET + 1;                                  // [ET]
+
+  // ---- which tile / job ----
+  const int s = blockIdx.y;
+  const int v_lo = min(max(a.job_begin - s * a.vpf, 0), a.vpf);
+  const int v_hi = min(max(a.job_begin + a.job_count - s * a.vpf, 0), a.vpf);
+  const int t = __ldg(d_view_ptr + v_lo) + blockIdx.x;
+  if (t >= __ldg(d_view_ptr + v_hi)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e_base = t * kPmEC;
+
+  // ---- level-1 loads: nothing below depends on another global load ----
+  int k[2];
+  float w[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    k[h] = __ldg(d_ent_k + e_base + h * 32 + lane);
+    w[h] = __ldg(d_ent_w + e_base + h * 32 + lane);
+  }
+  const int4 td = __ldg(d_tile + t);
+  const int r0 = td.x, view = td.y, cnt = td.z;
+  const int fb = d_fbegin != nullptr ? __ldg(d_fbegin + s) % a.F : 0;
+  bool liveA[2], liveB;
+  int fB;
+  {
+    const int fo_b = threadIdx.x & (FL - 1);
+    fB = fb + fo_b;
+    fB = fB >= a.F ? fB - a.F : fB;
+    liveB = d_ftab == nullptr || __ldg(d_ftab + fB) == s * FL + fo_b;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int fo = warp + j * kWarps;
+      int f = fb + fo;
+      f = f >= a.F ? f - a.F : f;
+      liveA[j] = d_ftab == nullptr || __ldg(d_ftab + f) == s * FL + fo;
+    }
+  }
+  if (threadIdx.x < cnt) {
+    s_rp[threadIdx.x] = __ldg(d_row_start + r0 + threadIdx.x) - e_base;
+    s_dst[threadIdx.x] = __ldg(d_row_dst + r0 + threadIdx.x);
+  } else if (threadIdx.x == cnt) {
+    s_rp[cnt] = td.w;
+  }
+  if (warp == 0) { s_w[lane] = w[0]; s_w[32 + lane] = w[1]; }
+
+  // ---- phase A: products (level-2 loads) ----
+  const int plane_stride = FL * a.hw;
+  const int job_off = (s * a.vpf + view - a.job_begin) * kPmPlanes * plane_stride;
+  T x[2][QN][2][4];                               // [half][payload][frame j][plane]
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int q = 0; q < QN; ++q)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (k[h] >= 0 && liveA[j]) {
+          const T* __restrict__ src = static_cast<const T*>(a.pay[q]) + job_off + (warp + j * kWarps) * a.hw + k[h];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) x[h][q][j][p] = ldg(src + p * plane_stride);
+        }
+      }
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int q = 0; q < QN; ++q)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (k[h] >= 0 && liveA[j])
+          prod[(q * kPmEC + h * 32 + lane) * SA + warp + j * kWarps] =
+              make_float4(__fmul_rn(Elem<T>::to_f(x[h][q][j][0]), w[h]), __fmul_rn(Elem<T>::to_f(x[h][q][j][1]), w[h]),
+                          __fmul_rn(Elem<T>::to_f(x[h][q][j][2]), w[h]), __fmul_rn(Elem<T>::to_f(x[h][q][j][3]), w[h]));
+  __syncthreads();
+
+  // ---- phase B: ordered accumulation, normalise, full-row stores ----
+  const int fo_b = threadIdx.x & (FL - 1), row_b = threadIdx.x / FL;
+#pragma unroll
+  for (int sw = 0; sw < kPmET / (kBlock / FL); ++sw) {
+    const int i = sw * (kBlock / FL) + row_b;
+    if (i >= cnt) continue;
+    const int lo = s_rp[i], hi = s_rp[i + 1];
+    float ws = 0.f;
+    float acc[QN][4];
+#pragma unroll
+    for (int q = 0; q < QN; ++q)
+#pragma unroll
+      for (int p = 0; p < 4; ++p) acc[q][p] = 0.f;
+    for (int e = lo; e < hi; ++e) {
+      ws = __fadd_rn(ws, s_w[e]);
+#pragma unroll
+      for (int q = 0; q < QN; ++q) {
+        const float4 pr = prod[(q * kPmEC + e) * SA + fo_b];
+        acc[q][0] = __fadd_rn(acc[q][0], pr.x);
+        acc[q][1] = __fadd_rn(acc[q][1], pr.y);
+        acc[q][2] = __fadd_rn(acc[q][2], pr.z);
+        acc[q][3] = __fadd_rn(acc[q][3], pr.w);
+      }
+    }
+    if (!(ws > 0.f)) continue;
+    const int dst = s_dst[i];
+    if (fo_b == 0 && a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
+    if (liveB) {
+      const size_t o = static_cast<size_t>(dst) * a.F + fB;
+#pragma unroll
+      for (int q = 0; q < QN; ++q) {
+        float r[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) r[p] = __fdiv_rn(acc[q][p], ws);
+        static_cast<A*>(a.pm[q])[o] = Atom<T>::pack(r);
+      }
+      if (a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[o] = atom_ones<T>();
+    }
+  }
+}
+
 // Generic (runtime f_len) weighted merge: each lane owns a row and walks its CSR entries
 // (tap-major, k ascending -- index_add_'s order) accumulating
 //   acc = acc + (payload * w);  ws = ws + w;   row = acc / ws     (each op rounded on its own)
@@ -642,7 +792,13 @@ static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* co
 // work items, raising the dynamic shared memory limit when needed.
 // ctas_per_sm: 0 = occupancy limit, > 0 = cap, < 0 = not persistent (one CTA per item).
 template <typename K, typename... Args>
+static int pm_launch_z(K kernel, long long items, int ctas_per_sm, unsigned grid_y, unsigned grid_z, size_t smem, cudaStream_t st, Args... args);
+template <typename K, typename... Args>
 static int pm_launch(K kernel, long long items, int ctas_per_sm, unsigned grid_y, size_t smem, cudaStream_t st, Args... args) {
+  return pm_launch_z(kernel, items, ctas_per_sm, grid_y, 1, smem, st, args...);
+}
+template <typename K, typename... Args>
+static int pm_launch_z(K kernel, long long items, int ctas_per_sm, unsigned grid_y, unsigned grid_z, size_t smem, cudaStream_t st, Args... args) {
   DS_REQUIRE(smem <= 200 * 1024, DS_ERR_DIM);
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   long long gx = items;
@@ -656,7 +812,7 @@ static int pm_launch(K kernel, long long items, int ctas_per_sm, unsigned grid_y
   }
   if (gx < 1) gx = 1;
   DS_REQUIRE(gx < (1ll << 31), DS_ERR_DIM);
-  kernel<<<dim3(static_cast<unsigned>(gx), grid_y), kBlock, smem, st>>>(args...);
+  kernel<<<dim3(static_cast<unsigned>(gx), grid_y, grid_z), kBlock, smem, st>>>(args...);
   return check_launch();
 }
 
@@ -717,9 +873,10 @@ extern "C" int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payl
   if (!g_merge_persistent) a.per_cta = 32;
   DS_DISPATCH_DTYPE(dtype, {
     using AT = typename Atom<ET>::type;
-    const size_t smem1 = static_cast<size_t>(Q > 0 ? Q : 1) * 32 * (f_len | 1) * sizeof(AT) + 32 * sizeof(int32_t);
+    const bool split = g_merge_qsplit && Q > 1;
+    const size_t smem1 = static_cast<size_t>(Q > 0 && !split ? Q : 1) * 32 * (f_len | 1) * sizeof(AT) + 32 * sizeof(int32_t);
     if (!g_merge_persistent) {
-      if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16, 1>, items, cps, n_fwin, smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+      if (f_len == 16) return pm_launch_z(pm_merge_nearest_kernel<ET, 16, 1>, items, cps, n_fwin, split ? Q : 1, smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
       return pm_launch(pm_merge_nearest_kernel<ET, 0, 1>, items, cps, n_fwin, smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
     }
     if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16, 2>, items, cps, n_fwin, 2 * smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
@@ -748,10 +905,13 @@ extern "C" int ds_pm_merge_bilinear(void* const* h_pms, const void* const* h_pay
   if (!g_merge_persistent) a.per_cta = kPmET;
   DS_DISPATCH_DTYPE(dtype, {
     if (f_len == 16) {
-      const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) +
+      const bool split = g_merge_qsplit && Q > 1;
+      const size_t smem = static_cast<size_t>(Q > 0 && !split ? Q : 1) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) +
                          (2 * kPmET + 1) * sizeof(int32_t);
-      if (Q <= 2) return pm_launch(pm_merge_bilinear_fl_kernel<ET, 16, 2>, items, cps, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin);
-      return pm_launch(pm_merge_bilinear_fl_kernel<ET, 16, 4>, items, cps, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin);
+#define DS_B(QM, MB) return pm_launch_z(pm_merge_bilinear_fl_kernel<ET, 16, QM, MB>, items, cps, n_fwin, split ? Q : 1, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin)
+      if (split) { switch (g_merge_minb) { case 5: DS_B(1, 5); case 6: DS_B(1, 6); case 8: DS_B(1, 8); default: DS_B(1, 4); } }
+      if (Q <= 2) { switch (g_merge_minb) { case 3: DS_B(2, 3); case 5: DS_B(2, 5); case 6: DS_B(2, 6); default: DS_B(2, 4); } }
+      DS_B(4, 2);
     }
     const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(typename Atom<ET>::type) + kPmET * sizeof(int32_t);
     return pm_launch(pm_merge_bilinear_kernel<ET>, items, cps, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin);
@@ -764,6 +924,36 @@ extern "C" int ds_tune(int knob, int value) {
     case DS_TUNE_PM_GATHER_CTAS_PER_SM: ds::g_gather_ctas_per_sm = value; return DS_OK;
     case DS_TUNE_PM_MERGE_PERSISTENT: ds::g_merge_persistent = value; return DS_OK;
     case DS_TUNE_PM_MERGE_CTAS_PER_SM: ds::g_merge_ctas_per_sm = value; return DS_OK;
+    case DS_TUNE_PM_MERGE_QSPLIT: ds::g_merge_qsplit = value; return DS_OK;
+    case 100: ds::g_merge_minb = value; return DS_OK;   /* experiment knob */
     default: return DS_ERR_DIM;
   }
+}
+
+extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const* h_payloads, int Q,
+                                          void* mask, int mask_mode, const int32_t* d_view_ptr,
+                                          const int32_t* d_tile, int n_tiles, const int32_t* d_row_dst,
+                                          const int32_t* d_row_start, int n_rows, const int32_t* d_ent_k,
+                                          const float* d_ent_w, const int32_t* d_ftab, const int32_t* d_fbegin,
+                                          int n_fwin, int views_per_fwin, int job_begin, int job_count,
+                                          int P, int F, int HW, int f_len, int hw, int dtype, void* stream) {
+  using namespace ds;
+  PmMergeArgs a;
+  int rc = pm_fill_merge_args(a, h_pms, h_payloads, Q, mask, mask_mode, n_rows, d_ftab, d_fbegin, n_fwin,
+                              views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw);
+  if (rc != DS_OK) return rc;
+  DS_REQUIRE(d_view_ptr != nullptr && d_tile != nullptr && d_row_dst != nullptr && d_row_start != nullptr &&
+             d_ent_k != nullptr && d_ent_w != nullptr, DS_ERR_NULL);
+  DS_REQUIRE(pm_aligned16(d_tile), DS_ERR_ALIGN);
+  const int4* d_tile4 = reinterpret_cast<const int4*>(d_tile);
+  DS_REQUIRE(f_len == 16 && (Q == 1 || Q == 2 || Q == 4) && n_tiles >= 0, DS_ERR_DIM);   // other shapes: ds_pm_merge_bilinear
+  if (n_tiles == 0) return DS_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
+  DS_DISPATCH_DTYPE(dtype, {
+    if (Q == 1) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+    if (Q == 2) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+    return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+  });
+  return DS_OK;
 }

@@ -285,6 +285,46 @@ def pm_bilinear_plan(vmaps):
             ent_src[ent_index].astype(np.int32), np.ascontiguousarray(ent_w[ent_index], dtype=F32))
 
 
+PM_TILE_ROWS, PM_TILE_ENTRIES = 32, 64        # csrc/pm.cu kPmET, kPmEC
+
+
+def pm_bilinear_tiled_plan(vmaps):
+    """``pm_bilinear_plan`` cut into tiles for ds_pm_merge_bilinear_tiled: tile t owns the
+    padded entries [64t, 64t+64) (ent_k = -1, w = 0 padding; k relative to the tile's view) and
+    at most 32 whole rows of ONE view.  Returns None when a row has more than 64 entries
+    (tiny panoramas; the untiled kernel handles those), else
+    (view_ptr[n_views+1] over tiles, tile[n_tiles, 4] = (first row, view, rows, entries),
+     row_dst[T], row_start[T] into the padded arrays, ent_k[64*n_tiles], ent_w[64*n_tiles])."""
+    view_ptr_rows, row_dst, row_ptr, ent_src, ent_w = pm_bilinear_plan(vmaps)
+    hw = vmaps[0].hw
+    n_rows = row_dst.size
+    counts = np.diff(row_ptr.astype(np.int64))
+    if n_rows and counts.max() > PM_TILE_ENTRIES:
+        return None
+    ce = np.concatenate([[0], np.cumsum(counts)])                  # entries before row r
+    tiles, view_ptr = [], [0]
+    for v in range(len(vmaps)):
+        i, end = int(view_ptr_rows[v]), int(view_ptr_rows[v + 1])
+        while i < end:
+            # furthest row boundary within 64 entries, 32 rows and the view
+            j = int(np.searchsorted(ce, ce[i] + PM_TILE_ENTRIES, side="right")) - 1
+            j = min(j, i + PM_TILE_ROWS, end)
+            tiles.append((i, v, j - i, int(ce[j] - ce[i])))
+            i = j
+        view_ptr.append(len(tiles))
+    n_tiles = len(tiles)
+    ent_k = np.full(n_tiles * PM_TILE_ENTRIES, -1, np.int32)
+    ent_wp = np.zeros(n_tiles * PM_TILE_ENTRIES, F32)
+    row_start = np.zeros(n_rows, np.int32)
+    for t, (r0, v, nr, ne) in enumerate(tiles):
+        e0, base = int(ce[r0]), t * PM_TILE_ENTRIES
+        ent_k[base:base + ne] = ent_src[e0:e0 + ne] - v * hw
+        ent_wp[base:base + ne] = ent_w[e0:e0 + ne]
+        row_start[r0:r0 + nr] = base + (ce[r0:r0 + nr] - e0)
+    tile = np.asarray(tiles, np.int32).reshape(n_tiles, 4)
+    return np.asarray(view_ptr, np.int32), tile, row_dst, row_start, ent_k, ent_wp
+
+
 def frame_table(F, frame_begins, f_len):
     """ftab[f] = s*f_len + fo of the LAST frame window s (in order) containing panorama
     frame f = (frame_begins[s] + fo) mod F, else -1 (shift_window_utils.py:181 composed
@@ -298,6 +338,12 @@ def frame_table(F, frame_begins, f_len):
 
 # -------------------------------------------------------------- device residency ----
 _DEVICE = _LRU(8192)
+_HOST = _LRU(1024)
+
+
+def host_cached(key, make):
+    """Build-once cache for host-side plans whose builder may return None (= not applicable)."""
+    return _HOST.get_or(key, make)
 
 
 def on_device(key, device, make_numpy):
@@ -319,3 +365,4 @@ def clear_caches():
     with _LOCK:
         _VIEWS.clear()
         _DEVICE.clear()
+        _HOST.clear()

@@ -245,6 +245,10 @@ class PanoramaStepper:
                 plan.pm_merge = maps.on_device(("pm_nplan", vkey), self.device, lambda: maps.pm_nearest_plan(vms))
             else:
                 plan.pm_merge = maps.on_device(("pm_bplan", vkey), self.device, lambda: maps.pm_bilinear_plan(vms))
+                if plan.f_len == 16 and "pm_tiled" not in plan.extra:
+                    host = maps.host_cached(("pm_btiled", vkey), lambda: maps.pm_bilinear_tiled_plan(vms))
+                    plan.extra["pm_tiled"] = None if host is None else maps.on_device(
+                        ("pm_btiled", vkey), self.device, lambda: host)
         return plan.pm_merge
 
     def _pm_gather(self, pm, plan, out, j0, nj):
@@ -272,6 +276,14 @@ class PanoramaStepper:
                                                   _lib.ptr(mask), mask_mode, view_ptr.data_ptr(),
                                                   ent_src.data_ptr(), ent_dst.data_ptr(), ent_src.numel(), *common),
                           "ds_pm_merge_nearest")
+            elif plan.extra.get("pm_tiled") is not None and len(pms) in (1, 2, 4):
+                view_ptr, tile, row_dst, row_start, ent_k, ent_w = plan.extra["pm_tiled"]
+                lib.check(lib.ds_pm_merge_bilinear_tiled(_lib.ptr_array(pms), _lib.ptr_array(payloads), len(pms),
+                                                         _lib.ptr(mask), mask_mode, view_ptr.data_ptr(),
+                                                         tile.data_ptr(), tile.shape[0], row_dst.data_ptr(),
+                                                         row_start.data_ptr(), row_dst.numel(), ent_k.data_ptr(),
+                                                         ent_w.data_ptr(), *common),
+                          "ds_pm_merge_bilinear_tiled")
             else:
                 view_ptr, row_dst, row_ptr, ent_src, ent_w = mp
                 lib.check(lib.ds_pm_merge_bilinear(_lib.ptr_array(pms), _lib.ptr_array(payloads), len(pms),

@@ -54,7 +54,8 @@ enum { DS_MASK_NONE = 0, DS_MASK_PLANE = 1 /* one [H*W] plane */, DS_MASK_FULL =
 enum {
   DS_TUNE_PM_GATHER_CTAS_PER_SM = 0,   /* persistent gather: CTAs per SM, 0 = occupancy limit */
   DS_TUNE_PM_MERGE_PERSISTENT = 1,     /* 0: one <= 32-entry tile per CTA; 1: persistent even split */
-  DS_TUNE_PM_MERGE_CTAS_PER_SM = 2     /* persistent merges: CTAs per SM, 0 = occupancy limit */
+  DS_TUNE_PM_MERGE_CTAS_PER_SM = 2,    /* persistent merges: CTAs per SM, 0 = occupancy limit */
+  DS_TUNE_PM_MERGE_QSPLIT = 3          /* 1: one payload per CTA (gridDim.z = Q) */
 };
 int ds_tune(int knob, int value);
 
@@ -199,6 +200,21 @@ int ds_pm_merge_bilinear(void* const* h_pms, const void* const* h_payloads, int 
                          const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
                          int views_per_fwin, int job_begin, int job_count,
                          int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
+
+/* ds_pm_merge_bilinear on a TILED plan (f_len == 16, Q in {1, 2, 4}; fast path).  The host pads
+ * the CSR entry list so that tile t owns entries [64t, 64t + 64) (d_ent_k < 0 = padding; all of
+ * one view, k relative to that view) and at most 32 whole rows:
+ * d_tile[t] = (first row, view, rows, entries) as 4 x int32 (16-byte aligned);
+ * d_view_ptr[v] = first tile of view v; d_row_start[r] = first padded entry of row r (the rows
+ * of a tile are contiguous in the padded arrays).  Same arithmetic and result as
+ * ds_pm_merge_bilinear. */
+int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const* h_payloads, int Q,
+                               void* mask, int mask_mode, const int32_t* d_view_ptr,
+                               const int32_t* d_tile, int n_tiles, const int32_t* d_row_dst,
+                               const int32_t* d_row_start, int n_rows, const int32_t* d_ent_k,
+                               const float* d_ent_w, const int32_t* d_ftab, const int32_t* d_fbegin,
+                               int n_fwin, int views_per_fwin, int job_begin, int job_count,
+                               int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
 
 /* ------------------------------------------------------------------ elementwise ---- */
 

@@ -177,3 +177,42 @@ def pm_merge_bilinear(pms, payloads, plan, ftab, fbegin, vpf, f_len, hw, mask=No
                     pms[q][row_dst[r], f, :] = acc / ws_
                 if mask_mode == 2:
                     mask[row_dst[r], f, :] = 1
+
+
+def pm_merge_bilinear_tiled(pms, payloads, plan, ftab, fbegin, vpf, f_len, hw, mask=None, mask_mode=0,
+                            job_begin=0, job_count=1 << 30):
+    """ds_pm_merge_bilinear_tiled, tile by tile (padding entries have ent_k < 0)."""
+    view_ptr, tile, row_dst, row_start, ent_k, ent_w = plan
+    F = pms[0].shape[1]
+    n_fwin = 1 if fbegin is None else len(fbegin)
+    for s in range(n_fwin):
+        t_lo, t_hi = _pm_view_range(view_ptr, vpf, s, job_begin, job_count)
+        fb = 0 if fbegin is None else fbegin[s] % F
+        for t in range(t_lo, t_hi):
+            r0, v, nr, ne = (int(x) for x in tile[t])
+            base = t * 64
+            assert nr <= 32 and ne <= 64 and np.all(ent_k[base:base + ne] >= 0) and np.all(ent_k[base + ne:base + 64] < 0)
+            job = s * vpf + v - job_begin
+            starts = [int(row_start[r0 + i]) for i in range(nr)] + [base + ne]
+            for i in range(nr):
+                e0, e1 = starts[i], starts[i + 1]
+                assert base <= e0 <= e1 <= base + ne
+                ws_ = F32(0)
+                for w in ent_w[e0:e1]:
+                    ws_ = F32(ws_ + w)
+                if not ws_ > 0:
+                    continue
+                d = row_dst[r0 + i]
+                if mask_mode == 1:
+                    mask[d] = 1
+                for fo in range(f_len):
+                    f = (fb + fo) % F
+                    if ftab is not None and ftab[f] != s * f_len + fo:
+                        continue
+                    for q in range(len(pms)):
+                        acc = np.zeros(pms[q].shape[2], F32)
+                        for k, w in zip(ent_k[e0:e1], ent_w[e0:e1]):
+                            acc = acc + payloads[q][job][:, fo, int(k)] * w
+                        pms[q][d, f, :] = acc / ws_
+                    if mask_mode == 2:
+                        mask[d, f, :] = 1

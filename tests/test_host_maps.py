@@ -132,13 +132,13 @@ def test_batched_plan_equals_reference_order(small, mode, world):
     assert np.array_equal(weight.reshape(1, 16, 32), small[f"step/batched_{mode}/mask"])
 
 
-@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+@pytest.mark.parametrize("mode", ["nearest", "bilinear", "bilinear_tiled"])
 @pytest.mark.parametrize("world", [1, 2])
 def test_pixel_major_plan_equals_plane_major(mode, world):
     """The scatter-form plans of the pixel-major kernels (maps.pm_*_plan) give the same
     panorama as the plane-major plans (pinned to the golden above), with wrapping frame
     windows and a sharded job list; the lists are sorted by view with a view_ptr offset table."""
-    from _emulate import pm_merge_bilinear, pm_merge_nearest, pm_pack, pm_unpack
+    from _emulate import pm_merge_bilinear, pm_merge_bilinear_tiled, pm_merge_nearest, pm_pack, pm_unpack
     H, W, F, h, w, f_len = 16, 32, 6, 6, 10, 4
     views = po.default_sphere_views(3)[:9]
     fbs = [0, 2, 4]                                                    # last window wraps: frames 4,5,0,1
@@ -151,8 +151,10 @@ def test_pixel_major_plan_equals_plane_major(mode, world):
     wmask = np.zeros((4, F, H * W), np.float32)
     got = [pm_pack(base), pm_pack(base)]
     gmask = np.zeros((H * W, F, 4), np.float32)
-    pm_plan = maps.pm_nearest_plan(vms) if mode == "nearest" else maps.pm_bilinear_plan(vms)
-    assert pm_plan[0][0] == 0 and pm_plan[0][-1] == pm_plan[1].size and np.all(np.diff(pm_plan[0]) >= 0)
+    pm_plan = {"nearest": maps.pm_nearest_plan, "bilinear": maps.pm_bilinear_plan,
+               "bilinear_tiled": maps.pm_bilinear_tiled_plan}[mode](vms)
+    assert pm_plan is not None
+    assert pm_plan[0][-1] == len(pm_plan[1]) and np.all(np.diff(pm_plan[0]) >= 0)
     for r in range(world):
         j0, n = shard_range(nj, r, world)
         local = [p[j0:j0 + n] for p in pay]
@@ -162,7 +164,8 @@ def test_pixel_major_plan_equals_plane_major(mode, world):
             pm_merge_nearest(got, local, pm_plan, ftab, fbs, len(views), f_len, h * w, gmask, 2, j0, n)
         else:
             merge_bilinear(want, local, maps.bilinear_merge_plan(vms), ftab, len(views), f_len, h * w, wmask, 2, j0, n)
-            pm_merge_bilinear(got, local, pm_plan, ftab, fbs, len(views), f_len, h * w, gmask, 2, j0, n)
+            emu = pm_merge_bilinear if mode == "bilinear" else pm_merge_bilinear_tiled
+            emu(got, local, pm_plan, ftab, fbs, len(views), f_len, h * w, gmask, 2, j0, n)
     for q in range(2):
         assert np.array_equal(pm_unpack(got[q]), want[q])
     assert np.array_equal(pm_unpack(gmask), wmask)

@@ -40,18 +40,15 @@ def main():
         run()
         return timed(run, False) / iters * 1e3
 
-    settings = [
-        {"gather_cps": 0, "persist": 0, "merge_cps": 0},
-        {"gather_cps": 0, "persist": 0, "merge_cps": 0},
-        {"gather_cps": 6, "persist": 1, "merge_cps": 0},
-        {"gather_cps": 4, "persist": 1, "merge_cps": 4},
-    ]
+    settings = [{"gather_cps": 0, "persist": 0, "merge_cps": 0, "qsplit": 0, "minb": 0}] * 2
     if os.environ.get("KBENCH_DEFAULT_ONLY"):
         settings = settings[:1]
     for cfg in settings:
         lib.check(lib.ds_tune(GATHER_CPS, cfg["gather_cps"]))
         lib.check(lib.ds_tune(MERGE_PERSIST, cfg["persist"]))
         lib.check(lib.ds_tune(MERGE_CPS, cfg["merge_cps"]))
+        lib.check(lib.ds_tune(3, cfg.get("qsplit", 0)))
+        lib.check(lib.ds_tune(100, cfg.get("minb", 0)))
         res = dict(cfg)
         for mode in ("nearest", "bilinear"):
             for kind in ("gather", "merge"):
