@@ -29,17 +29,49 @@ import numpy as np
 import torch
 
 WORKLOADS = {
-    # name: (C, F, H, W, view_w, view_h, fov)
-    "cfg2_sphere_128x256": dict(C=4, F=16, H=128, W=256, w=64, h=40, fov=120, views=44),
+    # BASELINE.json configs[1] -- the headline: T2V sphere panorama, 44 views/step
+    "cfg2_sphere_128x256": dict(kind="sphere", C=4, F=16, f_len=16, H=128, W=256, w=64, h=40, fov=120),
+    # north-star shape (configs[2] without the UNet)
+    "cfg3_sphere_256x512": dict(kind="sphere", C=4, F=16, f_len=16, H=256, W=512, w=64, h=40, fov=120),
+    # configs[3]: 64-frame panorama, 13 wrapping frame windows x 44 views = 572 jobs/step
+    "cfg4_sphere_f64": dict(kind="sphere", C=4, F=64, f_len=16, H=128, W=256, w=64, h=40, fov=120, frame_ring=True),
+    # configs[0] / configs[4]: planar ring shift windows
+    "cfg1_ring_64x128": dict(kind="ring", C=4, F=16, f_len=16, H=64, W=128, w=64, h=40, grid="stride8"),
+    "cfg5_ring_512x1024": dict(kind="ring", C=4, F=16, f_len=16, H=512, W=1024, w=64, h=40, grid="16x16"),
 }
 L2_BYTES = 126 * 1024 * 1024
 
 
 def default_views(i):
-    thetas = [360 * t // 6 for t in range(6)]
-    table = [(90, [0]), (-90, [0])] + [(p, thetas) for p in (75, -75, 60, -60, 45, -45, 0)]
-    off = (i % 10) * 12
-    return [(phi, th + off) for phi, ths in table for th in ths]
+    from dynamicscaler_b200.geometry import sphere_views
+    return sphere_views(i)
+
+
+def n_phases(wl):
+    return 10 if wl["kind"] == "sphere" else 16
+
+
+def modes_of(wl):
+    return ("bilinear", "nearest") if wl["kind"] == "sphere" else ("ring",)
+
+
+def ring_windows_of(wl, i):
+    """Planar windows of step i (latent units), reference loop order."""
+    from dynamicscaler_b200.geometry import ring_windows
+    if wl["grid"] == "stride8":      # SURVEY §8d config 1: 16 x 8 windows, stride 8, per-step offset (4, 1)
+        ow, oh = (i % 16) * 4, (i % 16) * 1
+        return [(ow + 8 * a, oh + 8 * b) for a in range(16) for b in range(8)]
+    return ring_windows(i, 16, 16, wl["W"] * 8, wl["H"] * 8)
+
+
+def make_plan(st, wl, mode, i):
+    if wl["kind"] == "ring":
+        return st.plan_ring(ring_windows_of(wl, i), wl["w"], wl["h"])
+    kw = {}
+    if wl.get("frame_ring"):
+        from dynamicscaler_b200.geometry import frame_windows
+        kw = dict(frame_begins=frame_windows(i, frames=wl["f_len"], total_f=wl["F"]), frames=wl["f_len"])
+    return st.plan_sphere(default_views(i), wl["w"], wl["h"], fov=wl["fov"], mode=mode, **kw)
 
 
 def peaks():
@@ -85,23 +117,31 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------ reference arm ----
 def cpu_step_time(wl, mode, reps):
-    """Times oracle/torch_port.sphere_step (the reference's per-call torch op sequence) on
-    the host cores.  Returns (seconds per step, cores, sample description)."""
+    """Times oracle/torch_port.{sphere,ring}_step (the reference's per-call torch op sequence)
+    on the host cores.  Returns (seconds per step, cores, sample description, windows/step)."""
     from oracle import torch_port as tp
+    if wl.get("frame_ring"):
+        return None                                    # no CPU port of the frame-ring composition
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(0)
     shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
-    vshape = (1, wl["C"], wl["F"], wl["h"], wl["w"])
+    vshape = (1, wl["C"], wl["f_len"], wl["h"], wl["w"])
+    n_win = len(default_views(0)) if wl["kind"] == "sphere" else len(ring_windows_of(wl, 0))
     lat = torch.randn(shape, generator=g)
-    xp = [torch.randn(vshape, generator=g) for _ in range(wl["views"])]
-    x0 = [torch.randn(vshape, generator=g) for _ in range(wl["views"])]
+    xp = [torch.randn(vshape, generator=g) for _ in range(n_win)]
+    x0 = [torch.randn(vshape, generator=g) for _ in range(n_win)]
     ts = []
     for i in range(reps + 1):
         t = time.perf_counter()
-        tp.sphere_step(lat, torch.zeros_like(lat), default_views(i), xp, x0, fov=wl["fov"], width=wl["w"],
-                       height=wl["h"], mode=mode)
+        if wl["kind"] == "sphere":
+            tp.sphere_step(lat, torch.zeros_like(lat), default_views(i), xp, x0, fov=wl["fov"], width=wl["w"],
+                           height=wl["h"], mode=mode)
+        else:
+            tp.ring_step(lat, torch.zeros_like(lat), [(l, t_, 0) for l, t_ in ring_windows_of(wl, i)], xp, x0,
+                         w=wl["w"], h=wl["h"])
         ts.append(time.perf_counter() - t)
-    return statistics.mean(ts[1:]), torch.get_num_threads(), f"{reps} full steps ({wl['views']} windows each) after 1 warm-up"
+    return (statistics.mean(ts[1:]), torch.get_num_threads(),
+            f"{reps} full steps ({n_win} windows each) after 1 warm-up", n_win)
 
 
 def run_reference(args, wl, wl_name):
@@ -109,14 +149,18 @@ def run_reference(args, wl, wl_name):
     if rank != 0:
         return
     reps = max(1, min(args.steps, 3 if args.mode == "bilinear" else 20))
-    sec, cores, sample = cpu_step_time(wl, args.mode, reps)
-    value = wl["views"] / sec
+    res = cpu_step_time(wl, args.mode, reps)
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": f"no CPU port of workload {wl_name}"}))
+        return
+    sec, cores, sample, n_win = res
+    value = n_win / sec
     print(json.dumps({
         "impl": "reference", "metric": "panorama denoise-step window-blends/sec", "value": value, "unit": "blends/s",
         "n_gpus": args.gpus, "steps": reps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl_name, "mode": args.mode, "latent": [1, wl["C"], wl["F"], wl["H"], wl["W"]],
-                   "windows_per_step": wl["views"], "window": [wl["h"], wl["w"]]},
+                   "windows_per_step": n_win, "window": [wl["h"], wl["w"]]},
         "cpu_baseline": {"value": value, "unit": "blends/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "blends/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -129,10 +173,13 @@ class Workset:
 
     def __init__(self, wl, n_local, dev, gen, st=None):
         shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
-        vshape = (n_local, 1, wl["C"], wl["F"], wl["h"], wl["w"])
+        vshape = (n_local, 1, wl["C"], wl["f_len"], wl["h"], wl["w"])
         self.lat = torch.randn(shape, device=dev, generator=gen)
         self.den = torch.zeros(shape, device=dev)
-        self.mask = torch.zeros(1, wl["H"], wl["W"], device=dev)
+        # T2V sphere: [1,H,W] mask plane (t2v_sphere_panorama_pipeline.py:159); frame ring (I2V) and the
+        # planar ring loops: latent-shaped mask (i2v_sphere_panorama_pipeline.py:220,810)
+        plane_mask = wl["kind"] == "sphere" and not wl.get("frame_ring")
+        self.mask = torch.zeros((1, wl["H"], wl["W"]) if plane_mask else shape, device=dev)
         self.wins = torch.empty(vshape, device=dev)
         self.x_prev = torch.randn(vshape, device=dev, generator=gen)
         self.x0 = torch.randn(vshape, device=dev, generator=gen)
@@ -216,14 +263,17 @@ def run_ours(args, wl, wl_name):
     sampler.start()
     st = PanoramaStepper(wl["H"], wl["W"], wl["F"], device=dev, rank=rank, world=world)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    plans = {m: [st.plan_sphere(default_views(i), wl["w"], wl["h"], fov=wl["fov"], mode=m) for i in range(10)]
-             for m in ("bilinear", "nearest")}
-    n_local = st.local_jobs(plans["nearest"][0])[1]
-    st_pm = st if args.layout == "pm" else None
+    modes, NP = modes_of(wl), n_phases(wl)
+    if args.mode not in modes:
+        args.mode = modes[0]
+    plans = {m: [make_plan(st, wl, m, i) for i in range(NP)] for m in modes}
+    n_local = st.local_jobs(plans[modes[0]][0])[1]
+    n_win = plans[modes[0]][0].n_jobs
+    st_pm = st if (args.layout == "pm" and wl["kind"] == "sphere") else None
     one = Workset(wl, n_local, dev, gen, st_pm)
-    n_sets = max(4, -(-3 * L2_BYTES // one.nbytes()))    # aggregate footprint >= 3x L2
+    n_sets = max(2, min(4, -(-3 * L2_BYTES // one.nbytes())))   # aggregate footprint >= 3x L2
     sets = [one] + [Workset(wl, n_local, dev, gen, st_pm) for _ in range(n_sets - 1)]
-    combos = [(i % 10, i % n_sets) for i in range(10 * n_sets // np.gcd(10, n_sets))]
+    combos = [(i % NP, i % n_sets) for i in range(NP * n_sets // np.gcd(NP, n_sets))]
 
     def make_step(mode, off, s):
         ws, plan = sets[s], plans[mode][off]
@@ -243,7 +293,7 @@ def run_ours(args, wl, wl_name):
 
     # warm-up outside graphs (module load, NCCL communicator setup)
     side = torch.cuda.Stream()
-    for mode in ("bilinear", "nearest"):
+    for mode in modes:
         for c in combos[:3]:
             make_step(mode, *c)()
     torch.cuda.synchronize()
@@ -261,7 +311,7 @@ def run_ours(args, wl, wl_name):
 
     results = {}
     K, Wm = args.steps, max(args.warmup, 3)
-    for mode in ("bilinear", "nearest"):
+    for mode in modes:
         launches_before = lib.launches
         make_step(mode, *combos[0])()                       # count this arm's own kernel launches per step
         launches_per_step = lib.launches - launches_before
@@ -305,7 +355,7 @@ def run_ours(args, wl, wl_name):
     e2e_steps = max(3, min(K, 30))
 
     def e2e_step(i):
-        plan = plans[mode][i % 10]
+        plan = plans[mode][i % NP]
         up = torch.cuda.Event()
         with torch.cuda.stream(copy_stream):               # this step's inputs: pinned host -> device
             ws.x_prev.copy_(h_xp, non_blocking=True)
@@ -337,7 +387,6 @@ def run_ours(args, wl, wl_name):
 
     if rank == 0:
         head = results[args.mode]
-        n_win = wl["views"]
         value = n_win / (head["ms_per_step"] * 1e-3)
         peak, peak_src = peaks()
         line = {
@@ -348,8 +397,8 @@ def run_ours(args, wl, wl_name):
                        "windows_per_step": n_win, "window": [wl["h"], wl["w"]], "payloads": 2,
                        "l2_policy": f"inputs larger than L2: {n_sets} rotating buffer sets, {n_sets * one.nbytes() / 2**20:.0f} MiB",
                        "cuda_graph": head["graph"], "steps_per_graph": len(combos) if head["graph"] else 0,
-                       "layout": "resident pixel-major [H*W][F][4] (csrc/pm.cu)" if args.layout == "pm"
-                                 else "reference [B,C,F,H,W] (csrc/sphere.cu)",
+                       "layout": "resident pixel-major [H*W][F][4] (csrc/pm.cu)" if st_pm is not None
+                                 else "reference [B,C,F,H,W] (csrc/sphere.cu, csrc/ring.cu)",
                        "maps": "precomputed on host (static geometry), cached on device",
                        "sharding": "windows split over ranks, 1 NCCL all-reduce/step" if dist_on else "none"},
             "steps_per_s": 1e3 / head["ms_per_step"],
@@ -377,8 +426,9 @@ def run_ours(args, wl, wl_name):
                         for m in results},
             }
             reps = 2 if args.mode == "bilinear" else 10
-            if not args.no_cpu:
-                sec, cores, sample = cpu_step_time(wl, args.mode, reps)
+            cpu = None if args.no_cpu else cpu_step_time(wl, args.mode, reps)
+            if cpu is not None:
+                sec, cores, sample, _ = cpu
                 line["cpu_baseline"] = {"value": n_win / sec, "unit": "blends/s", "cores": cores, "kind": "port",
                                         "sample": sample, "ms_per_step": sec * 1e3}
         print(json.dumps(line))
@@ -398,7 +448,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bilinear", choices=["bilinear", "nearest"])
+    ap.add_argument("--mode", default="bilinear", choices=["bilinear", "nearest", "ring"],
+                    help="sphere workloads: bilinear (headline) or nearest; ring workloads always run 'ring'")
     ap.add_argument("--layout", default="pm", choices=["pm", "ref"],
                     help="pm: panoramas resident in pixel-major order (PanoramaState); ref: reference order")
     ap.add_argument("--workload", default="cfg2_sphere_128x256", choices=list(WORKLOADS))
@@ -406,6 +457,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.mode not in modes_of(wl):
+        args.mode = modes_of(wl)[0]
     if args.impl == "reference":
         run_reference(args, wl, args.workload)
     else:

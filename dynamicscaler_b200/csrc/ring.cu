@@ -13,32 +13,13 @@ struct RingDims {
   int P, F, H, W, f_len, h, w;
 };
 
-// VEC = 4: w % 4 == 0 and W % 4 == 0 (host-checked); a window whose left edge is not a
-// multiple of 4 falls back to scalar loads inside the kernel (warp-uniform branch).
+// Generic tile copy: any window size / alignment, modulo per element.  Kept out of line so
+// its registers do not burden the fast path.
 template <typename T, int VEC, bool GATHER>
-__global__ void __launch_bounds__(kBlock)
-ring_copy_kernel(T* __restrict__ pano, T* __restrict__ win, const int32_t* __restrict__ d_wins,
-                 int h_left, int h_top, int h_f0, RingDims d) {
+__device__ __forceinline__ void ring_tile_generic(T* __restrict__ src_plane, T* __restrict__ win_tile,
+                                               int left, int top, const RingDims& d) {
   using V4 = typename Elem<T>::vec4;
-  // tile = (window j, plane pl, window frame fo)
-  const int tile = blockIdx.x;
-  const int fo = tile % d.f_len;
-  const int pl = (tile / d.f_len) % d.P;
-  const int j = tile / (d.f_len * d.P);
-  int left, top, f0;
-  if (d_wins != nullptr) {
-    left = __ldg(d_wins + 3 * j);
-    top = __ldg(d_wins + 3 * j + 1);
-    f0 = __ldg(d_wins + 3 * j + 2);
-  } else {
-    left = h_left; top = h_top; f0 = h_f0;
-  }
-  left %= d.W; top %= d.H;                       // begin may lie in [size, 2*size)
-  const int f = (f0 + fo) % d.F;
-  T* __restrict__ src_plane = pano + (static_cast<size_t>(pl) * d.F + f) * d.H * d.W;
-  T* __restrict__ win_tile = win + static_cast<size_t>(tile) * d.h * d.w;
-
-  const int wg = d.w / VEC;                       // groups per window row
+  const int wg = d.w / VEC;
   const int groups = d.h * wg;
   constexpr int U = 4;                            // independent accesses in flight per thread
   for (int base = threadIdx.x; base < groups; base += kBlock * U) {
@@ -91,6 +72,82 @@ ring_copy_kernel(T* __restrict__ pano, T* __restrict__ win, const int32_t* __res
   }
 }
 
+// VEC = 4: w % 4 == 0 and W % 4 == 0 (host-checked); a window whose left edge is not a
+// multiple of 4 falls back to scalar accesses (warp-uniform branch).
+// Persistent CTAs loop over the (window, plane, frame) tiles.  A thread owns a fixed column
+// group and walks down the rows, so the only per-element index work is one compare-subtract
+// wrap per axis (no division): the kernel is otherwise a plain 16-byte copy.
+// WG > 0: w / VEC known at compile time (power of two dividing the CTA), else runtime.
+template <typename T, int VEC, bool GATHER, int WG>
+__global__ void __launch_bounds__(kBlock)
+ring_copy_kernel(T* __restrict__ pano, T* __restrict__ win, const int32_t* __restrict__ d_wins,
+                 int h_left, int h_top, int h_f0, RingDims d, int n_tiles) {
+  using V4 = typename Elem<T>::vec4;
+  const int wg = WG > 0 ? WG : d.w / VEC;         // column groups per window row
+  const int rows_per_pass = WG > 0 ? kBlock / WG : 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // tile = (window j, plane pl, window frame fo)
+    const int fo = tile % d.f_len;
+    const int pl = (tile / d.f_len) % d.P;
+    const int j = tile / (d.f_len * d.P);
+    int left, top, f0;
+    if (d_wins != nullptr) {
+      left = __ldg(d_wins + 3 * j);
+      top = __ldg(d_wins + 3 * j + 1);
+      f0 = __ldg(d_wins + 3 * j + 2);
+    } else {
+      left = h_left; top = h_top; f0 = h_f0;
+    }
+    left %= d.W; top %= d.H;                       // begin may lie in [size, 2*size)
+    const int f = (f0 + fo) % d.F;
+    T* __restrict__ src_plane = pano + (static_cast<size_t>(pl) * d.F + f) * d.H * d.W;
+    T* __restrict__ win_tile = win + static_cast<size_t>(tile) * d.h * d.w;
+
+    if (WG > 0 && VEC == 4 && (left & 3) == 0 && d.w <= d.W && d.h <= d.H) {
+      // fast path: fixed column group per thread, rows strided by rows_per_pass
+      const int xg = threadIdx.x % WG, y0 = threadIdx.x / WG;
+      int c = left + xg * VEC;
+      c = c >= d.W ? c - d.W : c;
+      constexpr int U = 4;
+      for (int yb = y0; yb < d.h; yb += rows_per_pass * U) {
+        V4 v[U];
+        int r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int y = yb + u * rows_per_pass;
+          r[u] = top + y;
+          r[u] = r[u] >= d.H ? r[u] - d.H : r[u];
+          if (y < d.h) {
+            if (GATHER) v[u] = __ldg(reinterpret_cast<const V4*>(src_plane + static_cast<size_t>(r[u]) * d.W + c));
+            else v[u] = __ldg(reinterpret_cast<const V4*>(win_tile + y * d.w + xg * VEC));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int y = yb + u * rows_per_pass;
+          if (y < d.h) {
+            if (GATHER) *reinterpret_cast<V4*>(win_tile + y * d.w + xg * VEC) = v[u];
+            else *reinterpret_cast<V4*>(src_plane + static_cast<size_t>(r[u]) * d.W + c) = v[u];
+          }
+        }
+      }
+      continue;
+    }
+
+    if (WG > 0) {
+      // rare for this instantiation (left edge off the 4-grid, or window larger than the panorama):
+      // compact scalar loop, modulo per element
+      for (int g = threadIdx.x; g < d.h * d.w; g += kBlock) {
+        const int y = g / d.w, x = g - y * d.w;
+        T* pp = src_plane + static_cast<size_t>((top + y) % d.H) * d.W + (left + x) % d.W;
+        if (GATHER) win_tile[g] = ldg(pp); else *pp = ldg(win_tile + g);
+      }
+    } else {
+      ring_tile_generic<T, VEC, GATHER>(src_plane, win_tile, left, top, d);
+    }
+  }
+}
+
 // plan_src[p] = j*h*w + y*w + x of the last window (highest j) covering p, else -1.
 __global__ void __launch_bounds__(kBlock)
 ring_merge_plan_kernel(int32_t* __restrict__ plan_src, const int32_t* __restrict__ d_wins, int n,
@@ -133,13 +190,18 @@ static int ring_copy(void* pano, void* win, const int32_t* d_wins, int n, int le
   RingDims d{P, F, H, W, f_len, h, w};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool vec = (w % 4 == 0) && (W % 4 == 0);
+  // persistent: at most 8 CTAs per SM (the kernels use <= 32 registers), each looping over tiles
+  const unsigned grid = static_cast<unsigned>(tiles < static_cast<long long>(kSMs) * 8 ? tiles : kSMs * 8);
+  const int nt = static_cast<int>(tiles);
   DS_DISPATCH_DTYPE(dtype, {
     ET* pp = static_cast<ET*>(pano);
     ET* wp = static_cast<ET*>(win);
-    if (vec)
-      ring_copy_kernel<ET, 4, GATHER><<<static_cast<unsigned>(tiles), kBlock, 0, st>>>(pp, wp, d_wins, left, top, f0, d);
+    if (vec && w == 64)
+      ring_copy_kernel<ET, 4, GATHER, 16><<<grid, kBlock, 0, st>>>(pp, wp, d_wins, left, top, f0, d, nt);
+    else if (vec)
+      ring_copy_kernel<ET, 4, GATHER, 0><<<grid, kBlock, 0, st>>>(pp, wp, d_wins, left, top, f0, d, nt);
     else
-      ring_copy_kernel<ET, 1, GATHER><<<static_cast<unsigned>(tiles), kBlock, 0, st>>>(pp, wp, d_wins, left, top, f0, d);
+      ring_copy_kernel<ET, 1, GATHER, 0><<<grid, kBlock, 0, st>>>(pp, wp, d_wins, left, top, f0, d, nt);
   });
   return check_launch();
 }

@@ -198,3 +198,17 @@ def test_shard_range_partitions():
             assert spans[0][0] == 0 and sum(c for _, c in spans) == n
             assert all(spans[r][0] + spans[r][1] == spans[r + 1][0] for r in range(world - 1))
             assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_loop_geometry_matches_oracle():
+    """dynamicscaler_b200.geometry (what bench.py and callers use) vs the oracle's restatement
+    of the reference loops, for every step phase."""
+    from dynamicscaler_b200 import geometry as geo
+    for i in range(0, 33):
+        assert geo.sphere_views(i) == po.default_sphere_views(i)
+        assert geo.ring_windows(i, 16, 16, 8192, 4096) == po.ring_window_grid(i, 16, 16, 8192, 4096)
+        assert geo.ring_windows(i, 2, 2, 1024, 512) == po.ring_window_grid(i, 2, 2, 1024, 512)
+        assert geo.ring_windows(i, 4, 4, 2048, 1024) == po.ring_window_grid(i, 4, 4, 2048, 1024)
+        assert geo.frame_windows(i) == po.frame_window_begins(i)
+        assert geo.frame_windows(i, overlap=0.5) == po.frame_window_begins(i, overlap=0.5)
+    assert len(geo.sphere_views(0)) == 44 and len(geo.frame_windows(0)) == 13

@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from bench import WORKLOADS, Workset, default_views, make_runner, timed  # noqa: E402
+from bench import WORKLOADS, Workset, make_plan, make_runner, modes_of, n_phases, timed  # noqa: E402
 from dynamicscaler_b200 import lib  # noqa: E402
 from dynamicscaler_b200.step import PanoramaStepper  # noqa: E402
 
@@ -17,15 +17,18 @@ GATHER_CPS, MERGE_PERSIST, MERGE_CPS = 0, 1, 2
 
 
 def main():
-    wl = WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2_sphere_128x256"]
+    wl_name = sys.argv[1] if len(sys.argv) > 1 else "cfg2_sphere_128x256"
+    wl = WORKLOADS[wl_name]
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
     st = PanoramaStepper(wl["H"], wl["W"], wl["F"], device=dev)
     gen = torch.Generator(device=dev).manual_seed(0)
-    plans = {m: [st.plan_sphere(default_views(i), wl["w"], wl["h"], fov=wl["fov"], mode=m) for i in range(10)]
-             for m in ("bilinear", "nearest")}
-    sets = [Workset(wl, 44, dev, gen, st) for _ in range(4)]
-    combos = [(i % 10, i % 4) for i in range(20)]
+    modes, NP = modes_of(wl), n_phases(wl)
+    plans = {m: [make_plan(st, wl, m, i) for i in range(NP)] for m in modes}
+    n_jobs = plans[modes[0]][0].n_jobs
+    n_sets = 4 if n_jobs < 100 else 2
+    sets = [Workset(wl, n_jobs, dev, gen, st if wl["kind"] == "sphere" else None) for _ in range(n_sets)]
+    combos = [(i % NP, i % n_sets) for i in range(2 * NP)]
     side = torch.cuda.Stream()
 
     def t_kernel(kind, mode, iters=200):
@@ -49,10 +52,13 @@ def main():
         lib.check(lib.ds_tune(MERGE_CPS, cfg["merge_cps"]))
         lib.check(lib.ds_tune(3, cfg.get("qsplit", 0)))
         lib.check(lib.ds_tune(100, cfg.get("minb", 0)))
-        res = dict(cfg)
-        for mode in ("nearest", "bilinear"):
+        res = dict(cfg, workload=wl_name)
+        for mode in modes:
             for kind in ("gather", "merge"):
-                res[f"{kind}_{mode}_us"] = round(t_kernel(kind, mode), 2)
+                us = t_kernel(kind, mode, iters=200 if n_jobs < 100 else 40)
+                gb, mb = st.algorithmic_bytes(plans[mode][0], 4, 4, k=2)
+                res[f"{kind}_{mode}_us"] = round(us, 2)
+                res[f"{kind}_{mode}_GBps"] = round((gb if kind == "gather" else mb) / us / 1e3, 1)
         print(json.dumps(res), flush=True)
 
 
