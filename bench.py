@@ -81,6 +81,21 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kern, mode, pm):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/traffic.json, written by tools/summarise_ncu.py); None when not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not (pm and os.path.exists(p)):
+        return None
+    names = {("gather", "bilinear"): "pm_gather_kernel<float, 4,", ("gather", "nearest"): "pm_gather_kernel<float, 1,",
+             ("merge", "bilinear"): "pm_merge_weighted_tiled_kernel<float", ("merge", "nearest"): "pm_merge_nearest_kernel<float"}
+    want = names.get((kern, mode))
+    for k, v in json.load(open(p)).items():
+        if want and k.startswith(want):
+            return v["dram_bytes_per_launch"]
+    return None
+
+
 # ------------------------------------------------------------------ clock sampler ----
 class ClockSampler(threading.Thread):
     """NVML samples of SM clock + throttle reasons while ``self.load`` is set."""
@@ -257,7 +272,7 @@ def run_ours(args, wl, wl_name):
     dist_on = world > 1
     if dist_on:
         dist.init_process_group("nccl", device_id=dev)
-    assert lib.ds_abi_version() == 2                     # fails loudly if the .so is missing
+    assert lib.ds_abi_version() == 3                     # fails loudly if the .so is missing
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -328,7 +343,7 @@ def run_ours(args, wl, wl_name):
         results[mode] = {"ms_total": ms, "ms_per_step": ms / K, "graph": graphed,
                          "launches_per_step": launches_per_step}
         # per-kernel pass (same rotation) for the roofline
-        if not dist_on:
+        if not dist_on and not args.no_kernel_pass:
             iters = max(K, 5 * len(combos))
             for name, maker in (("gather", make_gather), ("merge", make_merge)):
                 krun, _ = runner(maker, mode, iters)
@@ -410,7 +425,7 @@ def run_ours(args, wl, wl_name):
             "variants": {m: {"ms_per_step": r["ms_per_step"], "blends_per_s": n_win / (r["ms_per_step"] * 1e-3),
                              **{k: v for k, v in r.items() if k.endswith("_us")}} for m, r in results.items()},
         }
-        if not dist_on:
+        if not dist_on and not args.no_kernel_pass:
             P = wl["C"]
             gb, mb = st.algorithmic_bytes(plans[args.mode][0], P, 4, k=2)
             kern = "merge" if head["merge_us"] >= head["gather_us"] else "gather"
@@ -418,7 +433,8 @@ def run_ours(args, wl, wl_name):
             dur = head[kern + "_us"] * 1e-6
             line["roofline"] = {
                 "bound": "hbm", "kernel": f"{kern}_{args.mode}", "achieved": bytes_launch / dur / 1e9, "peak": peak,
-                "unit": "GB/s", "frac": bytes_launch / dur / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": bytes_launch / dur / 1e9 / peak,
+                "traffic": ncu_traffic(kern, args.mode, st_pm is not None), "peak_source": peak_src,
                 "algorithmic_bytes": {"gather": gb, "merge": mb, "coverage": plans[args.mode][0].coverage},
                 "step_frac": (gb + mb) / (head["ms_per_step"] * 1e-3) / 1e9 / peak,
                 "all": {m: {kn: (st.algorithmic_bytes(plans[m][0], P, 4)[0 if kn == "gather" else 1]
@@ -455,6 +471,8 @@ def main():
     ap.add_argument("--workload", default="cfg2_sphere_128x256", choices=list(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-kernel-pass", action="store_true",
+                    help="skip the per-kernel timing pass and the roofline (profiling runs: launch list = steps only)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.mode not in modes_of(wl):

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libdynscaler_sm100.so")
 DS_F32, DS_BF16 = 0, 1
 DS_MASK_NONE, DS_MASK_PLANE, DS_MASK_FULL = 0, 1, 2
 DS_MAX_PAYLOADS = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -25,7 +25,8 @@ _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 PROTOTYPES = {
     "ds_abi_version": [],
     "ds_error_string": [_i],
-    "ds_tune": [_i, _i],
+    "ds_peer_table_size": [],
+    "ds_tune": [_i, _ll],
     "ds_ring_gather": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_ring_scatter": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_ring_merge_plan": [_vp, _vp, _i, _i, _i, _i, _i, _vp],
@@ -33,13 +34,27 @@ PROTOTYPES = {
     "ds_gather_bilinear": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_merge_nearest": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_merge_bilinear": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "ds_pm_gather": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "ds_pm_merge_nearest": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "ds_pm_merge_bilinear": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "ds_pm_merge_bilinear_tiled": [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "ds_pm_gather": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "ds_pm_merge_nearest": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "ds_pm_merge_bilinear": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "ds_pm_merge_bilinear_tiled": [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_mix_mask": [_vp, _vp, _vp, _vp, _f, _f, _ll, _i, _i, _vp],
     "ds_select_merged": [_vp, _vp, _vp, _ll, _ll, _ll, _i, _vp],
 }
+
+
+DS_MAX_PEERS = 8
+
+
+class PeerTable(C.Structure):
+    """Mirror of ``ds_peer_table_t`` (include/dynscaler.h); tests/test_abi.py checks the layout
+    against the header."""
+    _fields_ = [("merges_done", C.c_int32 * DS_MAX_PEERS), ("gathers_done", C.c_int32 * DS_MAX_PEERS),
+                ("my_merges", C.c_int32), ("my_gathers", C.c_int32), ("cta_gather", C.c_int32),
+                ("cta_merge", C.c_int32), ("error", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+                ("reserved", C.c_int32),
+                ("pm", (C.c_uint64 * DS_MAX_PAYLOADS) * DS_MAX_PEERS), ("mask", C.c_uint64 * DS_MAX_PEERS),
+                ("ctl", C.c_uint64 * DS_MAX_PEERS)]
 
 
 class LibraryMissing(RuntimeError):

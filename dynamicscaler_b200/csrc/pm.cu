@@ -13,9 +13,10 @@
 // [h*w] order -- the UNet consumes / produces them -- so every kernel here is a gather or
 // scatter fused with a [pixel][frame*plane] <-> [frame*plane][pixel] transpose through
 // shared memory:
-//   pm_gather_kernel         get_view_tensor_no_interpolate / _interpolate, all views of a step
-//   pm_merge_nearest_kernel  set_view_tensor_no_interpolation, all views, last writer wins
-//   pm_merge_bilinear_kernel set_view_tensor_bilinear, all views (weighted splat + normalise)
+//   pm_gather_kernel                get_view_tensor_no_interpolate / _interpolate, all views of a step
+//   pm_merge_nearest_kernel         set_view_tensor_no_interpolation, all views, last writer wins
+//   pm_merge_weighted_tiled_kernel  set_view_tensor_bilinear, all views (weighted splat + normalise)
+//   pm_merge_bilinear_kernel        the same for any window frame count / row length
 // and, with identity maps, the pack / unpack between the two layouts.
 //
 // Merges are in SCATTER form over a host-built list, sorted by view, of the view pixels
@@ -24,24 +25,31 @@
 // to the reference's sequential order, and per-rank outputs have disjoint support when the
 // job list is sharded.
 //
+// Multi-GPU (windows sharded over ranks): with a ds_peer_table_t every rank holds a
+// replica of the panorama in peer-mapped (symmetric) memory and the merge kernels are the
+// exchange step themselves: each surviving row is stored straight into EVERY replica over
+// NVLink (peer st.global), so there is no zeroed sum buffer, no all-reduce and no select pass.
+// Cross-GPU ordering is two monotonic counters per peer, signalled with st.release.sys by the
+// last CTA of a kernel and awaited with ld.acquire.sys by the first instructions of the next:
+//   gather  waits until every peer has pushed the previous step's rows   (merges_done)
+//   merge   waits until every peer has finished reading its replica      (gathers_done)
+//
 // Scheduling: these kernels run for 10-20 us, so wave quantisation and tails matter as much
-// as bandwidth.  Every kernel is launched with at most (SMs x resident CTAs) CTAs and
-// splits its work list evenly over them (persistent CTAs, static balanced partition).
+// as bandwidth: the gather runs persistent CTAs with an even static split, the merges one
+// small tile per CTA under the hardware CTA scheduler (measured faster than a static split).
 #include "ds_common.cuh"
 
 namespace ds {
 
 constexpr int kPmPlanes = 4;     // planes per atom (B*C of the latent); other counts use sphere.cu
-constexpr int kPmKT = 64;        // view pixels per gather CTA
-constexpr int kPmET = 32;        // panorama rows per pass of the weighted merge
+constexpr int kPmKT = 64;        // view pixels per gather work item
+constexpr int kPmET = 32;        // entries (nearest) / panorama rows (weighted) per merge CTA
+constexpr int kPmEC = 64;        // padded CSR entries per tile of the tiled weighted merge
 constexpr int kWarps = kBlock / 32;
 
-// Launch-shape knobs (ds_tune): defaults are the measured best on B200 for the bench workload.
-static int g_gather_ctas_per_sm = 0;   // 0: occupancy limit
-static int g_merge_persistent = 0;     // 0: one <= 32-entry tile per CTA (hardware CTA scheduling); 1: persistent balanced split
-static int g_merge_ctas_per_sm = 0;    // persistent scheme only; 0: occupancy limit
-static int g_merge_qsplit = 0;         // 1: one payload per CTA (gridDim.z = Q)
-static int g_merge_minb = 0;           // experiment: min blocks of the weighted merge
+// Launch-shape knobs (ds_tune); defaults are the measured best on B200 for the bench workload.
+static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
+static long long g_peer_timeout_ns = 2000000000ll;   // give up a cross-GPU wait after this long
 
 template <typename T> struct Atom;
 template <> struct Atom<float> {
@@ -97,6 +105,59 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// ------------------------------------------------------- cross-GPU ordering (peers) ----
+__device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int32_t* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Every CTA: block until each peer's counter in `done` (this rank's table, written remotely)
+// has reached `want`.  A timeout sets tab->error instead of hanging the GPU.
+__device__ __forceinline__ void pm_peer_wait(ds_peer_table_t* tab, const int32_t* done, int want, long long timeout_ns) {
+  if (static_cast<int>(threadIdx.x) < tab->world && static_cast<int>(threadIdx.x) != tab->rank) {
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(done + threadIdx.x) < want) {
+      if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) {
+        tab->error = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Every CTA, after its last access: the last CTA of the grid bumps this rank's own counter and
+// publishes it into slot `rank` of `done_offset` in every peer's table.
+__device__ __forceinline__ void pm_peer_signal(ds_peer_table_t* tab, int32_t* cta_counter, int32_t* my_count,
+                                               size_t done_offset_bytes) {
+  __threadfence_system();                        // this thread's peer stores are visible system-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned n = atomicAdd(reinterpret_cast<unsigned*>(cta_counter), 1u);
+    if (n == total - 1) {
+      *cta_counter = 0;
+      const int c = *my_count + 1;
+      *my_count = c;
+      __threadfence_system();
+      for (int p = 0; p < tab->world; ++p) {
+        if (p == tab->rank) continue;
+        char* peer = reinterpret_cast<char*>(tab->ctl[p]);
+        st_release_sys(reinterpret_cast<int32_t*>(peer + done_offset_bytes) + tab->rank, c);
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------- gather ----
 struct PmGatherArgs {
   int F, HW, f_len, hw;
@@ -116,8 +177,11 @@ template <typename T, int TAPS, int FL, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ out,
                  const int32_t* __restrict__ d_idx, const float* __restrict__ d_wt,
-                 const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a) {
+                 const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a, ds_peer_table_t* __restrict__ peer,
+                 long long peer_timeout_ns) {
   using A = typename Atom<T>::type;
+  // peers must have pushed every row of the previous step into this replica before it is read
+  if (peer != nullptr) pm_peer_wait(peer, peer->merges_done, peer->my_merges, peer_timeout_ns);
   constexpr int VE = 16 / sizeof(T);            // elements per 16-byte vector
   constexpr int S = kPmKT + VE;                 // padded row stride (elements): 4 banks mod 32
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -223,6 +287,8 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     }
     if (issued) bulk_commit_and_wait_read();    // the tile is reused / freed only after the copy read it
   }
+  // this replica may now be overwritten by the peers' merges
+  if (peer != nullptr) pm_peer_signal(peer, &peer->cta_gather, &peer->my_gathers, offsetof(ds_peer_table_t, gathers_done));
 }
 
 // ------------------------------------------------------------------------ merges ----
@@ -232,9 +298,10 @@ struct PmMergeArgs {
   void* mask;
   int mask_mode;
   int Q, n_ent;
-  int per_cta;                   // > 0: CTA b owns entries [b*per_cta, (b+1)*per_cta) of its slice; 0: even split over the grid
   int vpf, job_begin, job_count;
   int F, HW, f_len, hw;
+  ds_peer_table_t* peer;         // NULL: single replica (pm / mask above)
+  long long peer_timeout_ns;
 };
 
 // dynamic indexing of a kernel-parameter array would force a local-memory copy of the struct
@@ -245,16 +312,40 @@ template <typename PT> __device__ __forceinline__ PT pm_sel(PT const (&arr)[DS_M
   return r;
 }
 
-// gridDim.z > 1: payload q = blockIdx.z only (one payload per CTA: more, lighter CTAs).
-__device__ __forceinline__ PmMergeArgs pm_split_q(const PmMergeArgs& in) {
-  PmMergeArgs a = in;
-  if (gridDim.z > 1) {
-    a.pm[0] = pm_sel(in.pm, blockIdx.z);
-    a.pay[0] = pm_sel(in.pay, blockIdx.z);
-    a.Q = 1;
-    if (blockIdx.z > 0) a.mask_mode = DS_MASK_NONE;
+// Store one atom of payload q at element offset `o` of the panorama -- into the single local
+// replica, or into every rank's replica (peer stores over NVLink).
+template <typename A>
+__device__ __forceinline__ void pm_store(const PmMergeArgs& a, int q, size_t o, const A& v) {
+  if (a.peer == nullptr) {
+    static_cast<A*>(pm_sel(a.pm, q))[o] = v;
+  } else {
+    for (int r = 0; r < a.peer->world; ++r) reinterpret_cast<A*>(a.peer->pm[r][q])[o] = v;
   }
-  return a;
+}
+template <typename A>
+__device__ __forceinline__ void pm_store_mask_atom(const PmMergeArgs& a, size_t o, const A& v) {
+  if (a.peer == nullptr) {
+    static_cast<A*>(a.mask)[o] = v;
+  } else {
+    for (int r = 0; r < a.peer->world; ++r) reinterpret_cast<A*>(a.peer->mask[r])[o] = v;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void pm_store_mask_plane(const PmMergeArgs& a, int dst) {
+  if (a.peer == nullptr) {
+    static_cast<T*>(a.mask)[dst] = Elem<T>::one();
+  } else {
+    for (int r = 0; r < a.peer->world; ++r) reinterpret_cast<T*>(a.peer->mask[r])[dst] = Elem<T>::one();
+  }
+}
+
+// Prologue / epilogue of every merge CTA in peer mode.
+__device__ __forceinline__ void pm_merge_begin(const PmMergeArgs& a) {
+  // every peer must have finished reading its replica (this step's gather) before rows land in it
+  if (a.peer != nullptr) pm_peer_wait(a.peer, a.peer->gathers_done, a.peer->my_gathers, a.peer_timeout_ns);
+}
+__device__ __forceinline__ void pm_merge_end(const PmMergeArgs& a) {
+  if (a.peer != nullptr) pm_peer_signal(a.peer, &a.peer->cta_merge, &a.peer->my_merges, offsetof(ds_peer_table_t, merges_done));
 }
 
 struct PmRange {
@@ -263,8 +354,8 @@ struct PmRange {
 };
 
 // The list is sorted by view and d_view_ptr[v] is the first entry of view v, so the jobs of
-// this rank in frame window s = blockIdx.y are one contiguous slice; it is split evenly over
-// the gridDim.x CTAs.  false => nothing to do.
+// this rank in frame window s = blockIdx.y are one contiguous slice; CTA b owns entries
+// [b*32, b*32 + 32) of it.  false => nothing to do.
 __device__ __forceinline__ bool pm_range(const PmMergeArgs& a, const int32_t* __restrict__ d_view_ptr,
                                          const int32_t* __restrict__ d_fbegin, PmRange& r) {
   r.s = blockIdx.y;
@@ -276,14 +367,8 @@ __device__ __forceinline__ bool pm_range(const PmMergeArgs& a, const int32_t* __
     e_lo = __ldg(d_view_ptr + v_lo);
     e_hi = __ldg(d_view_ptr + v_hi);
   }
-  if (a.per_cta > 0) {
-    r.lo = e_lo + blockIdx.x * a.per_cta;
-    r.hi = min(r.lo + a.per_cta, e_hi);
-  } else {
-    const long long n = e_hi - e_lo;
-    r.lo = e_lo + static_cast<int>(n * blockIdx.x / gridDim.x);
-    r.hi = e_lo + static_cast<int>(n * (blockIdx.x + 1) / gridDim.x);
-  }
+  r.lo = e_lo + blockIdx.x * kPmET;
+  r.hi = min(r.lo + kPmET, e_hi);
   return r.hi > r.lo;
 }
 
@@ -302,53 +387,42 @@ __device__ __forceinline__ int pm_job_offset(const PmMergeArgs& a, int s, int sr
   return (s * a.vpf + v - a.job_begin) * kPmPlanes * plane_stride + k;
 }
 
-// Persistent CTAs over the surviving view pixels; a pass handles up to kPmCap entries, two per lane.
-// Load: warp <-> (payload q, window frame fo), lane <-> entries: 4 plane loads -> one atom ->
+// CTA = 32 surviving view pixels.
+// Load: warp <-> (payload q, window frame fo), lane <-> entry: 4 plane loads -> one atom ->
 // shared tile[q][entry][fo].  Store: f_len consecutive lanes write one full panorama row.
-template <typename T, int FL, int EPL>
+template <typename T, int FL>
 __global__ void __launch_bounds__(kBlock)
-pm_merge_nearest_kernel(const PmMergeArgs a_in, const int32_t* __restrict__ d_view_ptr,
+pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                         const int32_t* __restrict__ d_ent_src, const int32_t* __restrict__ d_ent_dst,
                         const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
-  const PmMergeArgs a = pm_split_q(a_in);
+  pm_merge_begin(a);
   PmRange rg;
-  if (!pm_range(a, d_view_ptr, d_fbegin, rg)) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int f_len = FL > 0 ? FL : a.f_len;
-  const int SA = f_len | 1;                                          // odd row stride in atoms
-  constexpr int CAP = 32 * EPL;                                      // entries per pass
-  A* tile = reinterpret_cast<A*>(smem_raw);                          // [Q][CAP][SA]
-  int32_t* s_dst = reinterpret_cast<int32_t*>(tile + a.Q * CAP * SA);
+  if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int f_len = FL > 0 ? FL : a.f_len;
+    const int SA = f_len | 1;                                          // odd row stride in atoms
+    A* tile = reinterpret_cast<A*>(smem_raw);                          // [Q][32][SA]
+    int32_t* s_dst = reinterpret_cast<int32_t*>(tile + (a.Q > 0 ? a.Q : 1) * kPmET * SA);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int plane_stride = f_len * a.hw;
-  const int n_pairs = a.Q * f_len;
-  const int n = rg.hi - rg.lo;
-  const int n_pass = (n + CAP - 1) / CAP;
-  const int per = (n + n_pass - 1) / n_pass;
-  for (int t0 = rg.lo; t0 < rg.hi; t0 += per) {
-    const int cnt = min(per, rg.hi - t0);
-    bool have[EPL];
-    int off[EPL];
-#pragma unroll
-    for (int j = 0; j < EPL; ++j) {
-      const int el = lane + 32 * j;
-      have[j] = el < cnt;
-      off[j] = 0;
-      if (have[j]) {
-        const int src = d_ent_src != nullptr ? __ldg(d_ent_src + t0 + el) : t0 + el;
-        off[j] = pm_job_offset(a, rg.s, src, plane_stride);
-        if (warp == 0) {
-          const int dst = d_ent_dst != nullptr ? __ldg(d_ent_dst + t0 + el) : t0 + el;
-          s_dst[el] = dst;
-          if (a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
-        }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int plane_stride = f_len * a.hw;
+    const int n_pairs = a.Q * f_len;
+    const int cnt = rg.hi - rg.lo;
+    const bool have = lane < cnt;
+    int off = 0;
+    if (have) {
+      const int src = d_ent_src != nullptr ? __ldg(d_ent_src + rg.lo + lane) : rg.lo + lane;
+      off = pm_job_offset(a, rg.s, src, plane_stride);
+      if (warp == 0) {
+        const int dst = d_ent_dst != nullptr ? __ldg(d_ent_dst + rg.lo + lane) : rg.lo + lane;
+        s_dst[lane] = dst;
+        if (a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, dst);
       }
     }
-    constexpr int U = 4 / EPL;
+    constexpr int U = 4;
     for (int p0 = warp * U; p0 < n_pairs; p0 += kWarps * U) {
-      T e[U][EPL][4];
+      T e[U][4];
       bool live[U];
       int q[U], fo[U];
 #pragma unroll
@@ -357,193 +431,33 @@ pm_merge_nearest_kernel(const PmMergeArgs a_in, const int32_t* __restrict__ d_vi
         q[u] = pr / f_len;
         fo[u] = pr - q[u] * f_len;
         int f;
-        live[u] = pr < n_pairs && pm_frame_live(a, d_ftab, rg, fo[u], f_len, f);
+        live[u] = pr < n_pairs && have && pm_frame_live(a, d_ftab, rg, fo[u], f_len, f);
         if (live[u]) {
-          const T* __restrict__ src = static_cast<const T*>(pm_sel(a.pay, q[u])) + fo[u] * a.hw;
+          const T* __restrict__ src = static_cast<const T*>(pm_sel(a.pay, q[u])) + fo[u] * a.hw + off;
 #pragma unroll
-          for (int j = 0; j < EPL; ++j)
-            if (have[j]) {
-#pragma unroll
-              for (int p = 0; p < 4; ++p) e[u][j][p] = ldg(src + off[j] + p * plane_stride);
-            }
+          for (int p = 0; p < 4; ++p) e[u][p] = ldg(src + p * plane_stride);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (live[u]) {
-#pragma unroll
-          for (int j = 0; j < EPL; ++j)
-            if (have[j]) tile[(q[u] * CAP + lane + 32 * j) * SA + fo[u]] = atom_join<T>(e[u][j]);
-        }
+        if (live[u]) tile[(q[u] * kPmET + lane) * SA + fo[u]] = atom_join<T>(e[u]);
     }
     __syncthreads();
 
     const int per_q = cnt * f_len;
-    for (int u = threadIdx.x; u < a.Q * per_q; u += kBlock) {
+    const int n_units = (a.Q > 0 ? a.Q : 1) * per_q;
+    for (int u = threadIdx.x; u < n_units; u += kBlock) {
       const int q = u / per_q, r = u - q * per_q;
       const int i = r / f_len, fo = r - i * f_len;
       int f;
       if (pm_frame_live(a, d_ftab, rg, fo, f_len, f)) {
         const size_t o = static_cast<size_t>(s_dst[i]) * a.F + f;
-        static_cast<A*>(pm_sel(a.pm, q))[o] = tile[(q * CAP + i) * SA + fo];
-        if (q == 0 && a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[o] = atom_ones<T>();
+        if (a.Q > 0) pm_store<A>(a, q, o, tile[(q * kPmET + i) * SA + fo]);
+        if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, o, atom_ones<T>());
       }
     }
-    if (a.Q == 0 && a.mask_mode == DS_MASK_FULL) {                   // mask-only call
-      for (int u = threadIdx.x; u < per_q; u += kBlock) {
-        const int i = u / f_len, fo = u - i * f_len;
-        int f;
-        if (pm_frame_live(a, d_ftab, rg, fo, f_len, f))
-          static_cast<A*>(a.mask)[static_cast<size_t>(s_dst[i]) * a.F + f] = atom_ones<T>();
-      }
-    }
-    __syncthreads();
   }
-}
-
-// Two-phase weighted merge for a compile-time window frame count FL.  Persistent CTAs over the
-// panorama rows (one row = one panorama pixel owned by one view); a pass handles <= 32 rows.
-//   phase A  lane <-> CSR ENTRY (dense, no divergence): product atom = payload * w -> shared
-//   phase B  lane <-> (row, window frame): acc = acc + product over the row's entries in CSR
-//            order (tap-major, k ascending: index_add_'s order); row = acc / ws; one full
-//            panorama row per FL consecutive lanes.
-// Entries are processed in chunks of kPmEC so any row length works; acc lives in registers.
-constexpr int kPmEC = 64;
-template <typename T, int FL, int QMAX, int MINB>
-__global__ void __launch_bounds__(kBlock, MINB)
-pm_merge_bilinear_fl_kernel(const PmMergeArgs a_in, const int32_t* __restrict__ d_view_ptr,
-                            const int32_t* __restrict__ d_row_dst, const int32_t* __restrict__ d_row_ptr,
-                            const int32_t* __restrict__ d_ent_src, const float* __restrict__ d_ent_w,
-                            const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
-  using A = typename Atom<T>::type;
-  const PmMergeArgs a = pm_split_q(a_in);
-  static_assert(kBlock % FL == 0 && (kPmET * FL) % kBlock == 0, "row/lane mapping");
-  constexpr int SA = FL | 1;
-  constexpr int RPP = kBlock / FL;               // rows per sweep of phase B
-  constexpr int NSW = kPmET / RPP;               // sweeps to cover a pass's rows
-  PmRange rg;
-  if (!pm_range(a, d_view_ptr, d_fbegin, rg)) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* prod = reinterpret_cast<float4*>(smem_raw);                 // [Q][EC][SA] fp32 products
-  float* s_w = reinterpret_cast<float*>(prod + (a.Q > 0 ? a.Q : 1) * kPmEC * SA);   // [EC]
-  int32_t* s_rp = reinterpret_cast<int32_t*>(s_w + kPmEC);            // [ET + 1]
-  int32_t* s_dst = s_rp + kPmET + 1;                                  // [ET]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int fo_b = threadIdx.x % FL, row_b = threadIdx.x / FL;       // phase-B ownership
-  int fB;
-  const bool liveB = pm_frame_live(a, d_ftab, rg, fo_b, FL, fB);
-  const int plane_stride = FL * a.hw;
-
-  const int n = rg.hi - rg.lo;
-  const int n_pass = (n + kPmET - 1) / kPmET;
-  const int per = (n + n_pass - 1) / n_pass;
-  for (int r0 = rg.lo; r0 < rg.hi; r0 += per) {
-    const int cnt = min(per, rg.hi - r0);
-    if (threadIdx.x <= cnt) s_rp[threadIdx.x] = __ldg(d_row_ptr + r0 + threadIdx.x);
-    if (threadIdx.x < cnt) s_dst[threadIdx.x] = __ldg(d_row_dst + r0 + threadIdx.x);
-    __syncthreads();
-    const int e_begin = s_rp[0], e_end = s_rp[cnt];
-    float acc[NSW][QMAX][4];
-    float ws[NSW];
-#pragma unroll
-    for (int sw = 0; sw < NSW; ++sw) {
-      ws[sw] = 0.f;
-#pragma unroll
-      for (int q = 0; q < QMAX; ++q)
-#pragma unroll
-        for (int p = 0; p < 4; ++p) acc[sw][q][p] = 0.f;
-    }
-    for (int c0 = e_begin; c0 < e_end; c0 += kPmEC) {
-      const int n_e = min(kPmEC, e_end - c0);
-      // ---- phase A: products ----
-#pragma unroll
-      for (int half = 0; half < kPmEC / 32; ++half) {
-        const int el = half * 32 + lane;
-        if (half * 32 >= n_e) break;
-        const bool have = el < n_e;
-        int off = 0;
-        float w = 0.f;
-        if (have) {
-          off = pm_job_offset(a, rg.s, __ldg(d_ent_src + c0 + el), plane_stride);
-          w = __ldg(d_ent_w + c0 + el);
-          if (warp == 0) s_w[el] = w;
-        }
-        constexpr int NF = (FL + kWarps - 1) / kWarps;       // window frames per warp
-        T x[QMAX][NF][4];
-        bool live[NF];
-#pragma unroll
-        for (int j = 0; j < NF; ++j) {
-          const int fo = warp + j * kWarps;
-          int f;
-          live[j] = have && fo < FL && pm_frame_live(a, d_ftab, rg, fo, FL, f);
-#pragma unroll
-          for (int q = 0; q < QMAX; ++q)
-            if (q < a.Q && live[j]) {
-              const T* __restrict__ src = static_cast<const T*>(a.pay[q]) + off + fo * a.hw;
-#pragma unroll
-              for (int p = 0; p < 4; ++p) x[q][j][p] = ldg(src + p * plane_stride);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < NF; ++j)
-#pragma unroll
-          for (int q = 0; q < QMAX; ++q)
-            if (q < a.Q && live[j]) {
-              const int fo = warp + j * kWarps;
-              prod[(q * kPmEC + el) * SA + fo] =
-                  make_float4(__fmul_rn(Elem<T>::to_f(x[q][j][0]), w), __fmul_rn(Elem<T>::to_f(x[q][j][1]), w),
-                              __fmul_rn(Elem<T>::to_f(x[q][j][2]), w), __fmul_rn(Elem<T>::to_f(x[q][j][3]), w));
-            }
-      }
-      __syncthreads();
-      // ---- phase B: ordered accumulation of this chunk ----
-#pragma unroll
-      for (int sw = 0; sw < NSW; ++sw) {
-        const int i = sw * RPP + row_b;
-        if (i < cnt) {
-          const int lo = max(s_rp[i], c0) - c0, hi = min(s_rp[i + 1], c0 + n_e) - c0;
-          for (int e = lo; e < hi; ++e) {
-            ws[sw] = __fadd_rn(ws[sw], s_w[e]);
-            if (liveB) {
-#pragma unroll
-              for (int q = 0; q < QMAX; ++q)
-                if (q < a.Q) {
-                  const float4 t = prod[(q * kPmEC + e) * SA + fo_b];
-                  acc[sw][q][0] = __fadd_rn(acc[sw][q][0], t.x);
-                  acc[sw][q][1] = __fadd_rn(acc[sw][q][1], t.y);
-                  acc[sw][q][2] = __fadd_rn(acc[sw][q][2], t.z);
-                  acc[sw][q][3] = __fadd_rn(acc[sw][q][3], t.w);
-                }
-            }
-          }
-        }
-      }
-      __syncthreads();
-    }
-    // ---- normalise + write full panorama rows ----
-#pragma unroll
-    for (int sw = 0; sw < NSW; ++sw) {
-      const int i = sw * RPP + row_b;
-      if (i < cnt && ws[sw] > 0.f) {
-        const int dst = s_dst[i];
-        if (fo_b == 0 && a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
-        if (liveB) {
-          const size_t o = static_cast<size_t>(dst) * a.F + fB;
-#pragma unroll
-          for (int q = 0; q < QMAX; ++q)
-            if (q < a.Q) {
-              float r[4];
-#pragma unroll
-              for (int p = 0; p < 4; ++p) r[p] = __fdiv_rn(acc[sw][q][p], ws[sw]);
-              static_cast<A*>(a.pm[q])[o] = Atom<T>::pack(r);
-            }
-          if (a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[o] = atom_ones<T>();
-        }
-      }
-    }
-    __syncthreads();                              // s_rp / s_dst are rewritten by the next pass
-  }
+  pm_merge_end(a);
 }
 
 // Tiled weighted merge (fast path): the host pads the CSR entry list so that tile t owns
@@ -573,7 +487,11 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   const int v_lo = min(max(a.job_begin - s * a.vpf, 0), a.vpf);
   const int v_hi = min(max(a.job_begin + a.job_count - s * a.vpf, 0), a.vpf);
   const int t = __ldg(d_view_ptr + v_lo) + blockIdx.x;
-  if (t >= __ldg(d_view_ptr + v_hi)) return;
+  pm_merge_begin(a);
+  if (t >= __ldg(d_view_ptr + v_hi)) {
+    pm_merge_end(a);
+    return;
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e_base = t * kPmEC;
 
@@ -665,7 +583,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
     }
     if (!(ws > 0.f)) continue;
     const int dst = s_dst[i];
-    if (fo_b == 0 && a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
+    if (fo_b == 0 && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, dst);
     if (liveB) {
       const size_t o = static_cast<size_t>(dst) * a.F + fB;
 #pragma unroll
@@ -673,48 +591,49 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
         float r[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) r[p] = __fdiv_rn(acc[q][p], ws);
-        static_cast<A*>(a.pm[q])[o] = Atom<T>::pack(r);
+        pm_store<A>(a, q, o, Atom<T>::pack(r));
       }
-      if (a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[o] = atom_ones<T>();
+      if (a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, o, atom_ones<T>());
     }
   }
+  pm_merge_end(a);
 }
 
-// Generic (runtime f_len) weighted merge: each lane owns a row and walks its CSR entries
-// (tap-major, k ascending -- index_add_'s order) accumulating
+// Generic (runtime f_len, any row length) weighted merge.  CTA = 32 panorama rows; each lane
+// owns a row and walks its CSR entries (tap-major, k ascending -- index_add_'s order):
 //   acc = acc + (payload * w);  ws = ws + w;   row = acc / ws     (each op rounded on its own)
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
-pm_merge_bilinear_kernel(PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
+pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                          const int32_t* __restrict__ d_row_dst, const int32_t* __restrict__ d_row_ptr,
                          const int32_t* __restrict__ d_ent_src, const float* __restrict__ d_ent_w,
                          const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
+  pm_merge_begin(a);
   PmRange rg;
-  if (!pm_range(a, d_view_ptr, d_fbegin, rg)) return;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int SA = a.f_len | 1;
-  A* tile = reinterpret_cast<A*>(smem_raw);                          // [Q][ET][SA]
-  int32_t* s_dst = reinterpret_cast<int32_t*>(tile + (a.Q > 0 ? a.Q : 1) * kPmET * SA);   // -1: row not written
+  if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int SA = a.f_len | 1;
+    A* tile = reinterpret_cast<A*>(smem_raw);                          // [Q][ET][SA]
+    int32_t* s_dst = reinterpret_cast<int32_t*>(tile + (a.Q > 0 ? a.Q : 1) * kPmET * SA);   // -1: row not written
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int plane_stride = a.f_len * a.hw;
-  const int n_pairs = a.Q * a.f_len;
-  for (int r0 = rg.lo; r0 < rg.hi; r0 += kPmET) {
-    const int cnt = min(kPmET, rg.hi - r0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int plane_stride = a.f_len * a.hw;
+    const int n_pairs = a.Q * a.f_len;
+    const int cnt = rg.hi - rg.lo;
     const bool have = lane < cnt;
     int e0 = 0, e1 = 0;
     if (have) {
-      e0 = __ldg(d_row_ptr + r0 + lane);
-      e1 = __ldg(d_row_ptr + r0 + lane + 1);
+      e0 = __ldg(d_row_ptr + rg.lo + lane);
+      e1 = __ldg(d_row_ptr + rg.lo + lane + 1);
     }
     float ws = 0.f;
     for (int e = e0; e < e1; ++e) ws = __fadd_rn(ws, __ldg(d_ent_w + e));
     const bool wr = have && ws > 0.f;
     if (warp == 0) {
-      const int dst = wr ? __ldg(d_row_dst + r0 + lane) : -1;
+      const int dst = wr ? __ldg(d_row_dst + rg.lo + lane) : -1;
       s_dst[lane] = dst;
-      if (wr && a.mask_mode == DS_MASK_PLANE) static_cast<T*>(a.mask)[dst] = Elem<T>::one();
+      if (wr && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, dst);
     }
     for (int pr = warp; pr < n_pairs; pr += kWarps) {
       const int q = pr / a.f_len, fo = pr - q * a.f_len;
@@ -743,12 +662,12 @@ pm_merge_bilinear_kernel(PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
       int f;
       if (s_dst[i] >= 0 && pm_frame_live(a, d_ftab, rg, fo, a.f_len, f)) {
         const size_t o = static_cast<size_t>(s_dst[i]) * a.F + f;
-        if (a.Q > 0) static_cast<A*>(pm_sel(a.pm, q))[o] = tile[(q * kPmET + i) * SA + fo];
-        if (q == 0 && a.mask_mode == DS_MASK_FULL) static_cast<A*>(a.mask)[o] = atom_ones<T>();
+        if (a.Q > 0) pm_store<A>(a, q, o, tile[(q * kPmET + i) * SA + fo]);
+        if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, o, atom_ones<T>());
       }
     }
-    __syncthreads();
   }
+  pm_merge_end(a);
 }
 
 static bool pm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -756,7 +675,7 @@ static bool pm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p)
 static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* const* h_payloads, int Q,
                               void* mask, int mask_mode, int n_ent, const int32_t* d_ftab,
                               const int32_t* d_fbegin, int n_fwin, int vpf, int job_begin, int job_count,
-                              int P, int F, int HW, int f_len, int hw) {
+                              int P, int F, int HW, int f_len, int hw, void* d_peer) {
   DS_REQUIRE(Q >= 0 && Q <= DS_MAX_PAYLOADS, DS_ERR_COUNT);
   DS_REQUIRE(Q == 0 || (h_pms != nullptr && h_payloads != nullptr), DS_ERR_NULL);
   DS_REQUIRE(P == kPmPlanes, DS_ERR_DIM);
@@ -765,7 +684,8 @@ static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* co
   DS_REQUIRE(mask_mode == DS_MASK_NONE || mask_mode == DS_MASK_PLANE || mask_mode == DS_MASK_FULL, DS_ERR_DIM);
   DS_REQUIRE(mask_mode == DS_MASK_NONE || mask != nullptr, DS_ERR_NULL);
   DS_REQUIRE(Q > 0 || mask_mode != DS_MASK_NONE, DS_ERR_COUNT);
-  DS_REQUIRE(job_begin >= 0 && job_begin < (1 << 30) && job_count > 0 && job_count <= (1 << 30), DS_ERR_DIM);
+  DS_REQUIRE(job_begin >= 0 && job_begin < (1 << 30) && job_count >= 0 && job_count <= (1 << 30), DS_ERR_DIM);
+  DS_REQUIRE(job_count > 0 || d_peer != nullptr, DS_ERR_DIM);   // an idle rank still takes part in the exchange
   // payload offsets are 32-bit inside the kernels
   const long long all_jobs = static_cast<long long>(n_fwin) * vpf;
   const long long jobs_here = job_count < all_jobs ? job_count : all_jobs;
@@ -777,28 +697,22 @@ static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* co
   for (int q = 0; q < DS_MAX_PAYLOADS; ++q) {
     a.pm[q] = q < Q ? h_pms[q] : nullptr;
     a.pay[q] = q < Q ? h_payloads[q] : nullptr;
-    if (q < Q) DS_REQUIRE(a.pm[q] != nullptr && a.pay[q] != nullptr, DS_ERR_NULL);
+    if (q < Q) DS_REQUIRE(a.pm[q] != nullptr && (a.pay[q] != nullptr || job_count == 0), DS_ERR_NULL);
     if (q < Q) DS_REQUIRE(pm_aligned16(a.pm[q]), DS_ERR_ALIGN);
   }
   if (mask_mode == DS_MASK_FULL) DS_REQUIRE(pm_aligned16(mask), DS_ERR_ALIGN);
   a.mask = mask; a.mask_mode = mask_mode;
-  a.Q = Q; a.n_ent = n_ent; a.per_cta = 0;
+  a.Q = Q; a.n_ent = n_ent;
   a.vpf = vpf; a.job_begin = job_begin; a.job_count = job_count;
   a.F = F; a.HW = HW; a.f_len = f_len; a.hw = hw;
+  a.peer = static_cast<ds_peer_table_t*>(d_peer);
+  a.peer_timeout_ns = g_peer_timeout_ns;
   return DS_OK;
 }
 
-// Persistent launch: at most (SMs x resident CTAs) CTAs along x, never more than `items`
-// work items, raising the dynamic shared memory limit when needed.
-// ctas_per_sm: 0 = occupancy limit, > 0 = cap, < 0 = not persistent (one CTA per item).
-template <typename K, typename... Args>
-static int pm_launch_z(K kernel, long long items, int ctas_per_sm, unsigned grid_y, unsigned grid_z, size_t smem, cudaStream_t st, Args... args);
+// ctas_per_sm: 0 = occupancy limit, > 0 = cap (persistent kernels); < 0 = one CTA per item.
 template <typename K, typename... Args>
 static int pm_launch(K kernel, long long items, int ctas_per_sm, unsigned grid_y, size_t smem, cudaStream_t st, Args... args) {
-  return pm_launch_z(kernel, items, ctas_per_sm, grid_y, 1, smem, st, args...);
-}
-template <typename K, typename... Args>
-static int pm_launch_z(K kernel, long long items, int ctas_per_sm, unsigned grid_y, unsigned grid_z, size_t smem, cudaStream_t st, Args... args) {
   DS_REQUIRE(smem <= 200 * 1024, DS_ERR_DIM);
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   long long gx = items;
@@ -812,7 +726,7 @@ static int pm_launch_z(K kernel, long long items, int ctas_per_sm, unsigned grid
   }
   if (gx < 1) gx = 1;
   DS_REQUIRE(gx < (1ll << 31), DS_ERR_DIM);
-  kernel<<<dim3(static_cast<unsigned>(gx), grid_y, grid_z), kBlock, smem, st>>>(args...);
+  kernel<<<dim3(static_cast<unsigned>(gx), grid_y), kBlock, smem, st>>>(args...);
   return check_launch();
 }
 
@@ -820,13 +734,14 @@ static int pm_launch_z(K kernel, long long items, int ctas_per_sm, unsigned grid
 
 extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d_wt, int taps,
                             const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
-                            int hw, int dtype, void* stream) {
+                            int hw, void* d_peer, int dtype, void* stream) {
   using namespace ds;
-  DS_REQUIRE(pm != nullptr && out != nullptr, DS_ERR_NULL);
+  DS_REQUIRE(pm != nullptr && (out != nullptr || n_jobs == 0), DS_ERR_NULL);
   DS_REQUIRE(taps == 1 || taps == 4, DS_ERR_DIM);
   DS_REQUIRE(taps == 1 || (d_idx != nullptr && d_wt != nullptr), DS_ERR_NULL);
   DS_REQUIRE(P == kPmPlanes, DS_ERR_DIM);
-  DS_REQUIRE(n_jobs > 0 && F > 0 && HW > 0 && f_len > 0 && f_len <= F && hw > 0 && h_f0 >= 0, DS_ERR_DIM);
+  DS_REQUIRE(n_jobs >= 0 && F > 0 && HW > 0 && f_len > 0 && f_len <= F && hw > 0 && h_f0 >= 0, DS_ERR_DIM);
+  DS_REQUIRE(n_jobs > 0 || d_peer != nullptr, DS_ERR_DIM);        // an idle rank still takes part in the exchange
   DS_REQUIRE(d_idx != nullptr || hw <= HW, DS_ERR_DIM);
   DS_REQUIRE(pm_aligned16(pm) && pm_aligned16(out), DS_ERR_ALIGN);
   const int tpj = static_cast<int>(div_up(hw, kPmKT));
@@ -835,6 +750,8 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   DS_REQUIRE(static_cast<long long>(n_jobs) * taps * hw < (1ll << 31), DS_ERR_DIM);
   PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ds_peer_table_t* peer = static_cast<ds_peer_table_t*>(d_peer);
+  const long long to = g_peer_timeout_ns;
   DS_DISPATCH_DTYPE(dtype, {
     constexpr int VE = 16 / sizeof(ET);
     DS_REQUIRE(hw % VE == 0, DS_ERR_ALIGN);
@@ -843,11 +760,11 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
     const AT* pmp = static_cast<const AT*>(pm);
     ET* op = static_cast<ET*>(out);
     if (taps == 1) {
-      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
-      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, peer, to);
+      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, peer, to);
     }
-    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
-    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, peer, to);
+    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, peer, to);
   });
   return DS_OK;
 }
@@ -857,30 +774,23 @@ extern "C" int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payl
                                    const int32_t* d_ent_src, const int32_t* d_ent_dst, int n_ent,
                                    const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
                                    int views_per_fwin, int job_begin, int job_count,
-                                   int P, int F, int HW, int f_len, int hw, int dtype, void* stream) {
+                                   int P, int F, int HW, int f_len, int hw, void* d_peer, int dtype, void* stream) {
   using namespace ds;
   PmMergeArgs a;
   int rc = pm_fill_merge_args(a, h_pms, h_payloads, Q, mask, mask_mode, n_ent, d_ftab, d_fbegin, n_fwin,
-                              views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw);
+                              views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, d_peer);
   if (rc != DS_OK) return rc;
   DS_REQUIRE((d_view_ptr == nullptr) == (d_ent_src == nullptr) && (d_view_ptr == nullptr) == (d_ent_dst == nullptr), DS_ERR_NULL);
   if (d_view_ptr == nullptr)                     // identity plan: entry i = (k = i, dst = i) of job 0
     DS_REQUIRE(n_ent <= HW && n_ent <= hw && views_per_fwin == 1 && n_fwin == 1 && job_begin == 0, DS_ERR_DIM);
-  if (n_ent == 0) return DS_OK;
+  if (n_ent == 0 && d_peer == nullptr) return DS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long items = div_up(n_ent, 32);
-  const int cps = g_merge_persistent ? g_merge_ctas_per_sm : -1;
-  if (!g_merge_persistent) a.per_cta = 32;
+  const long long items = div_up(n_ent, kPmET);
   DS_DISPATCH_DTYPE(dtype, {
     using AT = typename Atom<ET>::type;
-    const bool split = g_merge_qsplit && Q > 1;
-    const size_t smem1 = static_cast<size_t>(Q > 0 && !split ? Q : 1) * 32 * (f_len | 1) * sizeof(AT) + 32 * sizeof(int32_t);
-    if (!g_merge_persistent) {
-      if (f_len == 16) return pm_launch_z(pm_merge_nearest_kernel<ET, 16, 1>, items, cps, n_fwin, split ? Q : 1, smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
-      return pm_launch(pm_merge_nearest_kernel<ET, 0, 1>, items, cps, n_fwin, smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
-    }
-    if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16, 2>, items, cps, n_fwin, 2 * smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
-    return pm_launch(pm_merge_nearest_kernel<ET, 0, 2>, items, cps, n_fwin, 2 * smem1, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(AT) + kPmET * sizeof(int32_t);
+    if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    return pm_launch(pm_merge_nearest_kernel<ET, 0>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
   });
   return DS_OK;
 }
@@ -891,43 +801,21 @@ extern "C" int ds_pm_merge_bilinear(void* const* h_pms, const void* const* h_pay
                                     const int32_t* d_ent_src, const float* d_ent_w,
                                     const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
                                     int views_per_fwin, int job_begin, int job_count,
-                                    int P, int F, int HW, int f_len, int hw, int dtype, void* stream) {
+                                    int P, int F, int HW, int f_len, int hw, void* d_peer, int dtype, void* stream) {
   using namespace ds;
   PmMergeArgs a;
   int rc = pm_fill_merge_args(a, h_pms, h_payloads, Q, mask, mask_mode, n_rows, d_ftab, d_fbegin, n_fwin,
-                              views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw);
+                              views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, d_peer);
   if (rc != DS_OK) return rc;
   DS_REQUIRE(d_view_ptr != nullptr && d_row_dst != nullptr && d_row_ptr != nullptr && d_ent_src != nullptr && d_ent_w != nullptr, DS_ERR_NULL);
-  if (n_rows == 0) return DS_OK;
+  if (n_rows == 0 && d_peer == nullptr) return DS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long items = div_up(n_rows, kPmET);
-  const int cps = g_merge_persistent ? g_merge_ctas_per_sm : -1;
-  if (!g_merge_persistent) a.per_cta = kPmET;
   DS_DISPATCH_DTYPE(dtype, {
-    if (f_len == 16) {
-      const bool split = g_merge_qsplit && Q > 1;
-      const size_t smem = static_cast<size_t>(Q > 0 && !split ? Q : 1) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) +
-                         (2 * kPmET + 1) * sizeof(int32_t);
-#define DS_B(QM, MB) return pm_launch_z(pm_merge_bilinear_fl_kernel<ET, 16, QM, MB>, items, cps, n_fwin, split ? Q : 1, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin)
-      if (split) { switch (g_merge_minb) { case 5: DS_B(1, 5); case 6: DS_B(1, 6); case 8: DS_B(1, 8); default: DS_B(1, 4); } }
-      if (Q <= 2) { switch (g_merge_minb) { case 3: DS_B(2, 3); case 5: DS_B(2, 5); case 6: DS_B(2, 6); default: DS_B(2, 4); } }
-      DS_B(4, 2);
-    }
     const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(typename Atom<ET>::type) + kPmET * sizeof(int32_t);
-    return pm_launch(pm_merge_bilinear_kernel<ET>, items, cps, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin);
+    return pm_launch(pm_merge_bilinear_kernel<ET>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin);
   });
   return DS_OK;
-}
-
-extern "C" int ds_tune(int knob, int value) {
-  switch (knob) {
-    case DS_TUNE_PM_GATHER_CTAS_PER_SM: ds::g_gather_ctas_per_sm = value; return DS_OK;
-    case DS_TUNE_PM_MERGE_PERSISTENT: ds::g_merge_persistent = value; return DS_OK;
-    case DS_TUNE_PM_MERGE_CTAS_PER_SM: ds::g_merge_ctas_per_sm = value; return DS_OK;
-    case DS_TUNE_PM_MERGE_QSPLIT: ds::g_merge_qsplit = value; return DS_OK;
-    case 100: ds::g_merge_minb = value; return DS_OK;   /* experiment knob */
-    default: return DS_ERR_DIM;
-  }
 }
 
 extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const* h_payloads, int Q,
@@ -936,18 +824,18 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
                                           const int32_t* d_row_start, int n_rows, const int32_t* d_ent_k,
                                           const float* d_ent_w, const int32_t* d_ftab, const int32_t* d_fbegin,
                                           int n_fwin, int views_per_fwin, int job_begin, int job_count,
-                                          int P, int F, int HW, int f_len, int hw, int dtype, void* stream) {
+                                          int P, int F, int HW, int f_len, int hw, void* d_peer, int dtype, void* stream) {
   using namespace ds;
   PmMergeArgs a;
   int rc = pm_fill_merge_args(a, h_pms, h_payloads, Q, mask, mask_mode, n_rows, d_ftab, d_fbegin, n_fwin,
-                              views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw);
+                              views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, d_peer);
   if (rc != DS_OK) return rc;
   DS_REQUIRE(d_view_ptr != nullptr && d_tile != nullptr && d_row_dst != nullptr && d_row_start != nullptr &&
              d_ent_k != nullptr && d_ent_w != nullptr, DS_ERR_NULL);
   DS_REQUIRE(pm_aligned16(d_tile), DS_ERR_ALIGN);
   const int4* d_tile4 = reinterpret_cast<const int4*>(d_tile);
   DS_REQUIRE(f_len == 16 && (Q == 1 || Q == 2 || Q == 4) && n_tiles >= 0, DS_ERR_DIM);   // other shapes: ds_pm_merge_bilinear
-  if (n_tiles == 0) return DS_OK;
+  if (n_tiles == 0 && d_peer == nullptr) return DS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
@@ -956,4 +844,14 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
     return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
   });
   return DS_OK;
+}
+
+extern "C" int ds_peer_table_size(void) { return static_cast<int>(sizeof(ds_peer_table_t)); }
+
+extern "C" int ds_tune(int knob, long long value) {
+  switch (knob) {
+    case DS_TUNE_PM_GATHER_CTAS_PER_SM: ds::g_gather_ctas_per_sm = static_cast<int>(value); return DS_OK;
+    case DS_TUNE_PEER_TIMEOUT_NS: ds::g_peer_timeout_ns = value; return DS_OK;
+    default: return DS_ERR_DIM;
+  }
 }

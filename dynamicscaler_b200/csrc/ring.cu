@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(kBlock)
 ring_copy_kernel(T* __restrict__ pano, T* __restrict__ win, const int32_t* __restrict__ d_wins,
                  int h_left, int h_top, int h_f0, RingDims d, int n_tiles) {
   using V4 = typename Elem<T>::vec4;
-  const int wg = WG > 0 ? WG : d.w / VEC;         // column groups per window row
-  const int rows_per_pass = WG > 0 ? kBlock / WG : 0;
+  constexpr int WGS = WG > 0 ? WG : 1;            // column groups per window row (fast path only)
+  constexpr int rows_per_pass = kBlock / WGS;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     // tile = (window j, plane pl, window frame fo)
     const int fo = tile % d.f_len;
@@ -105,7 +105,7 @@ ring_copy_kernel(T* __restrict__ pano, T* __restrict__ win, const int32_t* __res
 
     if (WG > 0 && VEC == 4 && (left & 3) == 0 && d.w <= d.W && d.h <= d.H) {
       // fast path: fixed column group per thread, rows strided by rows_per_pass
-      const int xg = threadIdx.x % WG, y0 = threadIdx.x / WG;
+      const int xg = threadIdx.x % WGS, y0 = threadIdx.x / WGS;
       int c = left + xg * VEC;
       c = c >= d.W ? c - d.W : c;
       constexpr int U = 4;

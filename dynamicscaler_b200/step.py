@@ -81,26 +81,96 @@ class PanoramaState:
     t2v_sphere_panorama_pipeline.py:159; kept as is) or a latent-shaped tensor (I2V,
     i2v_sphere_panorama_pipeline.py:220; kept pixel-major)."""
 
-    def __init__(self, stepper, tensors, mask=None):
+    def __init__(self, stepper, tensors, mask=None, peer=False):
         t0 = tensors[0]
         _lib.require_cuda(t0, "panorama")
         B, C, F, H, W = t0.shape
         assert B * C == 4, "the pixel-major path needs B*C == 4 planes (use reference-order tensors otherwise)"
         assert (F, H, W) == (stepper.F, stepper.H, stepper.W)
+        assert len(tensors) <= _lib.DS_MAX_PAYLOADS
         self.stepper, self.shape, self.dtype, self.device = stepper, tuple(t0.shape), t0.dtype, t0.device
-        self.pms = [stepper._pack(t) for t in tensors]
         self.mask_plane, self.mask_pm = None, None
+        self._mask_shape = None if mask is None else tuple(mask.shape)
+        self.peer_table, self._peer_buf, self._peer_hdl = None, None, None
+        mask_is_plane = mask is not None and mask.numel() == H * W
         if mask is not None:
-            assert mask.dtype == t0.dtype
-            if mask.numel() == H * W:
+            assert mask.dtype == t0.dtype and (mask_is_plane or tuple(mask.shape) == self.shape)
+        if peer and stepper.world > 1:
+            self._init_peer(tensors, mask, mask_is_plane)
+            return
+        self.pms = [stepper._pack(t) for t in tensors]
+        if mask is not None:
+            if mask_is_plane:
                 self.mask_plane = mask.contiguous().clone()
             else:
-                assert tuple(mask.shape) == self.shape
                 self.mask_pm = stepper._pack(mask)
-        self._mask_shape = None if mask is None else tuple(mask.shape)
+
+    # ------------------------------------------------------------ peer replicas ----
+    def _init_peer(self, tensors, mask, mask_is_plane):
+        """Allocate [table | panoramas | mask] in ONE symmetric (peer-mapped) buffer, exchange the
+        addresses, fill this rank's ds_peer_table_t.  Collective over the stepper's group."""
+        import ctypes as C
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        st = self.stepper
+        assert st.world <= _lib.DS_MAX_PEERS
+        esz = tensors[0].element_size()
+        n = tensors[0].numel()
+        align = lambda x: (x + 255) // 256 * 256
+        tab_bytes = align(lib.ds_peer_table_size())
+        assert lib.ds_peer_table_size() == C.sizeof(_lib.PeerTable)
+        pm_bytes = align(n * esz)
+        mask_bytes = 0 if mask is None else align(mask.numel() * esz)
+        total = tab_bytes + len(tensors) * pm_bytes + mask_bytes
+        group = st.group if st.group is not None else dist.group.WORLD
+        buf = symm.empty(total, dtype=torch.uint8, device=self.device)
+        hdl = symm.rendezvous(buf, group.group_name)
+        buf.zero_()
+        base = [int(p) for p in hdl.buffer_ptrs]
+        F, HW = self.shape[2], self.shape[3] * self.shape[4]
+        self.pms = []
+        for q, t in enumerate(tensors):
+            off = tab_bytes + q * pm_bytes
+            pm = buf[off:off + n * esz].view(self.dtype).view(HW, F, 4)
+            st._pack(t, out=pm)
+            self.pms.append(pm)
+        m_off = tab_bytes + len(tensors) * pm_bytes
+        if mask is not None:
+            mview = buf[m_off:m_off + mask.numel() * esz].view(self.dtype)
+            if mask_is_plane:
+                self.mask_plane = mview.view(mask.shape)
+                self.mask_plane.copy_(mask)
+            else:
+                self.mask_pm = mview.view(HW, F, 4)
+                st._pack(mask, out=self.mask_pm)
+        tab = _lib.PeerTable()
+        tab.rank, tab.world = st.rank, st.world
+        for r in range(st.world):
+            for q in range(len(tensors)):
+                tab.pm[r][q] = base[r] + tab_bytes + q * pm_bytes
+            tab.mask[r] = base[r] + m_off if mask is not None else 0
+            tab.ctl[r] = base[r]
+        raw = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8)
+        buf[:raw.numel()].copy_(raw)
+        self.peer_table, self._peer_buf, self._peer_hdl = buf.data_ptr(), buf, hdl
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)                  # every table is filled before any kernel signals into it
+
+    def peer_error(self) -> bool:
+        """True if a cross-GPU wait of this state timed out (results are then undefined)."""
+        if self.peer_table is None:
+            return False
+        off = _lib.PeerTable.error.offset
+        return bool(self._peer_buf[off:off + 4].view(torch.int32).item())
 
     def export(self, index=None):
-        """Reference-order [B, C, F, H, W] copies of the resident panoramas (all, or one)."""
+        """Reference-order [B, C, F, H, W] copies of the resident panoramas (all, or one).  With
+        peer replicas this is a collective: it first waits until every rank's pushes have landed."""
+        if self.peer_table is not None:
+            import torch.distributed as dist
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.stepper.group)
+            assert not self.peer_error(), "a cross-GPU wait timed out"
         if index is not None:
             return self.stepper._unpack(self.pms[index], self.shape)
         return [self.stepper._unpack(pm, self.shape) for pm in self.pms]
@@ -210,20 +280,23 @@ class PanoramaStepper:
         return shard_range(plan.n_jobs, self.rank, self.world)
 
     # ------------------------------------------------------- pixel-major residency ----
-    def make_state(self, tensors: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None) -> PanoramaState:
+    def make_state(self, tensors: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None,
+                   peer: bool = False) -> PanoramaState:
         """Pack reference-order panoramas (latent, denoised, ...) into a resident
-        :class:`PanoramaState`; one pack kernel per tensor, once per stage."""
-        return PanoramaState(self, list(tensors), mask)
+        :class:`PanoramaState`; one pack kernel per tensor, once per stage.  ``peer=True`` (with
+        world_size > 1; collective) puts the replicas in symmetric memory so that ``merge_all``
+        pushes rows straight into every rank's replica instead of all-reducing."""
+        return PanoramaState(self, list(tensors), mask, peer)
 
-    def _pack(self, t: torch.Tensor) -> torch.Tensor:
+    def _pack(self, t: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[B, C, F, H, W] (B*C == 4) -> pm [H*W, F, 4]: ds_pm_merge_nearest with the identity plan."""
         B, C, F, H, W = t.shape
         t = t.contiguous()
-        pm = torch.empty((H * W, F, 4), dtype=t.dtype, device=t.device)
+        pm = torch.empty((H * W, F, 4), dtype=t.dtype, device=t.device) if out is None else out
         with torch.cuda.device(t.device):
             lib.check(lib.ds_pm_merge_nearest(_lib.ptr_array([pm]), _lib.ptr_array([t]), 1, None, _lib.DS_MASK_NONE,
                                               None, None, None, H * W, None, None, 1, 1, 0, 1,
-                                              4, F, H * W, F, H * W, _lib.dtype_code(t.dtype),
+                                              4, F, H * W, F, H * W, None, _lib.dtype_code(t.dtype),
                                               _lib.stream_ptr(t.device)), "ds_pm_merge_nearest(pack)")
         return pm
 
@@ -233,7 +306,7 @@ class PanoramaStepper:
         out = torch.empty(shape, dtype=pm.dtype, device=pm.device)
         with torch.cuda.device(pm.device):
             lib.check(lib.ds_pm_gather(pm.data_ptr(), out.data_ptr(), None, None, 1, None, 0, 1, 4, F, H * W, F,
-                                       H * W, _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)),
+                                       H * W, None, _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)),
                       "ds_pm_gather(unpack)")
         return out
 
@@ -251,24 +324,24 @@ class PanoramaStepper:
                         ("pm_btiled", vkey), self.device, lambda: host)
         return plan.pm_merge
 
-    def _pm_gather(self, pm, plan, out, j0, nj):
+    def _pm_gather(self, pm, plan, out, j0, nj, peer=None):
         F, HW = plan.F, plan.H * plan.W
-        d_jobs = plan.d_jobs[j0:j0 + nj]
+        d_jobs = plan.d_jobs[j0:j0 + max(nj, 1)]
         if plan.kind == "sphere_nearest":
             d_idx, d_wt, taps = plan.d_idx, None, 1
         else:
             (d_idx, d_wt), taps = plan.d_taps, 4
         with torch.cuda.device(pm.device):
             lib.check(lib.ds_pm_gather(pm.data_ptr(), out.data_ptr(), d_idx.data_ptr(), _lib.ptr(d_wt), taps,
-                                       d_jobs.data_ptr(), 0, nj, 4, F, HW, plan.f_len, plan.hw,
+                                       d_jobs.data_ptr(), 0, nj, 4, F, HW, plan.f_len, plan.hw, peer,
                                        _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)), "ds_pm_gather")
 
-    def _pm_merge_into(self, pms, payloads, mask, mask_mode, plan, j0, nj):
+    def _pm_merge_into(self, pms, payloads, mask, mask_mode, plan, j0, nj, peer=None):
         mp = self._pm_merge_plan(plan)
         F, HW = plan.F, plan.H * plan.W
         ref = pms[0] if pms else mask
         common = (_lib.ptr(plan.d_ftab), _lib.ptr(plan.d_fbegin), plan.n_fwin, plan.vpf, j0, nj,
-                  4, F, HW, plan.f_len, plan.hw, _lib.dtype_code(ref.dtype), _lib.stream_ptr(ref.device))
+                  4, F, HW, plan.f_len, plan.hw, peer, _lib.dtype_code(ref.dtype), _lib.stream_ptr(ref.device))
         with torch.cuda.device(ref.device):
             if plan.kind == "sphere_nearest":
                 view_ptr, ent_src, ent_dst = mp
@@ -304,8 +377,8 @@ class PanoramaStepper:
             if out is None:
                 out = torch.empty(shape, dtype=st.dtype, device=st.device)
             assert tuple(out.shape) == shape and out.is_contiguous()
-            if nj > 0:
-                self._pm_gather(st.pms[index], plan, out, j0, nj)
+            if nj > 0 or st.peer_table is not None:  # an idle rank still takes part in the exchange
+                self._pm_gather(st.pms[index], plan, out, j0, nj, st.peer_table)
             return out
         _lib.require_cuda(latent, "latent")
         assert latent.is_contiguous() and latent.dim() == 5
@@ -392,6 +465,10 @@ class PanoramaStepper:
             mask, mask_mode = st.mask_pm, _lib.DS_MASK_FULL
         if self.world == 1:
             self._pm_merge_into(pms, payloads, mask, mask_mode, plan, 0, plan.n_jobs)
+            return
+        if st.peer_table is not None:
+            # fused exchange: this rank's surviving rows go straight into every replica (csrc/pm.cu)
+            self._pm_merge_into(pms, payloads, mask, mask_mode, plan, j0, nj, st.peer_table)
             return
         # sharded: disjoint-support partial merge into zeroed buffers -> all-reduce -> select
         import torch.distributed as dist

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DS_ABI_VERSION 2
+#define DS_ABI_VERSION 3
 
 enum { DS_F32 = 0, DS_BF16 = 1 };
 
@@ -49,15 +49,12 @@ enum {
 /* mask_mode of the merge calls */
 enum { DS_MASK_NONE = 0, DS_MASK_PLANE = 1 /* one [H*W] plane */, DS_MASK_FULL = 2 /* [mask_planes][F][H*W] */ };
 
-/* Launch-shape knobs of the pixel-major kernels (process-wide; used by the autotuning script
- * tools/kbench.py -- results never depend on them, only speed). */
+/* Process-wide knobs (tools/kbench.py; results never depend on them, only speed / patience). */
 enum {
   DS_TUNE_PM_GATHER_CTAS_PER_SM = 0,   /* persistent gather: CTAs per SM, 0 = occupancy limit */
-  DS_TUNE_PM_MERGE_PERSISTENT = 1,     /* 0: one <= 32-entry tile per CTA; 1: persistent even split */
-  DS_TUNE_PM_MERGE_CTAS_PER_SM = 2,    /* persistent merges: CTAs per SM, 0 = occupancy limit */
-  DS_TUNE_PM_MERGE_QSPLIT = 3          /* 1: one payload per CTA (gridDim.z = Q) */
+  DS_TUNE_PEER_TIMEOUT_NS = 1          /* cross-GPU waits give up (and set ds_peer_table_t.error) after this */
 };
-int ds_tune(int knob, int value);
+int ds_tune(int knob, long long value);
 
 int ds_abi_version(void);
 /* Static string for a return code of this library (never NULL). */
@@ -151,6 +148,34 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
                       int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
 
 /* ------------------------------------------- pixel-major resident panorama path ---- */
+/* Multi-GPU exchange (windows sharded over ranks).  Every rank keeps a replica of
+ * the pixel-major panoramas, the mask and one ds_peer_table_t in PEER-MAPPED device memory
+ * (e.g. torch symmetric memory, cudaIpc or cuMem fabric handles: the host maps them, this
+ * library only dereferences the addresses).  Passing the LOCAL table as d_peer to the calls
+ * below switches them to exchange mode:
+ *   - merges store every surviving row into ALL replicas (pm[r][q], mask[r]) with peer
+ *     stores over NVLink -- no sum buffer, all-reduce or select;
+ *   - ordering across GPUs is carried by two monotonic counters per peer: the last CTA of a
+ *     gather publishes gathers_done[rank] into every peer's table, the last CTA of a merge
+ *     publishes merges_done[rank] (st.release.sys); a gather first waits until every peer's
+ *     merges_done reached its own merge count, a merge until every peer's gathers_done reached
+ *     its own gather count (ld.acquire.sys).  All ranks must issue the same gather / merge
+ *     sequence on a state.  A wait that exceeds DS_TUNE_PEER_TIMEOUT_NS sets `error`.
+ * The host zero-fills the table, then writes rank, world, pm, mask and ctl (the address of
+ * every rank's table, own included) before the first call. */
+#define DS_MAX_PEERS 8
+typedef struct ds_peer_table {
+  int32_t merges_done[DS_MAX_PEERS];            /* [p]: written by peer p */
+  int32_t gathers_done[DS_MAX_PEERS];           /* [p]: written by peer p */
+  int32_t my_merges, my_gathers;                /* this rank's own counts */
+  int32_t cta_gather, cta_merge;                /* last-CTA detection */
+  int32_t error, rank, world, reserved;
+  uint64_t pm[DS_MAX_PEERS][DS_MAX_PAYLOADS];   /* replica r, panorama q */
+  uint64_t mask[DS_MAX_PEERS];                  /* replica r of the mask panorama (or 0) */
+  uint64_t ctl[DS_MAX_PEERS];                   /* rank r's ds_peer_table_t */
+} ds_peer_table_t;
+int ds_peer_table_size(void);                   /* sizeof(ds_peer_table_t), for bindings */
+
 /* The batched step driver keeps the panorama of a stage resident as pm[pixel][frame][plane]
  * (H*W pixels, F frames, P == 4 planes; element (pl, f, p) of the reference's [P][F][H*W]
  * order lives at (p*F + f)*4 + pl).  Window tensors keep the reference's
@@ -162,10 +187,11 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
  *   out[j][pl][fo][k] = sum_t wt[map_j][t][k] * pm[idx[map_j][t][k]][(f0_j+fo) mod F][pl]
  * d_idx: [n_maps][taps][hw] int32; d_wt: [n_maps][4][hw] float32 (taps == 4 only).
  * d_idx == NULL (taps == 1): identity map, i.e. the unpack pm -> [P][F][hw], hw <= H*W.
- * d_jobs as in ds_gather_nearest.  Requires hw % (16 / elem_size) == 0. */
+ * d_jobs as in ds_gather_nearest.  Requires hw % (16 / elem_size) == 0.
+ * d_peer: NULL, or the local ds_peer_table_t (exchange mode; n_jobs may then be 0). */
 int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d_wt, int taps,
                  const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
-                 int hw, int dtype, void* stream);
+                 int hw, void* d_peer, int dtype, void* stream);
 
 /* Ordered sequence of set_view_tensor_no_interpolation calls (panorama_tensor_utils.py:
  * 154-183; ring twin ring_panorama_tensor_utils.py:170-198), scatter form over the surviving
@@ -178,13 +204,15 @@ int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d
  * identity).  All three plan arrays NULL: identity plan over n_ent pixels, i.e. the pack
  * [P][F][hw] -> pm.
  * mask: DS_MASK_PLANE -> mask[dst] = 1 ([H*W] plane); DS_MASK_FULL -> a pixel-major
- * panorama that receives 1 in every written atom. */
+ * panorama that receives 1 in every written atom.
+ * d_peer: NULL, or the local ds_peer_table_t: rows go to every replica listed there (h_pms /
+ * mask are then only validated) and job_count may be 0 (an idle rank still signals). */
 int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payloads, int Q,
                         void* mask, int mask_mode, const int32_t* d_view_ptr,
                         const int32_t* d_ent_src, const int32_t* d_ent_dst, int n_ent,
                         const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
                         int views_per_fwin, int job_begin, int job_count,
-                        int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
+                        int P, int F, int HW, int f_len, int hw, void* d_peer, int dtype, void* stream);
 
 /* Ordered sequence of set_view_tensor_bilinear calls (panorama_tensor_utils.py:98-152; ring
  * twin ring_panorama_tensor_utils.py:107-166).  Row r is panorama pixel d_row_dst[r], owned
@@ -199,7 +227,7 @@ int ds_pm_merge_bilinear(void* const* h_pms, const void* const* h_payloads, int 
                          const int32_t* d_ent_src, const float* d_ent_w,
                          const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin,
                          int views_per_fwin, int job_begin, int job_count,
-                         int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
+                         int P, int F, int HW, int f_len, int hw, void* d_peer, int dtype, void* stream);
 
 /* ds_pm_merge_bilinear on a TILED plan (f_len == 16, Q in {1, 2, 4}; fast path).  The host pads
  * the CSR entry list so that tile t owns entries [64t, 64t + 64) (d_ent_k < 0 = padding; all of
@@ -214,7 +242,7 @@ int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const* h_payloads
                                const int32_t* d_row_start, int n_rows, const int32_t* d_ent_k,
                                const float* d_ent_w, const int32_t* d_ftab, const int32_t* d_fbegin,
                                int n_fwin, int views_per_fwin, int job_begin, int job_count,
-                               int P, int F, int HW, int f_len, int hw, int dtype, void* stream);
+                               int P, int F, int HW, int f_len, int hw, void* d_peer, int dtype, void* stream);
 
 /* ------------------------------------------------------------------ elementwise ---- */
 

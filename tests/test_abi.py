@@ -102,3 +102,22 @@ def test_reference_assertions_fire_before_any_launch():
         RingImageTensor(None, torch.zeros(3, 8, 16), height=8, width=12)
     with pytest.raises(NotImplementedError):
         mix_latents_with_mask(torch.zeros(1, 1, 2, 4, 4), torch.zeros(1, 1, 2, 4, 4), torch.zeros(4, 4), 0.5)
+
+
+def test_peer_table_layout_matches_header(tmp_path):
+    """ctypes mirror of ds_peer_table_t vs the C header (compiled with gcc) and the library."""
+    import subprocess
+    src = tmp_path / "off.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dynscaler.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ds_peer_table_t),'
+                   'offsetof(ds_peer_table_t, gathers_done), offsetof(ds_peer_table_t, my_merges),'
+                   'offsetof(ds_peer_table_t, error), offsetof(ds_peer_table_t, pm),'
+                   'offsetof(ds_peer_table_t, mask), offsetof(ds_peer_table_t, ctl));return 0;}\n')
+    exe = tmp_path / "off"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    T = _lib.PeerTable
+    want = [ctypes.sizeof(T), T.gathers_done.offset, T.my_merges.offset, T.error.offset, T.pm.offset,
+            T.mask.offset, T.ctl.offset]
+    assert got == want
+    assert _lib.lib.ds_peer_table_size() == ctypes.sizeof(T)

@@ -19,7 +19,7 @@ BF16_TOL = 1e-2
 def dev():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     from dynamicscaler_b200 import lib
-    assert lib.ds_abi_version() == 2
+    assert lib.ds_abi_version() == 3
     return torch.device("cuda:0")
 
 

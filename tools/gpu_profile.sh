@@ -5,10 +5,10 @@
 TAG=${1:-r1}
 LAYOUT=${2:-pm}
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/launches_${TAG}.csv \
-    python bench.py --steps 10 --warmup 3 --no-graph --no-cpu --layout $LAYOUT > gpurun_out/ncu_bench_${TAG}.log 2>&1
+    python bench.py --steps 20 --warmup 3 --no-graph --no-cpu --no-kernel-pass --layout $LAYOUT > gpurun_out/ncu_bench_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'gather_|merge_' -s 12 -c 4 \
     -f -o gpurun_out/prof_${TAG} \
-    python bench.py --steps 4 --warmup 3 --no-graph --no-cpu --layout $LAYOUT > gpurun_out/ncu_full_${TAG}.log 2>&1
+    python bench.py --steps 4 --warmup 3 --no-graph --no-cpu --no-kernel-pass --layout $LAYOUT > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out/
