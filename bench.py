@@ -186,10 +186,10 @@ class Workset:
     """One rotating buffer set (panoramas + windows + payloads), so consecutive steps touch
     different memory and the aggregate footprint exceeds L2."""
 
-    def __init__(self, wl, n_local, dev, gen, st=None):
+    def __init__(self, wl, n_local, dev, gen, st=None, peer=False, gen_pano=None):
         shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
         vshape = (n_local, 1, wl["C"], wl["f_len"], wl["h"], wl["w"])
-        self.lat = torch.randn(shape, device=dev, generator=gen)
+        self.lat = torch.randn(shape, device=dev, generator=gen_pano if gen_pano is not None else gen)
         self.den = torch.zeros(shape, device=dev)
         # T2V sphere: [1,H,W] mask plane (t2v_sphere_panorama_pipeline.py:159); frame ring (I2V) and the
         # planar ring loops: latent-shaped mask (i2v_sphere_panorama_pipeline.py:220,810)
@@ -199,7 +199,7 @@ class Workset:
         self.x_prev = torch.randn(vshape, device=dev, generator=gen)
         self.x0 = torch.randn(vshape, device=dev, generator=gen)
         # resident pixel-major state (layout "pm"): gather/merge work on it in place
-        self.state = st.make_state([self.lat, self.den], mask=self.mask) if st is not None else None
+        self.state = st.make_state([self.lat, self.den], mask=self.mask, peer=peer) if st is not None else None
         self.pano = self.state if self.state is not None else self.lat
 
     def merge(self, st, plan):
@@ -285,9 +285,11 @@ def run_ours(args, wl, wl_name):
     n_local = st.local_jobs(plans[modes[0]][0])[1]
     n_win = plans[modes[0]][0].n_jobs
     st_pm = st if (args.layout == "pm" and wl["kind"] == "sphere") else None
-    one = Workset(wl, n_local, dev, gen, st_pm)
+    peer = dist_on and st_pm is not None and args.exchange == "peer"
+    gen_pano = torch.Generator(device=dev).manual_seed(99)      # replicas start identical on every rank
+    one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano)
     n_sets = max(2, min(4, -(-3 * L2_BYTES // one.nbytes())))   # aggregate footprint >= 3x L2
-    sets = [one] + [Workset(wl, n_local, dev, gen, st_pm) for _ in range(n_sets - 1)]
+    sets = [one] + [Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano) for _ in range(n_sets - 1)]
     combos = [(i % NP, i % n_sets) for i in range(NP * n_sets // np.gcd(NP, n_sets))]
 
     def make_step(mode, off, s):
@@ -415,7 +417,10 @@ def run_ours(args, wl, wl_name):
                        "layout": "resident pixel-major [H*W][F][4] (csrc/pm.cu)" if st_pm is not None
                                  else "reference [B,C,F,H,W] (csrc/sphere.cu, csrc/ring.cu)",
                        "maps": "precomputed on host (static geometry), cached on device",
-                       "sharding": "windows split over ranks, 1 NCCL all-reduce/step" if dist_on else "none"},
+                       "sharding": ("none" if not dist_on else
+                                    "windows split over ranks; merge kernels push rows into every replica over NVLink "
+                                    "(peer stores, release/acquire counters)" if peer else
+                                    "windows split over ranks, 1 NCCL all-reduce/step")},
             "steps_per_s": 1e3 / head["ms_per_step"],
             "gpu_launches": int(head["launches_per_step"] * K),
             "clocks": sampler.summary(),
@@ -468,6 +473,8 @@ def main():
                     help="sphere workloads: bilinear (headline) or nearest; ring workloads always run 'ring'")
     ap.add_argument("--layout", default="pm", choices=["pm", "ref"],
                     help="pm: panoramas resident in pixel-major order (PanoramaState); ref: reference order")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "allreduce"],
+                    help="N > 1: fused peer-store exchange in the merge kernels, or NCCL all-reduce + select")
     ap.add_argument("--workload", default="cfg2_sphere_128x256", choices=list(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

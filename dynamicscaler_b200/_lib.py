@@ -26,6 +26,7 @@ PROTOTYPES = {
     "ds_abi_version": [],
     "ds_error_string": [_i],
     "ds_peer_table_size": [],
+    "ds_pm_peer_sync": [_vp, _i, _vp],
     "ds_tune": [_i, _ll],
     "ds_ring_gather": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_ring_scatter": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
@@ -44,14 +45,15 @@ PROTOTYPES = {
 
 
 DS_MAX_PEERS = 8
+DS_PEER_AFTER_GATHER, DS_PEER_AFTER_MERGE = 0, 1
 
 
 class PeerTable(C.Structure):
     """Mirror of ``ds_peer_table_t`` (include/dynscaler.h); tests/test_abi.py checks the layout
     against the header."""
     _fields_ = [("merges_done", C.c_int32 * DS_MAX_PEERS), ("gathers_done", C.c_int32 * DS_MAX_PEERS),
-                ("my_merges", C.c_int32), ("my_gathers", C.c_int32), ("cta_gather", C.c_int32),
-                ("cta_merge", C.c_int32), ("error", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+                ("my_merges", C.c_int32), ("my_gathers", C.c_int32), ("reserved0", C.c_int32),
+                ("reserved1", C.c_int32), ("error", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("reserved", C.c_int32),
                 ("pm", (C.c_uint64 * DS_MAX_PAYLOADS) * DS_MAX_PEERS), ("mask", C.c_uint64 * DS_MAX_PEERS),
                 ("ctl", C.c_uint64 * DS_MAX_PEERS)]

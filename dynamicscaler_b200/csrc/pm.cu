@@ -120,39 +120,32 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// Every CTA: block until each peer's counter in `done` (this rank's table, written remotely)
-// has reached `want`.  A timeout sets tab->error instead of hanging the GPU.
-__device__ __forceinline__ void pm_peer_wait(ds_peer_table_t* tab, const int32_t* done, int want, long long timeout_ns) {
-  if (static_cast<int>(threadIdx.x) < tab->world && static_cast<int>(threadIdx.x) != tab->rank) {
+// One tiny kernel between the data kernels of a step (stream order does the rest):
+//   phase DS_PEER_AFTER_GATHER: this rank has finished reading its replica -> bump my_gathers,
+//     publish it into gathers_done[rank] of every peer, then wait until every peer has
+//     published at least as many gathers (so their replicas may be overwritten by my merge);
+//   phase DS_PEER_AFTER_MERGE: this rank's rows have been pushed (the merge kernel has
+//     retired, so its peer stores are performed) -> same with my_merges / merges_done, after
+//     which every replica holds the complete merged panorama and may be gathered from.
+// lane p talks to peer p.  A wait longer than timeout_ns sets tab->error instead of hanging.
+__global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, long long timeout_ns) {
+  const int p = threadIdx.x;
+  int32_t* mine = phase == DS_PEER_AFTER_GATHER ? &tab->my_gathers : &tab->my_merges;
+  const size_t off = phase == DS_PEER_AFTER_GATHER ? offsetof(ds_peer_table_t, gathers_done)
+                                                   : offsetof(ds_peer_table_t, merges_done);
+  const int c = *mine + 1;
+  __syncwarp();
+  if (p == 0) *mine = c;
+  __threadfence_system();
+  if (p < tab->world && p != tab->rank) {
+    char* peer = reinterpret_cast<char*>(tab->ctl[p]);
+    st_release_sys(reinterpret_cast<int32_t*>(peer + off) + tab->rank, c);
+    const int32_t* done = reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(tab) + off) + p;
     const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(done + threadIdx.x) < want) {
+    while (ld_acquire_sys(done) < c) {
       if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) {
         tab->error = 1;
         break;
-      }
-    }
-  }
-  __syncthreads();
-}
-
-// Every CTA, after its last access: the last CTA of the grid bumps this rank's own counter and
-// publishes it into slot `rank` of `done_offset` in every peer's table.
-__device__ __forceinline__ void pm_peer_signal(ds_peer_table_t* tab, int32_t* cta_counter, int32_t* my_count,
-                                               size_t done_offset_bytes) {
-  __threadfence_system();                        // this thread's peer stores are visible system-wide
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    const unsigned n = atomicAdd(reinterpret_cast<unsigned*>(cta_counter), 1u);
-    if (n == total - 1) {
-      *cta_counter = 0;
-      const int c = *my_count + 1;
-      *my_count = c;
-      __threadfence_system();
-      for (int p = 0; p < tab->world; ++p) {
-        if (p == tab->rank) continue;
-        char* peer = reinterpret_cast<char*>(tab->ctl[p]);
-        st_release_sys(reinterpret_cast<int32_t*>(peer + done_offset_bytes) + tab->rank, c);
       }
     }
   }
@@ -177,11 +170,8 @@ template <typename T, int TAPS, int FL, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ out,
                  const int32_t* __restrict__ d_idx, const float* __restrict__ d_wt,
-                 const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a, ds_peer_table_t* __restrict__ peer,
-                 long long peer_timeout_ns) {
+                 const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a) {
   using A = typename Atom<T>::type;
-  // peers must have pushed every row of the previous step into this replica before it is read
-  if (peer != nullptr) pm_peer_wait(peer, peer->merges_done, peer->my_merges, peer_timeout_ns);
   constexpr int VE = 16 / sizeof(T);            // elements per 16-byte vector
   constexpr int S = kPmKT + VE;                 // padded row stride (elements): 4 banks mod 32
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -287,8 +277,6 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     }
     if (issued) bulk_commit_and_wait_read();    // the tile is reused / freed only after the copy read it
   }
-  // this replica may now be overwritten by the peers' merges
-  if (peer != nullptr) pm_peer_signal(peer, &peer->cta_gather, &peer->my_gathers, offsetof(ds_peer_table_t, gathers_done));
 }
 
 // ------------------------------------------------------------------------ merges ----
@@ -301,7 +289,6 @@ struct PmMergeArgs {
   int vpf, job_begin, job_count;
   int F, HW, f_len, hw;
   ds_peer_table_t* peer;         // NULL: single replica (pm / mask above)
-  long long peer_timeout_ns;
 };
 
 // dynamic indexing of a kernel-parameter array would force a local-memory copy of the struct
@@ -312,40 +299,48 @@ template <typename PT> __device__ __forceinline__ PT pm_sel(PT const (&arr)[DS_M
   return r;
 }
 
+// Replica addresses of this launch, staged once per CTA: [r][q] panoramas, [r][DS_MAX_PAYLOADS] mask.
+struct PmReplicas {
+  unsigned long long ptr[DS_MAX_PEERS][DS_MAX_PAYLOADS + 1];
+  int world;
+};
+
+// Every merge CTA first: stage the replica table (peer mode) -- ends with a barrier.
+__device__ __forceinline__ void pm_merge_begin(const PmMergeArgs& a, PmReplicas& rep) {
+  if (a.peer == nullptr) return;
+  if (threadIdx.x == 0) rep.world = a.peer->world;
+  if (threadIdx.x < DS_MAX_PEERS * (DS_MAX_PAYLOADS + 1)) {
+    const int r = threadIdx.x / (DS_MAX_PAYLOADS + 1), q = threadIdx.x % (DS_MAX_PAYLOADS + 1);
+    rep.ptr[r][q] = q < DS_MAX_PAYLOADS ? a.peer->pm[r][q] : a.peer->mask[r];
+  }
+  __syncthreads();
+}
+
 // Store one atom of payload q at element offset `o` of the panorama -- into the single local
 // replica, or into every rank's replica (peer stores over NVLink).
 template <typename A>
-__device__ __forceinline__ void pm_store(const PmMergeArgs& a, int q, size_t o, const A& v) {
+__device__ __forceinline__ void pm_store(const PmMergeArgs& a, const PmReplicas& rep, int q, size_t o, const A& v) {
   if (a.peer == nullptr) {
     static_cast<A*>(pm_sel(a.pm, q))[o] = v;
   } else {
-    for (int r = 0; r < a.peer->world; ++r) reinterpret_cast<A*>(a.peer->pm[r][q])[o] = v;
+    for (int r = 0; r < rep.world; ++r) reinterpret_cast<A*>(rep.ptr[r][q])[o] = v;
   }
 }
 template <typename A>
-__device__ __forceinline__ void pm_store_mask_atom(const PmMergeArgs& a, size_t o, const A& v) {
+__device__ __forceinline__ void pm_store_mask_atom(const PmMergeArgs& a, const PmReplicas& rep, size_t o, const A& v) {
   if (a.peer == nullptr) {
     static_cast<A*>(a.mask)[o] = v;
   } else {
-    for (int r = 0; r < a.peer->world; ++r) reinterpret_cast<A*>(a.peer->mask[r])[o] = v;
+    for (int r = 0; r < rep.world; ++r) reinterpret_cast<A*>(rep.ptr[r][DS_MAX_PAYLOADS])[o] = v;
   }
 }
 template <typename T>
-__device__ __forceinline__ void pm_store_mask_plane(const PmMergeArgs& a, int dst) {
+__device__ __forceinline__ void pm_store_mask_plane(const PmMergeArgs& a, const PmReplicas& rep, int dst) {
   if (a.peer == nullptr) {
     static_cast<T*>(a.mask)[dst] = Elem<T>::one();
   } else {
-    for (int r = 0; r < a.peer->world; ++r) reinterpret_cast<T*>(a.peer->mask[r])[dst] = Elem<T>::one();
+    for (int r = 0; r < rep.world; ++r) reinterpret_cast<T*>(rep.ptr[r][DS_MAX_PAYLOADS])[dst] = Elem<T>::one();
   }
-}
-
-// Prologue / epilogue of every merge CTA in peer mode.
-__device__ __forceinline__ void pm_merge_begin(const PmMergeArgs& a) {
-  // every peer must have finished reading its replica (this step's gather) before rows land in it
-  if (a.peer != nullptr) pm_peer_wait(a.peer, a.peer->gathers_done, a.peer->my_gathers, a.peer_timeout_ns);
-}
-__device__ __forceinline__ void pm_merge_end(const PmMergeArgs& a) {
-  if (a.peer != nullptr) pm_peer_signal(a.peer, &a.peer->cta_merge, &a.peer->my_merges, offsetof(ds_peer_table_t, merges_done));
 }
 
 struct PmRange {
@@ -396,7 +391,8 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
                         const int32_t* __restrict__ d_ent_src, const int32_t* __restrict__ d_ent_dst,
                         const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
-  pm_merge_begin(a);
+  __shared__ PmReplicas rep;
+  pm_merge_begin(a, rep);
   PmRange rg;
   if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -417,7 +413,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
       if (warp == 0) {
         const int dst = d_ent_dst != nullptr ? __ldg(d_ent_dst + rg.lo + lane) : rg.lo + lane;
         s_dst[lane] = dst;
-        if (a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, dst);
+        if (a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, rep, dst);
       }
     }
     constexpr int U = 4;
@@ -442,22 +438,39 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
       for (int u = 0; u < U; ++u)
         if (live[u]) tile[(q[u] * kPmET + lane) * SA + fo[u]] = atom_join<T>(e[u]);
     }
+    // Exchange mode with whole rows (no frame ring): every staged 256-B row leaves through one TMA
+    // bulk copy per replica, so NVLink back-pressure never stalls the SM's load/store pipeline.
+    const bool row_bulk = sizeof(A) == 16 && a.peer != nullptr && d_ftab == nullptr && a.Q > 0 && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
+    if (row_bulk) fence_proxy_async_smem();
     __syncthreads();
 
-    const int per_q = cnt * f_len;
-    const int n_units = (a.Q > 0 ? a.Q : 1) * per_q;
-    for (int u = threadIdx.x; u < n_units; u += kBlock) {
-      const int q = u / per_q, r = u - q * per_q;
-      const int i = r / f_len, fo = r - i * f_len;
-      int f;
-      if (pm_frame_live(a, d_ftab, rg, fo, f_len, f)) {
-        const size_t o = static_cast<size_t>(s_dst[i]) * a.F + f;
-        if (a.Q > 0) pm_store<A>(a, q, o, tile[(q * kPmET + i) * SA + fo]);
-        if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, o, atom_ones<T>());
+    if (row_bulk) {
+      const uint32_t row_bytes = static_cast<uint32_t>(f_len * sizeof(A));
+      const int n_rows = a.Q * cnt;
+      bool issued = false;
+      for (int u = threadIdx.x; u < n_rows * rep.world; u += kBlock) {
+        const int r = u / n_rows, qi = u - r * n_rows;
+        const int q = qi / cnt, i = qi - q * cnt;
+        bulk_store(reinterpret_cast<A*>(rep.ptr[r][q]) + static_cast<size_t>(s_dst[i]) * a.F,
+                   tile + (q * kPmET + i) * SA, row_bytes);
+        issued = true;
+      }
+      if (issued) bulk_commit_and_wait_read();
+    } else {
+      const int per_q = cnt * f_len;
+      const int n_units = (a.Q > 0 ? a.Q : 1) * per_q;
+      for (int u = threadIdx.x; u < n_units; u += kBlock) {
+        const int q = u / per_q, r = u - q * per_q;
+        const int i = r / f_len, fo = r - i * f_len;
+        int f;
+        if (pm_frame_live(a, d_ftab, rg, fo, f_len, f)) {
+          const size_t o = static_cast<size_t>(s_dst[i]) * a.F + f;
+          if (a.Q > 0) pm_store<A>(a, rep, q, o, tile[(q * kPmET + i) * SA + fo]);
+          if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, rep, o, atom_ones<T>());
+        }
       }
     }
   }
-  pm_merge_end(a);
 }
 
 // Tiled weighted merge (fast path): the host pads the CSR entry list so that tile t owns
@@ -487,11 +500,9 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   const int v_lo = min(max(a.job_begin - s * a.vpf, 0), a.vpf);
   const int v_hi = min(max(a.job_begin + a.job_count - s * a.vpf, 0), a.vpf);
   const int t = __ldg(d_view_ptr + v_lo) + blockIdx.x;
-  pm_merge_begin(a);
-  if (t >= __ldg(d_view_ptr + v_hi)) {
-    pm_merge_end(a);
-    return;
-  }
+  if (t >= __ldg(d_view_ptr + v_hi)) return;
+  __shared__ PmReplicas rep;
+  pm_merge_begin(a, rep);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e_base = t * kPmEC;
 
@@ -558,10 +569,17 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   __syncthreads();
 
   // ---- phase B: ordered accumulation, normalise, full-row stores ----
+  // Exchange mode with whole rows (no frame ring): results are staged in shared memory (over the
+  // consumed products) and every 256-B row leaves through one TMA bulk copy per replica.
+  const bool row_bulk = sizeof(A) == 16 && a.peer != nullptr && d_ftab == nullptr && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
   const int fo_b = threadIdx.x & (FL - 1), row_b = threadIdx.x / FL;
+  constexpr int NSW = kPmET / (kBlock / FL);
+  float4 res[NSW][QN];
+  bool ok[NSW];
 #pragma unroll
-  for (int sw = 0; sw < kPmET / (kBlock / FL); ++sw) {
+  for (int sw = 0; sw < NSW; ++sw) {
     const int i = sw * (kBlock / FL) + row_b;
+    ok[sw] = false;
     if (i >= cnt) continue;
     const int lo = s_rp[i], hi = s_rp[i + 1];
     float ws = 0.f;
@@ -582,21 +600,55 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
       }
     }
     if (!(ws > 0.f)) continue;
+    ok[sw] = true;
+#pragma unroll
+    for (int q = 0; q < QN; ++q)
+      res[sw][q] = make_float4(__fdiv_rn(acc[q][0], ws), __fdiv_rn(acc[q][1], ws), __fdiv_rn(acc[q][2], ws),
+                               __fdiv_rn(acc[q][3], ws));
     const int dst = s_dst[i];
-    if (fo_b == 0 && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, dst);
-    if (liveB) {
+    if (fo_b == 0 && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, rep, dst);
+    if (!row_bulk && liveB) {
       const size_t o = static_cast<size_t>(dst) * a.F + fB;
 #pragma unroll
       for (int q = 0; q < QN; ++q) {
-        float r[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) r[p] = __fdiv_rn(acc[q][p], ws);
-        pm_store<A>(a, q, o, Atom<T>::pack(r));
+        const float r[4] = {res[sw][q].x, res[sw][q].y, res[sw][q].z, res[sw][q].w};
+        pm_store<A>(a, rep, q, o, Atom<T>::pack(r));
       }
-      if (a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, o, atom_ones<T>());
+      if (a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, rep, o, atom_ones<T>());
     }
   }
-  pm_merge_end(a);
+  if (row_bulk) {
+    __syncthreads();                               // every product has been consumed
+    A* rows = reinterpret_cast<A*>(prod);          // [QN][ET][SA] result atoms
+    int32_t* s_ok = s_rp;                          // row offsets are no longer needed
+#pragma unroll
+    for (int sw = 0; sw < NSW; ++sw) {
+      const int i = sw * (kBlock / FL) + row_b;
+      if (i < cnt && fo_b == 0) s_ok[i] = ok[sw] ? 1 : 0;
+      if (ok[sw]) {
+#pragma unroll
+        for (int q = 0; q < QN; ++q) {
+          const float r[4] = {res[sw][q].x, res[sw][q].y, res[sw][q].z, res[sw][q].w};
+          rows[(q * kPmET + i) * SA + fo_b] = Atom<T>::pack(r);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    const uint32_t row_bytes = static_cast<uint32_t>(FL * sizeof(A));
+    const int n_rows = QN * cnt;
+    bool issued = false;
+    for (int u = threadIdx.x; u < n_rows * rep.world; u += kBlock) {
+      const int r = u / n_rows, qi = u - r * n_rows;
+      const int q = qi / cnt, i = qi - q * cnt;
+      if (s_ok[i]) {
+        bulk_store(reinterpret_cast<A*>(rep.ptr[r][q]) + static_cast<size_t>(s_dst[i]) * a.F,
+                   rows + (q * kPmET + i) * SA, row_bytes);
+        issued = true;
+      }
+    }
+    if (issued) bulk_commit_and_wait_read();
+  }
 }
 
 // Generic (runtime f_len, any row length) weighted merge.  CTA = 32 panorama rows; each lane
@@ -609,7 +661,8 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
                          const int32_t* __restrict__ d_ent_src, const float* __restrict__ d_ent_w,
                          const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
-  pm_merge_begin(a);
+  __shared__ PmReplicas rep;
+  pm_merge_begin(a, rep);
   PmRange rg;
   if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -633,7 +686,7 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
     if (warp == 0) {
       const int dst = wr ? __ldg(d_row_dst + rg.lo + lane) : -1;
       s_dst[lane] = dst;
-      if (wr && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, dst);
+      if (wr && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, rep, dst);
     }
     for (int pr = warp; pr < n_pairs; pr += kWarps) {
       const int q = pr / a.f_len, fo = pr - q * a.f_len;
@@ -662,12 +715,11 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
       int f;
       if (s_dst[i] >= 0 && pm_frame_live(a, d_ftab, rg, fo, a.f_len, f)) {
         const size_t o = static_cast<size_t>(s_dst[i]) * a.F + f;
-        if (a.Q > 0) pm_store<A>(a, q, o, tile[(q * kPmET + i) * SA + fo]);
-        if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, o, atom_ones<T>());
+        if (a.Q > 0) pm_store<A>(a, rep, q, o, tile[(q * kPmET + i) * SA + fo]);
+        if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, rep, o, atom_ones<T>());
       }
     }
   }
-  pm_merge_end(a);
 }
 
 static bool pm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -706,7 +758,6 @@ static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* co
   a.vpf = vpf; a.job_begin = job_begin; a.job_count = job_count;
   a.F = F; a.HW = HW; a.f_len = f_len; a.hw = hw;
   a.peer = static_cast<ds_peer_table_t*>(d_peer);
-  a.peer_timeout_ns = g_peer_timeout_ns;
   return DS_OK;
 }
 
@@ -750,8 +801,6 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   DS_REQUIRE(static_cast<long long>(n_jobs) * taps * hw < (1ll << 31), DS_ERR_DIM);
   PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  ds_peer_table_t* peer = static_cast<ds_peer_table_t*>(d_peer);
-  const long long to = g_peer_timeout_ns;
   DS_DISPATCH_DTYPE(dtype, {
     constexpr int VE = 16 / sizeof(ET);
     DS_REQUIRE(hw % VE == 0, DS_ERR_ALIGN);
@@ -760,11 +809,11 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
     const AT* pmp = static_cast<const AT*>(pm);
     ET* op = static_cast<ET*>(out);
     if (taps == 1) {
-      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, peer, to);
-      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, peer, to);
+      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
     }
-    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, peer, to);
-    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, peer, to);
+    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
   });
   return DS_OK;
 }
@@ -844,6 +893,14 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
     return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
   });
   return DS_OK;
+}
+
+extern "C" int ds_pm_peer_sync(void* d_peer, int phase, void* stream) {
+  DS_REQUIRE(d_peer != nullptr, DS_ERR_NULL);
+  DS_REQUIRE(phase == DS_PEER_AFTER_GATHER || phase == DS_PEER_AFTER_MERGE, DS_ERR_DIM);
+  ds::pm_peer_sync_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<ds_peer_table_t*>(d_peer), phase,
+                                                                           ds::g_peer_timeout_ns);
+  return ds::check_launch();
 }
 
 extern "C" int ds_peer_table_size(void) { return static_cast<int>(sizeof(ds_peer_table_t)); }

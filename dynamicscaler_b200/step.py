@@ -324,6 +324,10 @@ class PanoramaStepper:
                         ("pm_btiled", vkey), self.device, lambda: host)
         return plan.pm_merge
 
+    def _peer_sync(self, st, phase):
+        with torch.cuda.device(st.device):
+            lib.check(lib.ds_pm_peer_sync(st.peer_table, phase, _lib.stream_ptr(st.device)), "ds_pm_peer_sync")
+
     def _pm_gather(self, pm, plan, out, j0, nj, peer=None):
         F, HW = plan.F, plan.H * plan.W
         d_jobs = plan.d_jobs[j0:j0 + max(nj, 1)]
@@ -377,8 +381,10 @@ class PanoramaStepper:
             if out is None:
                 out = torch.empty(shape, dtype=st.dtype, device=st.device)
             assert tuple(out.shape) == shape and out.is_contiguous()
-            if nj > 0 or st.peer_table is not None:  # an idle rank still takes part in the exchange
+            if nj > 0:
                 self._pm_gather(st.pms[index], plan, out, j0, nj, st.peer_table)
+            if st.peer_table is not None:            # replicas may be overwritten once every rank has read
+                self._peer_sync(st, _lib.DS_PEER_AFTER_GATHER)
             return out
         _lib.require_cuda(latent, "latent")
         assert latent.is_contiguous() and latent.dim() == 5
@@ -468,7 +474,9 @@ class PanoramaStepper:
             return
         if st.peer_table is not None:
             # fused exchange: this rank's surviving rows go straight into every replica (csrc/pm.cu)
-            self._pm_merge_into(pms, payloads, mask, mask_mode, plan, j0, nj, st.peer_table)
+            if nj > 0:
+                self._pm_merge_into(pms, payloads, mask, mask_mode, plan, j0, nj, st.peer_table)
+            self._peer_sync(st, _lib.DS_PEER_AFTER_MERGE)   # replicas are complete once every rank has pushed
             return
         # sharded: disjoint-support partial merge into zeroed buffers -> all-reduce -> select
         import torch.distributed as dist

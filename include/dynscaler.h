@@ -151,30 +151,31 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
 /* Multi-GPU exchange (windows sharded over ranks).  Every rank keeps a replica of
  * the pixel-major panoramas, the mask and one ds_peer_table_t in PEER-MAPPED device memory
  * (e.g. torch symmetric memory, cudaIpc or cuMem fabric handles: the host maps them, this
- * library only dereferences the addresses).  Passing the LOCAL table as d_peer to the calls
- * below switches them to exchange mode:
- *   - merges store every surviving row into ALL replicas (pm[r][q], mask[r]) with peer
- *     stores over NVLink -- no sum buffer, all-reduce or select;
- *   - ordering across GPUs is carried by two monotonic counters per peer: the last CTA of a
- *     gather publishes gathers_done[rank] into every peer's table, the last CTA of a merge
- *     publishes merges_done[rank] (st.release.sys); a gather first waits until every peer's
- *     merges_done reached its own merge count, a merge until every peer's gathers_done reached
- *     its own gather count (ld.acquire.sys).  All ranks must issue the same gather / merge
- *     sequence on a state.  A wait that exceeds DS_TUNE_PEER_TIMEOUT_NS sets `error`.
- * The host zero-fills the table, then writes rank, world, pm, mask and ctl (the address of
- * every rank's table, own included) before the first call. */
+ * library only dereferences the addresses).  Passing the LOCAL table as d_peer switches the
+ * merge calls below to exchange mode: every surviving row is stored into ALL replicas
+ * (pm[r][q], mask[r]) with peer stores over NVLink -- no sum buffer, all-reduce or select.
+ * Ordering across GPUs is two monotonic counters per peer, exchanged by ds_pm_peer_sync (one
+ * 32-thread kernel, st.release.sys / ld.acquire.sys), which the host enqueues
+ *   after every gather  (DS_PEER_AFTER_GATHER: replicas may be overwritten once all have read)
+ *   after every merge   (DS_PEER_AFTER_MERGE:  replicas are complete once all have pushed).
+ * All ranks must issue the same gather / merge sequence on a state.  A wait that exceeds
+ * DS_TUNE_PEER_TIMEOUT_NS sets `error`.  The host zero-fills the table, then writes rank,
+ * world, pm, mask and ctl (the address of every rank's table, own included) and makes sure
+ * (host barrier) that every rank has done so before the first call. */
 #define DS_MAX_PEERS 8
 typedef struct ds_peer_table {
   int32_t merges_done[DS_MAX_PEERS];            /* [p]: written by peer p */
   int32_t gathers_done[DS_MAX_PEERS];           /* [p]: written by peer p */
   int32_t my_merges, my_gathers;                /* this rank's own counts */
-  int32_t cta_gather, cta_merge;                /* last-CTA detection */
+  int32_t reserved0, reserved1;
   int32_t error, rank, world, reserved;
   uint64_t pm[DS_MAX_PEERS][DS_MAX_PAYLOADS];   /* replica r, panorama q */
   uint64_t mask[DS_MAX_PEERS];                  /* replica r of the mask panorama (or 0) */
   uint64_t ctl[DS_MAX_PEERS];                   /* rank r's ds_peer_table_t */
 } ds_peer_table_t;
 int ds_peer_table_size(void);                   /* sizeof(ds_peer_table_t), for bindings */
+enum { DS_PEER_AFTER_GATHER = 0, DS_PEER_AFTER_MERGE = 1 };
+int ds_pm_peer_sync(void* d_peer, int phase, void* stream);
 
 /* The batched step driver keeps the panorama of a stage resident as pm[pixel][frame][plane]
  * (H*W pixels, F frames, P == 4 planes; element (pl, f, p) of the reference's [P][F][H*W]
@@ -188,7 +189,7 @@ int ds_peer_table_size(void);                   /* sizeof(ds_peer_table_t), for 
  * d_idx: [n_maps][taps][hw] int32; d_wt: [n_maps][4][hw] float32 (taps == 4 only).
  * d_idx == NULL (taps == 1): identity map, i.e. the unpack pm -> [P][F][hw], hw <= H*W.
  * d_jobs as in ds_gather_nearest.  Requires hw % (16 / elem_size) == 0.
- * d_peer: NULL, or the local ds_peer_table_t (exchange mode; n_jobs may then be 0). */
+ * d_peer: NULL, or the local ds_peer_table_t (only relaxes n_jobs > 0: an idle rank may call). */
 int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d_wt, int taps,
                  const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
                  int hw, void* d_peer, int dtype, void* stream);
@@ -206,7 +207,7 @@ int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d
  * mask: DS_MASK_PLANE -> mask[dst] = 1 ([H*W] plane); DS_MASK_FULL -> a pixel-major
  * panorama that receives 1 in every written atom.
  * d_peer: NULL, or the local ds_peer_table_t: rows go to every replica listed there (h_pms /
- * mask are then only validated) and job_count may be 0 (an idle rank still signals). */
+ * mask are then only validated) and job_count may be 0. */
 int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payloads, int Q,
                         void* mask, int mask_mode, const int32_t* d_view_ptr,
                         const int32_t* d_ent_src, const int32_t* d_ent_dst, int n_ent,
