@@ -152,8 +152,7 @@ def cpu_step_time(wl, mode, reps):
             tp.sphere_step(lat, torch.zeros_like(lat), default_views(i), xp, x0, fov=wl["fov"], width=wl["w"],
                            height=wl["h"], mode=mode)
         else:
-            tp.ring_step(lat, torch.zeros_like(lat), [(l, t_, 0) for l, t_ in ring_windows_of(wl, i)], xp, x0,
-                         w=wl["w"], h=wl["h"])
+            tp.ring_step(lat, torch.zeros_like(lat), ring_windows_of(wl, i), xp, x0, w=wl["w"], h=wl["h"])
         ts.append(time.perf_counter() - t)
     return (statistics.mean(ts[1:]), torch.get_num_threads(),
             f"{reps} full steps ({n_win} windows each) after 1 warm-up", n_win)

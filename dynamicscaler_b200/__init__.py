@@ -6,6 +6,7 @@ Module map (reference module -> drop-in here):
     utils.panorama_tensor_utils       -> dynamicscaler_b200.panorama_tensor_utils
     utils.ring_panorama_tensor_utils  -> dynamicscaler_b200.ring_panorama_tensor_utils
     utils.tensor_utils                -> dynamicscaler_b200.tensor_utils
+    utils.diffusion_utils             -> dynamicscaler_b200.diffusion_utils
 ``install()`` registers them under the reference's names so the unmodified
 t2v/i2v_sphere_panorama_pipeline call sites pick them up.  ``step`` holds the additive
 batched step driver (gather-all / merge-all, sharded over GPUs).
@@ -24,7 +25,8 @@ def install():
     (``utils.shift_window_utils`` ...) so ``pipeline/*_pipeline.py`` import them."""
     import sys
     import types
-    from . import shift_window_utils, panorama_tensor_utils, ring_panorama_tensor_utils, tensor_utils
+    from . import (diffusion_utils, panorama_tensor_utils, ring_panorama_tensor_utils, shift_window_utils,
+                   tensor_utils)
 
     pkg = sys.modules.get("utils")
     if pkg is None:
@@ -34,6 +36,7 @@ def install():
     for name, mod in (("shift_window_utils", shift_window_utils),
                       ("panorama_tensor_utils", panorama_tensor_utils),
                       ("ring_panorama_tensor_utils", ring_panorama_tensor_utils),
-                      ("tensor_utils", tensor_utils)):
+                      ("tensor_utils", tensor_utils),
+                      ("diffusion_utils", diffusion_utils)):
         sys.modules["utils." + name] = mod
         setattr(pkg, name, mod)

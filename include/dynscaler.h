@@ -256,6 +256,13 @@ int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const* h_payloads
 int ds_mix_mask(const void* l1, const void* add, const void* mask, void* out,
                 float ratio, float one_minus_ratio, long long n, int mask_hw, int dtype, void* stream);
 
+/* resize_video_latent (utils/diffusion_utils.py:21-33): F.interpolate(mode, align_corners) of every
+ * (b, c, f) plane, in [planes][h][w] -> out [planes][H][W].  mode 'nearest' ignores
+ * align_corners (the reference forces it to None, :22-23). */
+enum { DS_RESIZE_NEAREST = 0, DS_RESIZE_BILINEAR = 1, DS_RESIZE_BICUBIC = 2 };
+int ds_resize_planes(const void* in, void* out, long long planes, int h, int w, int H, int W,
+                     int mode, int align_corners, int dtype, void* stream);
+
 /* Final select of the sharded merge:
  *   pano[i] = weight[(i / weight_group) mod weight_period] > 0 ? sum[i] : pano[i]   for i < n.
  * weight has the panorama's dtype.  Reference layout: weight_group = 1 and weight_period =

@@ -440,3 +440,39 @@ def test_raw_cabi_ring_gather_with_device_descriptors(dev):
     for j, (l, t, f0) in enumerate(wins.tolist()):
         assert np.array_equal(N(out[j]), po.ring_get(lat0, l, l + 12, t, t + 8, f0, f0 + 4)[0])
     assert lib.ds_ring_gather(lat.data_ptr(), out.data_ptr(), None, 1, 70, 0, 0, 3, 4, 16, 32, 4, 8, 12, 0, None) == -4
+
+
+# ------------------------------------------------------------ resize_video_latent ----
+def test_resize_video_latent_golden(dev):
+    """ds_resize_planes vs the reference's outputs (tests/golden/resize.npz): nearest bit-exact,
+    bilinear / bicubic within 1e-5; plus the oracle on a stage-transition-sized latent."""
+    import os
+    from dynamicscaler_b200.diffusion_utils import padding_latents_at_end, padding_latents_at_front, resize_video_latent
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "resize.npz"))
+    modes = ["nearest", "bilinear", "bicubic"]
+    for n, row in enumerate(g["cases"]):
+        seed, shape, th, tw = int(row[0]), tuple(int(v) for v in row[1:6]), int(row[6]), int(row[7])
+        mode, align = modes[row[8]], bool(row[9])
+        got = N(resize_video_latent(G(randn(seed, *shape), dev), th, tw, mode=mode, align_corners=align))
+        want = g[f"out/{n}"]
+        assert got.shape == want.shape
+        if mode == "nearest":
+            assert np.array_equal(got, want), n
+        else:
+            assert np.abs(got - want).max() <= FP32_TOL, (n, np.abs(got - want).max())
+    # stage transitions of gen_pano_360.py at full size: 128x256 -> 64x128 nearest, 64x128 -> 128x256 bicubic
+    x = randn(77, 1, 4, 16, 128, 256)
+    assert np.array_equal(N(resize_video_latent(G(x, dev), 64, 128, mode="nearest")),
+                          po.resize_video_latent(x, 64, 128, mode="nearest"))
+    y = randn(78, 1, 4, 16, 64, 128)
+    assert np.abs(N(resize_video_latent(G(y, dev), 128, 256, mode="bicubic")) -
+                  po.resize_video_latent(y, 128, 256, mode="bicubic")).max() <= FP32_TOL
+    # odd widths (scalar tail), bf16
+    z = G(randn(79, 1, 4, 2, 7, 9), dev).to(torch.bfloat16)
+    ref = po.resize_video_latent(z.float().cpu().numpy(), 15, 19, mode="bilinear")
+    assert np.abs(resize_video_latent(z, 15, 19).float().cpu().numpy() - ref).max() <= BF16_TOL * 4
+    with pytest.raises(RuntimeError):
+        resize_video_latent(torch.zeros(2, 4, 3, 8, 8, device=dev), 4, 4)       # the reference's .view fails too
+    t = G(randn(80, 1, 4, 3, 4, 4), dev)
+    assert padding_latents_at_front(t, 2).shape[2] == 5 and torch.equal(padding_latents_at_front(t, 2)[:, :, 1], t[:, :, 0])
+    assert padding_latents_at_end(t, 1).shape[2] == 4 and torch.equal(padding_latents_at_end(t, 1)[:, :, 3], t[:, :, 2])

@@ -1,6 +1,7 @@
 """The oracle (oracle/panorama_oracle.py) against outputs of the imported reference
 (tests/golden/*.npz, made by tests/golden/make_golden.py).  CPU only."""
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -222,3 +223,19 @@ def test_geometry_helpers():
     assert po.frame_window_begins(0) == [(4 * s) % 64 for s in range(13)]
     assert po.frame_window_begins(3)[0] == 3
     assert len(po.frame_window_begins(0, overlap=0.5)) == 7
+
+
+def test_resize_video_latent_golden():
+    """oracle.resize_video_latent vs the reference's utils/diffusion_utils.py outputs
+    (tests/golden/resize.npz, generated by tests/golden/make_golden_resize.py)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "resize.npz"))
+    modes = ["nearest", "bilinear", "bicubic"]
+    for n, row in enumerate(g["cases"]):
+        seed, shape, th, tw, mode, align = int(row[0]), tuple(int(v) for v in row[1:6]), int(row[6]), int(row[7]), modes[row[8]], bool(row[9])
+        got = po.resize_video_latent(randn(seed, *shape), th, tw, mode=mode, align_corners=align)
+        want = g[f"out/{n}"]
+        assert got.shape == want.shape
+        if mode == "nearest":
+            assert np.array_equal(got, want), n
+        else:
+            assert np.abs(got - want).max() <= 1e-5, (n, np.abs(got - want).max())
