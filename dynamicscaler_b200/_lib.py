@@ -40,6 +40,10 @@ PROTOTYPES = {
     "ds_pm_merge_bilinear": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_pm_merge_bilinear_tiled": [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_mix_mask": [_vp, _vp, _vp, _vp, _f, _f, _ll, _i, _i, _vp],
+    "ds_pm_merge_nearest_ddim": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i,
+                                 _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "ds_pm_merge_bilinear_tiled_ddim": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp,
+                                        _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_resize_planes": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_select_merged": [_vp, _vp, _vp, _ll, _ll, _ll, _i, _vp],
 }

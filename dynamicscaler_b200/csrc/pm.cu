@@ -280,6 +280,37 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
 }
 
 // ------------------------------------------------------------------------ merges ----
+// Fused denoise epilogue (DD kernels): the two payloads are not read but computed, per surviving
+// element only, from the window latent x and the UNet output(s), exactly like the reference's
+// elementwise torch chain (every op rounded on its own, no FMA):
+//   e       = eu + g * (ec - eu)                              classifier-free guidance
+//                                                              (t2v_sphere_panorama_pipeline.py:258)
+//   pred_x0 = (x - s1m * e) / sa                              pipeline/scheduler.py:84
+//   x_prev  = (sp * pred_x0 + sd * e) + sig * noise           :86-89  (sig * noise only if given)
+// pay[0] = x, pay[1] = ec, pay[2] = eu or NULL (then e = ec), pay[3] = noise or NULL;
+// pm[0] receives x_prev (latent panorama), pm[1] pred_x0 (denoised panorama).
+struct PmDdim {
+  float sa, s1m, sp, sd, sig, g;
+};
+template <typename T>
+__device__ __forceinline__ void pm_ddim(const PmDdim& c, const T (&x)[4], const T (&ec)[4], const T (&eu)[4],
+                                        const T (&nz)[4], bool has_eu, bool has_nz, float (&x_prev)[4],
+                                        float (&pred_x0)[4]) {
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    float e = Elem<T>::to_f(ec[p]);
+    if (has_eu) {
+      const float u = Elem<T>::to_f(eu[p]);
+      e = __fadd_rn(u, __fmul_rn(c.g, __fsub_rn(e, u)));
+    }
+    const float x0 = __fdiv_rn(__fsub_rn(Elem<T>::to_f(x[p]), __fmul_rn(c.s1m, e)), c.sa);
+    float xp = __fadd_rn(__fmul_rn(c.sp, x0), __fmul_rn(c.sd, e));
+    if (has_nz) xp = __fadd_rn(xp, __fmul_rn(c.sig, Elem<T>::to_f(nz[p])));
+    pred_x0[p] = x0;
+    x_prev[p] = xp;
+  }
+}
+
 struct PmMergeArgs {
   void* pm[DS_MAX_PAYLOADS];
   const void* pay[DS_MAX_PAYLOADS];
@@ -289,6 +320,7 @@ struct PmMergeArgs {
   int vpf, job_begin, job_count;
   int F, HW, f_len, hw;
   ds_peer_table_t* peer;         // NULL: single replica (pm / mask above)
+  PmDdim dd;                     // DD kernels only
 };
 
 // dynamic indexing of a kernel-parameter array would force a local-memory copy of the struct
@@ -385,7 +417,7 @@ __device__ __forceinline__ int pm_job_offset(const PmMergeArgs& a, int s, int sr
 // CTA = 32 surviving view pixels.
 // Load: warp <-> (payload q, window frame fo), lane <-> entry: 4 plane loads -> one atom ->
 // shared tile[q][entry][fo].  Store: f_len consecutive lanes write one full panorama row.
-template <typename T, int FL>
+template <typename T, int FL, bool DD>
 __global__ void __launch_bounds__(kBlock)
 pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                         const int32_t* __restrict__ d_ent_src, const int32_t* __restrict__ d_ent_dst,
@@ -416,6 +448,39 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
         if (a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, rep, dst);
       }
     }
+    if (DD) {
+      // fused denoise epilogue: warp <-> window frame, both outputs from (x, ec, eu, noise)
+      const bool has_eu = a.pay[2] != nullptr, has_nz = a.pay[3] != nullptr;
+      constexpr int U = 2;
+      for (int f0 = warp * U; f0 < f_len; f0 += kWarps * U) {
+        T x[U][4], ec[U][4], eu[U][4], nz[U][4];
+        bool live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int fo = f0 + u;
+          int f;
+          live[u] = fo < f_len && have && pm_frame_live(a, d_ftab, rg, fo, f_len, f);
+          if (live[u]) {
+            const int o = fo * a.hw + off;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              x[u][p] = ldg(static_cast<const T*>(a.pay[0]) + o + p * plane_stride);
+              ec[u][p] = ldg(static_cast<const T*>(a.pay[1]) + o + p * plane_stride);
+              if (has_eu) eu[u][p] = ldg(static_cast<const T*>(a.pay[2]) + o + p * plane_stride);
+              if (has_nz) nz[u][p] = ldg(static_cast<const T*>(a.pay[3]) + o + p * plane_stride);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (live[u]) {
+            float xp[4], x0[4];
+            pm_ddim<T>(a.dd, x[u], ec[u], eu[u], nz[u], has_eu, has_nz, xp, x0);
+            tile[(0 * kPmET + lane) * SA + f0 + u] = Atom<T>::pack(xp);
+            tile[(1 * kPmET + lane) * SA + f0 + u] = Atom<T>::pack(x0);
+          }
+      }
+    } else {
     constexpr int U = 4;
     for (int p0 = warp * U; p0 < n_pairs; p0 += kWarps * U) {
       T e[U][4];
@@ -437,6 +502,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
 #pragma unroll
       for (int u = 0; u < U; ++u)
         if (live[u]) tile[(q[u] * kPmET + lane) * SA + fo[u]] = atom_join<T>(e[u]);
+    }
     }
     // Exchange mode with whole rows (no frame ring): every staged 256-B row leaves through one TMA
     // bulk copy per replica, so NVLink back-pressure never stalls the SM's load/store pipeline.
@@ -479,7 +545,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
 // on nothing but blockIdx: global dependency depth 2 (entries -> payload) instead of 3, and
 // every loop bound of phase A is a compile-time constant.  d_view_ptr[v] = first tile of view
 // v; d_row_start[r] = first (padded) entry of row r, rows of a tile being contiguous.
-template <typename T, int FL, int QN>
+template <typename T, int FL, int QN, bool DD>
 __global__ void __launch_bounds__(kBlock)
 pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                                const int4* __restrict__ d_tile, const int32_t* __restrict__ d_row_dst,
@@ -543,6 +609,40 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   // ---- phase A: products (level-2 loads) ----
   const int plane_stride = FL * a.hw;
   const int job_off = (s * a.vpf + view - a.job_begin) * kPmPlanes * plane_stride;
+  if (DD) {
+    static_assert(!DD || QN == 2, "the fused denoise epilogue produces exactly x_prev and pred_x0");
+    const bool has_eu = a.pay[2] != nullptr, has_nz = a.pay[3] != nullptr;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      T x[2][4], ec[2][4], eu[2][4], nz[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (k[h] >= 0 && liveA[j]) {
+          const int o = job_off + (warp + j * kWarps) * a.hw + k[h];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            x[j][p] = ldg(static_cast<const T*>(a.pay[0]) + o + p * plane_stride);
+            ec[j][p] = ldg(static_cast<const T*>(a.pay[1]) + o + p * plane_stride);
+            if (has_eu) eu[j][p] = ldg(static_cast<const T*>(a.pay[2]) + o + p * plane_stride);
+            if (has_nz) nz[j][p] = ldg(static_cast<const T*>(a.pay[3]) + o + p * plane_stride);
+          }
+        }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (k[h] >= 0 && liveA[j]) {
+          float xp[4], x0[4];
+          pm_ddim<T>(a.dd, x[j], ec[j], eu[j], nz[j], has_eu, has_nz, xp, x0);
+          // the reference merges the ROUNDED payload tensors: round to T before the weighting
+          const int e = h * 32 + lane, fo = warp + j * kWarps;
+          prod[(0 * kPmEC + e) * SA + fo] = make_float4(
+              __fmul_rn(Elem<T>::to_f(Elem<T>::from_f(xp[0])), w[h]), __fmul_rn(Elem<T>::to_f(Elem<T>::from_f(xp[1])), w[h]),
+              __fmul_rn(Elem<T>::to_f(Elem<T>::from_f(xp[2])), w[h]), __fmul_rn(Elem<T>::to_f(Elem<T>::from_f(xp[3])), w[h]));
+          prod[(1 * kPmEC + e) * SA + fo] = make_float4(
+              __fmul_rn(Elem<T>::to_f(Elem<T>::from_f(x0[0])), w[h]), __fmul_rn(Elem<T>::to_f(Elem<T>::from_f(x0[1])), w[h]),
+              __fmul_rn(Elem<T>::to_f(Elem<T>::from_f(x0[2])), w[h]), __fmul_rn(Elem<T>::to_f(Elem<T>::from_f(x0[3])), w[h]));
+        }
+    }
+  } else {
   T x[2][QN][2][4];                               // [half][payload][frame j][plane]
 #pragma unroll
   for (int h = 0; h < 2; ++h)
@@ -566,6 +666,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
           prod[(q * kPmEC + h * 32 + lane) * SA + warp + j * kWarps] =
               make_float4(__fmul_rn(Elem<T>::to_f(x[h][q][j][0]), w[h]), __fmul_rn(Elem<T>::to_f(x[h][q][j][1]), w[h]),
                           __fmul_rn(Elem<T>::to_f(x[h][q][j][2]), w[h]), __fmul_rn(Elem<T>::to_f(x[h][q][j][3]), w[h]));
+  }
   __syncthreads();
 
   // ---- phase B: ordered accumulation, normalise, full-row stores ----
@@ -838,8 +939,8 @@ extern "C" int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payl
   DS_DISPATCH_DTYPE(dtype, {
     using AT = typename Atom<ET>::type;
     const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(AT) + kPmET * sizeof(int32_t);
-    if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
-    return pm_launch(pm_merge_nearest_kernel<ET, 0>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    return pm_launch(pm_merge_nearest_kernel<ET, 0, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
   });
   return DS_OK;
 }
@@ -888,9 +989,80 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
-    if (Q == 1) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
-    if (Q == 2) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
-    return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+    if (Q == 1) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+    if (Q == 2) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+    return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+  });
+  return DS_OK;
+}
+
+// Shared argument handling of the two fused-denoise entry points: panoramas 0 / 1 receive
+// x_prev / pred_x0; payload slots carry x, eps_cond, eps_uncond (or NULL), noise (or NULL).
+static int pm_fill_ddim_args(ds::PmMergeArgs& a, void* const* h_pms, const void* x, const void* eps_cond,
+                             const void* eps_uncond, const void* noise, const float* h_coef, void* mask, int mask_mode,
+                             int n_ent, const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin, int vpf,
+                             int job_begin, int job_count, int P, int F, int HW, int f_len, int hw, void* d_peer) {
+  using namespace ds;
+  DS_REQUIRE(h_coef != nullptr && x != nullptr && eps_cond != nullptr, DS_ERR_NULL);
+  const void* two[2] = {x, eps_cond};
+  int rc = pm_fill_merge_args(a, h_pms, two, 2, mask, mask_mode, n_ent, d_ftab, d_fbegin, n_fwin, vpf, job_begin,
+                              job_count, P, F, HW, f_len, hw, d_peer);
+  if (rc != DS_OK) return rc;
+  a.pay[2] = eps_uncond;
+  a.pay[3] = noise;
+  a.dd = PmDdim{h_coef[0], h_coef[1], h_coef[2], h_coef[3], h_coef[4], h_coef[5]};
+  DS_REQUIRE(a.dd.sa != 0.f, DS_ERR_DIM);
+  return DS_OK;
+}
+
+extern "C" int ds_pm_merge_nearest_ddim(void* const* h_pms, const void* x, const void* eps_cond, const void* eps_uncond,
+                                        const void* noise, const float* h_coef, void* mask, int mask_mode,
+                                        const int32_t* d_view_ptr, const int32_t* d_ent_src,
+                                        const int32_t* d_ent_dst, int n_ent, const int32_t* d_ftab,
+                                        const int32_t* d_fbegin, int n_fwin, int views_per_fwin, int job_begin,
+                                        int job_count, int P, int F, int HW, int f_len, int hw, void* d_peer,
+                                        int dtype, void* stream) {
+  using namespace ds;
+  PmMergeArgs a;
+  int rc = pm_fill_ddim_args(a, h_pms, x, eps_cond, eps_uncond, noise, h_coef, mask, mask_mode, n_ent, d_ftab, d_fbegin,
+                             n_fwin, views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, d_peer);
+  if (rc != DS_OK) return rc;
+  DS_REQUIRE(d_view_ptr != nullptr && d_ent_src != nullptr && d_ent_dst != nullptr, DS_ERR_NULL);
+  if (n_ent == 0 && d_peer == nullptr) return DS_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long items = div_up(n_ent, kPmET);
+  DS_DISPATCH_DTYPE(dtype, {
+    using AT = typename Atom<ET>::type;
+    const size_t smem = 2 * static_cast<size_t>(kPmET) * (f_len | 1) * sizeof(AT) + kPmET * sizeof(int32_t);
+    if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    return pm_launch(pm_merge_nearest_kernel<ET, 0, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+  });
+  return DS_OK;
+}
+
+extern "C" int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x, const void* eps_cond,
+                                               const void* eps_uncond, const void* noise, const float* h_coef,
+                                               void* mask, int mask_mode, const int32_t* d_view_ptr,
+                                               const int32_t* d_tile, int n_tiles, const int32_t* d_row_dst,
+                                               const int32_t* d_row_start, int n_rows, const int32_t* d_ent_k,
+                                               const float* d_ent_w, const int32_t* d_ftab, const int32_t* d_fbegin,
+                                               int n_fwin, int views_per_fwin, int job_begin, int job_count,
+                                               int P, int F, int HW, int f_len, int hw, void* d_peer, int dtype,
+                                               void* stream) {
+  using namespace ds;
+  PmMergeArgs a;
+  int rc = pm_fill_ddim_args(a, h_pms, x, eps_cond, eps_uncond, noise, h_coef, mask, mask_mode, n_rows, d_ftab, d_fbegin,
+                             n_fwin, views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, d_peer);
+  if (rc != DS_OK) return rc;
+  DS_REQUIRE(d_view_ptr != nullptr && d_tile != nullptr && d_row_dst != nullptr && d_row_start != nullptr &&
+             d_ent_k != nullptr && d_ent_w != nullptr, DS_ERR_NULL);
+  DS_REQUIRE(pm_aligned16(d_tile) && f_len == 16 && n_tiles >= 0, DS_ERR_DIM);
+  if (n_tiles == 0 && d_peer == nullptr) return DS_OK;
+  const int4* d_tile4 = reinterpret_cast<const int4*>(d_tile);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t smem = 2 * static_cast<size_t>(kPmEC) * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
+  DS_DISPATCH_DTYPE(dtype, {
+    return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
   });
   return DS_OK;
 }

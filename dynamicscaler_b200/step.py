@@ -30,6 +30,18 @@ from .panorama_tensor_utils import (_launch_gather_bilinear, _launch_gather_near
                                     _launch_merge_nearest)
 
 
+def ddim_coefficients(alpha_t, alpha_prev, sigma_t, sqrt_one_minus_alpha_t, guidance_scale=1.0):
+    """float32 scalars (sa, s1m, sp, sd, sig, g) of one ``ddim_step`` for the fused denoise epilogue
+    (include/dynscaler.h ds_pm_merge_*_ddim), derived with the same float32 torch ops the reference
+    applies to its ``torch.full`` tensors (pipeline/scheduler.py:78-86).  Arguments: the schedule
+    entries ``ddim_alphas[index]``, ``ddim_alphas_prev[index]``, ``ddim_sigmas[index]``,
+    ``ddim_sqrt_one_minus_alphas[index]`` and the classifier-free guidance scale."""
+    f = lambda v: torch.full((1,), float(v), dtype=torch.float32)
+    a_t, a_prev, sig, s1m = f(alpha_t), f(alpha_prev), f(sigma_t), f(sqrt_one_minus_alpha_t)
+    sd = (1. - a_prev - sig ** 2).sqrt()
+    return (float(a_t.sqrt()), float(s1m), float(a_prev.sqrt()), float(sd), float(sig), float(f(guidance_scale)))
+
+
 def shard_range(n_jobs: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous, balanced split of the ordered job list: (begin, count) of ``rank``."""
     base, rem = divmod(n_jobs, world)
@@ -454,6 +466,53 @@ class PanoramaStepper:
             self._merge_into(panos, payloads, mask, mask_mode, mask_planes, plan, P, 0, plan.n_jobs)
             return
         self._merge_sharded(panos, payloads, mask, plan, P, j0, nj)
+
+    def merge_denoised(self, st: PanoramaState, x: torch.Tensor, eps_cond: torch.Tensor,
+                       eps_uncond: Optional[torch.Tensor], coef, plan: StepPlan,
+                       noise: Optional[torch.Tensor] = None):
+        """merge_all fused with the denoise epilogue: the latent panorama (state
+        panorama 0) receives ``x_prev`` and the denoised panorama (1) ``pred_x0`` of
+        ``ddim_step(x, eps_uncond + g*(eps_cond - eps_uncond))`` -- computed inside the merge kernel
+        for the surviving pixels only, so the ~75 % of window pixels that lose to a later window are
+        never denoised, and x_prev / pred_x0 are never materialised.  ``x``: this rank's windows as
+        returned by ``gather_all``; ``eps_*``: UNet outputs of the same shape; ``coef``:
+        ``ddim_coefficients(...)``; ``noise``: the injected epsilon when sigma > 0."""
+        import ctypes as C
+        assert plan.kind != "ring" and len(st.pms) >= 2, "needs latent + denoised panoramas"
+        assert self.world == 1 or st.peer_table is not None, "sharded fused merge needs peer replicas (make_state(peer=True))"
+        j0, nj = self.local_jobs(plan)
+        for t in (x, eps_cond, eps_uncond, noise):
+            assert t is None or (t.is_contiguous() and t.dtype == st.dtype and t.shape == x.shape)
+        assert x.shape[0] == nj
+        mask, mask_mode = None, _lib.DS_MASK_NONE
+        if st.mask_plane is not None:
+            assert plan.d_ftab is None, "a [1, H, W] mask panorama has no frame axis"
+            mask, mask_mode = st.mask_plane, _lib.DS_MASK_PLANE
+        elif st.mask_pm is not None:
+            mask, mask_mode = st.mask_pm, _lib.DS_MASK_FULL
+        self._pm_merge_plan(plan)
+        h_coef = (C.c_float * 6)(*coef)
+        F, HW = plan.F, plan.H * plan.W
+        pms = st.pms[:2]
+        head = (_lib.ptr_array(pms), x.data_ptr(), eps_cond.data_ptr(), _lib.ptr(eps_uncond), _lib.ptr(noise), h_coef,
+                _lib.ptr(mask), mask_mode)
+        tail = (_lib.ptr(plan.d_ftab), _lib.ptr(plan.d_fbegin), plan.n_fwin, plan.vpf, j0, nj, 4, F, HW, plan.f_len,
+                plan.hw, st.peer_table, _lib.dtype_code(st.dtype), _lib.stream_ptr(st.device))
+        with torch.cuda.device(st.device):
+            if nj > 0 and plan.kind == "sphere_nearest":
+                view_ptr, ent_src, ent_dst = plan.pm_merge
+                lib.check(lib.ds_pm_merge_nearest_ddim(*head, view_ptr.data_ptr(), ent_src.data_ptr(), ent_dst.data_ptr(),
+                                                       ent_src.numel(), *tail), "ds_pm_merge_nearest_ddim")
+            elif nj > 0:
+                tiled = plan.extra.get("pm_tiled")
+                assert tiled is not None, "the fused weighted merge needs 16-frame windows and rows of <= 64 entries"
+                view_ptr, tile, row_dst, row_start, ent_k, ent_w = tiled
+                lib.check(lib.ds_pm_merge_bilinear_tiled_ddim(*head, view_ptr.data_ptr(), tile.data_ptr(), tile.shape[0],
+                                                              row_dst.data_ptr(), row_start.data_ptr(), row_dst.numel(),
+                                                              ent_k.data_ptr(), ent_w.data_ptr(), *tail),
+                          "ds_pm_merge_bilinear_tiled_ddim")
+        if st.peer_table is not None:
+            self._peer_sync(st, _lib.DS_PEER_AFTER_MERGE)
 
     def _merge_state(self, st: PanoramaState, payloads, plan: StepPlan):
         """merge_all on a resident state: payloads[q] -> st.pms[q]; the state's mask receives 1."""

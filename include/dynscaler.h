@@ -256,6 +256,37 @@ int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const* h_payloads
 int ds_mix_mask(const void* l1, const void* add, const void* mask, void* out,
                 float ratio, float one_minus_ratio, long long n, int mask_hw, int dtype, void* stream);
 
+/* Fused denoise epilogue + merge.  Instead of reading the payloads x_prev / pred_x0
+ * the merge computes them, for the surviving elements only, from the window latent x
+ * ([jobs][P][f_len][hw], what ds_pm_gather produced) and the UNet outputs, with the reference's
+ * elementwise arithmetic (each op rounded separately):
+ *   e       = eps_uncond + g * (eps_cond - eps_uncond)   (eps_uncond NULL: e = eps_cond)
+ *                                                   pipeline/t2v_sphere_panorama_pipeline.py:256-261
+ *   pred_x0 = (x - s1m * e) / sa                    pipeline/scheduler.py:84
+ *   x_prev  = (sp * pred_x0 + sd * e) + sig * noise :86-89   (noise NULL: the term is skipped)
+ * h_coef: HOST float[6] = { sa = sqrt(alpha_t), s1m = sqrt(1 - alpha_t), sp = sqrt(alpha_prev),
+ *   sd = sqrt(1 - alpha_prev - sigma^2), sig = sigma_t, g = guidance scale }, each computed in
+ *   float32 like the reference's torch.full(...) tensors.
+ * h_pms: exactly 2 panoramas: [0] <- x_prev (latent), [1] <- pred_x0 (denoised).
+ * Plans, frame windows, sharding, mask and d_peer as in ds_pm_merge_nearest /
+ * ds_pm_merge_bilinear_tiled. */
+int ds_pm_merge_nearest_ddim(void* const* h_pms, const void* x, const void* eps_cond, const void* eps_uncond,
+                             const void* noise, const float* h_coef, void* mask, int mask_mode,
+                             const int32_t* d_view_ptr, const int32_t* d_ent_src,
+                             const int32_t* d_ent_dst, int n_ent, const int32_t* d_ftab,
+                             const int32_t* d_fbegin, int n_fwin, int views_per_fwin, int job_begin,
+                             int job_count, int P, int F, int HW, int f_len, int hw, void* d_peer,
+                             int dtype, void* stream);
+int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x, const void* eps_cond,
+                                    const void* eps_uncond, const void* noise, const float* h_coef,
+                                    void* mask, int mask_mode, const int32_t* d_view_ptr,
+                                    const int32_t* d_tile, int n_tiles, const int32_t* d_row_dst,
+                                    const int32_t* d_row_start, int n_rows, const int32_t* d_ent_k,
+                                    const float* d_ent_w, const int32_t* d_ftab, const int32_t* d_fbegin,
+                                    int n_fwin, int views_per_fwin, int job_begin, int job_count,
+                                    int P, int F, int HW, int f_len, int hw, void* d_peer, int dtype,
+                                    void* stream);
+
 /* resize_video_latent (utils/diffusion_utils.py:21-33): F.interpolate(mode, align_corners) of every
  * (b, c, f) plane, in [planes][h][w] -> out [planes][H][W].  mode 'nearest' ignores
  * align_corners (the reference forces it to None, :22-23). */

@@ -239,3 +239,14 @@ def test_resize_video_latent_golden():
             assert np.array_equal(got, want), n
         else:
             assert np.abs(got - want).max() <= 1e-5, (n, np.abs(got - want).max())
+
+
+def test_ddim_step_cfg_golden():
+    """oracle.ddim_step_cfg vs the reference's scheduler.ddim_step + CFG combine (tests/golden/ddim.npz)."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddim.npz"))
+    shape = tuple(int(v) for v in g["shape"])
+    for n, (eta, index, gs, a_t, a_prev, sig, s1m) in enumerate(g["cases"]):
+        x, ec, eu, nz = (randn(s + n, *shape) for s in (100, 200, 300, 400))
+        x_prev, pred_x0 = po.ddim_step_cfg(x, ec, eu if gs != 1.0 else None, gs, a_t, a_prev, sig, s1m, noise=nz)
+        assert np.array_equal(pred_x0, g[f"pred_x0/{n}"]), n
+        assert np.array_equal(x_prev, g[f"x_prev/{n}"]), n
