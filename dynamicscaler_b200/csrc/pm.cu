@@ -338,8 +338,9 @@ struct PmReplicas {
 };
 
 // Every merge CTA first: stage the replica table (peer mode) -- ends with a barrier.
+template <bool PEER>
 __device__ __forceinline__ void pm_merge_begin(const PmMergeArgs& a, PmReplicas& rep) {
-  if (a.peer == nullptr) return;
+  if (!PEER) return;
   if (threadIdx.x == 0) rep.world = a.peer->world;
   if (threadIdx.x < DS_MAX_PEERS * (DS_MAX_PAYLOADS + 1)) {
     const int r = threadIdx.x / (DS_MAX_PAYLOADS + 1), q = threadIdx.x % (DS_MAX_PAYLOADS + 1);
@@ -350,25 +351,25 @@ __device__ __forceinline__ void pm_merge_begin(const PmMergeArgs& a, PmReplicas&
 
 // Store one atom of payload q at element offset `o` of the panorama -- into the single local
 // replica, or into every rank's replica (peer stores over NVLink).
-template <typename A>
+template <typename A, bool PEER>
 __device__ __forceinline__ void pm_store(const PmMergeArgs& a, const PmReplicas& rep, int q, size_t o, const A& v) {
-  if (a.peer == nullptr) {
+  if (!PEER) {
     static_cast<A*>(pm_sel(a.pm, q))[o] = v;
   } else {
     for (int r = 0; r < rep.world; ++r) reinterpret_cast<A*>(rep.ptr[r][q])[o] = v;
   }
 }
-template <typename A>
+template <typename A, bool PEER>
 __device__ __forceinline__ void pm_store_mask_atom(const PmMergeArgs& a, const PmReplicas& rep, size_t o, const A& v) {
-  if (a.peer == nullptr) {
+  if (!PEER) {
     static_cast<A*>(a.mask)[o] = v;
   } else {
     for (int r = 0; r < rep.world; ++r) reinterpret_cast<A*>(rep.ptr[r][DS_MAX_PAYLOADS])[o] = v;
   }
 }
-template <typename T>
+template <typename T, bool PEER>
 __device__ __forceinline__ void pm_store_mask_plane(const PmMergeArgs& a, const PmReplicas& rep, int dst) {
-  if (a.peer == nullptr) {
+  if (!PEER) {
     static_cast<T*>(a.mask)[dst] = Elem<T>::one();
   } else {
     for (int r = 0; r < rep.world; ++r) reinterpret_cast<T*>(rep.ptr[r][DS_MAX_PAYLOADS])[dst] = Elem<T>::one();
@@ -417,14 +418,14 @@ __device__ __forceinline__ int pm_job_offset(const PmMergeArgs& a, int s, int sr
 // CTA = 32 surviving view pixels.
 // Load: warp <-> (payload q, window frame fo), lane <-> entry: 4 plane loads -> one atom ->
 // shared tile[q][entry][fo].  Store: f_len consecutive lanes write one full panorama row.
-template <typename T, int FL, bool DD>
-__global__ void __launch_bounds__(kBlock)
+template <typename T, int FL, bool DD, bool PEER>
+__global__ void __launch_bounds__(kBlock, 5)
 pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                         const int32_t* __restrict__ d_ent_src, const int32_t* __restrict__ d_ent_dst,
                         const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
   __shared__ PmReplicas rep;
-  pm_merge_begin(a, rep);
+  pm_merge_begin<PEER>(a, rep);
   PmRange rg;
   if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -445,7 +446,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
       if (warp == 0) {
         const int dst = d_ent_dst != nullptr ? __ldg(d_ent_dst + rg.lo + lane) : rg.lo + lane;
         s_dst[lane] = dst;
-        if (a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, rep, dst);
+        if (a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T, PEER>(a, rep, dst);
       }
     }
     if (DD) {
@@ -506,7 +507,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
     }
     // Exchange mode with whole rows (no frame ring): every staged 256-B row leaves through one TMA
     // bulk copy per replica, so NVLink back-pressure never stalls the SM's load/store pipeline.
-    const bool row_bulk = sizeof(A) == 16 && a.peer != nullptr && d_ftab == nullptr && a.Q > 0 && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
+    const bool row_bulk = PEER && sizeof(A) == 16 && d_ftab == nullptr && a.Q > 0 && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
     if (row_bulk) fence_proxy_async_smem();
     __syncthreads();
 
@@ -531,8 +532,8 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
         int f;
         if (pm_frame_live(a, d_ftab, rg, fo, f_len, f)) {
           const size_t o = static_cast<size_t>(s_dst[i]) * a.F + f;
-          if (a.Q > 0) pm_store<A>(a, rep, q, o, tile[(q * kPmET + i) * SA + fo]);
-          if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, rep, o, atom_ones<T>());
+          if (a.Q > 0) pm_store<A, PEER>(a, rep, q, o, tile[(q * kPmET + i) * SA + fo]);
+          if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A, PEER>(a, rep, o, atom_ones<T>());
         }
       }
     }
@@ -545,7 +546,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
 // on nothing but blockIdx: global dependency depth 2 (entries -> payload) instead of 3, and
 // every loop bound of phase A is a compile-time constant.  d_view_ptr[v] = first tile of view
 // v; d_row_start[r] = first (padded) entry of row r, rows of a tile being contiguous.
-template <typename T, int FL, int QN, bool DD>
+template <typename T, int FL, int QN, bool DD, bool PEER>
 __global__ void __launch_bounds__(kBlock)
 pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                                const int4* __restrict__ d_tile, const int32_t* __restrict__ d_row_dst,
@@ -568,7 +569,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   const int t = __ldg(d_view_ptr + v_lo) + blockIdx.x;
   if (t >= __ldg(d_view_ptr + v_hi)) return;
   __shared__ PmReplicas rep;
-  pm_merge_begin(a, rep);
+  pm_merge_begin<PEER>(a, rep);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e_base = t * kPmEC;
 
@@ -672,7 +673,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   // ---- phase B: ordered accumulation, normalise, full-row stores ----
   // Exchange mode with whole rows (no frame ring): results are staged in shared memory (over the
   // consumed products) and every 256-B row leaves through one TMA bulk copy per replica.
-  const bool row_bulk = sizeof(A) == 16 && a.peer != nullptr && d_ftab == nullptr && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
+  const bool row_bulk = PEER && sizeof(A) == 16 && d_ftab == nullptr && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
   const int fo_b = threadIdx.x & (FL - 1), row_b = threadIdx.x / FL;
   constexpr int NSW = kPmET / (kBlock / FL);
   float4 res[NSW][QN];
@@ -707,15 +708,15 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
       res[sw][q] = make_float4(__fdiv_rn(acc[q][0], ws), __fdiv_rn(acc[q][1], ws), __fdiv_rn(acc[q][2], ws),
                                __fdiv_rn(acc[q][3], ws));
     const int dst = s_dst[i];
-    if (fo_b == 0 && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, rep, dst);
+    if (fo_b == 0 && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T, PEER>(a, rep, dst);
     if (!row_bulk && liveB) {
       const size_t o = static_cast<size_t>(dst) * a.F + fB;
 #pragma unroll
       for (int q = 0; q < QN; ++q) {
         const float r[4] = {res[sw][q].x, res[sw][q].y, res[sw][q].z, res[sw][q].w};
-        pm_store<A>(a, rep, q, o, Atom<T>::pack(r));
+        pm_store<A, PEER>(a, rep, q, o, Atom<T>::pack(r));
       }
-      if (a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, rep, o, atom_ones<T>());
+      if (a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A, PEER>(a, rep, o, atom_ones<T>());
     }
   }
   if (row_bulk) {
@@ -755,7 +756,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
 // Generic (runtime f_len, any row length) weighted merge.  CTA = 32 panorama rows; each lane
 // owns a row and walks its CSR entries (tap-major, k ascending -- index_add_'s order):
 //   acc = acc + (payload * w);  ws = ws + w;   row = acc / ws     (each op rounded on its own)
-template <typename T>
+template <typename T, bool PEER>
 __global__ void __launch_bounds__(kBlock)
 pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                          const int32_t* __restrict__ d_row_dst, const int32_t* __restrict__ d_row_ptr,
@@ -763,7 +764,7 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
                          const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
   __shared__ PmReplicas rep;
-  pm_merge_begin(a, rep);
+  pm_merge_begin<PEER>(a, rep);
   PmRange rg;
   if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -787,7 +788,7 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
     if (warp == 0) {
       const int dst = wr ? __ldg(d_row_dst + rg.lo + lane) : -1;
       s_dst[lane] = dst;
-      if (wr && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T>(a, rep, dst);
+      if (wr && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T, PEER>(a, rep, dst);
     }
     for (int pr = warp; pr < n_pairs; pr += kWarps) {
       const int q = pr / a.f_len, fo = pr - q * a.f_len;
@@ -816,8 +817,8 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
       int f;
       if (s_dst[i] >= 0 && pm_frame_live(a, d_ftab, rg, fo, a.f_len, f)) {
         const size_t o = static_cast<size_t>(s_dst[i]) * a.F + f;
-        if (a.Q > 0) pm_store<A>(a, rep, q, o, tile[(q * kPmET + i) * SA + fo]);
-        if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A>(a, rep, o, atom_ones<T>());
+        if (a.Q > 0) pm_store<A, PEER>(a, rep, q, o, tile[(q * kPmET + i) * SA + fo]);
+        if (q == 0 && a.mask_mode == DS_MASK_FULL) pm_store_mask_atom<A, PEER>(a, rep, o, atom_ones<T>());
       }
     }
   }
@@ -939,8 +940,8 @@ extern "C" int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payl
   DS_DISPATCH_DTYPE(dtype, {
     using AT = typename Atom<ET>::type;
     const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(AT) + kPmET * sizeof(int32_t);
-    if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
-    return pm_launch(pm_merge_nearest_kernel<ET, 0, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    if (f_len == 16) { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, false, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 16, false, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
+    { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 0, false, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 0, false, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
@@ -963,7 +964,7 @@ extern "C" int ds_pm_merge_bilinear(void* const* h_pms, const void* const* h_pay
   const long long items = div_up(n_rows, kPmET);
   DS_DISPATCH_DTYPE(dtype, {
     const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(typename Atom<ET>::type) + kPmET * sizeof(int32_t);
-    return pm_launch(pm_merge_bilinear_kernel<ET>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin);
+    { if (d_peer != nullptr) return pm_launch(pm_merge_bilinear_kernel<ET, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_bilinear_kernel<ET, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
@@ -989,9 +990,9 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
-    if (Q == 1) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
-    if (Q == 2) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
-    return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+    if (Q == 1) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
@@ -1034,8 +1035,8 @@ extern "C" int ds_pm_merge_nearest_ddim(void* const* h_pms, const void* x, const
   DS_DISPATCH_DTYPE(dtype, {
     using AT = typename Atom<ET>::type;
     const size_t smem = 2 * static_cast<size_t>(kPmET) * (f_len | 1) * sizeof(AT) + kPmET * sizeof(int32_t);
-    if (f_len == 16) return pm_launch(pm_merge_nearest_kernel<ET, 16, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
-    return pm_launch(pm_merge_nearest_kernel<ET, 0, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    if (f_len == 16) { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, true, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 16, true, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
+    { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 0, true, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 0, true, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
@@ -1062,7 +1063,7 @@ extern "C" int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = 2 * static_cast<size_t>(kPmEC) * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
-    return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin);
+    { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }

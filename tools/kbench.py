@@ -13,7 +13,7 @@ from bench import WORKLOADS, Workset, make_plan, make_runner, modes_of, n_phases
 from dynamicscaler_b200 import lib  # noqa: E402
 from dynamicscaler_b200.step import PanoramaStepper  # noqa: E402
 
-GATHER_CPS, MERGE_PERSIST, MERGE_CPS = 0, 1, 2
+GATHER_CPS = 0          # DS_TUNE_PM_GATHER_CTAS_PER_SM
 
 
 def main():
@@ -43,15 +43,11 @@ def main():
         run()
         return timed(run, False) / iters * 1e3
 
-    settings = [{"gather_cps": 0, "persist": 0, "merge_cps": 0, "qsplit": 0, "minb": 0}] * 2
+    settings = [{"gather_cps": c} for c in (0, 0, 4, 6)]
     if os.environ.get("KBENCH_DEFAULT_ONLY"):
         settings = settings[:1]
     for cfg in settings:
         lib.check(lib.ds_tune(GATHER_CPS, cfg["gather_cps"]))
-        lib.check(lib.ds_tune(MERGE_PERSIST, cfg["persist"]))
-        lib.check(lib.ds_tune(MERGE_CPS, cfg["merge_cps"]))
-        lib.check(lib.ds_tune(3, cfg.get("qsplit", 0)))
-        lib.check(lib.ds_tune(100, cfg.get("minb", 0)))
         res = dict(cfg, workload=wl_name)
         for mode in modes:
             for kind in ("gather", "merge"):
@@ -59,6 +55,30 @@ def main():
                 gb, mb = st.algorithmic_bytes(plans[mode][0], 4, 4, k=2)
                 res[f"{kind}_{mode}_us"] = round(us, 2)
                 res[f"{kind}_{mode}_GBps"] = round((gb if kind == "gather" else mb) / us / 1e3, 1)
+        if wl["kind"] == "sphere" and wl["f_len"] == 16:
+            # ddim_step + CFG fused into the merge vs the same chain as torch ops + merge_all
+            from dynamicscaler_b200.step import ddim_coefficients
+            coef = ddim_coefficients(0.5, 0.55, 0.0, 0.7071, 7.5)
+            eps_c = [torch.randn_like(ws.x0) for ws in sets]
+            eps_u = [torch.randn_like(ws.x0) for ws in sets]
+            sa, s1m, sp, sd, sig, g = coef
+            for mode in modes:
+                fused, unfused = [], []
+                for off, s_ in combos:
+                    ws, plan = sets[s_], plans[mode][off]
+                    fused.append(lambda ws=ws, plan=plan, s_=s_: st.merge_denoised(ws.state, ws.wins, eps_c[s_], eps_u[s_], coef, plan))
+
+                    def chain(ws=ws, plan=plan, s_=s_):
+                        e = eps_u[s_] + g * (eps_c[s_] - eps_u[s_])
+                        x0 = (ws.wins - s1m * e) / sa
+                        xp = sp * x0 + sd * e
+                        st.merge_all(ws.state, [xp, x0], plan)
+                    unfused.append(chain)
+                for name, fns in (("fused", fused), ("torch_chain", unfused)):
+                    it = 200 if n_jobs < 100 else 40
+                    run = make_runner(fns, it, True, side)
+                    run()
+                    res[f"denoise_merge_{name}_{mode}_us"] = round(timed(run, False) / it * 1e3, 2)
         print(json.dumps(res), flush=True)
 
 
