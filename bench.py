@@ -276,6 +276,8 @@ def run_ours(args, wl, wl_name):
     sampler = ClockSampler(local)
     sampler.start()
     st = PanoramaStepper(wl["H"], wl["W"], wl["F"], device=dev, rank=rank, world=world)
+    if args.multicast != "auto":
+        st.use_multicast = args.multicast == "on"
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     modes, NP = modes_of(wl), n_phases(wl)
     if args.mode not in modes:
@@ -417,8 +419,9 @@ def run_ours(args, wl, wl_name):
                                  else "reference [B,C,F,H,W] (csrc/sphere.cu, csrc/ring.cu)",
                        "maps": "precomputed on host (static geometry), cached on device",
                        "sharding": ("none" if not dist_on else
-                                    "windows split over ranks; merge kernels push rows into every replica over NVLink "
-                                    "(peer stores, release/acquire counters)" if peer else
+                                    "windows split over ranks; merge kernels push rows into every replica over NVLink ("
+                                    + ("NVLS multicast stores" if st.use_multicast else "per-replica TMA row copies")
+                                    + ", release/acquire counters)" if peer else
                                     "windows split over ranks, 1 NCCL all-reduce/step")},
             "steps_per_s": 1e3 / head["ms_per_step"],
             "gpu_launches": int(head["launches_per_step"] * K),
@@ -474,6 +477,8 @@ def main():
                     help="pm: panoramas resident in pixel-major order (PanoramaState); ref: reference order")
     ap.add_argument("--exchange", default="peer", choices=["peer", "allreduce"],
                     help="N > 1: fused peer-store exchange in the merge kernels, or NCCL all-reduce + select")
+    ap.add_argument("--multicast", default="auto", choices=["auto", "on", "off"],
+                    help="peer exchange: NVLS multicast stores (one store reaches every replica) or per-replica copies")
     ap.add_argument("--workload", default="cfg2_sphere_128x256", choices=list(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

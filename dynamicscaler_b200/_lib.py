@@ -61,7 +61,7 @@ class PeerTable(C.Structure):
                 ("reserved1", C.c_int32), ("error", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("reserved", C.c_int32),
                 ("pm", (C.c_uint64 * DS_MAX_PAYLOADS) * DS_MAX_PEERS), ("mask", C.c_uint64 * DS_MAX_PEERS),
-                ("ctl", C.c_uint64 * DS_MAX_PEERS)]
+                ("ctl", C.c_uint64 * DS_MAX_PEERS), ("mc_pm", C.c_uint64 * DS_MAX_PAYLOADS), ("mc_mask", C.c_uint64)]
 
 
 class LibraryMissing(RuntimeError):

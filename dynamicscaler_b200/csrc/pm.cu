@@ -114,6 +114,20 @@ __device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
 __device__ __forceinline__ void st_release_sys(int32_t* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
+// NVLS multicast stores: one store to a multicast address lands in EVERY GPU's replica (the
+// NVSwitch replicates it), so the exchange costs one store per row instead of one per peer.
+__device__ __forceinline__ void multimem_st(void* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st(void* p, const uint2& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};"
+               :: "l"(p), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
+}
+__device__ __forceinline__ void multimem_st(void* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -334,6 +348,7 @@ template <typename PT> __device__ __forceinline__ PT pm_sel(PT const (&arr)[DS_M
 // Replica addresses of this launch, staged once per CTA: [r][q] panoramas, [r][DS_MAX_PAYLOADS] mask.
 struct PmReplicas {
   unsigned long long ptr[DS_MAX_PEERS][DS_MAX_PAYLOADS + 1];
+  unsigned long long mc[DS_MAX_PAYLOADS + 1];     // multicast alias of [q] / mask, 0 = none
   int world;
 };
 
@@ -342,6 +357,10 @@ template <bool PEER>
 __device__ __forceinline__ void pm_merge_begin(const PmMergeArgs& a, PmReplicas& rep) {
   if (!PEER) return;
   if (threadIdx.x == 0) rep.world = a.peer->world;
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + DS_MAX_PAYLOADS + 1) {
+    const int q = threadIdx.x - 64;
+    rep.mc[q] = q < DS_MAX_PAYLOADS ? a.peer->mc_pm[q] : a.peer->mc_mask;
+  }
   if (threadIdx.x < DS_MAX_PEERS * (DS_MAX_PAYLOADS + 1)) {
     const int r = threadIdx.x / (DS_MAX_PAYLOADS + 1), q = threadIdx.x % (DS_MAX_PAYLOADS + 1);
     rep.ptr[r][q] = q < DS_MAX_PAYLOADS ? a.peer->pm[r][q] : a.peer->mask[r];
@@ -355,6 +374,8 @@ template <typename A, bool PEER>
 __device__ __forceinline__ void pm_store(const PmMergeArgs& a, const PmReplicas& rep, int q, size_t o, const A& v) {
   if (!PEER) {
     static_cast<A*>(pm_sel(a.pm, q))[o] = v;
+  } else if (rep.mc[q] != 0) {
+    multimem_st(reinterpret_cast<A*>(rep.mc[q]) + o, v);
   } else {
     for (int r = 0; r < rep.world; ++r) reinterpret_cast<A*>(rep.ptr[r][q])[o] = v;
   }
@@ -363,6 +384,8 @@ template <typename A, bool PEER>
 __device__ __forceinline__ void pm_store_mask_atom(const PmMergeArgs& a, const PmReplicas& rep, size_t o, const A& v) {
   if (!PEER) {
     static_cast<A*>(a.mask)[o] = v;
+  } else if (rep.mc[DS_MAX_PAYLOADS] != 0) {
+    multimem_st(reinterpret_cast<A*>(rep.mc[DS_MAX_PAYLOADS]) + o, v);
   } else {
     for (int r = 0; r < rep.world; ++r) reinterpret_cast<A*>(rep.ptr[r][DS_MAX_PAYLOADS])[o] = v;
   }
@@ -371,6 +394,8 @@ template <typename T, bool PEER>
 __device__ __forceinline__ void pm_store_mask_plane(const PmMergeArgs& a, const PmReplicas& rep, int dst) {
   if (!PEER) {
     static_cast<T*>(a.mask)[dst] = Elem<T>::one();
+  } else if (sizeof(T) == 4 && rep.mc[DS_MAX_PAYLOADS] != 0) {
+    multimem_st(reinterpret_cast<float*>(rep.mc[DS_MAX_PAYLOADS]) + dst, 1.0f);
   } else {
     for (int r = 0; r < rep.world; ++r) reinterpret_cast<T*>(rep.ptr[r][DS_MAX_PAYLOADS])[dst] = Elem<T>::one();
   }
@@ -507,7 +532,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
     }
     // Exchange mode with whole rows (no frame ring): every staged 256-B row leaves through one TMA
     // bulk copy per replica, so NVLink back-pressure never stalls the SM's load/store pipeline.
-    const bool row_bulk = PEER && sizeof(A) == 16 && d_ftab == nullptr && a.Q > 0 && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
+    const bool row_bulk = PEER && rep.mc[0] == 0 && sizeof(A) == 16 && d_ftab == nullptr && a.Q > 0 && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
     if (row_bulk) fence_proxy_async_smem();
     __syncthreads();
 
@@ -673,7 +698,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   // ---- phase B: ordered accumulation, normalise, full-row stores ----
   // Exchange mode with whole rows (no frame ring): results are staged in shared memory (over the
   // consumed products) and every 256-B row leaves through one TMA bulk copy per replica.
-  const bool row_bulk = PEER && sizeof(A) == 16 && d_ftab == nullptr && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
+  const bool row_bulk = PEER && rep.mc[0] == 0 && sizeof(A) == 16 && d_ftab == nullptr && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
   const int fo_b = threadIdx.x & (FL - 1), row_b = threadIdx.x / FL;
   constexpr int NSW = kPmET / (kBlock / FL);
   float4 res[NSW][QN];

@@ -162,6 +162,12 @@ class PanoramaState:
                 tab.pm[r][q] = base[r] + tab_bytes + q * pm_bytes
             tab.mask[r] = base[r] + m_off if mask is not None else 0
             tab.ctl[r] = base[r]
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0) if st.use_multicast else 0
+        if mc:                                     # NVLS: one multimem.st reaches every replica
+            for q in range(len(tensors)):
+                tab.mc_pm[q] = mc + tab_bytes + q * pm_bytes
+            tab.mc_mask = mc + m_off if mask is not None else 0
+        self.multicast = bool(mc)
         raw = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8)
         buf[:raw.numel()].copy_(raw)
         self.peer_table, self._peer_buf, self._peer_hdl = buf.data_ptr(), buf, hdl
@@ -202,6 +208,9 @@ class PanoramaStepper:
         self.H, self.W, self.F = int(H), int(W), int(F)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.rank, self.world, self.group = rank, world, group
+        # peer states: NVLS multicast stores win from 4 GPUs up (one store instead of world-1 copies);
+        # at 2 GPUs the per-replica TMA row copies are faster (tools/peer_probe.py)
+        self.use_multicast = world > 2
         self._plans = {}
         self._xbuf = {}
 

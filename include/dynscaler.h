@@ -153,7 +153,9 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
  * (e.g. torch symmetric memory, cudaIpc or cuMem fabric handles: the host maps them, this
  * library only dereferences the addresses).  Passing the LOCAL table as d_peer switches the
  * merge calls below to exchange mode: every surviving row is stored into ALL replicas
- * (pm[r][q], mask[r]) with peer stores over NVLink -- no sum buffer, all-reduce or select.
+ * -- one multimem.st to the NVLS multicast alias (mc_pm[q], mc_mask) when the host provides it,
+ * else one peer store / TMA bulk copy per replica (pm[r][q], mask[r]) -- so there is no sum
+ * buffer, all-reduce or select.
  * Ordering across GPUs is two monotonic counters per peer, exchanged by ds_pm_peer_sync (one
  * 32-thread kernel, st.release.sys / ld.acquire.sys), which the host enqueues
  *   after every gather  (DS_PEER_AFTER_GATHER: replicas may be overwritten once all have read)
@@ -172,6 +174,8 @@ typedef struct ds_peer_table {
   uint64_t pm[DS_MAX_PEERS][DS_MAX_PAYLOADS];   /* replica r, panorama q */
   uint64_t mask[DS_MAX_PEERS];                  /* replica r of the mask panorama (or 0) */
   uint64_t ctl[DS_MAX_PEERS];                   /* rank r's ds_peer_table_t */
+  uint64_t mc_pm[DS_MAX_PAYLOADS];              /* NVLS multicast alias of panorama q over ALL replicas, or 0 */
+  uint64_t mc_mask;                             /* multicast alias of the mask, or 0 */
 } ds_peer_table_t;
 int ds_peer_table_size(void);                   /* sizeof(ds_peer_table_t), for bindings */
 enum { DS_PEER_AFTER_GATHER = 0, DS_PEER_AFTER_MERGE = 1 };

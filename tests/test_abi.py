@@ -112,12 +112,12 @@ def test_peer_table_layout_matches_header(tmp_path):
                    'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(ds_peer_table_t),'
                    'offsetof(ds_peer_table_t, gathers_done), offsetof(ds_peer_table_t, my_merges),'
                    'offsetof(ds_peer_table_t, error), offsetof(ds_peer_table_t, pm),'
-                   'offsetof(ds_peer_table_t, mask), offsetof(ds_peer_table_t, ctl));return 0;}\n')
+                   'offsetof(ds_peer_table_t, mask), offsetof(ds_peer_table_t, mc_mask));return 0;}\n')
     exe = tmp_path / "off"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     T = _lib.PeerTable
     want = [ctypes.sizeof(T), T.gathers_done.offset, T.my_merges.offset, T.error.offset, T.pm.offset,
-            T.mask.offset, T.ctl.offset]
+            T.mask.offset, T.mc_mask.offset]
     assert got == want
     assert _lib.lib.ds_peer_table_size() == ctypes.sizeof(T)

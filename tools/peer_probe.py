@@ -20,9 +20,10 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 wl = WORKLOADS["cfg2_sphere_128x256"]
 st = PanoramaStepper(wl["H"], wl["W"], wl["F"], device=dev, rank=rank, world=world)
+st.use_multicast = os.environ.get("DS_NO_MULTICAST") is None
 gen = torch.Generator(device=dev).manual_seed(rank)
 gp = torch.Generator(device=dev).manual_seed(99)
-res = {}
+res = {"multicast": os.environ.get("DS_NO_MULTICAST") is None, "world": world}
 side = torch.cuda.Stream()
 for mode in ("nearest", "bilinear"):
     plans = [make_plan(st, wl, mode, i) for i in range(10)]
