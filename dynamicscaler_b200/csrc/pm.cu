@@ -282,8 +282,18 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     fence_proxy_async_smem();
     __syncthreads();
 
-    const uint32_t row_bytes = static_cast<uint32_t>(min(kPmKT, a.hw - k0) * sizeof(T));
     T* __restrict__ o = out + static_cast<size_t>(job) * R * a.hw + k0;
+    if (a.hw % VE != 0) {
+      // window rows are not 16-byte multiples (odd view sizes): element-wise copy of the tile
+      const int kt = min(kPmKT, a.hw - k0);
+      for (int u = threadIdx.x; u < R * kPmKT; u += kBlock) {
+        const int row = u / kPmKT, c = u - row * kPmKT;
+        if (c < kt) o[static_cast<size_t>(row) * a.hw + c] = tile[row * S + c];
+      }
+      __syncthreads();                            // the tile is rewritten by the next work item
+      continue;
+    }
+    const uint32_t row_bytes = static_cast<uint32_t>(min(kPmKT, a.hw - k0) * sizeof(T));
     bool issued = false;
     for (int row = threadIdx.x; row < R; row += kBlock) {
       bulk_store(o + static_cast<size_t>(row) * a.hw, tile + row * S, row_bytes);
@@ -930,7 +940,6 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DS_DISPATCH_DTYPE(dtype, {
     constexpr int VE = 16 / sizeof(ET);
-    DS_REQUIRE(hw % VE == 0, DS_ERR_ALIGN);
     const size_t smem = static_cast<size_t>(kPmPlanes) * f_len * (kPmKT + VE) * sizeof(ET) + static_cast<size_t>(taps) * kPmKT * 8;
     using AT = typename Atom<ET>::type;
     const AT* pmp = static_cast<const AT*>(pm);

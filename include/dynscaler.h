@@ -192,7 +192,8 @@ int ds_pm_peer_sync(void* d_peer, int phase, void* stream);
  *   out[j][pl][fo][k] = sum_t wt[map_j][t][k] * pm[idx[map_j][t][k]][(f0_j+fo) mod F][pl]
  * d_idx: [n_maps][taps][hw] int32; d_wt: [n_maps][4][hw] float32 (taps == 4 only).
  * d_idx == NULL (taps == 1): identity map, i.e. the unpack pm -> [P][F][hw], hw <= H*W.
- * d_jobs as in ds_gather_nearest.  Requires hw % (16 / elem_size) == 0.
+ * d_jobs as in ds_gather_nearest.  Window rows that are 16-byte multiples (hw % (16 / elem_size) == 0)
+ * leave through TMA bulk copies, other sizes through plain stores.
  * d_peer: NULL, or the local ds_peer_table_t (only relaxes n_jobs > 0: an idle rank may call). */
 int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d_wt, int taps,
                  const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
