@@ -207,6 +207,40 @@ def nearest_merge_plan(vmaps):
     return last_writer_plan(np.concatenate(t), np.concatenate(s))
 
 
+def _view_lut(n_views, local_views):
+    lut = np.full(n_views, -1, np.int64)
+    lut[np.asarray(local_views, np.int64)] = np.arange(len(local_views))
+    return lut
+
+
+def filter_nearest_plan(plan, hw, n_views, local_views):
+    """Restrict a (dst, src) last-writer plan to the views one rank owns and renumber them
+    0..len(local_views)-1 (src = local_view*hw + k).  Winners are decided GLOBALLY first, so the
+    ranks' filtered plans have disjoint support and their union is the global plan."""
+    dst, src = plan
+    lut = _view_lut(n_views, local_views)
+    lv = lut[src // hw]
+    keep = lv >= 0
+    return dst[keep].astype(np.int32), (lv[keep] * hw + src[keep] % hw).astype(np.int32)
+
+
+def filter_bilinear_plan(plan, hw, n_views, local_views):
+    """Same for a CSR weighted plan: keep the rows owned by this rank's views."""
+    row_dst, row_ptr, ent_src, ent_w = plan
+    if row_dst.size == 0:
+        return plan
+    row_ptr = row_ptr.astype(np.int64)
+    lut = _view_lut(n_views, local_views)
+    owner = lut[ent_src[row_ptr[:-1]] // hw]
+    keep = owner >= 0
+    counts = np.diff(row_ptr)[keep]
+    new_ptr = np.concatenate([[0], np.cumsum(counts)])
+    ent_index = np.repeat(row_ptr[:-1][keep] - new_ptr[:-1], counts) + np.arange(new_ptr[-1])
+    src = ent_src[ent_index].astype(np.int64)
+    return (row_dst[keep].astype(np.int32), new_ptr.astype(np.int32),
+            (lut[src // hw] * hw + src % hw).astype(np.int32), np.ascontiguousarray(ent_w[ent_index], dtype=F32))
+
+
 def round_merge_plan(vm, n_images, b):
     """Quirk Q3 of ``set_view_tensor`` (panorama_tensor_utils.py:89-93): image ``b`` of
     ``n_images`` scatters its first hw/n_images view pixels to the targets of view pixels
@@ -255,24 +289,27 @@ def _view_ptr(view_of_item, n_views):
     return np.searchsorted(view_of_item, np.arange(n_views + 1)).astype(np.int32)
 
 
-def pm_nearest_plan(vmaps):
+def pm_nearest_plan(vmaps, base=None, n_views=None):
     """``nearest_merge_plan`` regrouped for the scatter-form kernel: the surviving view
     pixels sorted by (view, k).  Returns (view_ptr[n_views + 1], ent_src[T] = view*hw + k,
-    ent_dst[T])."""
-    dst, src = nearest_merge_plan(vmaps)
+    ent_dst[T]).  ``base`` / ``n_views``: an already filtered (dst, src) plan and its view count."""
+    dst, src = nearest_merge_plan(vmaps) if base is None else base
+    n_views = len(vmaps) if n_views is None else n_views
     order = np.argsort(src, kind="stable")
     src, dst = src[order], dst[order]
-    return _view_ptr(src // vmaps[0].hw, len(vmaps)), src.astype(np.int32), dst.astype(np.int32)
+    return _view_ptr(src // vmaps[0].hw, n_views), src.astype(np.int32), dst.astype(np.int32)
 
 
-def pm_bilinear_plan(vmaps):
+def pm_bilinear_plan(vmaps, base=None, n_views=None):
     """``bilinear_merge_plan`` regrouped by owning view: rows sorted by (view, dst), CSR
     entries kept in index_add_ order inside each row.
-    Returns (view_ptr[n_views + 1] over rows, row_dst[T], row_ptr[T + 1], ent_src[E], ent_w[E])."""
-    row_dst, row_ptr, ent_src, ent_w = bilinear_merge_plan(vmaps)
+    Returns (view_ptr[n_views + 1] over rows, row_dst[T], row_ptr[T + 1], ent_src[E], ent_w[E]).
+    ``base`` / ``n_views``: an already filtered CSR plan and its view count."""
+    row_dst, row_ptr, ent_src, ent_w = bilinear_merge_plan(vmaps) if base is None else base
+    n_views = len(vmaps) if n_views is None else n_views
     hw = vmaps[0].hw
     if row_dst.size == 0:
-        return (np.zeros(len(vmaps) + 1, np.int32), row_dst, np.zeros(1, np.int32), np.zeros(0, np.int32),
+        return (np.zeros(n_views + 1, np.int32), row_dst, np.zeros(1, np.int32), np.zeros(0, np.int32),
                 np.zeros(0, F32))
     row_ptr = row_ptr.astype(np.int64)
     owner = ent_src[row_ptr[:-1]] // hw
@@ -281,21 +318,22 @@ def pm_bilinear_plan(vmaps):
     new_ptr = np.concatenate([[0], np.cumsum(counts)])
     # entry gather: for new row r, entries row_ptr[order[r]] + [0, counts[r])
     ent_index = np.repeat(row_ptr[:-1][order] - new_ptr[:-1], counts) + np.arange(new_ptr[-1])
-    return (_view_ptr(owner[order], len(vmaps)), row_dst[order].astype(np.int32), new_ptr.astype(np.int32),
+    return (_view_ptr(owner[order], n_views), row_dst[order].astype(np.int32), new_ptr.astype(np.int32),
             ent_src[ent_index].astype(np.int32), np.ascontiguousarray(ent_w[ent_index], dtype=F32))
 
 
 PM_TILE_ROWS, PM_TILE_ENTRIES = 32, 64        # csrc/pm.cu kPmET, kPmEC
 
 
-def pm_bilinear_tiled_plan(vmaps):
+def pm_bilinear_tiled_plan(vmaps, base=None, n_views=None):
     """``pm_bilinear_plan`` cut into tiles for ds_pm_merge_bilinear_tiled: tile t owns the
     padded entries [64t, 64t+64) (ent_k = -1, w = 0 padding; k relative to the tile's view) and
     at most 32 whole rows of ONE view.  Returns None when a row has more than 64 entries
     (tiny panoramas; the untiled kernel handles those), else
     (view_ptr[n_views+1] over tiles, tile[n_tiles, 4] = (first row, view, rows, entries),
      row_dst[T], row_start[T] into the padded arrays, ent_k[64*n_tiles], ent_w[64*n_tiles])."""
-    view_ptr_rows, row_dst, row_ptr, ent_src, ent_w = pm_bilinear_plan(vmaps)
+    view_ptr_rows, row_dst, row_ptr, ent_src, ent_w = pm_bilinear_plan(vmaps, base, n_views)
+    n_views = len(vmaps) if n_views is None else n_views
     hw = vmaps[0].hw
     n_rows = row_dst.size
     counts = np.diff(row_ptr.astype(np.int64))
@@ -303,7 +341,7 @@ def pm_bilinear_tiled_plan(vmaps):
         return None
     ce = np.concatenate([[0], np.cumsum(counts)])                  # entries before row r
     tiles, view_ptr = [], [0]
-    for v in range(len(vmaps)):
+    for v in range(n_views):
         i, end = int(view_ptr_rows[v]), int(view_ptr_rows[v + 1])
         while i < end:
             # furthest row boundary within 64 entries, 32 rows and the view

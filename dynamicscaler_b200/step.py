@@ -72,6 +72,8 @@ class StepPlan:
     d_fbegin: Optional[torch.Tensor] = None    # [n_fwin] frame_begin per frame window (pixel-major merges)
     pm_merge: Optional[tuple] = None           # scatter-form plan of the pixel-major merge (maps.pm_*_plan)
     coverage: float = 0.0                      # touched fraction of H*W (bytes accounting)
+    n_local: int = 0                           # jobs of THIS rank (== n_jobs on one GPU)
+    job_ids: Optional[List[int]] = None        # their indices in the global ordered job list, local order
     extra: dict = field(default_factory=dict)
 
     @property
@@ -80,7 +82,7 @@ class StepPlan:
 
     @property
     def n_fwin(self):
-        return self.n_jobs // self.vpf
+        return self.extra.get("n_fwin", 1)
 
 
 class PanoramaState:
@@ -242,27 +244,51 @@ class PanoramaStepper:
             return self._plans[key]
         vms = [maps.view_map(fov, th, ph, width, height, self.H, self.W) for (ph, th) in views]
         nv = len(vms)
-        plan = StepPlan(kind="sphere_" + mode, n_jobs=nv * len(fbs), vpf=nv, f_len=f_len, F=self.F,
+        # Sharding: views are dealt round-robin over the ranks -- rank r owns views
+        # r, r + world, ... of every frame window -- which balances both the job count and the number
+        # of surviving pixels (with last-writer-wins the late views own most of the panorama).
+        # Every plan array below is restricted to the local views and renumbers them 0..nlv-1; the
+        # winners themselves are decided globally, so the ranks' plans have disjoint support.
+        local_views = list(range(self.rank, nv, self.world))
+        nlv = len(local_views)
+        plan = StepPlan(kind="sphere_" + mode, n_jobs=nv * len(fbs), vpf=max(nlv, 1), f_len=f_len, F=self.F,
                         H=self.H, W=self.W, h=height, w=width)
+        plan.n_local = nlv * len(fbs)
+        plan.extra["n_fwin"] = len(fbs)
+        plan.job_ids = [s_ * nv + v for s_ in range(len(fbs)) for v in local_views]
         vkey = tuple(vm.key for vm in vms)
-        jobs = np.array([[v, fb] for fb in fbs for v in range(nv)], dtype=np.int32)
-        plan.d_jobs = maps.on_device(("jobs", nv, tuple(fbs)), self.device, lambda: jobs)
+        lkey = (vkey, self.rank, self.world)
+        hw = width * height
+        jobs = np.array([[v, fb] for fb in fbs for v in local_views], dtype=np.int32).reshape(-1, 2)
+        plan.d_jobs = maps.on_device(("jobs", nv, tuple(fbs), self.rank, self.world), self.device, lambda: jobs)
         plan.d_ftab = self._ftab(fbs, f_len)
         if plan.d_ftab is not None:
             plan.d_fbegin = maps.on_device(("fbegin", tuple(fbs)), self.device, lambda: np.array(fbs, dtype=np.int32))
         plan.extra["vms"] = vms
+        sharded = self.world > 1
         if mode == "nearest":
             plan.d_idx = maps.on_device(("idx_all", vkey), self.device, lambda: np.stack([vm.idx_read for vm in vms]))
-            plan.d_dst, plan.d_src = maps.on_device(("nplan", vkey), self.device, lambda: maps.nearest_merge_plan(vms))
-            plan.T = plan.d_dst.numel()
+            whole = maps.host_cached(("nplan", vkey), lambda: maps.nearest_merge_plan(vms))
+            base = maps.filter_nearest_plan(whole, hw, nv, local_views) if sharded else whole
+            plan.d_dst, plan.d_src = maps.on_device(("nplan", lkey), self.device, lambda: base)
+            plan.T = base[0].size
+            plan.pm_merge = maps.on_device(("pm_nplan", lkey), self.device,
+                                           lambda: maps.pm_nearest_plan(vms, base, nlv))
         else:
             plan.d_taps = maps.on_device(
                 ("taps_all", vkey), self.device,
                 lambda: (np.stack([vm.read_taps()[0] for vm in vms]), np.stack([vm.read_taps()[1] for vm in vms])))
-            plan.d_csr = maps.on_device(("bplan", vkey), self.device, lambda: maps.bilinear_merge_plan(vms))
-            plan.T = plan.d_csr[0].numel()
-        plan.coverage = plan.T / float(self.H * self.W)
-        self._pm_merge_plan(plan)          # uploaded now, so later launches are capturable in a CUDA graph
+            whole = maps.host_cached(("bplan", vkey), lambda: maps.bilinear_merge_plan(vms))
+            base = maps.filter_bilinear_plan(whole, hw, nv, local_views) if sharded else whole
+            plan.d_csr = maps.on_device(("bplan", lkey), self.device, lambda: base)
+            plan.T = base[0].size
+            plan.pm_merge = maps.on_device(("pm_bplan", lkey), self.device,
+                                           lambda: maps.pm_bilinear_plan(vms, base, nlv))
+            if f_len == 16:
+                host = maps.host_cached(("pm_btiled", lkey), lambda: maps.pm_bilinear_tiled_plan(vms, base, nlv))
+                plan.extra["pm_tiled"] = None if host is None else maps.on_device(("pm_btiled", lkey), self.device,
+                                                                                    lambda: host)
+        plan.coverage = whole[0].size / float(self.H * self.W)
         self._plans[key] = plan
         return plan
 
@@ -292,13 +318,21 @@ class PanoramaStepper:
         plan.T = self.H * self.W // plan.vec
         plan.d_ftab = self._ftab(fbs, f_len)
         plan.coverage = float((plan.d_src >= 0).float().mean().item())
+        plan.extra["n_fwin"] = len(fbs)
+        j0, nj = shard_range(plan.n_jobs, self.rank, self.world)     # planar windows: contiguous blocks
+        plan.n_local, plan.job_ids = nj, list(range(j0, j0 + nj))
         plan.extra["d_wins2"] = d_wins2
         self._plans[key] = plan
         return plan
 
     # --------------------------------------------------------------------- gather ----
     def local_jobs(self, plan: StepPlan) -> Tuple[int, int]:
-        return shard_range(plan.n_jobs, self.rank, self.world)
+        """(first job, count) of this rank INSIDE the plan's own job numbering.  Ring plans keep the
+        global numbering (contiguous blocks); sphere plans are already restricted to the rank's
+        views, so the range is (0, n_local).  ``plan.job_ids`` maps local jobs to global indices."""
+        if plan.kind == "ring":
+            return shard_range(plan.n_jobs, self.rank, self.world)
+        return 0, plan.n_local
 
     # ------------------------------------------------------- pixel-major residency ----
     def make_state(self, tensors: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None,
@@ -332,18 +366,7 @@ class PanoramaStepper:
         return out
 
     def _pm_merge_plan(self, plan: StepPlan):
-        if plan.pm_merge is None:
-            vms = plan.extra["vms"]
-            vkey = tuple(vm.key for vm in vms)
-            if plan.kind == "sphere_nearest":
-                plan.pm_merge = maps.on_device(("pm_nplan", vkey), self.device, lambda: maps.pm_nearest_plan(vms))
-            else:
-                plan.pm_merge = maps.on_device(("pm_bplan", vkey), self.device, lambda: maps.pm_bilinear_plan(vms))
-                if plan.f_len == 16 and "pm_tiled" not in plan.extra:
-                    host = maps.host_cached(("pm_btiled", vkey), lambda: maps.pm_bilinear_tiled_plan(vms))
-                    plan.extra["pm_tiled"] = None if host is None else maps.on_device(
-                        ("pm_btiled", vkey), self.device, lambda: host)
-        return plan.pm_merge
+        return plan.pm_merge                      # built (and uploaded) by plan_sphere
 
     def _peer_sync(self, st, phase):
         with torch.cuda.device(st.device):
@@ -362,6 +385,8 @@ class PanoramaStepper:
                                        _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)), "ds_pm_gather")
 
     def _pm_merge_into(self, pms, payloads, mask, mask_mode, plan, j0, nj, peer=None):
+        if plan.T == 0:
+            return                                 # none of this rank's views survives anywhere
         mp = self._pm_merge_plan(plan)
         F, HW = plan.F, plan.H * plan.W
         ref = pms[0] if pms else mask
@@ -435,6 +460,8 @@ class PanoramaStepper:
 
     # ---------------------------------------------------------------------- merge ----
     def _merge_into(self, panos, payloads, mask, mask_mode, mask_planes, plan, P, j0, nj):
+        if plan.T == 0:
+            return                                 # none of this rank's views survives anywhere
         HW = plan.H * plan.W
         if plan.kind == "sphere_bilinear":
             _launch_merge_bilinear(panos, payloads, mask, mask_mode, mask_planes, plan.d_csr, plan.d_ftab, plan.vpf,
@@ -472,7 +499,7 @@ class PanoramaStepper:
                 assert mask.numel() % (F * H * W) == 0
                 mask_mode, mask_planes = _lib.DS_MASK_FULL, mask.numel() // (F * H * W)
         if self.world == 1:
-            self._merge_into(panos, payloads, mask, mask_mode, mask_planes, plan, P, 0, plan.n_jobs)
+            self._merge_into(panos, payloads, mask, mask_mode, mask_planes, plan, P, 0, plan.n_local)
             return
         self._merge_sharded(panos, payloads, mask, plan, P, j0, nj)
 
@@ -508,11 +535,11 @@ class PanoramaStepper:
         tail = (_lib.ptr(plan.d_ftab), _lib.ptr(plan.d_fbegin), plan.n_fwin, plan.vpf, j0, nj, 4, F, HW, plan.f_len,
                 plan.hw, st.peer_table, _lib.dtype_code(st.dtype), _lib.stream_ptr(st.device))
         with torch.cuda.device(st.device):
-            if nj > 0 and plan.kind == "sphere_nearest":
+            if nj > 0 and plan.T > 0 and plan.kind == "sphere_nearest":
                 view_ptr, ent_src, ent_dst = plan.pm_merge
                 lib.check(lib.ds_pm_merge_nearest_ddim(*head, view_ptr.data_ptr(), ent_src.data_ptr(), ent_dst.data_ptr(),
                                                        ent_src.numel(), *tail), "ds_pm_merge_nearest_ddim")
-            elif nj > 0:
+            elif nj > 0 and plan.T > 0:
                 tiled = plan.extra.get("pm_tiled")
                 assert tiled is not None, "the fused weighted merge needs 16-frame windows and rows of <= 64 entries"
                 view_ptr, tile, row_dst, row_start, ent_k, ent_w = tiled
@@ -538,7 +565,7 @@ class PanoramaStepper:
         elif st.mask_pm is not None:
             mask, mask_mode = st.mask_pm, _lib.DS_MASK_FULL
         if self.world == 1:
-            self._pm_merge_into(pms, payloads, mask, mask_mode, plan, 0, plan.n_jobs)
+            self._pm_merge_into(pms, payloads, mask, mask_mode, plan, 0, plan.n_local)
             return
         if st.peer_table is not None:
             # fused exchange: this rank's surviving rows go straight into every replica (csrc/pm.cu)

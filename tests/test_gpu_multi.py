@@ -47,16 +47,17 @@ def _worker(rank, world, port, exchange, out_dir):
                                   peer=(exchange == "peer"))
             assert (state.peer_table is not None) == (exchange == "peer")
             for i in range(4):
-                views = geo.sphere_views(i)[:13]                              # 13 jobs over 2 ranks: 7 + 6
+                views = geo.sphere_views(i)[:13]                              # 13 views dealt round-robin: 7 + 6
                 plan_ref = ref_st.plan_sphere(views, w, h, fov=120, mode=mode)
                 plan = st.plan_sphere(views, w, h, fov=120, mode=mode)
                 wins_all = ref_st.gather_all(ref, plan_ref)
-                j0, nj = st.local_jobs(plan)
+                ids = torch.tensor(plan.job_ids, device=dev)                  # this rank's jobs, global numbering
+                assert len(plan.job_ids) == plan.n_local == st.local_jobs(plan)[1]
                 wins = st.gather_all(state, plan)
-                assert torch.equal(wins, wins_all[j0:j0 + nj]), (mode, i)
+                assert torch.equal(wins, wins_all[ids]), (mode, i)
                 xp, x0 = wins_all * 0.5 + (i + 1), wins_all * 0.25 - (i + 1)
                 ref_st.merge_all(ref, [xp, x0], plan_ref)
-                st.merge_all(state, [xp[j0:j0 + nj].contiguous(), x0[j0:j0 + nj].contiguous()], plan)
+                st.merge_all(state, [xp[ids].contiguous(), x0[ids].contiguous()], plan)
             a_lat, a_den = state.export()
             b_lat, b_den = ref.export()
             assert not state.peer_error()
@@ -66,6 +67,11 @@ def _worker(rank, world, port, exchange, out_dir):
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.array([ok]))
         torch.cuda.synchronize()
         dist.barrier()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        ok = False
     finally:
         os._exit(0 if ok else 1)             # no NCCL teardown (see bench.py)
 

@@ -212,3 +212,45 @@ def test_loop_geometry_matches_oracle():
         assert geo.frame_windows(i) == po.frame_window_begins(i)
         assert geo.frame_windows(i, overlap=0.5) == po.frame_window_begins(i, overlap=0.5)
     assert len(geo.sphere_views(0)) == 44 and len(geo.frame_windows(0)) == 13
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_round_robin_view_sharding_partitions_the_global_plan(mode, world):
+    """Views dealt round-robin over ranks (step.plan_sphere): the ranks' filtered plans have
+    disjoint support and, merged rank after rank in ANY order, reproduce the global merge."""
+    from _emulate import merge_bilinear as emu_b, merge_nearest as emu_n
+    H, W, F, h, w = 16, 32, 2, 6, 10
+    views = po.default_sphere_views(4)[:11]
+    nv, hw = len(views), h * w
+    vms = [maps.view_map(120, th, ph, w, h, H, W) for ph, th in views]
+    pay = [randn(40 + q, nv, 4, F, hw) for q in range(2)]
+    base = randn(6, 4, F, H * W)
+    want = [base.copy(), base.copy()]
+    whole = maps.nearest_merge_plan(vms) if mode == "nearest" else maps.bilinear_merge_plan(vms)
+    if mode == "nearest":
+        emu_n(want, pay, whole[0], whole[1], None, nv, F, hw)
+    else:
+        emu_b(want, pay, whole, None, nv, F, hw)
+    got = [base.copy(), base.copy()]
+    seen = np.zeros(H * W, np.int32)
+    for r in reversed(range(world)):                                   # order must not matter
+        local = list(range(r, nv, world))
+        if not local:
+            continue
+        loc_pay = [p[local] for p in pay]
+        if mode == "nearest":
+            d, s_ = maps.filter_nearest_plan(whole, hw, nv, local)
+            emu_n(got, loc_pay, d, s_, None, len(local), F, hw)
+            seen[d] += 1
+            pm = maps.pm_nearest_plan(vms, (d, s_), len(local))
+            assert pm[0][-1] == d.size and np.array_equal(np.sort(pm[2]), np.sort(d))
+        else:
+            part = maps.filter_bilinear_plan(whole, hw, nv, local)
+            emu_b(got, loc_pay, part, None, len(local), F, hw)
+            seen[part[0]] += 1
+            tiled = maps.pm_bilinear_tiled_plan(vms, part, len(local))
+            assert tiled is not None and tiled[1][:, 2].sum() == part[0].size
+    assert seen.max() == 1 and seen.sum() == whole[0].size              # disjoint, complete
+    for q in range(2):
+        assert np.array_equal(got[q], want[q])
