@@ -26,7 +26,7 @@ PROTOTYPES = {
     "ds_abi_version": [],
     "ds_error_string": [_i],
     "ds_peer_table_size": [],
-    "ds_pm_peer_sync": [_vp, _i, _vp],
+    "ds_pm_peer_sync": [_vp, _i, _i, _vp],
     "ds_tune": [_i, _ll],
     "ds_ring_gather": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_ring_scatter": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],

@@ -142,7 +142,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 //     retired, so its peer stores are performed) -> same with my_merges / merges_done, after
 //     which every replica holds the complete merged panorama and may be gathered from.
 // lane p talks to peer p.  A wait longer than timeout_ns sets tab->error instead of hanging.
-__global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, long long timeout_ns) {
+__global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, int wait, long long timeout_ns) {
   const int p = threadIdx.x;
   int32_t* mine = phase == DS_PEER_AFTER_GATHER ? &tab->my_gathers : &tab->my_merges;
   const size_t off = phase == DS_PEER_AFTER_GATHER ? offsetof(ds_peer_table_t, gathers_done)
@@ -156,7 +156,24 @@ __global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, long long t
     st_release_sys(reinterpret_cast<int32_t*>(peer + off) + tab->rank, c);
     const int32_t* done = reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(tab) + off) + p;
     const unsigned long long t0 = global_ns();
-    while (ld_acquire_sys(done) < c) {
+    while (wait && ld_acquire_sys(done) < c) {
+      if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) {
+        tab->error = 1;
+        break;
+      }
+    }
+  }
+}
+
+// In-kernel half of the ordering: lane p of every CTA waits until peer p's counter `done[p]` has
+// reached `want` (normally true already, or a few hundred ns away); `v` is a value of the flag
+// prefetched earlier so that the first round trip overlaps other work.
+__device__ __forceinline__ void pm_peer_spin(ds_peer_table_t* tab, const int32_t* done, int v, int want,
+                                             long long timeout_ns) {
+  if (static_cast<int>(threadIdx.x) < tab->world && static_cast<int>(threadIdx.x) != tab->rank) {
+    const unsigned long long t0 = global_ns();
+    while (v < want) {
+      v = ld_acquire_sys(done + threadIdx.x);
       if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) {
         tab->error = 1;
         break;
@@ -184,8 +201,14 @@ template <typename T, int TAPS, int FL, int MINB>
 __global__ void __launch_bounds__(kBlock, MINB)
 pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ out,
                  const int32_t* __restrict__ d_idx, const float* __restrict__ d_wt,
-                 const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a) {
+                 const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a, ds_peer_table_t* __restrict__ peer,
+                 long long peer_timeout_ns) {
   using A = typename Atom<T>::type;
+  if (peer != nullptr) {
+    // exchange mode: every peer must have pushed the previous step's rows into this replica
+    pm_peer_spin(peer, peer->merges_done, -1, peer->my_merges, peer_timeout_ns);
+    __syncthreads();
+  }
   constexpr int VE = 16 / sizeof(T);            // elements per 16-byte vector
   constexpr int S = kPmKT + VE;                 // padded row stride (elements): 4 banks mod 32
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -344,6 +367,7 @@ struct PmMergeArgs {
   int vpf, job_begin, job_count;
   int F, HW, f_len, hw;
   ds_peer_table_t* peer;         // NULL: single replica (pm / mask above)
+  long long peer_timeout_ns;
   PmDdim dd;                     // DD kernels only
 };
 
@@ -362,10 +386,16 @@ struct PmReplicas {
   int world;
 };
 
-// Every merge CTA first: stage the replica table (peer mode) -- ends with a barrier.
+// Every merge CTA first (peer mode): stage the replica table in shared memory and prefetch this
+// lane's peer flag.  No barrier here: the table is read, and pm_merge_wait called, only right
+// before the __syncthreads that precedes the store phase.
+struct PmPeerFlag {
+  int v, want;
+};
 template <bool PEER>
-__device__ __forceinline__ void pm_merge_begin(const PmMergeArgs& a, PmReplicas& rep) {
-  if (!PEER) return;
+__device__ __forceinline__ PmPeerFlag pm_merge_begin(const PmMergeArgs& a, PmReplicas& rep) {
+  PmPeerFlag f{0, 0};
+  if (!PEER) return f;
   if (threadIdx.x == 0) rep.world = a.peer->world;
   if (threadIdx.x >= 64 && threadIdx.x < 64 + DS_MAX_PAYLOADS + 1) {
     const int q = threadIdx.x - 64;
@@ -375,7 +405,17 @@ __device__ __forceinline__ void pm_merge_begin(const PmMergeArgs& a, PmReplicas&
     const int r = threadIdx.x / (DS_MAX_PAYLOADS + 1), q = threadIdx.x % (DS_MAX_PAYLOADS + 1);
     rep.ptr[r][q] = q < DS_MAX_PAYLOADS ? a.peer->pm[r][q] : a.peer->mask[r];
   }
-  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < a.peer->world && static_cast<int>(threadIdx.x) != a.peer->rank) {
+    f.want = a.peer->my_gathers;
+    f.v = ld_acquire_sys(a.peer->gathers_done + threadIdx.x);
+  }
+  return f;
+}
+// ... and right before that barrier: every peer must have finished reading its replica (this
+// step's gather) before rows land in it.
+template <bool PEER>
+__device__ __forceinline__ void pm_merge_wait(const PmMergeArgs& a, const PmPeerFlag& f) {
+  if (PEER) pm_peer_spin(a.peer, a.peer->gathers_done, f.v, f.want, a.peer_timeout_ns);
 }
 
 // Store one atom of payload q at element offset `o` of the panorama -- into the single local
@@ -460,7 +500,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
                         const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
   __shared__ PmReplicas rep;
-  pm_merge_begin<PEER>(a, rep);
+  const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
   PmRange rg;
   if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -481,7 +521,6 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
       if (warp == 0) {
         const int dst = d_ent_dst != nullptr ? __ldg(d_ent_dst + rg.lo + lane) : rg.lo + lane;
         s_dst[lane] = dst;
-        if (a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T, PEER>(a, rep, dst);
       }
     }
     if (DD) {
@@ -542,10 +581,12 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
     }
     // Exchange mode with whole rows (no frame ring): every staged 256-B row leaves through one TMA
     // bulk copy per replica, so NVLink back-pressure never stalls the SM's load/store pipeline.
-    const bool row_bulk = PEER && rep.mc[0] == 0 && sizeof(A) == 16 && d_ftab == nullptr && a.Q > 0 && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
+    const bool row_bulk = PEER && a.peer->mc_pm[0] == 0 && sizeof(A) == 16 && d_ftab == nullptr && a.Q > 0 && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
     if (row_bulk) fence_proxy_async_smem();
+    pm_merge_wait<PEER>(a, pflag);
     __syncthreads();
 
+    if (a.mask_mode == DS_MASK_PLANE && static_cast<int>(threadIdx.x) < cnt) pm_store_mask_plane<T, PEER>(a, rep, s_dst[threadIdx.x]);
     if (row_bulk) {
       const uint32_t row_bytes = static_cast<uint32_t>(f_len * sizeof(A));
       const int n_rows = a.Q * cnt;
@@ -604,7 +645,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   const int t = __ldg(d_view_ptr + v_lo) + blockIdx.x;
   if (t >= __ldg(d_view_ptr + v_hi)) return;
   __shared__ PmReplicas rep;
-  pm_merge_begin<PEER>(a, rep);
+  const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e_base = t * kPmEC;
 
@@ -703,12 +744,13 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
               make_float4(__fmul_rn(Elem<T>::to_f(x[h][q][j][0]), w[h]), __fmul_rn(Elem<T>::to_f(x[h][q][j][1]), w[h]),
                           __fmul_rn(Elem<T>::to_f(x[h][q][j][2]), w[h]), __fmul_rn(Elem<T>::to_f(x[h][q][j][3]), w[h]));
   }
+  pm_merge_wait<PEER>(a, pflag);
   __syncthreads();
 
   // ---- phase B: ordered accumulation, normalise, full-row stores ----
   // Exchange mode with whole rows (no frame ring): results are staged in shared memory (over the
   // consumed products) and every 256-B row leaves through one TMA bulk copy per replica.
-  const bool row_bulk = PEER && rep.mc[0] == 0 && sizeof(A) == 16 && d_ftab == nullptr && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
+  const bool row_bulk = PEER && a.peer->mc_pm[0] == 0 && sizeof(A) == 16 && d_ftab == nullptr && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
   const int fo_b = threadIdx.x & (FL - 1), row_b = threadIdx.x / FL;
   constexpr int NSW = kPmET / (kBlock / FL);
   float4 res[NSW][QN];
@@ -799,7 +841,7 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
                          const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
   __shared__ PmReplicas rep;
-  pm_merge_begin<PEER>(a, rep);
+  const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
   PmRange rg;
   if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -823,7 +865,6 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
     if (warp == 0) {
       const int dst = wr ? __ldg(d_row_dst + rg.lo + lane) : -1;
       s_dst[lane] = dst;
-      if (wr && a.mask_mode == DS_MASK_PLANE) pm_store_mask_plane<T, PEER>(a, rep, dst);
     }
     for (int pr = warp; pr < n_pairs; pr += kWarps) {
       const int q = pr / a.f_len, fo = pr - q * a.f_len;
@@ -843,7 +884,10 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
       for (int p = 0; p < 4; ++p) r[p] = __fdiv_rn(acc[p], ws);
       tile[(q * kPmET + lane) * SA + fo] = Atom<T>::pack(r);
     }
+    pm_merge_wait<PEER>(a, pflag);
     __syncthreads();
+    if (a.mask_mode == DS_MASK_PLANE && static_cast<int>(threadIdx.x) < cnt && s_dst[threadIdx.x] >= 0)
+      pm_store_mask_plane<T, PEER>(a, rep, s_dst[threadIdx.x]);
     const int per_q = cnt * a.f_len;
     const int n_units = (a.Q > 0 ? a.Q : 1) * per_q;
     for (int u = threadIdx.x; u < n_units; u += kBlock) {
@@ -895,6 +939,7 @@ static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* co
   a.vpf = vpf; a.job_begin = job_begin; a.job_count = job_count;
   a.F = F; a.HW = HW; a.f_len = f_len; a.hw = hw;
   a.peer = static_cast<ds_peer_table_t*>(d_peer);
+  a.peer_timeout_ns = g_peer_timeout_ns;
   return DS_OK;
 }
 
@@ -945,11 +990,11 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
     const AT* pmp = static_cast<const AT*>(pm);
     ET* op = static_cast<ET*>(out);
     if (taps == 1) {
-      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
-      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
+      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
     }
-    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
-    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a);
+    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
+    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
   });
   return DS_OK;
 }
@@ -1102,11 +1147,11 @@ extern "C" int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x
   return DS_OK;
 }
 
-extern "C" int ds_pm_peer_sync(void* d_peer, int phase, void* stream) {
+extern "C" int ds_pm_peer_sync(void* d_peer, int phase, int wait, void* stream) {
   DS_REQUIRE(d_peer != nullptr, DS_ERR_NULL);
   DS_REQUIRE(phase == DS_PEER_AFTER_GATHER || phase == DS_PEER_AFTER_MERGE, DS_ERR_DIM);
   ds::pm_peer_sync_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<ds_peer_table_t*>(d_peer), phase,
-                                                                           ds::g_peer_timeout_ns);
+                                                                           wait, ds::g_peer_timeout_ns);
   return ds::check_launch();
 }
 

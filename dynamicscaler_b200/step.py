@@ -368,9 +368,11 @@ class PanoramaStepper:
     def _pm_merge_plan(self, plan: StepPlan):
         return plan.pm_merge                      # built (and uploaded) by plan_sphere
 
-    def _peer_sync(self, st, phase):
+    def _peer_sync(self, st, phase, wait=False):
+        """Publish this rank's gather / merge count to the peers (the data kernels wait in-kernel)."""
         with torch.cuda.device(st.device):
-            lib.check(lib.ds_pm_peer_sync(st.peer_table, phase, _lib.stream_ptr(st.device)), "ds_pm_peer_sync")
+            lib.check(lib.ds_pm_peer_sync(st.peer_table, phase, 1 if wait else 0, _lib.stream_ptr(st.device)),
+                      "ds_pm_peer_sync")
 
     def _pm_gather(self, pm, plan, out, j0, nj, peer=None):
         F, HW = plan.F, plan.H * plan.W

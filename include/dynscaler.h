@@ -156,10 +156,14 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
  * -- one multimem.st to the NVLS multicast alias (mc_pm[q], mc_mask) when the host provides it,
  * else one peer store / TMA bulk copy per replica (pm[r][q], mask[r]) -- so there is no sum
  * buffer, all-reduce or select.
- * Ordering across GPUs is two monotonic counters per peer, exchanged by ds_pm_peer_sync (one
- * 32-thread kernel, st.release.sys / ld.acquire.sys), which the host enqueues
- *   after every gather  (DS_PEER_AFTER_GATHER: replicas may be overwritten once all have read)
- *   after every merge   (DS_PEER_AFTER_MERGE:  replicas are complete once all have pushed).
+ * Ordering across GPUs is two monotonic counters per peer.  The host enqueues ds_pm_peer_sync (one
+ * 32-thread kernel) after every gather (DS_PEER_AFTER_GATHER) and every merge
+ * (DS_PEER_AFTER_MERGE): it bumps this rank's count and publishes it into every peer's table
+ * (st.release.sys) and, if wait != 0, also waits for the peers' counts.  With d_peer the data
+ * kernels do the waiting themselves (ld.acquire.sys, overlapped with their first loads): a
+ * gather starts reading only when every peer has published as many merges as this rank (replicas
+ * complete), a merge starts storing only when every peer has published as many gathers
+ * (replicas may be overwritten) -- so wait = 0 is enough between them.
  * All ranks must issue the same gather / merge sequence on a state.  A wait that exceeds
  * DS_TUNE_PEER_TIMEOUT_NS sets `error`.  The host zero-fills the table, then writes rank,
  * world, pm, mask and ctl (the address of every rank's table, own included) and makes sure
@@ -179,7 +183,7 @@ typedef struct ds_peer_table {
 } ds_peer_table_t;
 int ds_peer_table_size(void);                   /* sizeof(ds_peer_table_t), for bindings */
 enum { DS_PEER_AFTER_GATHER = 0, DS_PEER_AFTER_MERGE = 1 };
-int ds_pm_peer_sync(void* d_peer, int phase, void* stream);
+int ds_pm_peer_sync(void* d_peer, int phase, int wait, void* stream);
 
 /* The batched step driver keeps the panorama of a stage resident as pm[pixel][frame][plane]
  * (H*W pixels, F frames, P == 4 planes; element (pl, f, p) of the reference's [P][F][H*W]
@@ -194,7 +198,7 @@ int ds_pm_peer_sync(void* d_peer, int phase, void* stream);
  * d_idx == NULL (taps == 1): identity map, i.e. the unpack pm -> [P][F][hw], hw <= H*W.
  * d_jobs as in ds_gather_nearest.  Window rows that are 16-byte multiples (hw % (16 / elem_size) == 0)
  * leave through TMA bulk copies, other sizes through plain stores.
- * d_peer: NULL, or the local ds_peer_table_t (only relaxes n_jobs > 0: an idle rank may call). */
+ * d_peer: NULL, or the local ds_peer_table_t: the kernel first waits for the peers' merges. */
 int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d_wt, int taps,
                  const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
                  int hw, void* d_peer, int dtype, void* stream);
