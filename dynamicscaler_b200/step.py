@@ -417,6 +417,46 @@ class PanoramaStepper:
                                                    ent_src.data_ptr(), ent_w.data_ptr(), *common),
                           "ds_pm_merge_bilinear")
 
+    # ---------------------------------------------- condition-image windows (§8f-3) ----
+    def gather_image_windows(self, image: torch.Tensor, windows: Sequence[Tuple[int, int]], w: int, h: int
+                             ) -> torch.Tensor:
+        """All planar condition-image windows of a step in ONE launch: ``RingImageTensor.
+        get_window_tensor`` (shift_window_utils.py:232-263) for every (left, top) in ``windows``
+        (pixel units, may wrap: 0 <= begin < end <= 2*size).  image [3, Hi, Wi] -> [n, 3, h, w],
+        ready to be fed to the CLIP image embedder as one batch
+        (i2v_sphere_panorama_pipeline.py:889-893 calls it once per window)."""
+        _lib.require_cuda(image, "image")
+        assert image.dim() == 3 and image.is_contiguous()
+        C, Hi, Wi = image.shape
+        for (l, t) in windows:
+            assert 0 <= l < l + w <= Wi * 2, f"[RingImageTensor.get_window_tensor] pos_left {l}, pos_right {l + w} not legal"
+            assert 0 <= t < t + h <= Hi * 2, f"[RingImageTensor.get_window_tensor] pos_top {t}, pos_down {t + h} not legal"
+        n = len(windows)
+        d_wins = torch.tensor([[l, t, 0] for (l, t) in windows], dtype=torch.int32, device=image.device)
+        out = torch.empty((n, C, h, w), dtype=image.dtype, device=image.device)
+        with torch.cuda.device(image.device):
+            lib.check(lib.ds_ring_gather(image.data_ptr(), out.data_ptr(), d_wins.data_ptr(), n, 0, 0, 0,
+                                         C, 1, Hi, Wi, 1, h, w, _lib.dtype_code(image.dtype),
+                                         _lib.stream_ptr(image.device)), "ds_ring_gather(image windows)")
+        return out
+
+    def gather_image_views(self, image: torch.Tensor, views: Sequence[Tuple[float, float]], width: int, height: int,
+                           fov=120) -> torch.Tensor:
+        """All sphere condition-image views of a step in ONE launch: ``PanoramaTensor(image).
+        get_view_tensor_no_interpolate`` (panorama_tensor_utils.py:53-70) for every (phi, theta)
+        (i2v_sphere_panorama_pipeline.py:367-372 calls it once per view on the [3, 1024, 2048]
+        image).  image [C, Hi, Wi] with Wi == 2*Hi -> [n, C, height, width]."""
+        _lib.require_cuda(image, "image")
+        assert image.dim() == 3 and image.is_contiguous()
+        C, Hi, Wi = image.shape
+        assert Wi == 2 * Hi
+        vms = [maps.view_map(fov, th, ph, width, height, Hi, Wi) for (ph, th) in views]
+        d_idx = maps.on_device(("idx_all", tuple(vm.key for vm in vms)), image.device,
+                               lambda: np.stack([vm.idx_read for vm in vms]))
+        out = torch.empty((len(vms), C, height, width), dtype=image.dtype, device=image.device)
+        _launch_gather_nearest(image, out, d_idx, None, 0, len(vms), C, 1, Hi * Wi, 1, width * height)
+        return out
+
     def gather_all(self, latent, plan: StepPlan, out: Optional[torch.Tensor] = None, index: int = 0) -> torch.Tensor:
         """latent [B, C, F, H, W] -- or a :class:`PanoramaState` (panorama ``index``) -- ->
         windows [n_local_jobs, B, C, f_len, h, w] (this rank's slice of the ordered job list)."""

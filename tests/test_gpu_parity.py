@@ -476,3 +476,27 @@ def test_resize_video_latent_golden(dev):
     t = G(randn(80, 1, 4, 3, 4, 4), dev)
     assert padding_latents_at_front(t, 2).shape[2] == 5 and torch.equal(padding_latents_at_front(t, 2)[:, :, 1], t[:, :, 0])
     assert padding_latents_at_end(t, 1).shape[2] == 4 and torch.equal(padding_latents_at_end(t, 1)[:, :, 3], t[:, :, 2])
+
+
+def test_batched_condition_image_windows(dev):
+    """§8f-3: all condition-image windows / views of a step in one launch each, vs the per-call
+    drop-in classes (themselves pinned to the reference's golden vectors above) and the oracle."""
+    from dynamicscaler_b200.panorama_tensor_utils import PanoramaTensor
+    from dynamicscaler_b200.shift_window_utils import RingImageTensor
+    from dynamicscaler_b200.step import PanoramaStepper
+    img0 = randn(91, 3, 64, 128)
+    img = G(img0, dev)
+    st = PanoramaStepper(8, 16, 4, device=dev)
+    windows = [(0, 0), (100, 40), (127, 63), (64, 10)]                      # wrapping on both axes
+    got = st.gather_image_windows(img, windows, 40, 32)
+    ring = RingImageTensor(image_path=None, image_tensor=img, height=64, width=128)
+    for n, (l, t) in enumerate(windows):
+        assert torch.equal(got[n], ring.get_window_tensor(l, l + 40, t, t + 32))
+        assert np.array_equal(N(got[n]), po.ring_get(img0[None, :, None], l, l + 40, t, t + 32, 0, 1)[0, :, 0])
+    with pytest.raises(AssertionError):
+        st.gather_image_windows(img, [(200, 0)], 80, 32)
+    views = po.default_sphere_views(2)[:9]
+    gv = st.gather_image_views(img, views, 20, 12, fov=120)
+    pt = PanoramaTensor(img)
+    for n, (ph, th) in enumerate(views):
+        assert torch.equal(gv[n], pt.get_view_tensor_no_interpolate(120, th, ph, 20, 12)[0])
