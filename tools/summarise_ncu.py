@@ -30,7 +30,7 @@ for r in rows[1:]:
 tot = sum(sum(v) for v in agg.values())
 with open(f"{P}/{label}_launches_summary.md", "w") as f:
     f.write(f"# {label} -- ncu launch list: {what}\n\n")
-    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv` (tools/gpu_profile.sh). "
+    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv` (tools/gpu_profile.sh). "
             "Times are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
     f.write("| kernel | launches | mean us | share of profiled GPU time |\n|---|---|---|---|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
