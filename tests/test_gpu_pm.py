@@ -235,3 +235,25 @@ def test_fused_denoise_golden_small(dev):
         want_x0 = g[f"pred_x0/{n}"].reshape(4, F, h * w)[:, :, ent_src]
         assert np.array_equal(lat[:, :, ent_dst], want_xp), n
         assert np.array_equal(den[:, :, ent_dst], want_x0), n
+
+
+def test_state_weighted_merge_long_rows_use_generic_kernel(dev):
+    """A tiny panorama under 16-frame windows: some panorama pixels collect more than 64 CSR entries,
+    so no tiled plan exists and the generic weighted kernel runs; must equal the plane-major path."""
+    from dynamicscaler_b200 import maps
+    from dynamicscaler_b200.step import PanoramaStepper
+    H, W, F, h, w = 8, 16, 16, 24, 32
+    st = PanoramaStepper(H, W, F, device=dev)
+    views = po.default_sphere_views(0)[:6]
+    plan = st.plan_sphere(views, w, h, fov=120, mode="bilinear")
+    assert plan.extra.get("pm_tiled") is None                    # rows with > 64 entries
+    lat = G(randn(17, 1, 4, F, H, W), dev)
+    den = torch.zeros_like(lat)
+    state = st.make_state([lat, den])
+    wins = st.gather_all(state, plan)
+    assert torch.equal(wins, st.gather_all(lat, plan))
+    xp, x0 = wins * 0.5 + 1, wins * 0.25 - 1
+    st.merge_all([lat, den], [xp, x0], plan)
+    st.merge_all(state, [xp, x0], plan)
+    e_lat, e_den = state.export()
+    assert torch.equal(e_lat, lat) and torch.equal(e_den, den)
