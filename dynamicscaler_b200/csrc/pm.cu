@@ -50,6 +50,11 @@ constexpr int kWarps = kBlock / 32;
 // Launch-shape knobs (ds_tune); defaults are the measured best on B200 for the bench workload.
 static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
 static long long g_peer_timeout_ns = 2000000000ll;   // give up a cross-GPU wait after this long
+static int g_pdl = 11;                          // programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
+                                                // 4 nearest merge, 8 weighted merges.  Measured (tools/kbench.py, cfg2): the
+                                                // 4-tap gather / weighted merge chain gains 7 % (31.7 -> 29.6 us); with BOTH
+                                                // nearest kernels on PDL their chain loses 8 % (25.5 -> 27.7 us), so the
+                                                // nearest merge keeps plain stream order
 
 template <typename T> struct Atom;
 template <> struct Atom<float> {
@@ -88,6 +93,13 @@ template <> __device__ __forceinline__ float4 atom_ones<float>() { return make_f
 template <> __device__ __forceinline__ uint2 atom_ones<__nv_bfloat16>() { return make_uint2(0x3f803f80u, 0x3f803f80u); }
 
 template <typename A> __device__ __forceinline__ A ldg_atom(const A* p) { return __ldg(p); }
+
+// ------------------------------------------- programmatic dependent launch (PDL) ----
+// The gather / merge kernels of consecutive steps form a chain of 10-20 us kernels; with PDL the
+// next kernel's CTAs are scheduled while the current one drains, run their prologue (plan / map
+// loads, which no earlier kernel writes) and only then wait for the predecessor's memory.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_predecessors() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------- async-proxy (TMA bulk) helpers ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -204,11 +216,8 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
                  const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a, ds_peer_table_t* __restrict__ peer,
                  long long peer_timeout_ns) {
   using A = typename Atom<T>::type;
-  if (peer != nullptr) {
-    // exchange mode: every peer must have pushed the previous step's rows into this replica
-    pm_peer_spin(peer, peer->merges_done, -1, peer->my_merges, peer_timeout_ns);
-    __syncthreads();
-  }
+  pdl_launch_dependents();
+  bool waited = false;                           // predecessors (the previous merge) not yet awaited
   constexpr int VE = 16 / sizeof(T);            // elements per 16-byte vector
   constexpr int S = kPmKT + VE;                 // padded row stride (elements): 4 banks mod 32
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -244,6 +253,13 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
       }
       s_idx[i] = idx;
       if (TAPS > 1) s_wt[i] = w;
+    }
+    if (!waited) {
+      // the map entries above are static; everything below reads the panorama
+      pdl_wait_predecessors();
+      if (peer != nullptr)   // exchange mode: every peer must have pushed the previous step's rows too
+        pm_peer_spin(peer, peer->merges_done, -1, peer->my_merges, peer_timeout_ns);
+      waited = true;
     }
     __syncthreads();        // also orders the previous tile's bulk-store reads before the STS below
 
@@ -499,8 +515,8 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
                         const int32_t* __restrict__ d_ent_src, const int32_t* __restrict__ d_ent_dst,
                         const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
+  pdl_launch_dependents();
   __shared__ PmReplicas rep;
-  const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
   PmRange rg;
   if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -523,6 +539,9 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
         s_dst[lane] = dst;
       }
     }
+    // the plan entries above are static; payloads (and, across GPUs, the counters) come from earlier kernels
+    pdl_wait_predecessors();
+    const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
     if (DD) {
       // fused denoise epilogue: warp <-> window frame, both outputs from (x, ec, eu, noise)
       const bool has_eu = a.pay[2] != nullptr, has_nz = a.pay[3] != nullptr;
@@ -643,9 +662,9 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   const int v_lo = min(max(a.job_begin - s * a.vpf, 0), a.vpf);
   const int v_hi = min(max(a.job_begin + a.job_count - s * a.vpf, 0), a.vpf);
   const int t = __ldg(d_view_ptr + v_lo) + blockIdx.x;
+  pdl_launch_dependents();
   if (t >= __ldg(d_view_ptr + v_hi)) return;
   __shared__ PmReplicas rep;
-  const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e_base = t * kPmEC;
 
@@ -682,6 +701,10 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
     s_rp[cnt] = td.w;
   }
   if (warp == 0) { s_w[lane] = w[0]; s_w[32 + lane] = w[1]; }
+
+  // the plan data above is static; payloads (and, across GPUs, the counters) come from earlier kernels
+  pdl_wait_predecessors();
+  const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
 
   // ---- phase A: products (level-2 loads) ----
   const int plane_stride = FL * a.hw;
@@ -840,8 +863,8 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
                          const int32_t* __restrict__ d_ent_src, const float* __restrict__ d_ent_w,
                          const int32_t* __restrict__ d_ftab, const int32_t* __restrict__ d_fbegin) {
   using A = typename Atom<T>::type;
+  pdl_launch_dependents();
   __shared__ PmReplicas rep;
-  const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
   PmRange rg;
   if (pm_range(a, d_view_ptr, d_fbegin, rg)) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -866,6 +889,8 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
       const int dst = wr ? __ldg(d_row_dst + rg.lo + lane) : -1;
       s_dst[lane] = dst;
     }
+    pdl_wait_predecessors();                       // plan data above is static, payloads are not
+    const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
     for (int pr = warp; pr < n_pairs; pr += kWarps) {
       const int q = pr / a.f_len, fo = pr - q * a.f_len;
       int f;
@@ -945,7 +970,7 @@ static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* co
 
 // ctas_per_sm: 0 = occupancy limit, > 0 = cap (persistent kernels); < 0 = one CTA per item.
 template <typename K, typename... Args>
-static int pm_launch(K kernel, long long items, int ctas_per_sm, unsigned grid_y, size_t smem, cudaStream_t st, Args... args) {
+static int pm_launch(K kernel, int pdl_bit, long long items, int ctas_per_sm, unsigned grid_y, size_t smem, cudaStream_t st, Args... args) {
   DS_REQUIRE(smem <= 200 * 1024, DS_ERR_DIM);
   if (smem > 48 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   long long gx = items;
@@ -959,8 +984,18 @@ static int pm_launch(K kernel, long long items, int ctas_per_sm, unsigned grid_y
   }
   if (gx < 1) gx = 1;
   DS_REQUIRE(gx < (1ll << 31), DS_ERR_DIM);
-  kernel<<<dim3(static_cast<unsigned>(gx), grid_y), kBlock, smem, st>>>(args...);
-  return check_launch();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(gx), grid_y);
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (g_pdl & pdl_bit) ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  return e == cudaSuccess ? check_launch() : static_cast<int>(e);
 }
 
 }  // namespace ds
@@ -990,11 +1025,11 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
     const AT* pmp = static_cast<const AT*>(pm);
     ET* op = static_cast<ET*>(out);
     if (taps == 1) {
-      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
-      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
+      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, 1, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
+      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, 1, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
     }
-    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
-    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
+    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, 2, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
+    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, 2, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
   });
   return DS_OK;
 }
@@ -1019,8 +1054,8 @@ extern "C" int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payl
   DS_DISPATCH_DTYPE(dtype, {
     using AT = typename Atom<ET>::type;
     const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(AT) + kPmET * sizeof(int32_t);
-    if (f_len == 16) { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, false, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 16, false, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
-    { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 0, false, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 0, false, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
+    if (f_len == 16) { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, false, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 16, false, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
+    { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 0, false, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 0, false, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
@@ -1043,7 +1078,7 @@ extern "C" int ds_pm_merge_bilinear(void* const* h_pms, const void* const* h_pay
   const long long items = div_up(n_rows, kPmET);
   DS_DISPATCH_DTYPE(dtype, {
     const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(typename Atom<ET>::type) + kPmET * sizeof(int32_t);
-    { if (d_peer != nullptr) return pm_launch(pm_merge_bilinear_kernel<ET, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_bilinear_kernel<ET, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin); }
+    { if (d_peer != nullptr) return pm_launch(pm_merge_bilinear_kernel<ET, true>, 8, items, -1, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_bilinear_kernel<ET, false>, 8, items, -1, n_fwin, smem, st, a, d_view_ptr, d_row_dst, d_row_ptr, d_ent_src, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
@@ -1069,9 +1104,9 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
-    if (Q == 1) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
-    if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
-    { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    if (Q == 1) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
@@ -1114,8 +1149,8 @@ extern "C" int ds_pm_merge_nearest_ddim(void* const* h_pms, const void* x, const
   DS_DISPATCH_DTYPE(dtype, {
     using AT = typename Atom<ET>::type;
     const size_t smem = 2 * static_cast<size_t>(kPmET) * (f_len | 1) * sizeof(AT) + kPmET * sizeof(int32_t);
-    if (f_len == 16) { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, true, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 16, true, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
-    { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 0, true, true>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 0, true, false>, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
+    if (f_len == 16) { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, true, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 16, true, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
+    { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 0, true, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 0, true, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
@@ -1142,7 +1177,7 @@ extern "C" int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = 2 * static_cast<size_t>(kPmEC) * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
-    { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, true>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, false>, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
@@ -1161,6 +1196,7 @@ extern "C" int ds_tune(int knob, long long value) {
   switch (knob) {
     case DS_TUNE_PM_GATHER_CTAS_PER_SM: ds::g_gather_ctas_per_sm = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PEER_TIMEOUT_NS: ds::g_peer_timeout_ns = value; return DS_OK;
+    case DS_TUNE_PDL: ds::g_pdl = static_cast<int>(value); return DS_OK;
     default: return DS_ERR_DIM;
   }
 }

@@ -43,12 +43,26 @@ def main():
         run()
         return timed(run, False) / iters * 1e3
 
-    settings = [{"gather_cps": c} for c in (0, 0, 4, 6)]
+    settings = [{"gather_cps": 0, "pdl": m} for m in (11, 0, 15)]
     if os.environ.get("KBENCH_DEFAULT_ONLY"):
         settings = settings[:1]
     for cfg in settings:
         lib.check(lib.ds_tune(GATHER_CPS, cfg["gather_cps"]))
+        lib.check(lib.ds_tune(2, cfg.get("pdl", 11)))                     # DS_TUNE_PDL
         res = dict(cfg, workload=wl_name)
+        for mode in modes:                                  # whole steps (gather -> merge chains)
+            fns = []
+            for off, s_ in combos:
+                ws, plan = sets[s_], plans[mode][off]
+
+                def full(ws=ws, plan=plan):
+                    st.gather_all(ws.pano, plan, out=ws.wins)
+                    ws.merge(st, plan)
+                fns.append(full)
+            it = 200 if n_jobs < 100 else 40
+            run = make_runner(fns, it, True, side)
+            run()
+            res[f"step_{mode}_us"] = round(timed(run, False) / it * 1e3, 2)
         for mode in modes:
             for kind in ("gather", "merge"):
                 us = t_kernel(kind, mode, iters=200 if n_jobs < 100 else 40)
