@@ -257,3 +257,39 @@ def test_state_weighted_merge_long_rows_use_generic_kernel(dev):
     st.merge_all(state, [xp, x0], plan)
     e_lat, e_den = state.export()
     assert torch.equal(e_lat, lat) and torch.equal(e_den, den)
+
+
+def test_full_size_properties_north_star_shape(dev):
+    """[1,4,16,256,512] (north-star shape), size-independent properties of the resident path:
+    linearity of the 4-tap gather, merge(gather(x)) leaves covered pixels' nearest round trip
+    intact, idempotence of both merges, and untouched pixels keep their value."""
+    from dynamicscaler_b200.step import PanoramaStepper
+    H, W, F = 256, 512, 16
+    st = PanoramaStepper(H, W, F, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn(1, 4, F, H, W, device=dev, generator=gen)
+    y = torch.randn(1, 4, F, H, W, device=dev, generator=gen)
+    views = po.default_sphere_views(5)
+    pb = st.plan_sphere(views, 64, 40, fov=120, mode="bilinear")
+    pn = st.plan_sphere(views, 64, 40, fov=120, mode="nearest")
+    sx, sy, sxy = st.make_state([x]), st.make_state([y]), st.make_state([2 * x - 3 * y])
+    lin = st.gather_all(sxy, pb) - (2 * st.gather_all(sx, pb) - 3 * st.gather_all(sy, pb))
+    assert lin.abs().max().item() <= 5e-5                              # fp32 rounding of the combination
+    # nearest: writing back what was read changes nothing (every written pixel gets a value read from
+    # the SAME panorama pixel: read map floor(u) mod W / clamp == write map for in-range pixels)
+    wins = st.gather_all(sx, pn)
+    st.merge_all(sx, [wins], pn)
+    assert torch.equal(sx.export(0), x)
+    # idempotence + untouched pixels
+    for plan in (pn, pb):
+        s1 = st.make_state([x, torch.zeros_like(x)], mask=torch.zeros(1, H, W, device=dev))
+        pay = torch.randn(len(views), 1, 4, F, 40, 64, device=dev, generator=gen)
+        st.merge_all(s1, [pay, pay * 2], plan)
+        a_lat, a_den = s1.export()
+        st.merge_all(s1, [pay, pay * 2], plan)
+        b_lat, b_den = s1.export()
+        assert torch.equal(a_lat, b_lat) and torch.equal(a_den, b_den)
+        m = s1.export_mask()[0] > 0
+        assert 0.4 < m.float().mean().item() < 0.7                     # coverage of 44 views at 256x512
+        assert torch.equal(a_lat[0, :, :, ~m], x[0, :, :, ~m])        # untouched pixels keep their value
+        assert (a_den[0, :, :, ~m] == 0).all()

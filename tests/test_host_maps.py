@@ -254,3 +254,17 @@ def test_round_robin_view_sharding_partitions_the_global_plan(mode, world):
     assert seen.max() == 1 and seen.sum() == whole[0].size              # disjoint, complete
     for q in range(2):
         assert np.array_equal(got[q], want[q])
+
+
+def test_ddim_coefficients_match_oracle_scalars():
+    """step.ddim_coefficients (torch float32 ops, product side) == oracle.ddim_scalars (numpy float32),
+    bit for bit, on the reference schedule entries stored with the golden vectors."""
+    import os
+    from dynamicscaler_b200.step import ddim_coefficients
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ddim.npz"))
+    for eta, index, gs, a_t, a_prev, sig, s1m in g["cases"]:
+        sa, s1, sp, sd, sg, gg = ddim_coefficients(a_t, a_prev, sig, s1m, gs)
+        want = po.ddim_scalars(a_t, a_prev, sig, s1m)
+        got = np.array([sa, s1, sp, sd, sg], np.float32)
+        assert np.array_equal(got, np.array(want, np.float32)), (index, got, want)
+        assert np.float32(gg) == np.float32(gs)
