@@ -288,7 +288,16 @@ def run_ours(args, wl, wl_name):
     st_pm = st if (args.layout == "pm" and wl["kind"] == "sphere") else None
     peer = dist_on and st_pm is not None and args.exchange == "peer"
     gen_pano = torch.Generator(device=dev).manual_seed(99)      # replicas start identical on every rank
-    one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano)
+    if peer:
+        lib.check(lib.ds_tune(1, 30_000_000_000))            # DS_TUNE_PEER_TIMEOUT_NS: ranks may start seconds apart
+    try:
+        one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano)
+    except Exception as e:                                   # no symmetric memory on this system
+        if not peer:
+            raise
+        print(f"[bench] peer exchange unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce path", file=sys.stderr)
+        peer = False
+        one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano)
     n_sets = max(2, min(4, -(-3 * L2_BYTES // one.nbytes())))   # aggregate footprint >= 3x L2
     sets = [one] + [Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano) for _ in range(n_sets - 1)]
     combos = [(i % NP, i % n_sets) for i in range(NP * n_sets // np.gcd(NP, n_sets))]
@@ -424,6 +433,7 @@ def run_ours(args, wl, wl_name):
                                     + ", release/acquire counters)" if peer else
                                     "windows split over ranks, 1 NCCL all-reduce/step")},
             "steps_per_s": 1e3 / head["ms_per_step"],
+            "peer_wait_timeouts": bool(peer and any(w.state.peer_error() for w in sets)),
             "gpu_launches": int(head["launches_per_step"] * K),
             "clocks": sampler.summary(),
             "e2e": {"value": n_win / (e2e_ms * 1e-3), "unit": "blends/s",
