@@ -1,3 +1,5 @@
+"""2-GPU+ probe (torchrun): does torch symmetric memory expose an NVLS multicast alias here?
+Prints the multicast pointer and the per-rank buffer addresses."""
 import os, torch, torch.distributed as dist
 import torch.distributed._symmetric_memory as symm
 rank=int(os.environ["RANK"]); torch.cuda.set_device(rank); dev=torch.device("cuda",rank)
