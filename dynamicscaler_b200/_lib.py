@@ -121,6 +121,26 @@ def require_cuda(t: torch.Tensor, what: str = "tensor"):
                            "this package has no CPU path")
 
 
+class _NoGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on(device):
+    """``with on(dev):`` -- make ``dev`` current for a launch; free when it already is (the usual
+    case: switching devices costs several microseconds per call)."""
+    idx = device.index
+    if idx is None or idx == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 

@@ -39,7 +39,7 @@ def resize_video_latent(input_latent, target_height, target_width, mode='bilinea
     src = input_latent.contiguous()
     out = torch.empty((batch, channel, frame, int(target_height), int(target_width)), dtype=src.dtype,
                       device=src.device)
-    with torch.cuda.device(src.device):
+    with _lib.on(src.device):
         lib.check(lib.ds_resize_planes(src.data_ptr(), out.data_ptr(), batch * channel * frame, h, w,
                                        int(target_height), int(target_width), _MODES[mode],
                                        1 if align_corners else 0, _lib.dtype_code(src.dtype),

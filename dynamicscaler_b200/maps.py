@@ -97,6 +97,11 @@ class ViewMap:
         """[h, w] bool of panorama_tensor_utils.py:198 (vacuously all True)."""
         return self._memo("read_valid", lambda: (self.u >= 0) & (self.u < self.W) & (self.v >= 0) & (self.v < self.H))
 
+    @property
+    def all_valid(self):
+        """True when the validity mask of :198 is all ones (always, in practice)."""
+        return self._memo("all_valid", lambda: bool(self.read_valid.all()))
+
     # A.3 nearest write: no wrap, validity mask, last writer wins (:166-181, SURVEY P4)
     @property
     def write_plan(self):
@@ -404,3 +409,5 @@ def clear_caches():
         _VIEWS.clear()
         _DEVICE.clear()
         _HOST.clear()
+    from . import panorama_tensor_utils
+    panorama_tensor_utils._VIEW_CALL_CACHE.clear()

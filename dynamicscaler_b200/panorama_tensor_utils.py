@@ -22,14 +22,14 @@ from ._lib import lib
 
 # ------------------------------------------------------------------ kernel glue ----
 def _launch_gather_nearest(store, out, d_idx, d_jobs, f0, n_jobs, P, F, HW, f_len, hw):
-    with torch.cuda.device(store.device):
+    with _lib.on(store.device):
         lib.check(lib.ds_gather_nearest(store.data_ptr(), out.data_ptr(), d_idx.data_ptr(), _lib.ptr(d_jobs),
                                         f0, n_jobs, P, F, HW, f_len, hw, _lib.dtype_code(store.dtype),
                                         _lib.stream_ptr(store.device)), "ds_gather_nearest")
 
 
 def _launch_gather_bilinear(store, out, d_idx4, d_wt4, d_jobs, f0, n_jobs, P, F, HW, f_len, hw):
-    with torch.cuda.device(store.device):
+    with _lib.on(store.device):
         lib.check(lib.ds_gather_bilinear(store.data_ptr(), out.data_ptr(), d_idx4.data_ptr(), d_wt4.data_ptr(),
                                          _lib.ptr(d_jobs), f0, n_jobs, P, F, HW, f_len, hw,
                                          _lib.dtype_code(store.dtype), _lib.stream_ptr(store.device)),
@@ -39,7 +39,7 @@ def _launch_gather_bilinear(store, out, d_idx4, d_wt4, d_jobs, f0, n_jobs, P, F,
 def _launch_merge_nearest(panos, payloads, mask, mask_mode, mask_planes, d_dst, d_src, T, d_ftab,
                           vpf, P, F, HW, f_len, hw, vec=1, job_begin=0, job_count=1 << 30):
     ref = panos[0] if panos else mask
-    with torch.cuda.device(ref.device):
+    with _lib.on(ref.device):
         lib.check(lib.ds_merge_nearest(_lib.ptr_array(panos), _lib.ptr_array(payloads), len(panos),
                                        _lib.ptr(mask), mask_mode, mask_planes, _lib.ptr(d_dst), d_src.data_ptr(),
                                        T, _lib.ptr(d_ftab), vpf, job_begin, job_count, P, F, HW, f_len, hw, vec,
@@ -50,7 +50,7 @@ def _launch_merge_bilinear(panos, payloads, mask, mask_mode, mask_planes, plan, 
                            job_begin=0, job_count=1 << 30):
     row_dst, row_ptr, ent_src, ent_w = plan
     ref = panos[0] if panos else mask
-    with torch.cuda.device(ref.device):
+    with _lib.on(ref.device):
         lib.check(lib.ds_merge_bilinear(_lib.ptr_array(panos), _lib.ptr_array(payloads), len(panos),
                                         _lib.ptr(mask), mask_mode, mask_planes, row_dst.data_ptr(),
                                         row_ptr.data_ptr(), row_dst.numel(), ent_src.data_ptr(), ent_w.data_ptr(),
@@ -63,6 +63,9 @@ def _frame_table(F, f0, f_len, device):
     if f0 == 0 and f_len == F:
         return None
     return maps.on_device(("ftab1", F, f0, f_len), device, lambda: maps.frame_table(F, [f0], f_len))
+
+
+_VIEW_CALL_CACHE = {}      # (kind, fov, theta, phi, w, h, H, W, device) -> (ViewMap, device arrays)
 
 
 class _Block:
@@ -90,32 +93,57 @@ class PanoramaTensor:
         self.device = equirect_tensor.device
         self.dtype = equirect_tensor.dtype
 
+    # per-call host overhead matters for the unmodified call sites (one launch per call): the
+    # storage block and the device maps of a view are looked up once and remembered
+    _blk_cache = None
+
+    def _view_maps(self, what, fov, theta, phi, width, height, device, make):
+        """Device arrays of one view (``what`` names the kind): one dict lookup per call (handlers
+        are re-created every step, e.g. the mask panorama, so the cache is shared)."""
+        key = (what, fov, theta, phi, width, height, self.H, self.W, device)
+        hit = _VIEW_CALL_CACHE.get(key)
+        if hit is None:
+            vm = maps.view_map(fov, theta, phi, width, height, self.H, self.W)
+            hit = _VIEW_CALL_CACHE[key] = (vm, make(vm, device))
+            if len(_VIEW_CALL_CACHE) > 8192:
+                _VIEW_CALL_CACHE.pop(next(iter(_VIEW_CALL_CACHE)))
+        return hit
+
     # -- storage resolution -------------------------------------------------------
     def _block(self, frame_begin=None, frame_end=None) -> _Block:   # frames: ring twin only
         t = self.equirect_tensor
+        hit = self._blk_cache
+        if hit is not None and hit[0] is t:
+            return hit[1]
         _lib.require_cuda(t, "PanoramaTensor.equirect_tensor")
         if t.dim() == 5 and not t.is_contiguous() and t.permute(0, 2, 1, 3, 4).is_contiguous():
             B, F, C = t.shape[0], t.shape[1], t.shape[2]                 # proxy layout underneath
-            return _Block(t.permute(0, 2, 1, 3, 4), B * C, F, 0, F, True, (B, F))
-        if not t.is_contiguous():
-            t = self.equirect_tensor = t.contiguous()
-        lead = tuple(t.shape[:-3]) if t.dim() > 3 else ()
-        return _Block(t, t.numel() // (self.H * self.W), 1, 0, 1, False, lead)
+            blk = _Block(t.permute(0, 2, 1, 3, 4), B * C, F, 0, F, True, (B, F))
+        else:
+            if not t.is_contiguous():
+                t = self.equirect_tensor = t.contiguous()
+            lead = tuple(t.shape[:-3]) if t.dim() > 3 else ()
+            blk = _Block(t, t.numel() // (self.H * self.W), 1, 0, 1, False, lead)
+        self._blk_cache = (t, blk)
+        return blk
 
     def _view_shape(self, blk: _Block, height, width):
         if blk.proxied:
             return (blk.lead[0], self.C, blk.f_len, height, width)       # kernel order [B,C,f,h,w]
         return (*blk.lead, self.C, height, width)
 
-    def _finish_view(self, blk: _Block, out):
-        if blk.proxied:
+    def _finish_view(self, blk: _Block, out, kernel_order=False):
+        if blk.proxied and not kernel_order:
             return out.permute(0, 2, 1, 3, 4)                             # caller order [B,f,C,h,w]
         return out
 
-    def _payload(self, blk: _Block, view_tensor, height, width):
-        """View tensor -> dense [P, f_len, h*w] block in the panorama's dtype."""
-        v = view_tensor.to(device=blk.store.device, dtype=blk.store.dtype)
-        if blk.proxied:
+    def _payload(self, blk: _Block, view_tensor, height, width, kernel_order=False):
+        """View tensor -> dense [P, f_len, h*w] block in the panorama's dtype.  ``kernel_order``:
+        the proxies hand over their callers' [B, C, f, h, w] tensors as they are."""
+        v = view_tensor
+        if v.device != blk.store.device or v.dtype != blk.store.dtype:
+            v = v.to(device=blk.store.device, dtype=blk.store.dtype)
+        if blk.proxied and not kernel_order:
             if v.dim() != 5:
                 v = v.reshape(blk.lead[0], blk.f_len, self.C, height, width)
             v = v.permute(0, 2, 1, 3, 4)
@@ -141,32 +169,37 @@ class PanoramaTensor:
                                 self.H * self.W, blk.f_len, vm.hw)
         return self._finish_view(blk, out)
 
-    def get_view_tensor_no_interpolate(self, fov, theta, phi, width, height, _frames=(None, None)):
+    def get_view_tensor_no_interpolate(self, fov, theta, phi, width, height, _frames=(None, None),
+                                       _kernel_order=False):
         """Reference :53-70 + :185-202 -- nearest read, returns (view, ones[h, w])."""
         blk = self._block(*_frames)
-        vm = maps.view_map(fov, theta, phi, width, height, self.H, self.W)
-        d_idx = maps.on_device(("idx_read", vm.key), blk.store.device, lambda: vm.idx_read)
-        out = torch.empty(self._view_shape(blk, height, width), dtype=blk.store.dtype, device=blk.store.device)
+        dev = blk.store.device
+        vm, d_idx = self._view_maps("idx_read", fov, theta, phi, width, height, dev,
+                                    lambda vm, dev: maps.on_device(("idx_read", vm.key), dev, lambda: vm.idx_read))
+        out = torch.empty(self._view_shape(blk, height, width), dtype=blk.store.dtype, device=dev)
         _launch_gather_nearest(blk.store, out, d_idx, None, blk.f0, 1, blk.P, blk.F, self.H * self.W, blk.f_len, vm.hw)
-        mask = torch.ones((height, width), dtype=self.dtype, device=blk.store.device)
-        if not vm.read_valid.all():                                       # :198-200 (never taken: u, v in range)
-            bad = torch.from_numpy(~vm.read_valid).to(blk.store.device)
+        mask = torch.ones((height, width), dtype=self.dtype, device=dev)
+        if not vm.all_valid:                                              # :198-200 (never taken: u, v in range)
+            bad = torch.from_numpy(~vm.read_valid).to(dev)
             mask[bad] = 0
             out[..., bad] = 0
-        return self._finish_view(blk, out), mask
+        return self._finish_view(blk, out, _kernel_order), mask
 
     # -- writes ---------------------------------------------------------------------
-    def set_view_tensor_no_interpolation(self, view_tensor, fov, theta, phi, _frames=(None, None)):
+    def set_view_tensor_no_interpolation(self, view_tensor, fov, theta, phi, _frames=(None, None),
+                                         _kernel_order=False):
         """Reference :154-183 -- forward nearest scatter, last view pixel wins (P4)."""
         if view_tensor.dim() == 3:
             view_tensor = view_tensor.unsqueeze(0)
         height, width = view_tensor.shape[-2], view_tensor.shape[-1]
         blk = self._block(*_frames)
-        vm = maps.view_map(fov, theta, phi, width, height, self.H, self.W)
-        d_dst, d_src = maps.on_device(("write_plan", vm.key), blk.store.device, lambda: vm.write_plan)
-        pay = self._payload(blk, view_tensor, height, width)
+        dev = blk.store.device
+        vm, (d_dst, d_src) = self._view_maps(
+            "write_plan", fov, theta, phi, width, height, dev,
+            lambda vm, dev: maps.on_device(("write_plan", vm.key), dev, lambda: vm.write_plan))
+        pay = self._payload(blk, view_tensor, height, width, _kernel_order)
         _launch_merge_nearest([blk.store], [pay], None, _lib.DS_MASK_NONE, 0, d_dst, d_src, d_dst.numel(),
-                              _frame_table(blk.F, blk.f0, blk.f_len, blk.store.device), 1,
+                              _frame_table(blk.F, blk.f0, blk.f_len, dev), 1,
                               blk.P, blk.F, self.H * self.W, blk.f_len, vm.hw)
 
     def set_view_tensor_bilinear(self, view_tensor, fov, theta, phi, _frames=(None, None)):
@@ -271,8 +304,8 @@ class PanoramaLatentProxy:
         return view.permute(0, 2, 1, 3, 4).clone()
 
     def get_view_tensor_no_interpolate(self, fov, theta, phi, width, height):
-        view, mask = self.panorama_tensor.get_view_tensor_no_interpolate(fov, theta, phi, width, height)
-        return view.permute(0, 2, 1, 3, 4), mask
+        # the kernel already produces the caller's [B, C, N, h, w] order
+        return self.panorama_tensor.get_view_tensor_no_interpolate(fov, theta, phi, width, height, _kernel_order=True)
 
     def set_view_tensor(self, view_tensor, fov, theta, phi):
         self.panorama_tensor.set_view_tensor(view_tensor.permute(0, 2, 1, 3, 4), fov, theta, phi)
@@ -284,4 +317,7 @@ class PanoramaLatentProxy:
         return self.panorama_tensor.equirect_tensor.permute(0, 2, 1, 3, 4)
 
     def set_view_tensor_no_interpolation(self, view_tensor, fov, theta, phi):
-        self.panorama_tensor.set_view_tensor_no_interpolation(view_tensor.permute(0, 2, 1, 3, 4), fov, theta, phi)
+        if view_tensor.dim() == 5:
+            self.panorama_tensor.set_view_tensor_no_interpolation(view_tensor, fov, theta, phi, _kernel_order=True)
+        else:
+            self.panorama_tensor.set_view_tensor_no_interpolation(view_tensor.permute(0, 2, 1, 3, 4), fov, theta, phi)

@@ -66,7 +66,7 @@ class RingLatent:
         lat = self._storage()
         B, C, F, H, W = lat.shape
         out = torch.empty((B, C, fe - fb, d - t, r - l), dtype=lat.dtype, device=lat.device)
-        with torch.cuda.device(lat.device):
+        with _lib.on(lat.device):
             lib.check(lib.ds_ring_gather(lat.data_ptr(), out.data_ptr(), None, 1, l, t, fb,
                                          B * C, F, H, W, fe - fb, d - t, r - l,
                                          _lib.dtype_code(lat.dtype), _lib.stream_ptr(lat.device)),
@@ -89,7 +89,7 @@ class RingLatent:
         if tuple(src.shape[:2]) != (B, C):
             src = src.expand(B, C, *target)                              # slice-assign broadcasts
         src = src.contiguous()
-        with torch.cuda.device(lat.device):
+        with _lib.on(lat.device):
             lib.check(lib.ds_ring_scatter(lat.data_ptr(), src.data_ptr(), l, t, fb, B * C, F, H, W,
                                           fe - fb, d - t, r - l, _lib.dtype_code(lat.dtype),
                                           _lib.stream_ptr(lat.device)), "ds_ring_scatter")
@@ -139,7 +139,7 @@ class RingImageTensor:
         img = self._storage()
         h, w = int(pos_down - pos_top), int(pos_right - pos_left)
         out = torch.empty((3, h, w), dtype=img.dtype, device=img.device)
-        with torch.cuda.device(img.device):
+        with _lib.on(img.device):
             lib.check(lib.ds_ring_gather(img.data_ptr(), out.data_ptr(), None, 1, int(pos_left), int(pos_top), 0,
                                          3, 1, height, width, 1, h, w, _lib.dtype_code(img.dtype),
                                          _lib.stream_ptr(img.device)), "ds_ring_gather")

@@ -310,7 +310,7 @@ class PanoramaStepper:
         plan.d_jobs = torch.from_numpy(jobs3).to(self.device)
         d_wins2 = torch.from_numpy(np.array(windows, dtype=np.int32).reshape(-1, 2)).to(self.device)
         plan.d_src = torch.empty(self.H * self.W, dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
+        with _lib.on(self.device):
             lib.check(lib.ds_ring_merge_plan(plan.d_src.data_ptr(), d_wins2.data_ptr(), nv, self.H, self.W, h, w,
                                              _lib.stream_ptr(self.device)), "ds_ring_merge_plan")
         aligned = self.W % 4 == 0 and w % 4 == 0 and all(l % 4 == 0 for l, _ in windows)
@@ -348,7 +348,7 @@ class PanoramaStepper:
         B, C, F, H, W = t.shape
         t = t.contiguous()
         pm = torch.empty((H * W, F, 4), dtype=t.dtype, device=t.device) if out is None else out
-        with torch.cuda.device(t.device):
+        with _lib.on(t.device):
             lib.check(lib.ds_pm_merge_nearest(_lib.ptr_array([pm]), _lib.ptr_array([t]), 1, None, _lib.DS_MASK_NONE,
                                               None, None, None, H * W, None, None, 1, 1, 0, 1,
                                               4, F, H * W, F, H * W, None, _lib.dtype_code(t.dtype),
@@ -359,7 +359,7 @@ class PanoramaStepper:
         """pm [H*W, F, 4] -> [B, C, F, H, W]: ds_pm_gather with the identity map."""
         B, C, F, H, W = shape
         out = torch.empty(shape, dtype=pm.dtype, device=pm.device)
-        with torch.cuda.device(pm.device):
+        with _lib.on(pm.device):
             lib.check(lib.ds_pm_gather(pm.data_ptr(), out.data_ptr(), None, None, 1, None, 0, 1, 4, F, H * W, F,
                                        H * W, None, _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)),
                       "ds_pm_gather(unpack)")
@@ -370,7 +370,7 @@ class PanoramaStepper:
 
     def _peer_sync(self, st, phase, wait=False):
         """Publish this rank's gather / merge count to the peers (the data kernels wait in-kernel)."""
-        with torch.cuda.device(st.device):
+        with _lib.on(st.device):
             lib.check(lib.ds_pm_peer_sync(st.peer_table, phase, 1 if wait else 0, _lib.stream_ptr(st.device)),
                       "ds_pm_peer_sync")
 
@@ -381,7 +381,7 @@ class PanoramaStepper:
             d_idx, d_wt, taps = plan.d_idx, None, 1
         else:
             (d_idx, d_wt), taps = plan.d_taps, 4
-        with torch.cuda.device(pm.device):
+        with _lib.on(pm.device):
             lib.check(lib.ds_pm_gather(pm.data_ptr(), out.data_ptr(), d_idx.data_ptr(), _lib.ptr(d_wt), taps,
                                        d_jobs.data_ptr(), 0, nj, 4, F, HW, plan.f_len, plan.hw, peer,
                                        _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)), "ds_pm_gather")
@@ -394,7 +394,7 @@ class PanoramaStepper:
         ref = pms[0] if pms else mask
         common = (_lib.ptr(plan.d_ftab), _lib.ptr(plan.d_fbegin), plan.n_fwin, plan.vpf, j0, nj,
                   4, F, HW, plan.f_len, plan.hw, peer, _lib.dtype_code(ref.dtype), _lib.stream_ptr(ref.device))
-        with torch.cuda.device(ref.device):
+        with _lib.on(ref.device):
             if plan.kind == "sphere_nearest":
                 view_ptr, ent_src, ent_dst = mp
                 lib.check(lib.ds_pm_merge_nearest(_lib.ptr_array(pms), _lib.ptr_array(payloads), len(pms),
@@ -434,7 +434,7 @@ class PanoramaStepper:
         n = len(windows)
         d_wins = torch.tensor([[l, t, 0] for (l, t) in windows], dtype=torch.int32, device=image.device)
         out = torch.empty((n, C, h, w), dtype=image.dtype, device=image.device)
-        with torch.cuda.device(image.device):
+        with _lib.on(image.device):
             lib.check(lib.ds_ring_gather(image.data_ptr(), out.data_ptr(), d_wins.data_ptr(), n, 0, 0, 0,
                                          C, 1, Hi, Wi, 1, h, w, _lib.dtype_code(image.dtype),
                                          _lib.stream_ptr(image.device)), "ds_ring_gather(image windows)")
@@ -487,7 +487,7 @@ class PanoramaStepper:
             return out
         if plan.kind == "ring":
             d_jobs = plan.d_jobs[j0:j0 + nj]
-            with torch.cuda.device(latent.device):
+            with _lib.on(latent.device):
                 lib.check(lib.ds_ring_gather(latent.data_ptr(), out.data_ptr(), d_jobs.data_ptr(), nj, 0, 0, 0,
                                              B * C, F, H, W, plan.f_len, plan.h, plan.w,
                                              _lib.dtype_code(latent.dtype), _lib.stream_ptr(latent.device)),
@@ -576,7 +576,7 @@ class PanoramaStepper:
                 _lib.ptr(mask), mask_mode)
         tail = (_lib.ptr(plan.d_ftab), _lib.ptr(plan.d_fbegin), plan.n_fwin, plan.vpf, j0, nj, 4, F, HW, plan.f_len,
                 plan.hw, st.peer_table, _lib.dtype_code(st.dtype), _lib.stream_ptr(st.device))
-        with torch.cuda.device(st.device):
+        with _lib.on(st.device):
             if nj > 0 and plan.T > 0 and plan.kind == "sphere_nearest":
                 view_ptr, ent_src, ent_dst = plan.pm_merge
                 lib.check(lib.ds_pm_merge_nearest_ddim(*head, view_ptr.data_ptr(), ent_src.data_ptr(), ent_dst.data_ptr(),
@@ -634,7 +634,7 @@ class PanoramaStepper:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
         group, period = (1, n) if per_frame else (n // HW, HW)
         code, sp = _lib.dtype_code(st.dtype), _lib.stream_ptr(st.device)
-        with torch.cuda.device(st.device):
+        with _lib.on(st.device):
             for q in range(Q):
                 lib.check(lib.ds_select_merged(pms[q].data_ptr(), sums[q].data_ptr(), weight.data_ptr(), n, period,
                                                group, code, sp), "ds_select_merged")
@@ -667,7 +667,7 @@ class PanoramaStepper:
             self._merge_into(sums, payloads, weight, _lib.DS_MASK_FULL if per_frame else _lib.DS_MASK_PLANE,
                              1 if per_frame else 0, plan, P, j0, nj)
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
-        with torch.cuda.device(buf.device):
+        with _lib.on(buf.device):
             for q in range(Q):
                 lib.check(lib.ds_select_merged(panos[q].data_ptr(), sums[q].data_ptr(), weight.data_ptr(), n, wlen, 1,
                                                _lib.dtype_code(buf.dtype), _lib.stream_ptr(buf.device)),

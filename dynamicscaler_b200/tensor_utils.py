@@ -37,7 +37,7 @@ def mix_latents_with_mask(latent_1, latent_to_add, mask, mix_ratio):
     m = m.contiguous()
     out = torch.empty_like(l1)
     r = float(mix_ratio)
-    with torch.cuda.device(l1.device):
+    with _lib.on(l1.device):
         lib.check(lib.ds_mix_mask(l1.data_ptr(), add.data_ptr(), m.data_ptr(), out.data_ptr(),
                                   r, 1 - r, l1.numel(), mask_hw, _lib.dtype_code(l1.dtype),
                                   _lib.stream_ptr(l1.device)), "ds_mix_mask")
