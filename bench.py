@@ -162,7 +162,7 @@ def run_reference(args, wl, wl_name):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    reps = max(1, min(args.steps, 3 if args.mode == "bilinear" else 20))
+    reps = max(1, min(args.steps, 8 if args.mode == "bilinear" else 20))     # about 10-20 s of CPU work
     res = cpu_step_time(wl, args.mode, reps)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": f"no CPU port of workload {wl_name}"}))
@@ -458,7 +458,7 @@ def run_ours(args, wl, wl_name):
                                  / (results[m][kn + "_us"] * 1e-6) / 1e9) for kn in ("gather", "merge")}
                         for m in results},
             }
-            reps = 2 if args.mode == "bilinear" else 10
+            reps = 8 if args.mode == "bilinear" else 20                 # about 10-20 s of CPU work
             cpu = None if args.no_cpu else cpu_step_time(wl, args.mode, reps)
             if cpu is not None:
                 sec, cores, sample, _ = cpu
