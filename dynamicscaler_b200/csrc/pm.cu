@@ -45,6 +45,7 @@ constexpr int kPmPlanes = 4;     // planes per atom (B*C of the latent); other c
 constexpr int kPmKT = 64;        // view pixels per gather work item
 constexpr int kPmET = 32;        // entries (nearest) / panorama rows (weighted) per merge CTA
 constexpr int kPmEC = 64;        // padded CSR entries per tile of the tiled weighted merge
+constexpr int kPmTR = 32;        // panorama rows per tile of the tiled weighted merge (64 measured slower on cfg2: 15.3 -> 16.2 us)
 constexpr int kWarps = kBlock / 32;
 
 // Launch-shape knobs (ds_tune); defaults are the measured best on B200 for the bench workload.
@@ -654,8 +655,8 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float4* prod = reinterpret_cast<float4*>(smem_raw);                 // [QN][EC][SA] fp32 products
   float* s_w = reinterpret_cast<float*>(prod + QN * kPmEC * SA);      // [EC]
-  int32_t* s_rp = reinterpret_cast<int32_t*>(s_w + kPmEC);            // [ET + 1] local entry offsets
-  int32_t* s_dst = s_rp + kPmET + 1;                                  // [ET]
+  int32_t* s_rp = reinterpret_cast<int32_t*>(s_w + kPmEC);            // [TR + 1] local entry offsets
+  int32_t* s_dst = s_rp + kPmTR + 1;                                  // [TR]
 
   // ---- which tile / job ----
   const int s = blockIdx.y;
@@ -775,7 +776,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   // consumed products) and every 256-B row leaves through one TMA bulk copy per replica.
   const bool row_bulk = PEER && a.peer->mc_pm[0] == 0 && sizeof(A) == 16 && d_ftab == nullptr && a.mask_mode != DS_MASK_FULL;   // fp32: 16-byte aligned rows
   const int fo_b = threadIdx.x & (FL - 1), row_b = threadIdx.x / FL;
-  constexpr int NSW = kPmET / (kBlock / FL);
+  constexpr int NSW = kPmTR / (kBlock / FL);
   float4 res[NSW][QN];
   bool ok[NSW];
 #pragma unroll
@@ -821,7 +822,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   }
   if (row_bulk) {
     __syncthreads();                               // every product has been consumed
-    A* rows = reinterpret_cast<A*>(prod);          // [QN][ET][SA] result atoms
+    A* rows = reinterpret_cast<A*>(prod);          // [QN][TR][SA] result atoms (TR <= EC: fits over the products)
     int32_t* s_ok = s_rp;                          // row offsets are no longer needed
 #pragma unroll
     for (int sw = 0; sw < NSW; ++sw) {
@@ -831,7 +832,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
 #pragma unroll
         for (int q = 0; q < QN; ++q) {
           const float r[4] = {res[sw][q].x, res[sw][q].y, res[sw][q].z, res[sw][q].w};
-          rows[(q * kPmET + i) * SA + fo_b] = Atom<T>::pack(r);
+          rows[(q * kPmTR + i) * SA + fo_b] = Atom<T>::pack(r);
         }
       }
     }
@@ -845,7 +846,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
       const int q = qi / cnt, i = qi - q * cnt;
       if (s_ok[i]) {
         bulk_store(reinterpret_cast<A*>(rep.ptr[r][q]) + static_cast<size_t>(s_dst[i]) * a.F,
-                   rows + (q * kPmET + i) * SA, row_bytes);
+                   rows + (q * kPmTR + i) * SA, row_bytes);
         issued = true;
       }
     }
@@ -1102,7 +1103,7 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
   DS_REQUIRE(f_len == 16 && (Q == 1 || Q == 2 || Q == 4) && n_tiles >= 0, DS_ERR_DIM);   // other shapes: ds_pm_merge_bilinear
   if (n_tiles == 0 && d_peer == nullptr) return DS_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
+  const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmTR + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
     if (Q == 1) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
     if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
@@ -1175,7 +1176,7 @@ extern "C" int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x
   if (n_tiles == 0 && d_peer == nullptr) return DS_OK;
   const int4* d_tile4 = reinterpret_cast<const int4*>(d_tile);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t smem = 2 * static_cast<size_t>(kPmEC) * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmET + 1) * sizeof(int32_t);
+  const size_t smem = 2 * static_cast<size_t>(kPmEC) * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmTR + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
     { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
   });

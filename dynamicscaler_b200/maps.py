@@ -327,7 +327,7 @@ def pm_bilinear_plan(vmaps, base=None, n_views=None):
             ent_src[ent_index].astype(np.int32), np.ascontiguousarray(ent_w[ent_index], dtype=F32))
 
 
-PM_TILE_ROWS, PM_TILE_ENTRIES = 32, 64        # csrc/pm.cu kPmET, kPmEC
+PM_TILE_ROWS, PM_TILE_ENTRIES = 32, 64        # csrc/pm.cu kPmTR, kPmEC
 
 
 def pm_bilinear_tiled_plan(vmaps, base=None, n_views=None):
