@@ -58,6 +58,15 @@ def _worker(rank, world, port, exchange, out_dir):
                 xp, x0 = wins_all * 0.5 + (i + 1), wins_all * 0.25 - (i + 1)
                 ref_st.merge_all(ref, [xp, x0], plan_ref)
                 st.merge_all(state, [xp[ids].contiguous(), x0[ids].contiguous()], plan)
+            if exchange == "peer":
+                # fused denoise epilogue (CFG + ddim_step inside the merge) across ranks
+                from dynamicscaler_b200.step import ddim_coefficients
+                coef = ddim_coefficients(0.5, 0.55, 0.1, 0.70710677, 7.5)
+                gen = torch.Generator(device=dev).manual_seed(11)
+                ec, eu, nz = (torch.randn(wins_all.shape, device=dev, generator=gen) for _ in range(3))
+                ref_st.merge_denoised(ref, wins_all, ec, eu, coef, plan_ref, noise=nz)
+                st.merge_denoised(state, wins_all[ids].contiguous(), ec[ids].contiguous(), eu[ids].contiguous(), coef,
+                                  plan, noise=nz[ids].contiguous())
             a_lat, a_den = state.export()
             b_lat, b_den = ref.export()
             assert not state.peer_error()
