@@ -28,11 +28,13 @@
 // Multi-GPU (windows sharded over ranks): with a ds_peer_table_t every rank holds a
 // replica of the panorama in peer-mapped (symmetric) memory and the merge kernels are the
 // exchange step themselves: each surviving row is stored straight into EVERY replica over
-// NVLink (peer st.global), so there is no zeroed sum buffer, no all-reduce and no select pass.
-// Cross-GPU ordering is two monotonic counters per peer, signalled with st.release.sys by the
-// last CTA of a kernel and awaited with ld.acquire.sys by the first instructions of the next:
-//   gather  waits until every peer has pushed the previous step's rows   (merges_done)
-//   merge   waits until every peer has finished reading its replica      (gathers_done)
+// NVLink -- one multimem.st to the NVLS multicast alias, or one TMA bulk copy / peer st.global per
+// replica -- so there is no zeroed sum buffer, no all-reduce and no select pass.
+// Cross-GPU ordering is two monotonic counters per peer: a 32-thread kernel after every gather /
+// merge publishes this rank's count into every peer's table (st.release.sys), and the data
+// kernels wait on them (ld.acquire.sys, prefetched so the round trip overlaps their loads):
+//   gather  reads the panorama only when every peer has pushed the previous step's rows
+//   merge   stores rows only when every peer has finished reading its replica
 //
 // Scheduling: these kernels run for 10-20 us, so wave quantisation and tails matter as much
 // as bandwidth: the gather runs persistent CTAs with an even static split, the merges one
@@ -147,14 +149,14 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
-// One tiny kernel between the data kernels of a step (stream order does the rest):
-//   phase DS_PEER_AFTER_GATHER: this rank has finished reading its replica -> bump my_gathers,
-//     publish it into gathers_done[rank] of every peer, then wait until every peer has
-//     published at least as many gathers (so their replicas may be overwritten by my merge);
-//   phase DS_PEER_AFTER_MERGE: this rank's rows have been pushed (the merge kernel has
-//     retired, so its peer stores are performed) -> same with my_merges / merges_done, after
-//     which every replica holds the complete merged panorama and may be gathered from.
-// lane p talks to peer p.  A wait longer than timeout_ns sets tab->error instead of hanging.
+// One tiny kernel after each data kernel of a step (stream order does the rest):
+//   phase DS_PEER_AFTER_GATHER: this rank has finished reading its replica -> bump my_gathers and
+//     publish it into gathers_done[rank] of every peer (their merges may then overwrite it);
+//   phase DS_PEER_AFTER_MERGE: this rank's rows have been pushed (the merge kernel has retired,
+//     so its peer stores are performed) -> same with my_merges / merges_done.
+// wait != 0 additionally blocks until every peer has published as much (a full barrier); the
+// data kernels normally do that part themselves (pm_peer_spin).  lane p talks to peer p.  A wait
+// longer than timeout_ns sets tab->error instead of hanging.
 __global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, int wait, long long timeout_ns) {
   const int p = threadIdx.x;
   int32_t* mine = phase == DS_PEER_AFTER_GATHER ? &tab->my_gathers : &tab->my_merges;
