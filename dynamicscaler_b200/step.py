@@ -7,14 +7,21 @@ multi-GPU path BASELINE.json names -- is
     gather_all  : every window of the step is cut from the step-start panorama (1 launch)
     denoise     : the caller's UNet + ddim_step over the stacked windows
     merge_all   : all windows written back "in window order, last writer wins" or
-                  "weighted splat + normalise" (1 launch, gather form)
+                  "weighted splat + normalise" (1 launch)
 
 which equals the reference's own get_*/set_* functions composed in that order
-(oracle.panorama_oracle.sphere_step_batched / ring_step_batched).  With world_size > 1
-the ordered job list is split contiguously over the ranks; each rank merges only the
-pixels its own windows win into zeroed sum / weight buffers, one NCCL all-reduce adds the
-(disjoint-support) buffers, and a final select produces the next step-start replica on
-every rank.
+(oracle.panorama_oracle.sphere_step_batched / ring_step_batched).  ``merge_denoised`` fuses the
+denoise epilogue (classifier-free guidance + ddim_step) into the merge.
+
+Panoramas live either in the reference's [B, C, F, H, W] order (any tensor; csrc/sphere.cu,
+csrc/ring.cu) or, for the sphere path, in a resident pixel-major ``PanoramaState`` (csrc/pm.cu).
+
+With world_size > 1 the views of every frame window are dealt round-robin over the ranks
+(planar ring windows: contiguous blocks) and each rank merges only the pixels its own windows win.
+With ``make_state(..., peer=True)`` the replicas sit in symmetric memory and the merge kernels
+store the surviving rows straight into every rank's replica over NVLink; otherwise the
+disjoint-support partial merges go into zeroed sum / weight buffers, one NCCL all-reduce adds
+them and a final select produces the next step-start replica on every rank.
 """
 from __future__ import annotations
 

@@ -10,7 +10,7 @@
  *
  * Conventions
  *   - Every pointer is a DEVICE pointer unless its name starts with h_ (host).
- *   - The library allocates nothing, keeps no global state, and is stream-ordered and
+ *   - The library allocates nothing, keeps no state besides the ds_tune knobs, and is stream-ordered and
  *     re-entrant: every call only enqueues kernels on `stream` (a cudaStream_t).
  *   - Return value: 0 = ok; < 0 = argument error (DS_ERR_*); > 0 = a cudaError_t.
  *   - dtype: DS_F32 or DS_BF16 for every latent/payload/window buffer of one call.
