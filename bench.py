@@ -185,18 +185,18 @@ class Workset:
     """One rotating buffer set (panoramas + windows + payloads), so consecutive steps touch
     different memory and the aggregate footprint exceeds L2."""
 
-    def __init__(self, wl, n_local, dev, gen, st=None, peer=False, gen_pano=None):
+    def __init__(self, wl, n_local, dev, gen, st=None, peer=False, gen_pano=None, dtype=torch.float32):
         shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
         vshape = (n_local, 1, wl["C"], wl["f_len"], wl["h"], wl["w"])
-        self.lat = torch.randn(shape, device=dev, generator=gen_pano if gen_pano is not None else gen)
-        self.den = torch.zeros(shape, device=dev)
+        self.lat = torch.randn(shape, device=dev, generator=gen_pano if gen_pano is not None else gen).to(dtype)
+        self.den = torch.zeros(shape, device=dev, dtype=dtype)
         # T2V sphere: [1,H,W] mask plane (t2v_sphere_panorama_pipeline.py:159); frame ring (I2V) and the
         # planar ring loops: latent-shaped mask (i2v_sphere_panorama_pipeline.py:220,810)
         plane_mask = wl["kind"] == "sphere" and not wl.get("frame_ring")
-        self.mask = torch.zeros((1, wl["H"], wl["W"]) if plane_mask else shape, device=dev)
-        self.wins = torch.empty(vshape, device=dev)
-        self.x_prev = torch.randn(vshape, device=dev, generator=gen)
-        self.x0 = torch.randn(vshape, device=dev, generator=gen)
+        self.mask = torch.zeros((1, wl["H"], wl["W"]) if plane_mask else shape, device=dev, dtype=dtype)
+        self.wins = torch.empty(vshape, device=dev, dtype=dtype)
+        self.x_prev = torch.randn(vshape, device=dev, generator=gen).to(dtype)
+        self.x0 = torch.randn(vshape, device=dev, generator=gen).to(dtype)
         # resident pixel-major state (layout "pm"): gather/merge work on it in place
         self.state = st.make_state([self.lat, self.den], mask=self.mask, peer=peer) if st is not None else None
         self.pano = self.state if self.state is not None else self.lat
@@ -290,16 +290,18 @@ def run_ours(args, wl, wl_name):
     gen_pano = torch.Generator(device=dev).manual_seed(99)      # replicas start identical on every rank
     if peer:
         lib.check(lib.ds_tune(1, 30_000_000_000))            # DS_TUNE_PEER_TIMEOUT_NS: ranks may start seconds apart
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    esz = 2 if args.dtype == "bf16" else 4
     try:
-        one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano)
+        one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano, dtype)
     except Exception as e:                                   # no symmetric memory on this system
         if not peer:
             raise
         print(f"[bench] peer exchange unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce path", file=sys.stderr)
         peer = False
-        one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano)
+        one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano, dtype)
     n_sets = max(2, min(4, -(-3 * L2_BYTES // one.nbytes())))   # aggregate footprint >= 3x L2
-    sets = [one] + [Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano) for _ in range(n_sets - 1)]
+    sets = [one] + [Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano, dtype) for _ in range(n_sets - 1)]
     combos = [(i % NP, i % n_sets) for i in range(NP * n_sets // np.gcd(NP, n_sets))]
 
     def make_step(mode, off, s):
@@ -379,9 +381,9 @@ def run_ours(args, wl, wl_name):
     # its own stream.  Exactly e2e_steps uploads and downloads happen inside the timed region.
     mode = args.mode
     ws = sets[0]
-    h_xp = torch.randn(ws.x_prev.shape).pin_memory()
-    h_x0 = torch.randn(ws.x0.shape).pin_memory()
-    h_wins = torch.empty(ws.wins.shape).pin_memory()
+    h_xp = torch.randn(ws.x_prev.shape).to(dtype).pin_memory()
+    h_x0 = torch.randn(ws.x0.shape).to(dtype).pin_memory()
+    h_wins = torch.empty(ws.wins.shape, dtype=dtype).pin_memory()
     up_stream, down_stream = torch.cuda.Stream(), torch.cuda.Stream()
     dev_pay = [(ws.x_prev, ws.x0), (torch.empty_like(ws.x_prev), torch.empty_like(ws.x0))]
     ready = [torch.cuda.Event(), torch.cuda.Event()]       # payload buffer b holds a fresh upload
@@ -446,7 +448,7 @@ def run_ours(args, wl, wl_name):
         line = {
             "metric": "panorama denoise-step window-blends/sec", "value": value, "unit": "blends/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": head["ms_per_step"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": wl_name, "mode": args.mode, "latent": [1, wl["C"], wl["F"], wl["H"], wl["W"]],
                        "windows_per_step": n_win, "window": [wl["h"], wl["w"]], "payloads": 2,
                        "l2_policy": f"inputs larger than L2: {n_sets} rotating buffer sets, {n_sets * one.nbytes() / 2**20:.0f} MiB",
@@ -464,29 +466,29 @@ def run_ours(args, wl, wl_name):
             "gpu_launches": int(head["launches_per_step"] * K),
             "clocks": sampler.summary(),
             "e2e": {"value": n_win / (e2e_ms * 1e-3), "unit": "blends/s",
-                    "h2d_bytes_per_step": int(h_xp.numel() * 4 + h_x0.numel() * 4),
-                    "d2h_bytes_per_step": int(h_wins.numel() * 4), "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "h2d_bytes_per_step": int((h_xp.numel() + h_x0.numel()) * esz),
+                    "d2h_bytes_per_step": int(h_wins.numel() * esz), "ms_per_step": e2e_ms, "steps": e2e_steps},
             "variants": {m: {"ms_per_step": r["ms_per_step"], "blends_per_s": n_win / (r["ms_per_step"] * 1e-3),
                              **{k: v for k, v in r.items() if k.endswith("_us")}} for m, r in results.items()},
         }
         if not dist_on and not args.no_kernel_pass:
             P = wl["C"]
-            gb, mb = st.algorithmic_bytes(plans[args.mode][0], P, 4, k=2)
+            gb, mb = st.algorithmic_bytes(plans[args.mode][0], P, esz, k=2)
             kern = "merge" if head["merge_us"] >= head["gather_us"] else "gather"
             bytes_launch = mb if kern == "merge" else gb
             dur = head[kern + "_us"] * 1e-6
             line["roofline"] = {
                 "bound": "hbm", "kernel": f"{kern}_{args.mode}", "achieved": bytes_launch / dur / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": bytes_launch / dur / 1e9 / peak,
-                "traffic": ncu_traffic(kern, args.mode, st_pm is not None), "peak_source": peak_src,
+                "traffic": ncu_traffic(kern, args.mode, st_pm is not None and args.dtype == "f32"), "peak_source": peak_src,
                 "algorithmic_bytes": {"gather": gb, "merge": mb, "coverage": plans[args.mode][0].coverage},
                 "step_frac": (gb + mb) / (head["ms_per_step"] * 1e-3) / 1e9 / peak,
-                "all": {m: {kn: (st.algorithmic_bytes(plans[m][0], P, 4)[0 if kn == "gather" else 1]
+                "all": {m: {kn: (st.algorithmic_bytes(plans[m][0], P, esz)[0 if kn == "gather" else 1]
                                  / (results[m][kn + "_us"] * 1e-6) / 1e9) for kn in ("gather", "merge")}
                         for m in results},
             }
             reps = 8 if args.mode == "bilinear" else 20                 # about 10-20 s of CPU work
-            cpu = None if args.no_cpu else cpu_step_time(wl, args.mode, reps)
+            cpu = None if (args.no_cpu or args.dtype != "f32") else cpu_step_time(wl, args.mode, reps)
             if cpu is not None:
                 sec, cores, sample, _ = cpu
                 line["cpu_baseline"] = {"value": n_win / sec, "unit": "blends/s", "cores": cores, "kind": "port",
@@ -510,6 +512,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="bilinear", choices=["bilinear", "nearest", "ring"],
                     help="sphere workloads: bilinear (headline) or nearest; ring workloads always run 'ring'")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"],
+                    help="latent dtype: f32 is the reference's (headline); bf16 halves every byte count (maps stay fp32)")
     ap.add_argument("--layout", default="pm", choices=["pm", "ref"],
                     help="pm: panoramas resident in pixel-major order (PanoramaState); ref: reference order")
     ap.add_argument("--exchange", default="peer", choices=["peer", "allreduce"],
