@@ -268,3 +268,24 @@ def test_ddim_coefficients_match_oracle_scalars():
         got = np.array([sa, s1, sp, sd, sg], np.float32)
         assert np.array_equal(got, np.array(want, np.float32)), (index, got, want)
         assert np.float32(gg) == np.float32(gs)
+
+
+def test_wrap_slices_property():
+    """get_dimension_slices_and_sizes (shift_window_utils.py:14-38) for random legal windows: the
+    slices concatenate to the modular index vector (begin + j) mod size and agree with
+    the oracle's segments."""
+    from hypothesis import given, settings, strategies as stn
+
+    @settings(max_examples=300, deadline=None)
+    @given(stn.integers(1, 64).flatmap(lambda size: stn.tuples(
+        stn.just(size), stn.integers(0, 2 * size - 1)).flatmap(lambda sb: stn.tuples(
+            stn.just(sb[0]), stn.just(sb[1]), stn.integers(sb[1] + 1, 2 * sb[0])))))
+    def check(args):
+        size, begin, end = args
+        slices, sizes = get_dimension_slices_and_sizes(begin, end, size)
+        idx = np.concatenate([np.arange(s.start, s.stop) for s in slices])
+        assert np.array_equal(idx, (begin + np.arange(end - begin)) % size)
+        assert sizes == [s.stop - s.start for s in slices] and sum(sizes) == end - begin
+        assert [(s.start, s.stop - s.start) for s in slices] == po.ring_segments(begin, end, size)
+
+    check()
