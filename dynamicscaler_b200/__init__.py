@@ -30,9 +30,12 @@ def install():
 
     pkg = sys.modules.get("utils")
     if pkg is None:
-        pkg = types.ModuleType("utils")
-        pkg.__path__ = []
-        sys.modules["utils"] = pkg
+        try:                                   # the reference's own ``utils`` package, when its checkout is on
+            import utils as pkg                # sys.path: its other modules (multi_prompt_utils, ...) stay reachable
+        except ImportError:
+            pkg = types.ModuleType("utils")
+            pkg.__path__ = []
+            sys.modules["utils"] = pkg
     for name, mod in (("shift_window_utils", shift_window_utils),
                       ("panorama_tensor_utils", panorama_tensor_utils),
                       ("ring_panorama_tensor_utils", ring_panorama_tensor_utils),

@@ -87,3 +87,66 @@ def test_signatures_match_the_reference():
         for k in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_unmodified_pipelines_import_the_dropins():
+    """``install()`` + the reference's UNMODIFIED pipeline modules: their call sites
+    (t2v/i2v_sphere_panorama_pipeline.py) resolve to the replacement classes.  diffusers /
+    pytorch_lightning are absent here, so they are stubbed like in SURVEY §8c; nothing is computed."""
+    import torch
+    saved_path = list(sys.path)
+    prefixes = ("utils", "pipeline", "lvdm", "diffusers", "pytorch_lightning")
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in prefixes}
+    try:
+        for k in list(saved):
+            del sys.modules[k]
+
+        def mod(name, **attrs):
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+            return m
+
+        mod("pytorch_lightning", LightningModule=torch.nn.Module, seed_everything=lambda *a, **k: None)
+        mod("pytorch_lightning.utilities", rank_zero_only=lambda f: f)
+
+        class DiffusionPipeline:
+            def register_modules(self, **kw):
+                self.__dict__.update(kw)
+
+        class _Mixin:
+            pass
+
+        logging = mod("diffusers.logging", get_logger=lambda name: __import__("logging").getLogger(name))
+        d = mod("diffusers", DiffusionPipeline=DiffusionPipeline, logging=logging,
+                ConfigMixin=type("ConfigMixin", (), {}), SchedulerMixin=type("SchedulerMixin", (), {}))
+        d.__path__ = []
+        mod("diffusers.configuration_utils", ConfigMixin=d.ConfigMixin, register_to_config=lambda f: f)
+        mod("diffusers.schedulers", __path__=[])
+        mod("diffusers.schedulers.scheduling_utils", SchedulerMixin=d.SchedulerMixin)
+        mod("diffusers.utils", BaseOutput=type("BaseOutput", (dict,), {}), logging=logging, __path__=[])
+        mod("diffusers.utils.torch_utils", randn_tensor=lambda *a, **k: None)
+        sys.path.insert(0, REF)
+        sys.dont_write_bytecode = True
+        import dynamicscaler_b200
+        dynamicscaler_b200.install()
+        t2v = importlib.import_module("pipeline.t2v_sphere_panorama_pipeline")
+        i2v = importlib.import_module("pipeline.i2v_sphere_panorama_pipeline")
+        from dynamicscaler_b200 import (diffusion_utils, panorama_tensor_utils, ring_panorama_tensor_utils,
+                                        shift_window_utils, tensor_utils)
+        assert t2v.PanoramaLatentProxy is panorama_tensor_utils.PanoramaLatentProxy
+        assert t2v.PanoramaTensor is panorama_tensor_utils.PanoramaTensor
+        assert t2v.RingLatent is shift_window_utils.RingLatent and t2v.RingImageTensor is shift_window_utils.RingImageTensor
+        assert t2v.mix_latents_with_mask is tensor_utils.mix_latents_with_mask
+        assert t2v.resize_video_latent is diffusion_utils.resize_video_latent
+        assert i2v.RingPanoramaLatentProxy is ring_panorama_tensor_utils.RingPanoramaLatentProxy
+        assert i2v.PanoramaTensor is panorama_tensor_utils.PanoramaTensor
+        # the reference's other utils modules are still the reference's own
+        assert importlib.import_module("utils.multi_prompt_utils").__file__.startswith(REF)
+        assert hasattr(t2v.VC2_Pipeline_T2V_SpherePano, "basic_sample_shift_shpere_panorama")
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k.split(".")[0] in prefixes]:
+            del sys.modules[k]
+        sys.modules.update(saved)
