@@ -392,7 +392,10 @@ def host_cached(key, make):
 def on_device(key, device, make_numpy):
     """Upload-once cache of small int32/float32 map arrays, keyed by (key, device)."""
     device = torch.device(device)
-    dkey = (key, device.type, device.index if device.index is not None else torch.cuda.current_device())
+    index = device.index
+    if index is None and device.type == "cuda":
+        index = torch.cuda.current_device()
+    dkey = (key, device.type, index)
 
     def make():
         arrs = make_numpy()

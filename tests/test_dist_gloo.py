@@ -92,3 +92,89 @@ def test_sharded_merge_world2_gloo(tmp_path, mode):
     assert np.array_equal(got["lat"], pm_unpack(want[0]))
     assert np.array_equal(got["den"], pm_unpack(want[1]))
     assert np.array_equal(got["weight"], pm_unpack(wmask))
+
+
+# ---------------------------------------------------------------- peer-replica exchange ----
+_PEER_CASE = dict(H=16, W=32, F=6, h=6, w=10, f_len=4, fbs=[0, 2, 4], n_views=9)
+
+
+def _peer_case():
+    from conftest import randn
+    from oracle import panorama_oracle as po
+    c = dict(_PEER_CASE)
+    c["views"] = po.default_sphere_views(3)[:c["n_views"]]
+    nj = c["n_views"] * len(c["fbs"])
+    c["pay"] = [randn(700 + q, nj, 4, c["f_len"], c["h"] * c["w"]) for q in range(2)]
+    c["base"] = randn(9, 4, c["F"], c["H"] * c["W"])
+    return c
+
+
+def _peer_worker(rank, world, port, mode, out_dir):
+    """What step._merge_state does in peer mode, with the kernels replaced by their numpy contracts
+    and the NVLink stores by an all_gather: every rank merges ITS views' surviving rows (plans
+    built by the real PanoramaStepper.plan_sphere for this rank) and the rows land in every
+    replica.  No reduction is involved -- supports are disjoint -- so replicas end identical."""
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from _emulate import pm_merge_bilinear, pm_merge_nearest, pm_pack, pm_unpack
+    from dynamicscaler_b200.step import PanoramaStepper
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        c = _peer_case()
+        H, W, F, hw, f_len, fbs = c["H"], c["W"], c["F"], c["h"] * c["w"], c["f_len"], c["fbs"]
+        st = PanoramaStepper(H, W, F, torch.device("cpu"), rank, world)
+        plan = st.plan_sphere(c["views"], c["w"], c["h"], fov=120, mode=mode, frame_begins=fbs, frames=f_len)
+        assert plan.n_local == len(plan.job_ids) == len(range(rank, c["n_views"], world)) * len(fbs)
+        pm_plan = [t.numpy() for t in plan.pm_merge]
+        ftab = plan.d_ftab.numpy()
+        pay = [p[plan.job_ids] for p in c["pay"]]                      # the windows this rank denoised
+        rows = [np.zeros((H * W, F, 4), np.float32) for _ in range(2)]  # what this rank would push
+        touched = np.zeros((H * W, F, 4), np.float32)
+        merge = pm_merge_nearest if mode == "nearest" else pm_merge_bilinear
+        j0, nj = st.local_jobs(plan)
+        merge(rows, pay, pm_plan, ftab, fbs, plan.vpf, f_len, hw, touched, 2, j0, nj)
+        mine = torch.from_numpy(np.stack(rows + [touched]))
+        everyone = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(everyone, mine)                                # stands in for the peer stores
+        replica = [pm_pack(c["base"]), pm_pack(c["base"])]
+        owners = np.zeros((H * W, F, 4), np.float32)
+        for r in range(world):
+            got = everyone[r].numpy()
+            for q in range(2):
+                replica[q] = np.where(got[2] > 0, got[q], replica[q])
+            owners += got[2]
+        assert owners.max() == 1.0                                      # one writer per (pixel, frame)
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), lat=pm_unpack(replica[0]), den=pm_unpack(replica[1]),
+                 owners=pm_unpack(owners), job_ids=np.asarray(plan.job_ids))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["nearest", "bilinear"])
+def test_peer_replica_exchange_world2_gloo(tmp_path, mode):
+    sys.path.insert(0, HERE)
+    from _emulate import pm_merge_bilinear, pm_merge_nearest, pm_pack, pm_unpack
+    from dynamicscaler_b200 import maps
+
+    mp.spawn(_peer_worker, args=(2, _free_port(), mode, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(str(tmp_path / f"r{r}.npz")) for r in range(2)]
+
+    c = _peer_case()
+    H, W, F, hw, f_len, fbs = c["H"], c["W"], c["F"], c["h"] * c["w"], c["f_len"], c["fbs"]
+    vms = [maps.view_map(120, th, ph, c["w"], c["h"], H, W) for ph, th in c["views"]]
+    ftab = maps.frame_table(F, fbs, f_len)
+    want = [pm_pack(c["base"]), pm_pack(c["base"])]
+    wmask = np.zeros((H * W, F, 4), np.float32)
+    if mode == "nearest":
+        pm_merge_nearest(want, c["pay"], maps.pm_nearest_plan(vms), ftab, fbs, len(vms), f_len, hw, wmask, 2)
+    else:
+        pm_merge_bilinear(want, c["pay"], maps.pm_bilinear_plan(vms), ftab, fbs, len(vms), f_len, hw, wmask, 2)
+    ids = np.sort(np.concatenate([g["job_ids"] for g in got]))
+    assert np.array_equal(ids, np.arange(len(vms) * len(fbs)))         # every job on exactly one rank
+    for g in got:                                                       # both replicas == single-rank merge
+        assert np.array_equal(g["lat"], pm_unpack(want[0]))
+        assert np.array_equal(g["den"], pm_unpack(want[1]))
+        assert np.array_equal(g["owners"], pm_unpack(wmask))
