@@ -52,6 +52,7 @@ constexpr int kWarps = kBlock / 32;
 
 // Launch-shape knobs (ds_tune); defaults are the measured best on B200 for the bench workload.
 static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
+static int g_gather_blocked = 0;                // bit 1: copy-only gather, bit 2: 4-tap gather walk consecutive tiles
 static long long g_peer_timeout_ns = 2000000000ll;   // give up a cross-GPU wait after this long
 static int g_pdl = 11;                          // programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
                                                 // 4 nearest merge, 8 weighted merges.  Measured (tools/kbench.py, cfg2): the
@@ -212,7 +213,7 @@ struct PmGatherArgs {
 // TMA bulk copy (cp.async.bulk shared -> global), issued by one thread per row.
 // FL > 0: f_len known at compile time; FL == 0: runtime f_len.  MINB: min resident CTAs per SM
 // (register budget; measured best on B200: 8 for the copy-only gather, 4 for the 4-tap one).
-template <typename T, int TAPS, int FL, int MINB>
+template <typename T, int TAPS, int FL, int MINB, bool BLK>
 __global__ void __launch_bounds__(kBlock, MINB)
 pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ out,
                  const int32_t* __restrict__ d_idx, const float* __restrict__ d_wt,
@@ -235,7 +236,12 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
   const int n_fblk = (f_len + 7) >> 3;
   const int n_it = (kPmKT / 16) * n_fblk;       // warp iterations: 4 pixel groups x 8 frames each
 
-  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+  // blocked order: consecutive tiles are adjacent rows of one view, whose tap footprints overlap,
+  // so the rows a CTA just read are still in its SM's L1 when the next tile asks for them
+  const int chunk = BLK ? (a.n_tiles + gridDim.x - 1) / gridDim.x : 0;
+  const int t_step = BLK ? 1 : gridDim.x;
+  const int t_end = BLK ? min(a.n_tiles, (static_cast<int>(blockIdx.x) + 1) * chunk) : a.n_tiles;
+  for (int t = BLK ? blockIdx.x * chunk : blockIdx.x; t < t_end; t += t_step) {
     const int job = t / a.tiles_per_job;
     const int k0 = (t - job * a.tiles_per_job) * kPmKT;
     int map = job, f0 = h_f0;
@@ -1020,6 +1026,7 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   DS_REQUIRE(n_tiles < (1ll << 31) && static_cast<long long>(n_jobs) * P * f_len * hw < (1ll << 40), DS_ERR_DIM);
   DS_REQUIRE(static_cast<long long>(n_jobs) * taps * hw < (1ll << 31), DS_ERR_DIM);
   PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj};
+  const bool blk = (g_gather_blocked & (taps == 1 ? 1 : 2)) != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DS_DISPATCH_DTYPE(dtype, {
     constexpr int VE = 16 / sizeof(ET);
@@ -1027,12 +1034,17 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
     using AT = typename Atom<ET>::type;
     const AT* pmp = static_cast<const AT*>(pm);
     ET* op = static_cast<ET*>(out);
+#define DS_PM_GATHER(TAPS_, FL_, MINB_, BLK_, PDL_)                                                              \
+  return pm_launch(pm_gather_kernel<ET, TAPS_, FL_, MINB_, BLK_>, PDL_, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, \
+                   op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns)
     if (taps == 1) {
-      if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 1, 16, 8>, 1, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
-      return pm_launch(pm_gather_kernel<ET, 1, 0, 4>, 1, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
+      if (f_len == 16) { if (blk) DS_PM_GATHER(1, 16, 8, true, 1); DS_PM_GATHER(1, 16, 8, false, 1); }
+      if (blk) DS_PM_GATHER(1, 0, 4, true, 1);
+      DS_PM_GATHER(1, 0, 4, false, 1);
     }
-    if (f_len == 16) return pm_launch(pm_gather_kernel<ET, 4, 16, 4>, 2, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
-    return pm_launch(pm_gather_kernel<ET, 4, 0, 4>, 2, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns);
+    if (f_len == 16) { if (blk) DS_PM_GATHER(4, 16, 4, true, 2); DS_PM_GATHER(4, 16, 4, false, 2); }
+    if (blk) DS_PM_GATHER(4, 0, 4, true, 2);
+    DS_PM_GATHER(4, 0, 4, false, 2);
   });
   return DS_OK;
 }
@@ -1200,6 +1212,7 @@ extern "C" int ds_tune(int knob, long long value) {
     case DS_TUNE_PM_GATHER_CTAS_PER_SM: ds::g_gather_ctas_per_sm = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PEER_TIMEOUT_NS: ds::g_peer_timeout_ns = value; return DS_OK;
     case DS_TUNE_PDL: ds::g_pdl = static_cast<int>(value); return DS_OK;
+    case DS_TUNE_PM_GATHER_BLOCKED: ds::g_gather_blocked = static_cast<int>(value); return DS_OK;
     default: return DS_ERR_DIM;
   }
 }

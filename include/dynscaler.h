@@ -53,8 +53,10 @@ enum { DS_MASK_NONE = 0, DS_MASK_PLANE = 1 /* one [H*W] plane */, DS_MASK_FULL =
 enum {
   DS_TUNE_PM_GATHER_CTAS_PER_SM = 0,   /* persistent gather: CTAs per SM, 0 = occupancy limit */
   DS_TUNE_PEER_TIMEOUT_NS = 1,         /* cross-GPU waits give up (and set ds_peer_table_t.error) after this */
-  DS_TUNE_PDL = 2                      /* programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
+  DS_TUNE_PDL = 2,                     /* programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
                                           4 nearest merge, 8 weighted merges (default: 11) */
+  DS_TUNE_PM_GATHER_BLOCKED = 3        /* gather tile order, bit mask: 1 copy-only gather, 2 4-tap gather give each CTA a
+                                          run of consecutive tiles (adjacent view rows) instead of a grid-strided set */
 };
 int ds_tune(int knob, long long value);
 

@@ -13,6 +13,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # DS_TUNE="knob=value,..." runs the suite under non-default launch knobs (results must not change)
+    if os.environ.get("DS_TUNE"):
+        from dynamicscaler_b200 import lib
+        for item in os.environ["DS_TUNE"].split(","):
+            knob, value = item.split("=")
+            lib.check(lib.ds_tune(int(knob), int(value)), "ds_tune")
 
 
 @pytest.fixture(scope="session")

@@ -46,9 +46,12 @@ def main():
     settings = [{"gather_cps": 0, "pdl": m} for m in (11, 0, 15)]
     if os.environ.get("KBENCH_DEFAULT_ONLY"):
         settings = settings[:1]
+    if os.environ.get("KBENCH_SETTINGS"):                                 # JSON list of {gather_cps, pdl, blocked}
+        settings = json.loads(os.environ["KBENCH_SETTINGS"])
     for cfg in settings:
-        lib.check(lib.ds_tune(GATHER_CPS, cfg["gather_cps"]))
+        lib.check(lib.ds_tune(GATHER_CPS, cfg.get("gather_cps", 0)))
         lib.check(lib.ds_tune(2, cfg.get("pdl", 11)))                     # DS_TUNE_PDL
+        lib.check(lib.ds_tune(3, cfg.get("blocked", 0)))                  # DS_TUNE_PM_GATHER_BLOCKED
         res = dict(cfg, workload=wl_name)
         for mode in modes:                                  # whole steps (gather -> merge chains)
             fns = []
@@ -69,7 +72,7 @@ def main():
                 gb, mb = st.algorithmic_bytes(plans[mode][0], 4, 4, k=2)
                 res[f"{kind}_{mode}_us"] = round(us, 2)
                 res[f"{kind}_{mode}_GBps"] = round((gb if kind == "gather" else mb) / us / 1e3, 1)
-        if wl["kind"] == "sphere" and wl["f_len"] == 16:
+        if wl["kind"] == "sphere" and wl["f_len"] == 16 and not os.environ.get("KBENCH_NO_DENOISE"):
             # ddim_step + CFG fused into the merge vs the same chain as torch ops + merge_all
             from dynamicscaler_b200.step import ddim_coefficients
             coef = ddim_coefficients(0.5, 0.55, 0.0, 0.7071, 7.5)
