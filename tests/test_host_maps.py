@@ -289,3 +289,64 @@ def test_wrap_slices_property():
         assert [(s.start, s.stop - s.start) for s in slices] == po.ring_segments(begin, end, size)
 
     check()
+
+
+def test_random_view_lists_merge_plans_property():
+    """Random ordered view lists -- angles outside [0, 360), views on the poles and across the
+    seam, narrow and wide FOVs, odd view sizes -- merged through the product's host plans (plane-major,
+    pixel-major and tiled, kernels emulated) equal the oracle's set_view_* calls applied one view
+    after the other, and the gather maps equal the oracle's get_view_* calls."""
+    from hypothesis import given, settings, strategies as stn
+    from _emulate import pm_merge_bilinear, pm_merge_bilinear_tiled, pm_merge_nearest, pm_pack, pm_unpack
+
+    view = stn.tuples(stn.sampled_from([-90.0, -60.0, -33.5, 0.0, 12.25, 45.0, 90.0]),           # phi
+                      stn.one_of(stn.sampled_from([-370.0, -180.0, 0.0, 179.5, 355.0, 360.0, 725.0]),
+                                 stn.floats(-400, 800, allow_nan=False, width=32)))               # theta
+    case = stn.tuples(stn.lists(view, min_size=1, max_size=4), stn.sampled_from([50, 90, 120, 150]),
+                      stn.sampled_from([(8, 16), (16, 32)]), stn.integers(2, 7), stn.integers(2, 9),
+                      stn.integers(0, 10 ** 6))
+
+    @settings(max_examples=80, deadline=None)
+    @given(case)
+    def check(args):
+        views, fov, (H, W), h, w, seed = args
+        P, nv, hw = 4, len(views), h * w
+        vms = [maps.view_map(fov, th, ph, w, h, H, W) for ph, th in views]
+        pay = randn(seed, nv, P, 1, hw)
+        base = randn(seed + 1, P, 1, H * W)
+        # gathers
+        pano = base.reshape(P, H, W)
+        for n, (ph, th) in enumerate(views):
+            got = gather_nearest(base, np.stack([vm.idx_read for vm in vms]), [(n, 0)], 1)[0, :, 0]
+            assert np.array_equal(got.reshape(P, h, w), po.sphere_get_nearest(pano, fov, th, ph, w, h)[0])
+            idx4, wt4 = vms[n].read_taps()
+            got = gather_bilinear(base, idx4[None], wt4[None], [(0, 0)], 1)[0, :, 0]
+            assert np.array_equal(got.reshape(P, h, w), po.sphere_get_bilinear(pano, fov, th, ph, w, h))
+        # merges
+        want_n, want_b = pano.copy(), pano.copy()
+        for n, (ph, th) in enumerate(views):
+            po.sphere_set_nearest(want_n, pay[n, :, 0].reshape(P, h, w), fov, th, ph)
+            po.sphere_set_bilinear(want_b, pay[n, :, 0].reshape(P, h, w), fov, th, ph)
+        got = base.copy()
+        d, s_ = maps.nearest_merge_plan(vms)
+        merge_nearest([got], [pay], d, s_, None, nv, 1, hw)
+        assert np.array_equal(got.reshape(P, H, W), want_n)
+        got = pm_pack(base)
+        pm_merge_nearest([got], [pay], maps.pm_nearest_plan(vms), None, None, nv, 1, hw)
+        assert np.array_equal(pm_unpack(got).reshape(P, H, W), want_n)
+        got = base.copy()
+        merge_bilinear([got], [pay], maps.bilinear_merge_plan(vms), None, nv, 1, hw)
+        assert np.array_equal(got.reshape(P, H, W), want_b)
+        got = pm_pack(base)
+        pm_merge_bilinear([got], [pay], maps.pm_bilinear_plan(vms), None, None, nv, 1, hw)
+        assert np.array_equal(pm_unpack(got).reshape(P, H, W), want_b)
+        tiled = maps.pm_bilinear_tiled_plan(vms)
+        if tiled is not None:                      # None: a row with > 64 entries (generic kernel instead)
+            _, tile, row_dst, row_start, ent_k, ent_w = tiled
+            assert tile[:, 2].max(initial=0) <= maps.PM_TILE_ROWS and tile[:, 3].max(initial=0) <= maps.PM_TILE_ENTRIES
+            assert tile[:, 2].sum() == row_dst.size and (ent_k >= 0).sum() == tile[:, 3].sum()
+            got = pm_pack(base)
+            pm_merge_bilinear_tiled([got], [pay], tiled, None, None, nv, 1, hw)
+            assert np.array_equal(pm_unpack(got).reshape(P, H, W), want_b)
+
+    check()
