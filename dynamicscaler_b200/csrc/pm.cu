@@ -52,7 +52,7 @@ constexpr int kWarps = kBlock / 32;
 
 // Launch-shape knobs (ds_tune); defaults are the measured best on B200 for the bench workload.
 static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
-static int g_gather_blocked = 0;                // bit 1: copy-only gather, bit 2: 4-tap gather walk consecutive tiles
+static int g_gather_pipe = 2;                   // bit 1: copy-only gather, bit 2: 4-tap gather use the pipelined tile loop
 static long long g_peer_timeout_ns = 2000000000ll;   // give up a cross-GPU wait after this long
 static int g_pdl = 11;                          // programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
                                                 // 4 nearest merge, 8 weighted merges.  Measured (tools/kbench.py, cfg2): the
@@ -116,10 +116,19 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_commit_and_wait_read() {
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  bulk_commit();
+  bulk_wait_read();
 }
+
+// 4-byte asynchronous copy global -> shared (SASS LDGSTS): no register holds the value, so a
+// prefetch costs nothing while it is in flight.  bytes == 0 writes a zero instead.
+__device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc, int bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ------------------------------------------------------- cross-GPU ordering (peers) ----
 __device__ __forceinline__ int ld_acquire_sys(const int32_t* p) {
@@ -212,56 +221,100 @@ struct PmGatherArgs {
 // Store: every tile row is 256 contiguous bytes of the window tensor and leaves through one
 // TMA bulk copy (cp.async.bulk shared -> global), issued by one thread per row.
 // FL > 0: f_len known at compile time; FL == 0: runtime f_len.  MINB: min resident CTAs per SM
-// (register budget; measured best on B200: 8 for the copy-only gather, 4 for the 4-tap one).
-template <typename T, int TAPS, int FL, int MINB, bool BLK>
+// (register budget).
+// PIPE: software pipeline over the CTA's tiles.  Per tile the plain loop is a serial chain -- job
+// descriptor -> map entries -> barrier -> tap loads -> transpose -> barrier -> bulk store -> wait
+// for the copy to have read the tile -- and a CTA walks it 2-3 times, so the kernel is bound by
+// that latency, not by bandwidth (3 instead of 4 CTAs per SM costs 25 %).  The pipelined loop
+// takes the first three links and the last one out of the chain: the NEXT tile's map entries
+// arrive through cp.async (LDGSTS, no registers) into the other half of a double-buffered
+// s_idx / s_wt while this tile's taps are in flight, the job descriptor is fetched two tiles
+// ahead, and the wait for the bulk copy moves to the top of the next tile.
+template <typename T, int TAPS, int FL, int MINB, bool PIPE>
 __global__ void __launch_bounds__(kBlock, MINB)
 pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ out,
                  const int32_t* __restrict__ d_idx, const float* __restrict__ d_wt,
                  const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a, ds_peer_table_t* __restrict__ peer,
                  long long peer_timeout_ns) {
   using A = typename Atom<T>::type;
+  static_assert(TAPS * kPmKT <= kBlock, "one map entry per thread");
   pdl_launch_dependents();
   bool waited = false;                           // predecessors (the previous merge) not yet awaited
   constexpr int VE = 16 / sizeof(T);            // elements per 16-byte vector
   constexpr int S = kPmKT + VE;                 // padded row stride (elements): 4 banks mod 32
+  constexpr int NB = PIPE ? 2 : 1;              // map-entry buffers
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int f_len = FL > 0 ? FL : a.f_len;
   const int R = kPmPlanes * f_len;
   T* tile = reinterpret_cast<T*>(smem_raw);                                   // [R][S]
-  int32_t* s_idx = reinterpret_cast<int32_t*>(tile + R * S);                  // [TAPS][KT]
-  float* s_wt = reinterpret_cast<float*>(s_idx + TAPS * kPmKT);               // [TAPS][KT] (bilinear)
+  int32_t* s_idx0 = reinterpret_cast<int32_t*>(tile + R * S);                 // [NB][TAPS][KT]
+  float* s_wt0 = reinterpret_cast<float*>(s_idx0 + NB * TAPS * kPmKT);        // [NB][TAPS][KT] (bilinear)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kgl = lane >> 3, fl = lane & 7;
   const int n_fblk = (f_len + 7) >> 3;
   const int n_it = (kPmKT / 16) * n_fblk;       // warp iterations: 4 pixel groups x 8 frames each
 
-  // blocked order: consecutive tiles are adjacent rows of one view, whose tap footprints overlap,
-  // so the rows a CTA just read are still in its SM's L1 when the next tile asks for them
-  const int chunk = BLK ? (a.n_tiles + gridDim.x - 1) / gridDim.x : 0;
-  const int t_step = BLK ? 1 : gridDim.x;
-  const int t_end = BLK ? min(a.n_tiles, (static_cast<int>(blockIdx.x) + 1) * chunk) : a.n_tiles;
-  for (int t = BLK ? blockIdx.x * chunk : blockIdx.x; t < t_end; t += t_step) {
-    const int job = t / a.tiles_per_job;
-    const int k0 = (t - job * a.tiles_per_job) * kPmKT;
-    int map = job, f0 = h_f0;
+  // (map row, first frame) of the job of tile tt
+  auto job_of = [&](int tt, int& map, int& f0) {
+    const int job = tt / a.tiles_per_job;
+    map = job;
+    f0 = h_f0;
     if (d_jobs != nullptr) {
       map = __ldg(d_jobs + 2 * job);
       f0 = __ldg(d_jobs + 2 * job + 1);
     }
-    f0 %= a.F;
-    for (int i = threadIdx.x; i < TAPS * kPmKT; i += kBlock) {
-      const int tap = i / kPmKT, kl = i % kPmKT;
-      const int k = k0 + kl;
-      int idx = 0;
-      float w = 0.f;
-      if (k < a.hw) {
-        if (d_idx != nullptr) idx = __ldg(d_idx + (map * TAPS + tap) * a.hw + k);
-        else idx = k;                                                  // identity map: unpack
-        if (TAPS > 1) w = __ldg(d_wt + (map * TAPS + tap) * a.hw + k);
+  };
+  // PIPE: start the asynchronous copy of tile tt's map entries into buffer b
+  auto stage_async = [&](int tt, int map, int b) {
+    if (threadIdx.x < TAPS * kPmKT) {
+      const int tap = threadIdx.x / kPmKT, kl = threadIdx.x % kPmKT;
+      const int k = (tt % a.tiles_per_job) * kPmKT + kl;
+      const int ok = k < a.hw ? 4 : 0;                                   // ragged last tile: zero-fill
+      const size_t e = static_cast<size_t>(map * TAPS + tap) * a.hw + min(k, a.hw - 1);
+      int32_t* di = s_idx0 + b * TAPS * kPmKT + threadIdx.x;
+      if (d_idx != nullptr) cp_async4(di, d_idx + e, ok);
+      else *di = ok ? k : 0;                                             // identity map: unpack
+      if (TAPS > 1) cp_async4(s_wt0 + b * TAPS * kPmKT + threadIdx.x, d_wt + e, ok);
+    }
+  };
+
+  int cur_f0 = 0, nxt_map = 0, nxt_f0 = 0, buf = 0;
+  bool in_flight = false;                        // PIPE: this thread's bulk copies of the previous tile
+  if (PIPE && static_cast<int>(blockIdx.x) < a.n_tiles) {
+    int map;
+    job_of(blockIdx.x, map, cur_f0);
+    stage_async(blockIdx.x, map, 0);
+    if (blockIdx.x + gridDim.x < a.n_tiles) job_of(blockIdx.x + gridDim.x, nxt_map, nxt_f0);
+  }
+
+  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int job = t / a.tiles_per_job;
+    const int k0 = (t - job * a.tiles_per_job) * kPmKT;
+    const int32_t* s_idx = s_idx0 + buf * TAPS * kPmKT;
+    const float* s_wt = s_wt0 + buf * TAPS * kPmKT;
+    int f0;
+    if (PIPE) {
+      f0 = cur_f0 % a.F;
+      cp_async_wait_all();                       // this tile's map entries (copied during the previous tile)
+      if (in_flight) bulk_wait_read();           // the previous tile's rows have left the shared tile
+    } else {
+      int map;
+      job_of(t, map, f0);
+      f0 %= a.F;
+      for (int i = threadIdx.x; i < TAPS * kPmKT; i += kBlock) {
+        const int tap = i / kPmKT, kl = i % kPmKT;
+        const int k = k0 + kl;
+        int idx = 0;
+        float w = 0.f;
+        if (k < a.hw) {
+          if (d_idx != nullptr) idx = __ldg(d_idx + (map * TAPS + tap) * a.hw + k);
+          else idx = k;                                                  // identity map: unpack
+          if (TAPS > 1) w = __ldg(d_wt + (map * TAPS + tap) * a.hw + k);
+        }
+        s_idx0[i] = idx;
+        if (TAPS > 1) s_wt0[i] = w;
       }
-      s_idx[i] = idx;
-      if (TAPS > 1) s_wt[i] = w;
     }
     if (!waited) {
       // the map entries above are static; everything below reads the panorama
@@ -271,6 +324,15 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
       waited = true;
     }
     __syncthreads();        // also orders the previous tile's bulk-store reads before the STS below
+    if (PIPE) {
+      const int tn = t + gridDim.x;
+      cur_f0 = nxt_f0;
+      if (tn < a.n_tiles) {
+        stage_async(tn, nxt_map, buf ^ 1);       // lands while this tile's taps are in flight
+        if (tn + gridDim.x < a.n_tiles) job_of(tn + gridDim.x, nxt_map, nxt_f0);
+      }
+      buf ^= 1;
+    }
 
     for (int it = warp; it < n_it; it += kWarps) {
       const int kgb = it / n_fblk, fb = it - kgb * n_fblk;
@@ -347,8 +409,14 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
       bulk_store(o + static_cast<size_t>(row) * a.hw, tile + row * S, row_bytes);
       issued = true;
     }
-    if (issued) bulk_commit_and_wait_read();    // the tile is reused / freed only after the copy read it
+    if (PIPE) {
+      if (issued) bulk_commit();
+      in_flight = issued;
+    } else if (issued) {
+      bulk_commit_and_wait_read();              // the tile is reused / freed only after the copy read it
+    }
   }
+  if (PIPE && in_flight) bulk_wait_read();      // shared memory must outlive the last copy
 }
 
 // ------------------------------------------------------------------------ merges ----
@@ -1026,24 +1094,25 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   DS_REQUIRE(n_tiles < (1ll << 31) && static_cast<long long>(n_jobs) * P * f_len * hw < (1ll << 40), DS_ERR_DIM);
   DS_REQUIRE(static_cast<long long>(n_jobs) * taps * hw < (1ll << 31), DS_ERR_DIM);
   PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj};
-  const bool blk = (g_gather_blocked & (taps == 1 ? 1 : 2)) != 0;
+  const bool pipe = (g_gather_pipe & (taps == 1 ? 1 : 2)) != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DS_DISPATCH_DTYPE(dtype, {
     constexpr int VE = 16 / sizeof(ET);
-    const size_t smem = static_cast<size_t>(kPmPlanes) * f_len * (kPmKT + VE) * sizeof(ET) + static_cast<size_t>(taps) * kPmKT * 8;
+    const size_t smem = static_cast<size_t>(kPmPlanes) * f_len * (kPmKT + VE) * sizeof(ET) +
+                        static_cast<size_t>(taps) * kPmKT * 8 * (pipe ? 2 : 1);
     using AT = typename Atom<ET>::type;
     const AT* pmp = static_cast<const AT*>(pm);
     ET* op = static_cast<ET*>(out);
-#define DS_PM_GATHER(TAPS_, FL_, MINB_, BLK_, PDL_)                                                              \
-  return pm_launch(pm_gather_kernel<ET, TAPS_, FL_, MINB_, BLK_>, PDL_, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, \
+#define DS_PM_GATHER(TAPS_, FL_, MINB_, PIPE_, PDL_)                                                              \
+  return pm_launch(pm_gather_kernel<ET, TAPS_, FL_, MINB_, PIPE_>, PDL_, n_tiles, g_gather_ctas_per_sm, 1, smem, st, pmp, \
                    op, d_idx, d_wt, d_jobs, h_f0, a, static_cast<ds_peer_table_t*>(d_peer), g_peer_timeout_ns)
     if (taps == 1) {
-      if (f_len == 16) { if (blk) DS_PM_GATHER(1, 16, 8, true, 1); DS_PM_GATHER(1, 16, 8, false, 1); }
-      if (blk) DS_PM_GATHER(1, 0, 4, true, 1);
+      if (f_len == 16) { if (pipe) DS_PM_GATHER(1, 16, 8, true, 1); DS_PM_GATHER(1, 16, 8, false, 1); }
+      if (pipe) DS_PM_GATHER(1, 0, 4, true, 1);
       DS_PM_GATHER(1, 0, 4, false, 1);
     }
-    if (f_len == 16) { if (blk) DS_PM_GATHER(4, 16, 4, true, 2); DS_PM_GATHER(4, 16, 4, false, 2); }
-    if (blk) DS_PM_GATHER(4, 0, 4, true, 2);
+    if (f_len == 16) { if (pipe) DS_PM_GATHER(4, 16, 4, true, 2); DS_PM_GATHER(4, 16, 4, false, 2); }
+    if (pipe) DS_PM_GATHER(4, 0, 4, true, 2);
     DS_PM_GATHER(4, 0, 4, false, 2);
   });
   return DS_OK;
@@ -1212,7 +1281,7 @@ extern "C" int ds_tune(int knob, long long value) {
     case DS_TUNE_PM_GATHER_CTAS_PER_SM: ds::g_gather_ctas_per_sm = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PEER_TIMEOUT_NS: ds::g_peer_timeout_ns = value; return DS_OK;
     case DS_TUNE_PDL: ds::g_pdl = static_cast<int>(value); return DS_OK;
-    case DS_TUNE_PM_GATHER_BLOCKED: ds::g_gather_blocked = static_cast<int>(value); return DS_OK;
+    case DS_TUNE_PM_GATHER_PIPELINE: ds::g_gather_pipe = static_cast<int>(value); return DS_OK;
     default: return DS_ERR_DIM;
   }
 }

@@ -55,8 +55,8 @@ enum {
   DS_TUNE_PEER_TIMEOUT_NS = 1,         /* cross-GPU waits give up (and set ds_peer_table_t.error) after this */
   DS_TUNE_PDL = 2,                     /* programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
                                           4 nearest merge, 8 weighted merges (default: 11) */
-  DS_TUNE_PM_GATHER_BLOCKED = 3        /* gather tile order, bit mask: 1 copy-only gather, 2 4-tap gather give each CTA a
-                                          run of consecutive tiles (adjacent view rows) instead of a grid-strided set */
+  DS_TUNE_PM_GATHER_PIPELINE = 3       /* software-pipelined gather tile loop (next tile's map entries prefetched with
+                                          cp.async, deferred bulk-copy wait), bit mask: 1 copy-only gather, 2 4-tap gather */
 };
 int ds_tune(int knob, long long value);
 
