@@ -53,6 +53,7 @@ constexpr int kWarps = kBlock / 32;
 // Launch-shape knobs (ds_tune); defaults are the measured best on B200 for the bench workload.
 static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
 static int g_gather_tile_w = 0;                 // 0: linear tiles of 64 view pixels; 8 / 16 / 32: 2-D tiles (64/w rows x w pixels)
+static int g_merge_weighted_minb = 0;           // 5: two-payload tiled weighted merge compiled for 5 CTAs per SM
 static int g_gather_pipe = 2;                   // bit 1: copy-only gather, bit 2: 4-tap gather use the pipelined tile loop
 static long long g_peer_timeout_ns = 2000000000ll;   // give up a cross-GPU wait after this long
 static int g_pdl = 11;                          // programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
@@ -742,8 +743,10 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
 // on nothing but blockIdx: global dependency depth 2 (entries -> payload) instead of 3, and
 // every loop bound of phase A is a compile-time constant.  d_view_ptr[v] = first tile of view
 // v; d_row_start[r] = first (padded) entry of row r, rows of a tile being contiguous.
-template <typename T, int FL, int QN, bool DD, bool PEER>
-__global__ void __launch_bounds__(kBlock)
+// MINB: min resident CTAs per SM (register budget; 0 = unconstrained).  At 5 the two-payload kernel fits 48 registers
+// without spilling and the cfg2 grid of 1090 tiles is 1.47 waves instead of 1.84.
+template <typename T, int FL, int QN, bool DD, bool PEER, int MINB = 0>
+__global__ void __launch_bounds__(kBlock, MINB)
 pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                                const int4* __restrict__ d_tile, const int32_t* __restrict__ d_row_dst,
                                const int32_t* __restrict__ d_row_start, const int32_t* __restrict__ d_ent_k,
@@ -1227,7 +1230,7 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
   const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmTR + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
     if (Q == 1) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
-    if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); if (g_merge_weighted_minb == 5) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false, 5>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
     { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
@@ -1321,6 +1324,7 @@ extern "C" int ds_tune(int knob, long long value) {
     case DS_TUNE_PDL: ds::g_pdl = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PM_GATHER_PIPELINE: ds::g_gather_pipe = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PM_GATHER_TILE_W: ds::g_gather_tile_w = static_cast<int>(value); return DS_OK;
+    case DS_TUNE_PM_MERGE_WEIGHTED_MINB: ds::g_merge_weighted_minb = static_cast<int>(value); return DS_OK;
     default: return DS_ERR_DIM;
   }
 }

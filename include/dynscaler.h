@@ -59,6 +59,7 @@ enum {
                                           cp.async, deferred bulk-copy wait), bit mask: 1 copy-only gather, 2 4-tap gather */
   DS_TUNE_PM_GATHER_TILE_W = 4         /* gather tile shape: 0 = 64 consecutive view pixels; 8 / 16 / 32 = 2-D tiles of
                                           (64 / value) view rows x value pixels when ds_pm_gather knows the view width */
+  , DS_TUNE_PM_MERGE_WEIGHTED_MINB = 5 /* 5: the two-payload tiled weighted merge runs the variant compiled for 5 CTAs/SM */
 };
 int ds_tune(int knob, long long value);
 

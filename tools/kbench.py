@@ -53,6 +53,7 @@ def main():
         lib.check(lib.ds_tune(2, cfg.get("pdl", 11)))                     # DS_TUNE_PDL
         lib.check(lib.ds_tune(3, cfg.get("pipe", 2)))                     # DS_TUNE_PM_GATHER_PIPELINE
         lib.check(lib.ds_tune(4, cfg.get("tile_w", 0)))                   # DS_TUNE_PM_GATHER_TILE_W
+        lib.check(lib.ds_tune(5, cfg.get("merge_minb", 0)))               # DS_TUNE_PM_MERGE_WEIGHTED_MINB
         res = dict(cfg, workload=wl_name)
         for mode in modes:                                  # whole steps (gather -> merge chains)
             fns = []
