@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DS_ABI_VERSION 3
+#define DS_ABI_VERSION 4
 
 enum { DS_F32 = 0, DS_BF16 = 1 };
 
@@ -55,8 +55,11 @@ enum {
   DS_TUNE_PEER_TIMEOUT_NS = 1,         /* cross-GPU waits give up (and set ds_peer_table_t.error) after this */
   DS_TUNE_PDL = 2,                     /* programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
                                           4 nearest merge, 8 weighted merges (default: 11) */
-  DS_TUNE_PM_GATHER_PIPELINE = 3       /* software-pipelined gather tile loop (next tile's map entries prefetched with
+  DS_TUNE_PM_GATHER_PIPELINE = 3,      /* software-pipelined gather tile loop (next tile's map entries prefetched with
                                           cp.async, deferred bulk-copy wait), bit mask: 1 copy-only gather, 2 4-tap gather */
+  DS_TUNE_PM_GATHER_TILE_W = 4         /* gather tile shape: 0 = 64 consecutive view pixels; 8 / 16 / 32 = 2-D tiles of
+                                          (64 / value) view rows x value pixels when ds_pm_gather knows the view width */
+  , DS_TUNE_PM_MERGE_WEIGHTED_MINB = 5 /* 5: the two-payload tiled weighted merge runs the variant compiled for 5 CTAs/SM */
 };
 int ds_tune(int knob, long long value);
 
@@ -202,10 +205,12 @@ int ds_pm_peer_sync(void* d_peer, int phase, int wait, void* stream);
  * d_idx == NULL (taps == 1): identity map, i.e. the unpack pm -> [P][F][hw], hw <= H*W.
  * d_jobs as in ds_gather_nearest.  Window rows that are 16-byte multiples (hw % (16 / elem_size) == 0)
  * leave through TMA bulk copies, other sizes through plain stores.
+ * view_w: width of the view in pixels (hw = h*view_w), or 0 if unknown / not a 2-D view; it only
+ * lets the kernel cut 2-D tiles (DS_TUNE_PM_GATHER_TILE_W), the result does not depend on it.
  * d_peer: NULL, or the local ds_peer_table_t: the kernel first waits for the peers' merges. */
 int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d_wt, int taps,
                  const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
-                 int hw, void* d_peer, int dtype, void* stream);
+                 int hw, int view_w, void* d_peer, int dtype, void* stream);
 
 /* Ordered sequence of set_view_tensor_no_interpolation calls (panorama_tensor_utils.py:
  * 154-183; ring twin ring_panorama_tensor_utils.py:170-198), scatter form over the surviving
