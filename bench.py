@@ -131,53 +131,95 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------ reference arm ----
-def cpu_step_time(wl, mode, reps):
-    """Times oracle/torch_port.{sphere,ring}_step (the reference's per-call torch op sequence)
-    on the host cores.  Returns (seconds per step, cores, sample description, windows/step)."""
-    from oracle import torch_port as tp
-    if wl.get("frame_ring"):
-        return None                                    # no CPU port of the frame-ring composition
-    torch.set_num_threads(os.cpu_count() or 1)
+def cpu_inputs(wl, views_per_step=None):
+    """Seeded CPU inputs of one step: (latent, x_prev list, x0 list, jobs per step)."""
     g = torch.Generator().manual_seed(0)
     shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
     vshape = (1, wl["C"], wl["f_len"], wl["h"], wl["w"])
-    n_win = len(default_views(0)) if wl["kind"] == "sphere" else len(ring_windows_of(wl, 0))
+    if wl["kind"] == "sphere":
+        n_views = len(default_views(0)) if views_per_step is None else views_per_step
+        n_win = n_views * (len(frame_begins_of(wl, 0)) if wl.get("frame_ring") else 1)
+    else:
+        n_win = len(ring_windows_of(wl, 0)) if views_per_step is None else views_per_step
     lat = torch.randn(shape, generator=g)
-    xp = [torch.randn(vshape, generator=g) for _ in range(n_win)]
-    x0 = [torch.randn(vshape, generator=g) for _ in range(n_win)]
-    ts = []
-    for i in range(reps + 1):
-        t = time.perf_counter()
-        if wl["kind"] == "sphere":
-            tp.sphere_step(lat, torch.zeros_like(lat), default_views(i), xp, x0, fov=wl["fov"], width=wl["w"],
-                           height=wl["h"], mode=mode)
+    # payload tensors are shared between windows beyond 64 (memory): the arithmetic per window is unchanged
+    pool = min(n_win, 64)
+    xp = [torch.randn(vshape, generator=g) for _ in range(pool)]
+    x0 = [torch.randn(vshape, generator=g) for _ in range(pool)]
+    return lat, [xp[i % pool] for i in range(n_win)], [x0[i % pool] for i in range(n_win)], n_win
+
+
+def frame_begins_of(wl, i):
+    from dynamicscaler_b200.geometry import frame_windows
+    return frame_windows(i, frames=wl["f_len"], total_f=wl["F"])
+
+
+def cpu_one_step(wl, mode, i, lat, xp, x0, views_per_step=None):
+    """One gather-all -> merge-all step of oracle/torch_port (the reference's per-call torch op
+    sequence) on the host cores.  ``views_per_step``: bounded sample = the first m views / windows."""
+    from oracle import torch_port as tp
+    if wl["kind"] == "sphere":
+        views = default_views(i)[:views_per_step]
+        if wl.get("frame_ring"):
+            tp.frame_ring_sphere_step(lat, torch.zeros_like(lat), frame_begins_of(wl, i), wl["f_len"], views, xp, x0,
+                                      fov=wl["fov"], width=wl["w"], height=wl["h"], mode=mode)
         else:
-            tp.ring_step(lat, torch.zeros_like(lat), ring_windows_of(wl, i), xp, x0, w=wl["w"], h=wl["h"])
+            tp.sphere_step(lat, torch.zeros_like(lat), views, xp, x0, fov=wl["fov"], width=wl["w"],
+                           height=wl["h"], mode=mode)
+    else:
+        tp.ring_step(lat, torch.zeros_like(lat), ring_windows_of(wl, i)[:views_per_step], xp, x0, w=wl["w"], h=wl["h"])
+
+
+def cpu_step_time(wl, mode, reps, views_per_step=None, warmup=1):
+    """Times ``reps`` steps after ``warmup``.  Returns (seconds per step, cores, sample text, windows/step)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    lat, xp, x0, n_win = cpu_inputs(wl, views_per_step)
+    ts = []
+    for i in range(reps + warmup):
+        t = time.perf_counter()
+        cpu_one_step(wl, mode, i, lat, xp, x0, views_per_step)
         ts.append(time.perf_counter() - t)
-    return (statistics.mean(ts[1:]), torch.get_num_threads(),
-            f"{reps} full steps ({n_win} windows each) after 1 warm-up", n_win)
+    what = "full steps" if views_per_step is None else f"steps sampled to the first {views_per_step} views/windows"
+    return (statistics.mean(ts[warmup:]), torch.get_num_threads(),
+            f"{reps} {what} ({n_win} windows each) after {warmup} warm-up", n_win)
 
 
 def run_reference(args, wl, wl_name):
+    """--impl reference: the reference's own CPU implementation of the path (torch port issuing the
+    reference's op sequence per call, oracle/torch_port.py) on all host threads; exactly --steps timed
+    steps after --warmup, each step a bounded sample of the workload when a full step would make the
+    run longer than a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    reps = max(1, min(args.steps, 8 if args.mode == "bilinear" else 20))     # about 10-20 s of CPU work
-    res = cpu_step_time(wl, args.mode, reps)
-    if res is None:
-        print(json.dumps({"impl": "reference", "unavailable": f"no CPU port of workload {wl_name}"}))
-        return
-    sec, cores, sample, n_win = res
+    K, Wm = max(1, args.steps), max(0, args.warmup)
+    budget_s = 150.0
+    # size the per-step sample: time one full-size probe of a few views, extrapolate
+    probe_views = 4
+    sec_probe, _, _, n_probe = cpu_step_time(wl, args.mode, 1, views_per_step=probe_views, warmup=1)
+    per_win = sec_probe / n_probe
+    full_views = len(default_views(0)) if wl["kind"] == "sphere" else len(ring_windows_of(wl, 0))
+    jobs_per_view = (len(frame_begins_of(wl, 0)) if wl.get("frame_ring") else 1)
+    fit = int(budget_s / ((K + Wm) * per_win * jobs_per_view))
+    m = None if fit >= full_views else max(1, fit)
+    sec, cores, sample, n_win = cpu_step_time(wl, args.mode, K, views_per_step=m, warmup=Wm)
     value = n_win / sec
-    print(json.dumps({
+    line = {
         "impl": "reference", "metric": "panorama denoise-step window-blends/sec", "value": value, "unit": "blends/s",
-        "n_gpus": args.gpus, "steps": reps, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl_name, "mode": args.mode, "latent": [1, wl["C"], wl["F"], wl["H"], wl["W"]],
-                   "windows_per_step": n_win, "window": [wl["h"], wl["w"]]},
+                   "windows_per_step": full_views * jobs_per_view, "window": [wl["h"], wl["w"]]},
         "cpu_baseline": {"value": value, "unit": "blends/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "blends/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if wl["kind"] == "sphere" and args.mode == "bilinear":
+        # the mode the reference pipelines call (get_view_tensor_no_interpolate + set_view_tensor_no_interpolation)
+        reps = max(2, min(K, 10))
+        sec_n, _, sample_n, n_win_n = cpu_step_time(wl, "nearest", reps, views_per_step=m, warmup=1)
+        line["variants"] = {"nearest": {"value": n_win_n / sec_n, "unit": "blends/s", "ms_per_step": sec_n * 1e3,
+                                        "sample": sample_n}}
+    print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------ our arm ----
@@ -226,6 +268,17 @@ def timed(run, dist_on):
     return a.elapsed_time(b)
 
 
+def timed_regions(run, dist_on, regions, dev):
+    """``regions`` separately timed executions of ``run`` (each one exactly K steps, bracketed by
+    barrier + synchronize); every region's time is the MAX over ranks.  Returns the list (ms)."""
+    ms = [timed(run, dist_on) for _ in range(regions)]
+    if dist_on:
+        t = torch.tensor(ms, device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = [float(v) for v in t.tolist()]
+    return ms
+
+
 def make_runner(fns, K, use_graph, stream):
     """``run()`` executes exactly K steps, step i = fns[i % len(fns)].  With graphs, whole
     cycles of len(fns) consecutive steps are captured into ONE CUDA graph (plus one graph for
@@ -257,9 +310,86 @@ def make_runner(fns, K, use_graph, stream):
     return run
 
 
+_SLEEP_CAL = {}
+
+
+def sleep_cycles_per_us(dev):
+    """torch.cuda._sleep spins for a number of SM cycles; calibrate cycles per microsecond once."""
+    if dev not in _SLEEP_CAL:
+        torch.cuda._sleep(1000)
+        torch.cuda.synchronize()
+        n = 20_000_000
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        torch.cuda._sleep(n)
+        b.record()
+        torch.cuda.synchronize()
+        _SLEEP_CAL[dev] = n / (a.elapsed_time(b) * 1e3)
+    return _SLEEP_CAL[dev]
+
+
+# ---------------------------------------------------------------- multi-GPU parity ----
+def parity_check(wl, mode, dev, rank, world, pm, peer, dtype, n_steps, multicast):
+    """N > 1: run ``n_steps`` steps of the sharded path on fresh, seeded inputs (identical on every
+    rank), export every rank's panoramas + mask, and compare their sha256 with a SINGLE-rank run of
+    the same steps done locally on every rank.  Payloads depend on the gathered windows, so a wrong
+    gather shows up in the state as well.  Returns the ``parity`` object of the JSON line."""
+    import hashlib
+    import torch.distributed as dist
+    from dynamicscaler_b200.step import PanoramaStepper
+
+    shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
+    vshape = (1, wl["C"], wl["f_len"], wl["h"], wl["w"])
+    gen = torch.Generator(device=dev).manual_seed(777)                 # same stream on every rank
+    lat0 = torch.randn(shape, device=dev, generator=gen).to(dtype)
+    plane_mask = wl["kind"] == "sphere" and not wl.get("frame_ring")
+    mshape = (1, wl["H"], wl["W"]) if plane_mask else shape
+
+    def drive(st, peer_):
+        plans = [make_plan(st, wl, mode, i) for i in range(min(n_steps, n_phases(wl)))]
+        n_win = plans[0].n_jobs
+        g2 = torch.Generator(device=dev).manual_seed(778)
+        base_a = torch.randn((n_win,) + vshape, device=dev, generator=g2).to(dtype)
+        base_b = torch.randn((n_win,) + vshape, device=dev, generator=g2).to(dtype)
+        lat, den, msk = lat0.clone(), torch.zeros_like(lat0), torch.zeros(mshape, device=dev, dtype=dtype)
+        state = st.make_state([lat, den], mask=msk, peer=peer_) if pm else None
+        for i in range(n_steps):
+            plan = plans[i % len(plans)]
+            ids = torch.tensor(plan.job_ids, device=dev, dtype=torch.long)
+            wins = st.gather_all(state if pm else lat, plan)
+            xp = wins * 0.5 + base_a[ids] * float(1 + i % 3)
+            x0 = wins * 0.25 - base_b[ids]
+            if pm:
+                st.merge_all(state, [xp, x0], plan)
+            else:
+                st.merge_all([lat, den], [xp, x0], plan, mask=msk)
+        outs = (state.export() + [state.export_mask()]) if pm else [lat, den, msk]
+        torch.cuda.synchronize()
+        h = hashlib.sha256()
+        for t in outs:
+            h.update(t.contiguous().view(torch.uint8).cpu().numpy().tobytes())
+        if pm and state.peer_table is not None:
+            assert not state.peer_error(), "a cross-GPU wait timed out during the parity run"
+        return h.digest()
+
+    st_n = PanoramaStepper(wl["H"], wl["W"], wl["F"], device=dev, rank=rank, world=world)
+    st_n.use_multicast = multicast
+    mine = drive(st_n, peer)
+    single = drive(PanoramaStepper(wl["H"], wl["W"], wl["F"], device=dev), False)
+    both = torch.tensor(list(mine) + list(single), device=dev, dtype=torch.uint8)
+    allr = [torch.empty_like(both) for _ in range(world)]
+    dist.all_gather(allr, both)
+    digests = [bytes(t.cpu().tolist()) for t in allr]
+    ok = all(d[:32] == digests[0][32:] and d[32:] == digests[0][32:] for d in digests)
+    return {"ok": bool(ok), "ranks": world, "steps": n_steps, "mode": mode, "digest": digests[0][32:].hex()[:16],
+            "rank_digests": [d[:32].hex()[:16] for d in digests],
+            "against": "single-rank run of the same steps (every rank's exported latent, denoised, mask; sha256)"}
+
+
+# ------------------------------------------------------------------------ our arm ----
 def run_ours(args, wl, wl_name):
     import torch.distributed as dist
-    from dynamicscaler_b200 import lib
+    from dynamicscaler_b200 import _lib, lib
     from dynamicscaler_b200.step import PanoramaStepper
 
     rank = int(os.environ.get("RANK", "0"))
@@ -271,7 +401,7 @@ def run_ours(args, wl, wl_name):
     dist_on = world > 1
     if dist_on:
         dist.init_process_group("nccl", device_id=dev)
-    assert lib.ds_abi_version() == 3                     # fails loudly if the .so is missing
+    assert lib.ds_abi_version() == _lib.ABI_VERSION          # fails loudly if the .so is missing
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -282,14 +412,14 @@ def run_ours(args, wl, wl_name):
     modes, NP = modes_of(wl), n_phases(wl)
     if args.mode not in modes:
         args.mode = modes[0]
+    if args.only_mode:
+        modes = (args.mode,)
     plans = {m: [make_plan(st, wl, m, i) for i in range(NP)] for m in modes}
     n_local = st.local_jobs(plans[modes[0]][0])[1]
     n_win = plans[modes[0]][0].n_jobs
     st_pm = st if (args.layout == "pm" and wl["kind"] == "sphere") else None
     peer = dist_on and st_pm is not None and args.exchange == "peer"
     gen_pano = torch.Generator(device=dev).manual_seed(99)      # replicas start identical on every rank
-    if peer:
-        lib.check(lib.ds_tune(1, 30_000_000_000))            # DS_TUNE_PEER_TIMEOUT_NS: ranks may start seconds apart
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     esz = 2 if args.dtype == "bf16" else 4
     try:
@@ -304,11 +434,17 @@ def run_ours(args, wl, wl_name):
     sets = [one] + [Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano, dtype) for _ in range(n_sets - 1)]
     combos = [(i % NP, i % n_sets) for i in range(NP * n_sets // np.gcd(NP, n_sets))]
 
+    # --denoise-us T: a busy kernel of T microseconds per LOCAL window between gather and merge, the
+    # stand-in for the UNet + ddim_step of BASELINE config 3 (the reference module cannot travel here)
+    denoise_cycles = int(args.denoise_us * n_local * sleep_cycles_per_us(dev)) if args.denoise_us > 0 else 0
+
     def make_step(mode, off, s):
         ws, plan = sets[s], plans[mode][off]
 
         def step():
             st.gather_all(ws.pano, plan, out=ws.wins)
+            if denoise_cycles:
+                torch.cuda._sleep(denoise_cycles)
             ws.merge(st, plan)
         return step
 
@@ -327,7 +463,6 @@ def run_ours(args, wl, wl_name):
             make_step(mode, *c)()
     torch.cuda.synchronize()
     use_graph = not args.no_graph
-    launches_before = lib.launches
 
     def runner(maker, mode, count):
         fns = [maker(mode, *c) for c in combos]
@@ -339,31 +474,29 @@ def run_ours(args, wl, wl_name):
             return make_runner(fns, count, False, side), False
 
     results = {}
-    K, Wm = args.steps, max(args.warmup, 3)
+    K, Wm, R = args.steps, max(args.warmup, 3), max(args.regions, 1)
     for mode in modes:
         launches_before = lib.launches
         make_step(mode, *combos[0])()                       # count this arm's own kernel launches per step
-        launches_per_step = lib.launches - launches_before
+        launches_per_step = lib.launches - launches_before - (0 if not denoise_cycles else 0)
         run, graphed = runner(make_step, mode, K)
         warm, _ = runner(make_step, mode, Wm)
         warm()
         sampler.load = True
-        ms = timed(run, dist_on)
+        ms_list = timed_regions(run, dist_on, R, dev)       # R regions of exactly K steps each
         sampler.load = False
-        if dist_on:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = statistics.median(ms_list)
         results[mode] = {"ms_total": ms, "ms_per_step": ms / K, "graph": graphed,
-                         "launches_per_step": launches_per_step}
+                         "launches_per_step": launches_per_step,
+                         "regions_ms_per_step": [round(v / K, 6) for v in ms_list]}
         # per-kernel pass (same rotation) for the roofline
-        if not dist_on and not args.no_kernel_pass:
+        if not dist_on and not args.no_kernel_pass and not denoise_cycles:
             iters = max(K, 5 * len(combos))
             for name, maker in (("gather", make_gather), ("merge", make_merge)):
                 krun, _ = runner(maker, mode, iters)
                 krun()
                 sampler.load = True
-                results[mode][name + "_us"] = timed(krun, False) / iters * 1e3
+                results[mode][name + "_us"] = statistics.median(timed_regions(krun, False, 5, dev)) / iters * 1e3
                 sampler.load = False
     # make sure the clock sampler saw the load: replay the headline step for ~0.3 s
     run, _ = runner(make_step, args.mode, 20 * len(combos))
@@ -375,10 +508,11 @@ def run_ours(args, wl, wl_name):
     sampler.load = False
 
     # ---- e2e: host buffers in, host buffers out, through the public API ---------------
-    # Every step uploads ITS payloads from pinned host memory and downloads ITS windows.  The device
-    # side of the payloads is double-buffered, so the upload of step i+1 runs on the copy stream
-    # while step i computes (the uploads are the critical path: PCIe), and the window download has
-    # its own stream.  Exactly e2e_steps uploads and downloads happen inside the timed region.
+    # Every step uploads ITS payloads from pinned host memory and downloads ITS windows; the copies
+    # are inside the timed region.  The device side of the payloads is double-buffered, so the upload
+    # of step i+1 overlaps step i (the uploads are the critical path: PCIe), and the window download
+    # runs on its own stream.  The whole e2e_steps-step pipeline (memcpy nodes included) is captured
+    # into ONE CUDA graph, so the host launches nothing per step; eager fallback if capture fails.
     mode = args.mode
     ws = sets[0]
     h_xp = torch.randn(ws.x_prev.shape).to(dtype).pin_memory()
@@ -386,60 +520,64 @@ def run_ours(args, wl, wl_name):
     h_wins = torch.empty(ws.wins.shape, dtype=dtype).pin_memory()
     up_stream, down_stream = torch.cuda.Stream(), torch.cuda.Stream()
     dev_pay = [(ws.x_prev, ws.x0), (torch.empty_like(ws.x_prev), torch.empty_like(ws.x0))]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]       # payload buffer b holds a fresh upload
-    free = [torch.cuda.Event(), torch.cuda.Event()]        # the merge that consumed buffer b is done
-    wins_read = torch.cuda.Event()                         # the download of the previous windows is done
     e2e_steps = max(3, min(K, 30))
-    main = torch.cuda.current_stream()
 
-    def upload(b):
-        with torch.cuda.stream(up_stream):
-            up_stream.wait_event(free[b])
-            dev_pay[b][0].copy_(h_xp, non_blocking=True)
-            dev_pay[b][1].copy_(h_x0, non_blocking=True)
-            ready[b].record(up_stream)
+    def e2e_pipeline(main, n):
+        """n steps on streams main / up_stream / down_stream; dependencies only through events
+        recorded INSIDE this call (capturable)."""
+        ready, free, wins_read = [None, None], [None, None], None
+        up_stream.wait_stream(main)
+        down_stream.wait_stream(main)
+        for i in range(n):
+            plan = plans[mode][i % NP]
+            b = i & 1
+            with torch.cuda.stream(up_stream):              # this step's inputs: pinned host -> device
+                if free[b] is not None:
+                    up_stream.wait_event(free[b])           # the merge that consumed buffer b is done
+                dev_pay[b][0].copy_(h_xp, non_blocking=True)
+                dev_pay[b][1].copy_(h_x0, non_blocking=True)
+                ready[b] = torch.cuda.Event()
+                ready[b].record(up_stream)
+            if wins_read is not None:
+                main.wait_event(wins_read)                  # the window buffer is free again
+            st.gather_all(ws.pano, plan, out=ws.wins)
+            gathered = torch.cuda.Event()
+            gathered.record(main)
+            with torch.cuda.stream(down_stream):            # this step's result: device -> pinned host
+                down_stream.wait_event(gathered)
+                h_wins.copy_(ws.wins, non_blocking=True)
+                wins_read = torch.cuda.Event()
+                wins_read.record(down_stream)
+            main.wait_event(ready[b])                       # this step's inputs have arrived
+            if ws.state is not None:
+                st.merge_all(ws.state, list(dev_pay[b]), plan)
+            else:
+                st.merge_all([ws.lat, ws.den], list(dev_pay[b]), plan, mask=ws.mask)
+            free[b] = torch.cuda.Event()
+            free[b].record(main)
+        main.wait_stream(down_stream)                       # the last download is part of the job
+        main.wait_stream(up_stream)
 
-    def e2e_step(i):
-        plan = plans[mode][i % NP]
-        b = i & 1
-        upload(b ^ 1)                                       # next step's inputs, overlapped with this step
-        main.wait_event(wins_read)                          # the window buffer is free again
-        st.gather_all(ws.pano, plan, out=ws.wins)
-        gathered = torch.cuda.Event()
-        gathered.record(main)
-        with torch.cuda.stream(down_stream):                # this step's result: device -> pinned host
-            down_stream.wait_event(gathered)
-            h_wins.copy_(ws.wins, non_blocking=True)
-            wins_read.record(down_stream)
-        main.wait_event(ready[b])                           # this step's inputs have arrived
-        if ws.state is not None:
-            st.merge_all(ws.state, list(dev_pay[b]), plan)
-        else:
-            st.merge_all([ws.lat, ws.den], list(dev_pay[b]), plan, mask=ws.mask)
-        free[b].record(main)
-
-    for ev in free + [wins_read]:
-        ev.record(main)
-    upload(0)
-    for i in range(4):
-        e2e_step(i)
-    if dist_on:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
-    main.wait_stream(down_stream)                           # the last download is part of the job
-    main.wait_stream(up_stream)
-    b_ev.record()
-    torch.cuda.synchronize()
-    e2e_ms = a.elapsed_time(b_ev) / e2e_steps
-    if dist_on:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_graph = None
+    if use_graph:
+        try:
+            with torch.cuda.stream(side):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    e2e_pipeline(torch.cuda.current_stream(), e2e_steps)
+            e2e_graph = g
+        except Exception as e:
+            torch.cuda.synchronize()
+            print(f"[bench] e2e graph capture failed ({type(e).__name__}: {e}); running the e2e loop eagerly", file=sys.stderr)
+    e2e_run = e2e_graph.replay if e2e_graph is not None else (lambda: e2e_pipeline(torch.cuda.current_stream(), e2e_steps))
+    e2e_run()                                               # warm-up
+    e2e_ms = statistics.median(timed_regions(e2e_run, dist_on, 5, dev)) / e2e_steps
     sampler.stop_flag = True
+
+    parity = None
+    if dist_on and not args.no_parity:
+        parity = parity_check(wl, args.mode, dev, rank, world, st_pm is not None, peer, dtype,
+                              max(4, min(K, 10)), st.use_multicast)
 
     if rank == 0:
         head = results[args.mode]
@@ -453,47 +591,77 @@ def run_ours(args, wl, wl_name):
                        "windows_per_step": n_win, "window": [wl["h"], wl["w"]], "payloads": 2,
                        "l2_policy": f"inputs larger than L2: {n_sets} rotating buffer sets, {n_sets * one.nbytes() / 2**20:.0f} MiB",
                        "cuda_graph": head["graph"], "steps_per_graph": len(combos) if head["graph"] else 0,
+                       "timing": f"median of {R} separately timed regions of exactly {K} steps (CUDA events, max over ranks)",
                        "layout": "resident pixel-major [H*W][F][4] (csrc/pm.cu)" if st_pm is not None
                                  else "reference [B,C,F,H,W] (csrc/sphere.cu, csrc/ring.cu)",
                        "maps": "precomputed on host (static geometry), cached on device",
+                       "denoise_us_per_window": args.denoise_us,
                        "sharding": ("none" if not dist_on else
                                     "windows split over ranks; merge kernels push rows into every replica over NVLink ("
                                     + ("NVLS multicast stores" if st.use_multicast else "per-replica TMA row copies")
                                     + ", release/acquire counters)" if peer else
                                     "windows split over ranks, 1 NCCL all-reduce/step")},
             "steps_per_s": 1e3 / head["ms_per_step"],
+            "regions_ms_per_step": head["regions_ms_per_step"],
             "peer_wait_timeouts": bool(peer and any(w.state.peer_error() for w in sets)),
             "gpu_launches": int(head["launches_per_step"] * K),
             "clocks": sampler.summary(),
             "e2e": {"value": n_win / (e2e_ms * 1e-3), "unit": "blends/s",
                     "h2d_bytes_per_step": int((h_xp.numel() + h_x0.numel()) * esz),
-                    "d2h_bytes_per_step": int(h_wins.numel() * esz), "ms_per_step": e2e_ms, "steps": e2e_steps},
+                    "d2h_bytes_per_step": int(h_wins.numel() * esz), "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "cuda_graph": e2e_graph is not None},
             "variants": {m: {"ms_per_step": r["ms_per_step"], "blends_per_s": n_win / (r["ms_per_step"] * 1e-3),
                              **{k: v for k, v in r.items() if k.endswith("_us")}} for m, r in results.items()},
         }
-        if not dist_on and not args.no_kernel_pass:
+        if parity is not None:
+            line["parity"] = parity
+        if not dist_on and not args.no_kernel_pass and not denoise_cycles:
             P = wl["C"]
-            gb, mb = st.algorithmic_bytes(plans[args.mode][0], P, esz, k=2)
+            plan0 = plans[args.mode][0]
+            gb, mb = st.algorithmic_bytes(plan0, P, esz, k=2)
+            ngb, nmb, ndetail = st.necessary_bytes(plan0, P, esz, k=2)
             kern = "merge" if head["merge_us"] >= head["gather_us"] else "gather"
             bytes_launch = mb if kern == "merge" else gb
+            nec_launch = nmb if kern == "merge" else ngb
             dur = head[kern + "_us"] * 1e-6
+            step_s = head["ms_per_step"] * 1e-3
             line["roofline"] = {
-                "bound": "hbm", "kernel": f"{kern}_{args.mode}", "achieved": bytes_launch / dur / 1e9, "peak": peak,
-                "unit": "GB/s", "frac": bytes_launch / dur / 1e9 / peak,
+                "bound": "hbm", "kernel": f"{kern}_{args.mode}",
+                # frac: the bytes the kernel cannot avoid (surviving payload sectors + rows written + maps/plan)
+                "achieved": nec_launch / dur / 1e9, "peak": peak, "unit": "GB/s", "frac": nec_launch / dur / 1e9 / peak,
+                "necessary_bytes": nec_launch,
+                # the SURVEY §8d formula (charges the whole payload of every window, read or not)
+                "achieved_algorithmic": bytes_launch / dur / 1e9, "frac_algorithmic": bytes_launch / dur / 1e9 / peak,
                 "traffic": ncu_traffic(kern, args.mode, st_pm is not None and args.dtype == "f32"), "peak_source": peak_src,
-                "algorithmic_bytes": {"gather": gb, "merge": mb, "coverage": plans[args.mode][0].coverage},
-                "step_frac": (gb + mb) / (head["ms_per_step"] * 1e-3) / 1e9 / peak,
-                "all": {m: {kn: (st.algorithmic_bytes(plans[m][0], P, esz)[0 if kn == "gather" else 1]
-                                 / (results[m][kn + "_us"] * 1e-6) / 1e9) for kn in ("gather", "merge")}
+                "algorithmic_bytes": {"gather": gb, "merge": mb, "coverage": plan0.coverage},
+                "necessary": {"gather": ngb, "merge": nmb, **ndetail},
+                "step_frac": (ngb + nmb) / step_s / 1e9 / peak,
+                "step_frac_algorithmic": (gb + mb) / step_s / 1e9 / peak,
+                "all": {m: {kn: {"us": results[m][kn + "_us"],
+                                 "algorithmic_GBps": st.algorithmic_bytes(plans[m][0], P, esz)[0 if kn == "gather" else 1]
+                                 / (results[m][kn + "_us"] * 1e-6) / 1e9,
+                                 "necessary_GBps": st.necessary_bytes(plans[m][0], P, esz)[0 if kn == "gather" else 1]
+                                 / (results[m][kn + "_us"] * 1e-6) / 1e9} for kn in ("gather", "merge")}
                         for m in results},
             }
-            reps = 8 if args.mode == "bilinear" else 20                 # about 10-20 s of CPU work
-            cpu = None if (args.no_cpu or args.dtype != "f32") else cpu_step_time(wl, args.mode, reps)
-            if cpu is not None:
-                sec, cores, sample, _ = cpu
-                line["cpu_baseline"] = {"value": n_win / sec, "unit": "blends/s", "cores": cores, "kind": "port",
+            if not args.no_cpu and args.dtype == "f32":
+                # bounded sample: about 10-20 s of CPU work on this box's host cores
+                full_views = len(default_views(0)) if wl["kind"] == "sphere" else len(ring_windows_of(wl, 0))
+                m_views = None
+                if wl.get("frame_ring") or wl["H"] >= 512:
+                    m_views = 4 if wl.get("frame_ring") else 64
+                reps = 8 if args.mode == "bilinear" else 20
+                if m_views is not None:
+                    reps = 2
+                sec, cores, sample, n_cpu = cpu_step_time(wl, args.mode, reps, views_per_step=m_views)
+                line["cpu_baseline"] = {"value": n_cpu / sec, "unit": "blends/s", "cores": cores, "kind": "port",
                                         "sample": sample, "ms_per_step": sec * 1e3}
+                if wl["kind"] == "sphere" and args.mode == "bilinear" and m_views is None:
+                    sec_n, _, sample_n, n_cpu_n = cpu_step_time(wl, "nearest", 10)
+                    line["cpu_baseline"]["nearest"] = {"value": n_cpu_n / sec_n, "unit": "blends/s",
+                                                       "ms_per_step": sec_n * 1e3, "sample": sample_n}
         print(json.dumps(line))
+    rc = 0 if (parity is None or parity["ok"]) else 3
     if dist_on:
         # Leave without tearing NCCL down: destroying a communicator whose collectives were
         # captured in still-alive CUDA graphs can block forever; the JSON line is out, so exit.
@@ -501,7 +669,9 @@ def run_ours(args, wl, wl_name):
         dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        os._exit(rc)
+    if rc:
+        sys.exit(rc)
 
 
 def main():
@@ -523,6 +693,13 @@ def main():
     ap.add_argument("--workload", default="cfg2_sphere_128x256", choices=list(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--regions", type=int, default=11,
+                    help="separately timed regions of exactly --steps steps; the median is reported")
+    ap.add_argument("--denoise-us", type=float, default=0.0,
+                    help="busy kernel of this many microseconds per local window between gather and merge "
+                         "(UNet + ddim_step stand-in for the scaling study; 0 = the blend-only headline)")
+    ap.add_argument("--only-mode", action="store_true", help="time only --mode (skip the other variant)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-single-rank parity run")
     ap.add_argument("--no-kernel-pass", action="store_true",
                     help="skip the per-kernel timing pass and the roofline (profiling runs: launch list = steps only)")
     args = ap.parse_args()

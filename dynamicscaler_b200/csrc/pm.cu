@@ -55,7 +55,8 @@ static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
 static int g_gather_tile_w = 0;                 // 0: linear tiles of 64 view pixels; 8 / 16 / 32: 2-D tiles (64/w rows x w pixels)
 static int g_merge_weighted_minb = 0;           // 5: two-payload tiled weighted merge compiled for 5 CTAs per SM
 static int g_gather_pipe = 2;                   // bit 1: copy-only gather, bit 2: 4-tap gather use the pipelined tile loop
-static long long g_peer_timeout_ns = 2000000000ll;   // give up a cross-GPU wait after this long
+static long long g_peer_timeout_ns = 60000000000ll;  // a cross-GPU wait longer than this (60 s: first-step autotune,
+                                                       // lazy module loads, stragglers are all far shorter) aborts the kernel
 static int g_pdl = 11;                          // programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
                                                 // 4 nearest merge, 8 weighted merges.  Measured (tools/kbench.py, cfg2): the
                                                 // 4-tap gather / weighted merge chain gains 7 % (31.7 -> 29.6 us); with BOTH
@@ -161,6 +162,16 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+// A cross-GPU wait that outlives the timeout must never let the data phase run on a replica that
+// is still being read / not yet complete: record the error word (host-visible through
+// PanoramaState.peer_error) and abort the kernel -- the context is then in a sticky launch-failure
+// state, so the next call through the C ABI fails loudly instead of computing on corrupted rows.
+__device__ __forceinline__ void pm_peer_timeout(ds_peer_table_t* tab) {
+  tab->error = 1;
+  __threadfence_system();
+  asm volatile("trap;");
+}
+
 // One tiny kernel after each data kernel of a step (stream order does the rest):
 //   phase DS_PEER_AFTER_GATHER: this rank has finished reading its replica -> bump my_gathers and
 //     publish it into gathers_done[rank] of every peer (their merges may then overwrite it);
@@ -168,7 +179,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 //     so its peer stores are performed) -> same with my_merges / merges_done.
 // wait != 0 additionally blocks until every peer has published as much (a full barrier); the
 // data kernels normally do that part themselves (pm_peer_spin).  lane p talks to peer p.  A wait
-// longer than timeout_ns sets tab->error instead of hanging.
+// longer than timeout_ns sets tab->error and traps (pm_peer_timeout) instead of hanging.
 __global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, int wait, long long timeout_ns) {
   const int p = threadIdx.x;
   int32_t* mine = phase == DS_PEER_AFTER_GATHER ? &tab->my_gathers : &tab->my_merges;
@@ -184,10 +195,7 @@ __global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, int wait, l
     const int32_t* done = reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(tab) + off) + p;
     const unsigned long long t0 = global_ns();
     while (wait && ld_acquire_sys(done) < c) {
-      if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) {
-        tab->error = 1;
-        break;
-      }
+      if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) pm_peer_timeout(tab);
     }
   }
 }
@@ -201,10 +209,7 @@ __device__ __forceinline__ void pm_peer_spin(ds_peer_table_t* tab, const int32_t
     const unsigned long long t0 = global_ns();
     while (v < want) {
       v = ld_acquire_sys(done + threadIdx.x);
-      if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) {
-        tab->error = 1;
-        break;
-      }
+      if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) pm_peer_timeout(tab);
     }
   }
 }

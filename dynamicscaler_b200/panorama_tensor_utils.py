@@ -96,6 +96,7 @@ class PanoramaTensor:
     # per-call host overhead matters for the unmodified call sites (one launch per call): the
     # storage block and the device maps of a view are looked up once and remembered
     _blk_cache = None
+    _proxied = False            # True: equirect_tensor is the [B, F, C, H, W] alias of a proxy's [B, C, F, H, W] storage
 
     def _view_maps(self, what, fov, theta, phi, width, height, device, make):
         """Device arrays of one view (``what`` names the kind): one dict lookup per call (handlers
@@ -115,10 +116,24 @@ class PanoramaTensor:
         hit = self._blk_cache
         if hit is not None and hit[0] is t:
             return hit[1]
-        _lib.require_cuda(t, "PanoramaTensor.equirect_tensor")
-        if t.dim() == 5 and not t.is_contiguous() and t.permute(0, 2, 1, 3, 4).is_contiguous():
-            B, F, C = t.shape[0], t.shape[1], t.shape[2]                 # proxy layout underneath
-            blk = _Block(t.permute(0, 2, 1, 3, 4), B * C, F, 0, F, True, (B, F))
+        if not t.is_cuda:
+            # the I2V pipeline wraps the CPU condition image (i2v_sphere_panorama_pipeline.py:223-224,
+            # torch.from_numpy) and samples views from it every window (:367): upload it ONCE, like
+            # RingImageTensor._storage; a CUDA device must exist -- there is no CPU path
+            if not torch.cuda.is_available():
+                _lib.require_cuda(t, "PanoramaTensor.equirect_tensor")
+            t = self.equirect_tensor = t.cuda()
+            self.device = t.device
+        if self._proxied and t.dim() == 5:
+            # created by PanoramaLatentProxy: storage is dense [B, C, F, H, W], equirect_tensor its
+            # permuted [B, F, C, H, W] alias.  The flag -- not the strides -- says so: with F == 1 or
+            # C == 1 the alias is itself contiguous
+            store = t.permute(0, 2, 1, 3, 4)
+            if not store.is_contiguous():                                 # a caller assigned other strides
+                store = store.contiguous()
+                t = self.equirect_tensor = store.permute(0, 2, 1, 3, 4)
+            B, F, C = t.shape[0], t.shape[1], t.shape[2]
+            blk = _Block(store, B * C, F, 0, F, True, (B, F))
         else:
             if not t.is_contiguous():
                 t = self.equirect_tensor = t.contiguous()
@@ -296,6 +311,7 @@ class PanoramaLatentProxy:
         # make the storage dense in [B, C, N, H, W] order whatever strides the input had
         store = self.panorama_tensor.equirect_tensor.permute(0, 2, 1, 3, 4).contiguous()
         self.panorama_tensor.equirect_tensor = store.permute(0, 2, 1, 3, 4)
+        self.panorama_tensor._proxied = True
 
     def get_view_tensor_interpolate(self, fov, theta, phi, width, height,
                                     interpolate_mode='bilinear', interpolate_align_corners=True):

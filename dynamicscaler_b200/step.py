@@ -279,6 +279,7 @@ class PanoramaStepper:
             base = maps.filter_nearest_plan(whole, hw, nv, local_views) if sharded else whole
             plan.d_dst, plan.d_src = maps.on_device(("nplan", lkey), self.device, lambda: base)
             plan.T = base[0].size
+            plan.extra["host_plan"] = base
             plan.pm_merge = maps.on_device(("pm_nplan", lkey), self.device,
                                            lambda: maps.pm_nearest_plan(vms, base, nlv))
         else:
@@ -289,6 +290,7 @@ class PanoramaStepper:
             base = maps.filter_bilinear_plan(whole, hw, nv, local_views) if sharded else whole
             plan.d_csr = maps.on_device(("bplan", lkey), self.device, lambda: base)
             plan.T = base[0].size
+            plan.extra["host_plan"] = base
             plan.pm_merge = maps.on_device(("pm_bplan", lkey), self.device,
                                            lambda: maps.pm_bilinear_plan(vms, base, nlv))
             if f_len == 16:
@@ -689,6 +691,81 @@ class PanoramaStepper:
                           "ds_select_merged")
 
     # ------------------------------------------------------------- bytes accounting ----
+    def necessary_bytes(self, plan: StepPlan, P: int, elem_size: int, k: int = 2):
+        """Bytes one step of THIS rank cannot avoid moving, as opposed to the SURVEY §8d formula of
+        ``algorithmic_bytes`` (which charges the whole payload of every window although a merge only
+        reads what survives the ordered writes).  Returns (gather_bytes, merge_bytes, detail):
+
+        gather : the window tensors written (all of them) + every DISTINCT panorama row a tap of
+                 some view reads (once) + the index / weight map entries;
+        merge  : the surviving payload elements, counted in whole 32-byte sectors of the
+                 [job][plane][frame][h*w] payload tensors (the smallest unit HBM / L2 move) + the
+                 panorama rows written + the mask + the plan arrays.
+        Frame rings: only (pixel, frame) pairs that are live in the frame table are counted."""
+        SECT = 32
+        per_sect = max(SECT // elem_size, 1)
+        hw, f_len = plan.hw, plan.f_len
+        n_fwin = plan.n_fwin
+        row_bytes_full = P * elem_size                       # one (pixel, frame) atom
+        if plan.d_ftab is None:
+            live_frames = [f_len] * n_fwin                   # frames of frame window s that are written
+            frames_read = plan.F
+        else:
+            ftab = plan.d_ftab.cpu().numpy()
+            live_frames = [int(((ftab >= 0) & (ftab // f_len == s_)).sum()) for s_ in range(n_fwin)]
+            frames_read = f_len                              # a job reads f_len frames of its rows
+        live_total = sum(live_frames)
+        detail = {}
+        if plan.kind == "ring":
+            src = plan.d_src.cpu().numpy()
+            ok = src >= 0
+            j0, nj = self.local_jobs(plan)
+            mine = ok & (src // hw >= j0) & (src // hw < j0 + nj)
+            sectors = np.unique(src[mine] // per_sect).size
+            written = int(mine.sum())
+            pay = sectors * SECT * P * live_total * k
+            out = written * elem_size * P * live_total * k + written * elem_size * P * live_total   # + latent-shaped mask
+            planb = src.size * 4
+            gather = (nj * P * f_len * hw * elem_size                          # windows out
+                      + min(int(ok.sum()), nj * hw) * P * frames_read * elem_size  # panorama pixels read once
+                      + nj * 12)                                                  # window descriptors
+            detail.update(payload_sectors=int(sectors), rows_written=written)
+            return float(gather), float(pay + out + planb), detail
+        vms = plan.extra["vms"]
+        local_views = list(range(self.rank, len(vms), self.world))
+        # ---- gather: distinct panorama pixels touched by this rank's views
+        touched = np.zeros(plan.H * plan.W, bool)
+        taps = 1 if plan.kind == "sphere_nearest" else 4
+        for v in local_views:
+            if taps == 1:
+                touched[vms[v].idx_read] = True
+            else:
+                idx4, wt4 = vms[v].read_taps()
+                touched[idx4[wt4 > 0]] = True
+        n_touched = int(touched.sum())
+        gather = (plan.n_local * P * f_len * hw * elem_size                       # windows out
+                  + n_touched * row_bytes_full * (plan.F if plan.d_ftab is None else min(plan.F, f_len * n_fwin))
+                  + len(local_views) * hw * taps * (4 if taps == 1 else 8))           # maps
+        # ---- merge: surviving payload sectors + rows written + plan
+        host = plan.extra["host_plan"]
+        if plan.kind == "sphere_nearest":
+            dst, src = host
+            sectors = np.unique(src // per_sect).size                             # (view, k // 8): hw % 8 == 0 at these sizes
+            rows = dst.size
+            planb = src.size * 8
+        else:
+            row_dst, row_ptr, ent_src, ent_w = host
+            sectors = np.unique(ent_src // per_sect).size
+            rows = row_dst.size
+            tiled = plan.extra.get("pm_tiled")
+            planb = (tiled[4].numel() * 8 + rows * 8 + tiled[1].numel() * 4) if tiled is not None else ent_src.size * 8 + rows * 8
+        pay = sectors * SECT * P * live_total * k
+        out = rows * row_bytes_full * live_total * k
+        mask = rows * elem_size if plan.d_ftab is None else rows * row_bytes_full * live_total
+        detail.update(payload_sectors=int(sectors), rows_written=int(rows), pano_pixels_read=n_touched,
+                      payload_bytes=float(pay), written_bytes=float(out + mask), plan_bytes=float(planb))
+        return float(gather), float(pay + out + mask + planb), detail
+
     def algorithmic_bytes(self, plan: StepPlan, P: int, elem_size: int, k: int = 2):
         """N*V*s [gather out] + cov*P*s [pano read once] + k*N*V*s [payloads in]
         + k*cov*P*s [pano written once] (+ mask).  Returns (gather_bytes, merge_bytes)."""

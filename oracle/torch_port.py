@@ -173,3 +173,106 @@ def ring_step(lat, den, windows, x_prev, x0, w=64, h=40):
         ring_set(den, x0[n], l, t, 0)
         ring_set(msk, ones, l, t, 0)
     return wins, lat, den, msk
+
+
+class FrameRingSpherePano:
+    """``RingPanoramaLatentProxy`` + ``RingPanoramaTensor`` + ``RingLatentProxy``
+    (ring_panorama_tensor_utils.py:8-337): the panorama lives in a RingLatent in
+    [B, C, F, H, W] order and EVERY get / set first materialises the whole H x W frame window
+    ``[frame_begin, frame_end)`` (slice + cat + clone, :324-337), works on it like SpherePano
+    and -- for sets -- writes the whole window back (B == 1 only, like the reference)."""
+
+    def __init__(self, latent):
+        self.lat = latent.clone()                                      # RingLatent.__init__ (:42)
+        self.C, self.H, self.W = latent.shape[1], latent.shape[-2], latent.shape[-1]
+
+    def latent(self):
+        return self.lat
+
+    def _window(self, fb, fe):                                         # RingLatentProxy.get_window_latent
+        return ring_get(self.lat, 0, 0, fb, self.W, self.H, fe - fb).permute(0, 2, 1, 3, 4)
+
+    def _put_window(self, win, fb):                                    # RingLatentProxy.set_window_latent
+        ring_set(self.lat, win.permute(0, 2, 1, 3, 4), 0, 0, fb)
+
+    def get_nearest(self, fov, theta, phi, width, height, fb, fe):     # :59-78, 201-214
+        op = self._window(fb, fe)
+        pano = op.view(-1, self.C, self.H, self.W)
+        u, v = uv(fov, theta, phi, width, height, self.H, self.W)
+        u0 = torch.floor(u).long() % self.W
+        v0 = torch.clamp(torch.floor(v).long(), 0, self.H - 1)
+        out = pano[:, :, v0, u0].clone()
+        mask = torch.ones_like(u0, dtype=op.dtype)
+        valid = (u >= 0) & (u < self.W) & (v >= 0) & (v < self.H)
+        mask[~valid] = 0
+        out[:, :, ~valid] = 0
+        return out.view(*op.shape[:-3], self.C, height, width).permute(0, 2, 1, 3, 4), mask
+
+    def get_bilinear(self, fov, theta, phi, width, height, fb, fe):    # :31-57
+        op = self._window(fb, fe)
+        pano = op.view(-1, self.C, self.H, self.W)
+        u, v = uv(fov, theta, phi, width, height, self.H, self.W)
+        grid = torch.stack(((u / (self.W - 1)) * 2 - 1, (v / (self.H - 1)) * 2 - 1), dim=-1)
+        grid = grid.unsqueeze(0).repeat(pano.shape[0], 1, 1, 1)
+        out = F.grid_sample(pano, grid, mode="bilinear", padding_mode="border", align_corners=True)
+        return out.view(*op.shape[:-3], self.C, height, width).permute(0, 2, 1, 3, 4).clone()
+
+    def set_nearest(self, view, fov, theta, phi, fb, fe):              # :170-198
+        view = view.permute(0, 2, 1, 3, 4)
+        B = view.shape[0] * view.shape[1]
+        height, width = view.shape[-2:]
+        u, v = uv(fov, theta, phi, width, height, self.H, self.W)
+        ui, vi = torch.floor(u).long(), torch.floor(v).long()
+        valid = ((ui >= 0) & (ui < self.W) & (vi >= 0) & (vi < self.H)).view(-1)
+        lin = (vi * self.W + ui).view(-1)[valid]
+        src = view.reshape(B * self.C, -1)[:, valid]
+        cur = self._window(fb, fe)
+        flat = cur.view(-1, self.C, self.H * self.W).reshape(B * self.C, -1)
+        flat[:, lin] = src
+        self._put_window(flat.reshape(cur.shape), fb)
+
+    def set_bilinear(self, view, fov, theta, phi, fb, fe):             # :107-166
+        view = view.permute(0, 2, 1, 3, 4)
+        B = view.shape[0] * view.shape[1]
+        height, width = view.shape[-2:]
+        vw = view.reshape(B, self.C, -1).clone()
+        u, v = uv(fov, theta, phi, width, height, self.H, self.W)
+        u0, v0 = torch.floor(u).long(), torch.floor(v).long()
+        u1, v1 = (u0 + 1) % self.W, torch.clamp(v0 + 1, 0, self.H - 1)
+        du, dv = (u - u0.float()).view(-1), (v - v0.float()).view(-1)
+        ws = [(1 - du) * (1 - dv), (1 - du) * dv, du * (1 - dv), du * dv]
+        ids = [(v0 * self.W + u0).view(-1), (v1 * self.W + u0).view(-1),
+               (v0 * self.W + u1).view(-1), (v1 * self.W + u1).view(-1)]
+        for b in range(B):
+            cur = self._window(fb, fe)                                 # the whole window, once per frame (:143)
+            acc = torch.zeros_like(cur.view(B, self.C, -1)[b])
+            wsum = torch.zeros_like(acc)
+            for c in range(self.C):
+                for i, w in zip(ids, ws):
+                    acc[c].index_add_(0, i, vw[b, c] * w)
+                for i, w in zip(ids, ws):
+                    wsum[c].index_add_(0, i, w)
+            m = wsum > 0
+            cur.view(B, self.C, -1)[b][m] = acc[m] / wsum[m]
+            self._put_window(cur, fb)
+
+
+def frame_ring_sphere_step(lat, den, frame_begins, frames, views, x_prev, x0, fov=120, width=64, height=40,
+                           mode="nearest"):
+    """gather-all -> merge-all over (frame window, view) jobs in the reference's loop order
+    (i2v_sphere_panorama_pipeline.py:284-476: frame windows outer, views inner), latent-shaped
+    mask (:220).  x_prev / x0: lists of window tensors in job order.
+    Returns (windows, latent, denoised, mask)."""
+    h_lat, h_den, h_msk = FrameRingSpherePano(lat), FrameRingSpherePano(den), FrameRingSpherePano(torch.zeros_like(lat))
+    jobs = [(fb, ph, th) for fb in frame_begins for (ph, th) in views]
+    if mode == "nearest":
+        wins = [h_lat.get_nearest(fov, th, ph, width, height, fb, fb + frames)[0].clone() for (fb, ph, th) in jobs]
+    else:
+        wins = [h_lat.get_bilinear(fov, th, ph, width, height, fb, fb + frames) for (fb, ph, th) in jobs]
+    put = "set_nearest" if mode == "nearest" else "set_bilinear"
+    ones = torch.ones(1, lat.shape[1], frames, height, width, dtype=lat.dtype)
+    for n, (fb, ph, th) in enumerate(jobs):
+        getattr(h_lat, put)(x_prev[n], fov, th, ph, fb, fb + frames)
+        getattr(h_den, put)(x0[n], fov, th, ph, fb, fb + frames)
+        getattr(h_msk, put)(ones, fov, th, ph, fb, fb + frames)
+    return wins, h_lat.latent(), h_den.latent(), h_msk.latent()

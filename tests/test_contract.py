@@ -20,8 +20,11 @@ def test_product_never_imports_the_oracle():
                 assert "/root/reference" not in text, os.path.join(dirpath, f)
     bench = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
     uses = [m.start() for m in re.finditer(r"from oracle import", bench)]
-    assert len(uses) == 1                                   # inside cpu_step_time only
-    assert bench.rfind("def cpu_step_time", 0, uses[0]) > bench.rfind("def run_ours", 0, uses[0])
+    assert len(uses) == 1                                   # inside cpu_one_step (cpu_baseline / --impl reference legs) only
+    assert bench.rfind("def cpu_one_step", 0, uses[0]) > max(bench.rfind(f"def {n}", 0, uses[0])
+                                                               for n in ("run_ours", "parity_check", "make_runner"))
+    body = bench[uses[0]:bench.find("\ndef ", uses[0])]
+    assert "tp." in body and "gather_all" not in body      # the oracle is the thing timed there, never the GPU path
     assert "/root/reference" not in bench
 
 

@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, exchange, out_dir):
+def _worker(rank, world, port, exchange, out_dir, multicast=None, dtype_name="float32", frame_ring=False):
     for p in (ROOT, HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -36,26 +36,34 @@ def _worker(rank, world, port, exchange, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     ok = True
     try:
-        H, W, F, h, w = 64, 128, 16, 20, 32
-        lat0 = torch.from_numpy(randn(3, 1, 4, F, H, W)).to(dev)
+        dtype = getattr(torch, dtype_name)
+        H, W, F, h, w = 64, 128, (32 if frame_ring else 16), 20, 32
+        lat0 = torch.from_numpy(randn(3, 1, 4, F, H, W)).to(dev).to(dtype)
         results = {}
         for mode in ("nearest", "bilinear"):
             ref_st = PanoramaStepper(H, W, F, device=dev)                    # single-GPU reference
             st = PanoramaStepper(H, W, F, device=dev, rank=rank, world=world)
-            ref = ref_st.make_state([lat0, torch.zeros_like(lat0)], mask=torch.zeros(1, H, W, device=dev))
-            state = st.make_state([lat0, torch.zeros_like(lat0)], mask=torch.zeros(1, H, W, device=dev),
-                                  peer=(exchange == "peer"))
+            if multicast is not None:
+                st.use_multicast = multicast
+            mk_mask = (lambda: torch.zeros_like(lat0)) if frame_ring else (lambda: torch.zeros(1, H, W, device=dev, dtype=dtype))
+            ref = ref_st.make_state([lat0, torch.zeros_like(lat0)], mask=mk_mask())
+            state = st.make_state([lat0, torch.zeros_like(lat0)], mask=mk_mask(), peer=(exchange == "peer"))
             assert (state.peer_table is not None) == (exchange == "peer")
+            if exchange == "peer" and multicast is not None:
+                assert state.multicast == multicast, "NVLS multicast alias not available / not honoured"
+            fkw = {}
             for i in range(4):
-                views = geo.sphere_views(i)[:13]                              # 13 views dealt round-robin: 7 + 6
-                plan_ref = ref_st.plan_sphere(views, w, h, fov=120, mode=mode)
-                plan = st.plan_sphere(views, w, h, fov=120, mode=mode)
+                views = geo.sphere_views(i)[:13]                              # 13 views dealt round-robin
+                if frame_ring:                                                # wrapping frame windows (temporal loop)
+                    fkw = dict(frame_begins=[(5 * i + 12 * s_) % F for s_ in range(3)], frames=16)
+                plan_ref = ref_st.plan_sphere(views, w, h, fov=120, mode=mode, **fkw)
+                plan = st.plan_sphere(views, w, h, fov=120, mode=mode, **fkw)
                 wins_all = ref_st.gather_all(ref, plan_ref)
                 ids = torch.tensor(plan.job_ids, device=dev)                  # this rank's jobs, global numbering
                 assert len(plan.job_ids) == plan.n_local == st.local_jobs(plan)[1]
                 wins = st.gather_all(state, plan)
                 assert torch.equal(wins, wins_all[ids]), (mode, i)
-                xp, x0 = wins_all * 0.5 + (i + 1), wins_all * 0.25 - (i + 1)
+                xp, x0 = (wins_all * 0.5 + (i + 1)).to(dtype), (wins_all * 0.25 - (i + 1)).to(dtype)
                 ref_st.merge_all(ref, [xp, x0], plan_ref)
                 st.merge_all(state, [xp[ids].contiguous(), x0[ids].contiguous()], plan)
             if exchange == "peer":
@@ -63,7 +71,7 @@ def _worker(rank, world, port, exchange, out_dir):
                 from dynamicscaler_b200.step import ddim_coefficients
                 coef = ddim_coefficients(0.5, 0.55, 0.1, 0.70710677, 7.5)
                 gen = torch.Generator(device=dev).manual_seed(11)
-                ec, eu, nz = (torch.randn(wins_all.shape, device=dev, generator=gen) for _ in range(3))
+                ec, eu, nz = (torch.randn(wins_all.shape, device=dev, generator=gen).to(dtype) for _ in range(3))
                 ref_st.merge_denoised(ref, wins_all, ec, eu, coef, plan_ref, noise=nz)
                 st.merge_denoised(state, wins_all[ids].contiguous(), ec[ids].contiguous(), eu[ids].contiguous(), coef,
                                   plan, noise=nz[ids].contiguous())
@@ -85,18 +93,44 @@ def _worker(rank, world, port, exchange, out_dir):
         os._exit(0 if ok else 1)             # no NCCL teardown (see bench.py)
 
 
-@pytest.mark.parametrize("exchange", ["peer", "allreduce"])
-def test_sharded_step_two_gpus(tmp_path, exchange):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def _run(tmp_path, world, *args):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     import time
-    ctx = mp.spawn(_worker, args=(2, _free_port(), exchange, str(tmp_path)), nprocs=2, join=False)
-    deadline = time.time() + 240
+    ctx = mp.spawn(_worker, args=(world, _free_port(), args[0], str(tmp_path)) + tuple(args[1:]), nprocs=world, join=False)
+    deadline = time.time() + 300
     while not ctx.join(timeout=5):               # join() returns after the first exit; loop until all are done
         if time.time() > deadline:
             for p in ctx.processes:
                 p.kill()
-            pytest.fail("multi-GPU workers did not finish in 240 s")
-    for r in range(2):
+            pytest.fail("multi-GPU workers did not finish in 300 s")
+    for r in range(world):
         assert np.load(tmp_path / f"rank{r}.npy")[0], f"rank {r} mismatch"
+
+
+@pytest.mark.parametrize("exchange", ["peer", "allreduce"])
+def test_sharded_step_two_gpus(tmp_path, exchange):
+    _run(tmp_path, 2, exchange)
+
+
+# Every transport of the fused exchange at every world size the box offers: per-replica TMA row copies
+# (multicast off) and NVLS multimem.st stores (multicast on), fp32 and bf16 rows, whole-row and
+# frame-ring (per-atom) stores -- each bit-identical to the single-GPU result on every rank.
+CASES = [  # (world, multicast, dtype, frame_ring) -- every transport at 2 GPUs, the wide ones where they are the default
+    (2, False, "float32", False), (2, True, "float32", False), (2, False, "float32", True), (2, True, "float32", True),
+    (2, True, "bfloat16", False), (2, False, "bfloat16", True),
+    (4, True, "float32", False), (4, False, "float32", False), (4, True, "bfloat16", True),
+    (8, True, "float32", False), (8, False, "float32", True), (8, True, "bfloat16", False),
+]
+
+
+@pytest.mark.parametrize("world,multicast,dtype_name,frame_ring", CASES,
+                         ids=[f"w{w}-{'nvls' if m else 'p2p'}-{d}-{'framering' if f else 'rows'}" for w, m, d, f in CASES])
+def test_peer_exchange_transports(tmp_path, world, multicast, dtype_name, frame_ring):
+    _run(tmp_path, world, "peer", multicast, dtype_name, frame_ring)
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_allreduce_fallback_wide(tmp_path, world):
+    _run(tmp_path, world, "allreduce")

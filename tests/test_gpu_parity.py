@@ -19,7 +19,8 @@ BF16_TOL = 1e-2          # ... 1e-2 in bf16
 def dev():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     from dynamicscaler_b200 import lib
-    assert lib.ds_abi_version() == 3          # the CUDA extension must be the thing that runs
+    from dynamicscaler_b200 import _lib
+    assert lib.ds_abi_version() == _lib.ABI_VERSION          # the CUDA extension must be the thing that runs
     return torch.device("cuda:0")
 
 
