@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libdynscaler_sm100.so")
 DS_F32, DS_BF16 = 0, 1
 DS_MASK_NONE, DS_MASK_PLANE, DS_MASK_FULL = 0, 1, 2
 DS_MAX_PAYLOADS = 4
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -40,10 +40,11 @@ PROTOTYPES = {
     "ds_pm_merge_bilinear": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_pm_merge_bilinear_tiled": [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_mix_mask": [_vp, _vp, _vp, _vp, _f, _f, _ll, _i, _i, _vp],
-    "ds_pm_merge_nearest_ddim": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i,
-                                 _i, _i, _i, _i, _i, _vp, _i, _vp],
-    "ds_pm_merge_bilinear_tiled_ddim": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp,
-                                        _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "ds_pm_merge_nearest_ddim": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i,
+                                 _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "ds_pm_merge_bilinear_tiled_ddim": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _i,
+                                        _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "ds_pm_gather_renoise": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_resize_planes": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_select_merged": [_vp, _vp, _vp, _ll, _ll, _ll, _i, _vp],
 }

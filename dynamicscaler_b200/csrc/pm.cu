@@ -101,6 +101,18 @@ template <> __device__ __forceinline__ uint2 atom_ones<__nv_bfloat16>() { return
 
 template <typename A> __device__ __forceinline__ A ldg_atom(const A* p) { return __ldg(p); }
 
+// mix_latents_with_mask on one element, every op rounded on its own and -- like the reference's
+// elementwise tensor ops -- in the tensor dtype T.
+template <typename T>
+__device__ __forceinline__ float pm_mix1(float l1, float add, float m, float r, float omr) {
+  auto rt = [](float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); };
+  const float a = rt(__fmul_rn(l1, omr));
+  const float b = rt(__fmul_rn(add, r));
+  const float mixed = rt(__fadd_rn(a, b));
+  const float keep = rt(__fmul_rn(l1, rt(__fsub_rn(1.0f, m))));
+  return rt(__fadd_rn(keep, rt(__fmul_rn(mixed, m))));
+}
+
 // ------------------------------------------- programmatic dependent launch (PDL) ----
 // The gather / merge kernels of consecutive steps form a chain of 10-20 us kernels; with PDL the
 // next kernel's CTAs are scheduled while the current one drains, run their prologue (plan / map
@@ -449,6 +461,139 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
   if (PIPE && in_flight) bulk_wait_read();      // shared memory must outlive the last copy
 }
 
+// -------------------------------------------------- gather + re-noise + mask mix ----
+// The sequential / grouped regime of the reference loop reads, per view, the latent AND the
+// denoised-mask panorama and blends a re-noised copy of the window into the already-denoised
+// part (t2v_sphere_panorama_pipeline.py:194-221, i2v_...:330-365):
+//   view   = get_view_tensor_no_interpolate(latent)                 panorama_tensor_utils.py:53-70
+//   m      = get_view_tensor_no_interpolate(mask panorama)          (nearest read, same map family)
+//   noised = c * view + s * eps                                      pipeline/scheduler.py:98-110
+//   out    = mix_latents_with_mask(view, noised, m, ratio)          utils/tensor_utils.py:19-39
+// One launch does all four for every job of the group.  eps is INJECTED (window layout; the
+// reference draws randn_like inside re_noise -- SURVEY Q6).  Optional extra outputs, both needed by
+// the merge prologue (PmDdim::prev / mview): out_raw = the unmixed view (view_latent_prev_denoise),
+// out_mask = m ([job][hw] for the [1,H,W] T2V mask plane, window layout for the I2V mask).
+// Every elementwise op is rounded on its own in T, like the reference's tensor ops.
+struct PmRenoiseArgs {
+  const void* eps;
+  const void* mask;              // MM == DS_MASK_PLANE: [H*W] elements; DS_MASK_FULL: pixel-major panorama
+  void* out_raw;                 // or NULL
+  void* out_mask;                // or NULL
+  float c, s, r, omr;
+};
+
+// One pass = one quantity through the [plane*f_len + fo][k] shared tile and out to `dst`.
+// WHAT: 0 mixed window, 1 raw window, 2 mask view (DS_MASK_FULL only).
+template <typename T, int MM, int WHAT>
+__device__ __forceinline__ void pm_renoise_pass(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ dst,
+                                                const int32_t* s_idx, const int32_t* s_midx, T* tile,
+                                                const PmGatherArgs& a, const PmRenoiseArgs& e, int job, int k0, int f0) {
+  using A = typename Atom<T>::type;
+  constexpr int VE = 16 / sizeof(T);
+  constexpr int S = kPmKT + VE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kgl = lane >> 3, fl = lane & 7;
+  const int f_len = a.f_len, R = kPmPlanes * f_len;
+  const int n_fblk = (f_len + 7) >> 3;
+  const int n_it = (kPmKT / 16) * n_fblk;
+  auto rt = [](float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); };
+  for (int it = warp; it < n_it; it += kWarps) {
+    const int kgb = it / n_fblk, fb = it - kgb * n_fblk;
+    const int kl = (kgb * 4 + kgl) * 4;
+    const int fo = fb * 8 + fl;
+    if (fo >= f_len || k0 + kl >= a.hw) continue;
+    int f = f0 + fo;
+    f = f >= a.F ? f - a.F : f;
+    float val[4][4];                                            // [pixel j][plane p]
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + kl + j;
+      if (k >= a.hw) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) val[j][p] = 0.f;
+        continue;
+      }
+      float x[4], m[4];
+      if (WHAT != 2) Atom<T>::unpack(ldg_atom(pm + static_cast<size_t>(s_idx[kl + j]) * a.F + f), x);
+      if (WHAT != 1) {
+        if (MM == DS_MASK_PLANE) {
+          const float mp = Elem<T>::to_f(ldg(static_cast<const T*>(e.mask) + s_midx[kl + j]));
+          m[0] = m[1] = m[2] = m[3] = mp;
+        } else {
+          Atom<T>::unpack(ldg_atom(static_cast<const A*>(e.mask) + static_cast<size_t>(s_midx[kl + j]) * a.F + f), m);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        if (WHAT == 1) {
+          val[j][p] = x[p];
+        } else if (WHAT == 2) {
+          val[j][p] = m[p];
+        } else {
+          const float ep = Elem<T>::to_f(ldg(static_cast<const T*>(e.eps) +
+                                             (static_cast<size_t>(job) * R + p * f_len + fo) * a.hw + k));
+          const float noised = rt(__fadd_rn(rt(__fmul_rn(e.c, x[p])), rt(__fmul_rn(e.s, ep))));
+          val[j][p] = pm_mix1<T>(x[p], noised, m[p], e.r, e.omr);
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const T col[4] = {Elem<T>::from_f(val[0][p]), Elem<T>::from_f(val[1][p]), Elem<T>::from_f(val[2][p]),
+                        Elem<T>::from_f(val[3][p])};
+      *reinterpret_cast<A*>(tile + (p * f_len + fo) * S + kl) = atom_join<T>(col);
+    }
+  }
+  __syncthreads();
+  // tile rows -> window tensor (plain coalesced stores: this is the small-group path)
+  T* __restrict__ o = dst + static_cast<size_t>(job) * R * a.hw + k0;
+  const int kt = min(kPmKT, a.hw - k0);
+  for (int u = threadIdx.x; u < R * kPmKT; u += kBlock) {
+    const int row = u / kPmKT, c = u - row * kPmKT;
+    if (c < kt) o[static_cast<size_t>(row) * a.hw + c] = tile[row * S + c];
+  }
+  __syncthreads();
+}
+
+template <typename T, int MM>
+__global__ void __launch_bounds__(kBlock)
+pm_gather_renoise_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ out,
+                         const int32_t* __restrict__ d_idx, const int32_t* __restrict__ d_midx,
+                         const int32_t* __restrict__ d_jobs, int h_f0, PmGatherArgs a, PmRenoiseArgs e,
+                         ds_peer_table_t* __restrict__ peer, long long peer_timeout_ns) {
+  constexpr int VE = 16 / sizeof(T);
+  constexpr int S = kPmKT + VE;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int R = kPmPlanes * a.f_len;
+  T* tile = reinterpret_cast<T*>(smem_raw);                                   // [R][S]
+  int32_t* s_idx = reinterpret_cast<int32_t*>(tile + R * S);                  // [KT] latent map
+  int32_t* s_midx = s_idx + kPmKT;                                            // [KT] mask map
+  if (peer != nullptr) pm_peer_spin(peer, peer->merges_done, -1, peer->my_merges, peer_timeout_ns);
+  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int job = t / a.tiles_per_job;
+    const int k0 = (t - job * a.tiles_per_job) * kPmKT;
+    int map = job, f0 = h_f0;
+    if (d_jobs != nullptr) {
+      map = __ldg(d_jobs + 2 * job);
+      f0 = __ldg(d_jobs + 2 * job + 1);
+    }
+    f0 %= a.F;
+    if (threadIdx.x < kPmKT) {
+      const int k = min(k0 + static_cast<int>(threadIdx.x), a.hw - 1);
+      s_idx[threadIdx.x] = __ldg(d_idx + static_cast<size_t>(map) * a.hw + k);
+      s_midx[threadIdx.x] = __ldg(d_midx + static_cast<size_t>(map) * a.hw + k);
+    }
+    __syncthreads();
+    if (MM == DS_MASK_PLANE && e.out_mask != nullptr && threadIdx.x < kPmKT && k0 + threadIdx.x < a.hw)
+      static_cast<T*>(e.out_mask)[static_cast<size_t>(job) * a.hw + k0 + threadIdx.x] =
+          ldg(static_cast<const T*>(e.mask) + s_midx[threadIdx.x]);
+    pm_renoise_pass<T, MM, 0>(pm, out, s_idx, s_midx, tile, a, e, job, k0, f0);
+    if (e.out_raw != nullptr) pm_renoise_pass<T, MM, 1>(pm, static_cast<T*>(e.out_raw), s_idx, s_midx, tile, a, e, job, k0, f0);
+    if (MM == DS_MASK_FULL && e.out_mask != nullptr)
+      pm_renoise_pass<T, MM, 2>(pm, static_cast<T*>(e.out_mask), s_idx, s_midx, tile, a, e, job, k0, f0);
+  }
+}
+
 // ------------------------------------------------------------------------ merges ----
 // Fused denoise epilogue (DD kernels): the two payloads are not read but computed, per surviving
 // element only, from the window latent x and the UNet output(s), exactly like the reference's
@@ -461,7 +606,18 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
 // pm[0] receives x_prev (latent panorama), pm[1] pred_x0 (denoised panorama).
 struct PmDdim {
   float sa, s1m, sp, sd, sig, g;
+  // merge_prev_denoised_ratio mix that precedes the latent set in the I2V loop
+  // (i2v_sphere_panorama_pipeline.py:430-435, :938-943):
+  //   x_prev <- mix_latents_with_mask(x_prev, prev, m, r)      utils/tensor_utils.py:19-39
+  // prev  = the window as gathered (view_latent_prev_denoise, :345), window layout like x;
+  // mview = the denoised-mask view read at gather time (:347-355): [job][hw] (mview_full == 0,
+  //         T2V plane mask) or window layout (mview_full == 1, I2V latent-shaped mask).
+  const void* prev;
+  const void* mview;
+  int mview_full;
+  float mr, momr;                // mix ratio r and (1 - r), formed in double on the host like the reference
 };
+
 template <typename T>
 __device__ __forceinline__ void pm_ddim(const PmDdim& c, const T (&x)[4], const T (&ec)[4], const T (&eu)[4],
                                         const T (&nz)[4], bool has_eu, bool has_nz, float (&x_prev)[4],
@@ -478,6 +634,25 @@ __device__ __forceinline__ void pm_ddim(const PmDdim& c, const T (&x)[4], const 
     if (has_nz) xp = __fadd_rn(xp, __fmul_rn(c.sig, Elem<T>::to_f(nz[p])));
     pred_x0[p] = x0;
     x_prev[p] = xp;
+  }
+}
+
+// x_prev (4 planes of one window element) <- mix(x_prev, prev, mask view, r).  o = element offset of
+// (job, plane 0, frame fo, k) in window layout, o0 = the same for frame 0 (job*4*plane_stride + k).
+template <typename T>
+__device__ __forceinline__ void pm_prev_mix(const PmDdim& c, int o, int o0, int plane_stride, int hw, float (&xp)[4]) {
+  const T* __restrict__ prev = static_cast<const T*>(c.prev);
+  const T* __restrict__ mv = static_cast<const T*>(c.mview);
+  float m_plane = 0.f;
+  if (!c.mview_full) {                           // [job][hw]: job = o0 / (4*plane_stride), k = o0 mod plane_stride mod hw
+    const int job = o0 / (kPmPlanes * plane_stride), k = o0 - job * kPmPlanes * plane_stride;
+    m_plane = Elem<T>::to_f(ldg(mv + job * hw + k));
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float m = c.mview_full ? Elem<T>::to_f(ldg(mv + o + p * plane_stride)) : m_plane;
+    const float l1 = Elem<T>::to_f(Elem<T>::from_f(xp[p]));     // the reference mixes the rounded x_prev tensor
+    xp[p] = pm_mix1<T>(l1, Elem<T>::to_f(ldg(prev + o + p * plane_stride)), m, c.mr, c.momr);
   }
 }
 
@@ -677,6 +852,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
           if (live[u]) {
             float xp[4], x0[4];
             pm_ddim<T>(a.dd, x[u], ec[u], eu[u], nz[u], has_eu, has_nz, xp, x0);
+            if (a.dd.prev != nullptr) pm_prev_mix<T>(a.dd, (f0 + u) * a.hw + off, off, plane_stride, a.hw, xp);
             tile[(0 * kPmET + lane) * SA + f0 + u] = Atom<T>::pack(xp);
             tile[(1 * kPmET + lane) * SA + f0 + u] = Atom<T>::pack(x0);
           }
@@ -841,6 +1017,8 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
         if (k[h] >= 0 && liveA[j]) {
           float xp[4], x0[4];
           pm_ddim<T>(a.dd, x[j], ec[j], eu[j], nz[j], has_eu, has_nz, xp, x0);
+          if (a.dd.prev != nullptr)
+            pm_prev_mix<T>(a.dd, job_off + (warp + j * kWarps) * a.hw + k[h], job_off + k[h], plane_stride, a.hw, xp);
           // the reference merges the ROUNDED payload tensors: round to T before the weighting
           const int e = h * 32 + lane, fo = warp + j * kWarps;
           prod[(0 * kPmEC + e) * SA + fo] = make_float4(
@@ -1164,6 +1342,39 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   return DS_OK;
 }
 
+extern "C" int ds_pm_gather_renoise(const void* pm, void* out, void* out_raw, void* out_mask, const void* eps,
+                                    const void* mask, int mask_mode, const int32_t* d_idx, const int32_t* d_midx,
+                                    const float* h_coef, const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F,
+                                    int HW, int f_len, int hw, void* d_peer, int dtype, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(pm != nullptr && eps != nullptr && mask != nullptr && d_idx != nullptr && d_midx != nullptr &&
+             h_coef != nullptr && (out != nullptr || n_jobs == 0), DS_ERR_NULL);
+  DS_REQUIRE(mask_mode == DS_MASK_PLANE || mask_mode == DS_MASK_FULL, DS_ERR_DIM);
+  DS_REQUIRE(P == kPmPlanes, DS_ERR_DIM);
+  DS_REQUIRE(n_jobs >= 0 && F > 0 && HW > 0 && f_len > 0 && f_len <= F && hw > 0 && h_f0 >= 0, DS_ERR_DIM);
+  DS_REQUIRE(n_jobs > 0 || d_peer != nullptr, DS_ERR_DIM);
+  DS_REQUIRE(pm_aligned16(pm) && (mask_mode != DS_MASK_FULL || pm_aligned16(mask)), DS_ERR_ALIGN);
+  const int tpj = static_cast<int>(div_up(hw, kPmKT));
+  const long long n_tiles = static_cast<long long>(n_jobs) * tpj;
+  DS_REQUIRE(n_tiles < (1ll << 31) && static_cast<long long>(n_jobs) * P * f_len * hw < (1ll << 40), DS_ERR_DIM);
+  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj, 6, kPmKT, 1};
+  PmRenoiseArgs e{eps, mask, out_raw, out_mask, h_coef[0], h_coef[1], h_coef[2], h_coef[3]};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DS_DISPATCH_DTYPE(dtype, {
+    constexpr int VE = 16 / sizeof(ET);
+    const size_t smem = static_cast<size_t>(kPmPlanes) * f_len * (kPmKT + VE) * sizeof(ET) + 2 * kPmKT * sizeof(int32_t);
+    using AT = typename Atom<ET>::type;
+    if (mask_mode == DS_MASK_PLANE)
+      return pm_launch(pm_gather_renoise_kernel<ET, DS_MASK_PLANE>, 0, n_tiles, 0, 1, smem, st, static_cast<const AT*>(pm),
+                       static_cast<ET*>(out), d_idx, d_midx, d_jobs, h_f0, a, e, static_cast<ds_peer_table_t*>(d_peer),
+                       g_peer_timeout_ns);
+    return pm_launch(pm_gather_renoise_kernel<ET, DS_MASK_FULL>, 0, n_tiles, 0, 1, smem, st, static_cast<const AT*>(pm),
+                     static_cast<ET*>(out), d_idx, d_midx, d_jobs, h_f0, a, e, static_cast<ds_peer_table_t*>(d_peer),
+                     g_peer_timeout_ns);
+  });
+  return DS_OK;
+}
+
 extern "C" int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payloads, int Q,
                                    void* mask, int mask_mode, const int32_t* d_view_ptr,
                                    const int32_t* d_ent_src, const int32_t* d_ent_dst, int n_ent,
@@ -1244,7 +1455,8 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
 // Shared argument handling of the two fused-denoise entry points: panoramas 0 / 1 receive
 // x_prev / pred_x0; payload slots carry x, eps_cond, eps_uncond (or NULL), noise (or NULL).
 static int pm_fill_ddim_args(ds::PmMergeArgs& a, void* const* h_pms, const void* x, const void* eps_cond,
-                             const void* eps_uncond, const void* noise, const float* h_coef, void* mask, int mask_mode,
+                             const void* eps_uncond, const void* noise, const void* prev, const void* mask_view,
+                             int mask_view_full, const float* h_coef, void* mask, int mask_mode,
                              int n_ent, const int32_t* d_ftab, const int32_t* d_fbegin, int n_fwin, int vpf,
                              int job_begin, int job_count, int P, int F, int HW, int f_len, int hw, void* d_peer) {
   using namespace ds;
@@ -1255,13 +1467,16 @@ static int pm_fill_ddim_args(ds::PmMergeArgs& a, void* const* h_pms, const void*
   if (rc != DS_OK) return rc;
   a.pay[2] = eps_uncond;
   a.pay[3] = noise;
-  a.dd = PmDdim{h_coef[0], h_coef[1], h_coef[2], h_coef[3], h_coef[4], h_coef[5]};
+  DS_REQUIRE((prev == nullptr) == (mask_view == nullptr), DS_ERR_NULL);
+  a.dd = PmDdim{h_coef[0], h_coef[1], h_coef[2], h_coef[3], h_coef[4], h_coef[5], prev, mask_view,
+                mask_view_full ? 1 : 0, h_coef[6], h_coef[7]};
   DS_REQUIRE(a.dd.sa != 0.f, DS_ERR_DIM);
   return DS_OK;
 }
 
 extern "C" int ds_pm_merge_nearest_ddim(void* const* h_pms, const void* x, const void* eps_cond, const void* eps_uncond,
-                                        const void* noise, const float* h_coef, void* mask, int mask_mode,
+                                        const void* noise, const void* prev, const void* mask_view, int mask_view_full,
+                                        const float* h_coef, void* mask, int mask_mode,
                                         const int32_t* d_view_ptr, const int32_t* d_ent_src,
                                         const int32_t* d_ent_dst, int n_ent, const int32_t* d_ftab,
                                         const int32_t* d_fbegin, int n_fwin, int views_per_fwin, int job_begin,
@@ -1269,7 +1484,7 @@ extern "C" int ds_pm_merge_nearest_ddim(void* const* h_pms, const void* x, const
                                         int dtype, void* stream) {
   using namespace ds;
   PmMergeArgs a;
-  int rc = pm_fill_ddim_args(a, h_pms, x, eps_cond, eps_uncond, noise, h_coef, mask, mask_mode, n_ent, d_ftab, d_fbegin,
+  int rc = pm_fill_ddim_args(a, h_pms, x, eps_cond, eps_uncond, noise, prev, mask_view, mask_view_full, h_coef, mask, mask_mode, n_ent, d_ftab, d_fbegin,
                              n_fwin, views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, d_peer);
   if (rc != DS_OK) return rc;
   DS_REQUIRE(d_view_ptr != nullptr && d_ent_src != nullptr && d_ent_dst != nullptr, DS_ERR_NULL);
@@ -1286,7 +1501,8 @@ extern "C" int ds_pm_merge_nearest_ddim(void* const* h_pms, const void* x, const
 }
 
 extern "C" int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x, const void* eps_cond,
-                                               const void* eps_uncond, const void* noise, const float* h_coef,
+                                               const void* eps_uncond, const void* noise, const void* prev,
+                                               const void* mask_view, int mask_view_full, const float* h_coef,
                                                void* mask, int mask_mode, const int32_t* d_view_ptr,
                                                const int32_t* d_tile, int n_tiles, const int32_t* d_row_dst,
                                                const int32_t* d_row_start, int n_rows, const int32_t* d_ent_k,
@@ -1296,7 +1512,7 @@ extern "C" int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x
                                                void* stream) {
   using namespace ds;
   PmMergeArgs a;
-  int rc = pm_fill_ddim_args(a, h_pms, x, eps_cond, eps_uncond, noise, h_coef, mask, mask_mode, n_rows, d_ftab, d_fbegin,
+  int rc = pm_fill_ddim_args(a, h_pms, x, eps_cond, eps_uncond, noise, prev, mask_view, mask_view_full, h_coef, mask, mask_mode, n_rows, d_ftab, d_fbegin,
                              n_fwin, views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, d_peer);
   if (rc != DS_OK) return rc;
   DS_REQUIRE(d_view_ptr != nullptr && d_tile != nullptr && d_row_dst != nullptr && d_row_start != nullptr &&

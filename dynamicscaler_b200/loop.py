@@ -1,0 +1,147 @@
+"""Denoising-loop driver over the resident panorama state (VERDICT row N1):
+the reference's DDIM loop (pipeline/t2v_sphere_panorama_pipeline.py:166-293, I2V twin
+pipeline/i2v_sphere_panorama_pipeline.py:232-476) with the UNet -- the reference's own torch module,
+untouched -- BATCHED over the windows of a group, and everything either side of it fused into two
+launches per group:
+
+    gather  (+ mask read + re_noise + mask mix)            ds_pm_gather / ds_pm_gather_renoise
+    UNet    model(x[n, C, f, h, w], timesteps of length n*f, ...)   one call for the whole group (P9)
+    merge   (CFG combine + ddim_step + merge_prev mix + latent / denoised / mask sets)
+                                                           ds_pm_merge_*_ddim
+
+``group_size``: how many consecutive windows are read before any of them is written back.
+``None`` = the whole step (the batched order BASELINE.json config 3 shards over GPUs); ``1`` = the
+reference's own sequential order, reproduced bit for bit (tests/golden/loop.npz comes from the real
+``basic_sample_shift_shpere_panorama``).  With ``stepper.world > 1`` the views of every group are dealt
+round-robin over the ranks, each rank runs the UNet on its own windows only, and the merge kernels
+push the surviving rows into every replica (step.py).
+
+The model is called exactly like the reference calls ``self.pretrained_t2v.model`` (:236-254):
+``model(x, ts, c_crossattn=[ctx], fps=fps, curr_time_steps=ts, temporal_length=frames, **kwargs)``.
+``UNetModel.forward`` with a batch of b > 1 windows needs ``timesteps`` of length b*t, not b
+(lvdm/modules/networks/openaimodel3d.py:667-682: the time embedding is not repeated over t), so the
+driver passes ``ts`` of length n*frames for n > 1 and of length n for a single window, as the reference does.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from .step import PanoramaState, PanoramaStepper, ddim_coefficients, renoise_coefficients
+
+
+def _get(schedule, name):
+    return schedule[name] if isinstance(schedule, dict) else getattr(schedule, name)
+
+
+def unet_eval(model: Callable, x: torch.Tensor, t: int, cond: dict, frames: int, model_kwargs: Optional[dict] = None,
+              uncond: Optional[dict] = None, cfg_batch: bool = True):
+    """Run the UNet on ``x`` [n, C, f, h, w] for the conditional and (if ``uncond`` is given) the
+    unconditional branch.  ``cond`` / ``uncond``: the reference's dicts ``{"c_crossattn": [emb], "fps": fps}``
+    with ``emb`` [1 or n, L, D].  ``cfg_batch``: evaluate both branches as ONE batch of 2n windows.
+    Returns (eps_cond, eps_uncond or None), each [n, C, f, h, w] contiguous."""
+    n = x.shape[0]
+    kwargs = dict(model_kwargs or {})
+
+    def ctx_of(c):
+        emb = torch.cat(c["c_crossattn"], dim=1)
+        return emb.expand(n, -1, -1) if emb.shape[0] == 1 and n > 1 else emb
+
+    def call(xx, ctx, fps):
+        b = xx.shape[0]
+        ts = torch.full((b * frames if b > 1 else b,), int(t), device=xx.device, dtype=torch.long)
+        return model(xx, ts, c_crossattn=[ctx], fps=fps, curr_time_steps=ts, temporal_length=frames, **kwargs)
+
+    if uncond is None:
+        return call(x, ctx_of(cond), cond.get("fps", 16)).contiguous(), None
+    if cfg_batch:
+        y = call(torch.cat([x, x], dim=0), torch.cat([ctx_of(cond), ctx_of(uncond)], dim=0), cond.get("fps", 16))
+        return y[:n].contiguous(), y[n:].contiguous()
+    return (call(x, ctx_of(cond), cond.get("fps", 16)).contiguous(),
+            call(x, ctx_of(uncond), uncond.get("fps", 16)).contiguous())
+
+
+def sphere_denoise_step(stepper: PanoramaStepper, state: PanoramaState, views: Sequence, width: int, height: int, *,
+                        model: Callable, t: int, step_i: int, schedule, cond: dict, uncond: Optional[dict],
+                        guidance_scale: float, frames: int, fov=120, group_size: Optional[int] = None,
+                        renoise_ratio: Optional[float] = None, prev_ratio: Optional[float] = None,
+                        eps_fn: Optional[Callable] = None, noise_fn: Optional[Callable] = None,
+                        model_kwargs: Optional[dict] = None, cfg_batch: bool = True, frame_begins=None,
+                        on_input: Optional[Callable] = None):
+    """One DDIM step i over ``views`` (ordered (phi, theta) list of the step).  ``schedule``: object or
+    dict with the reference scheduler's ``ddim_timesteps, alphas_cumprod, ddim_alphas, ddim_alphas_prev,
+    ddim_sigmas, ddim_sqrt_one_minus_alphas`` (pipeline/scheduler.py:17-57).  ``eps_fn(step_i, job_ids,
+    shape, device)`` supplies the re_noise epsilon, ``noise_fn`` the ddim noise when sigma > 0 (the
+    reference draws them from the global RNG).  ``on_input(step_i, job_ids, x)``: observer of
+    the model inputs (tests)."""
+    total = len(_get(schedule, "ddim_timesteps"))
+    index = total - step_i - 1                                          # t2v_sphere_panorama_pipeline.py:263
+    coef = ddim_coefficients(_get(schedule, "ddim_alphas")[index], _get(schedule, "ddim_alphas_prev")[index],
+                             _get(schedule, "ddim_sigmas")[index], _get(schedule, "ddim_sqrt_one_minus_alphas")[index],
+                             guidance_scale if uncond is not None else 1.0)
+    sigma = float(_get(schedule, "ddim_sigmas")[index])
+    mixing = step_i < total - 1                                         # :212, i2v :430
+    use_renoise = renoise_ratio is not None and mixing
+    use_prev = prev_ratio is not None and mixing
+    if use_renoise or use_prev:
+        assert eps_fn is not None or not use_renoise, "re_noise needs an epsilon source (eps_fn)"
+        rc, rs = renoise_coefficients(_get(schedule, "alphas_cumprod"), _get(schedule, "ddim_timesteps"),
+                                      total - step_i - 2, total - step_i - 1) if use_renoise else (1.0, 0.0)
+    state.reset_mask()                                                  # :173 fresh mask panorama every step
+    gs = len(views) if group_size is None else int(group_size)
+    fkw = {} if frame_begins is None else dict(frame_begins=frame_begins, frames=frames)
+    for g0 in range(0, len(views), gs):
+        plan = stepper.plan_sphere(list(views[g0:g0 + gs]), width, height, fov=fov, mode="nearest", **fkw)
+        n_fw = plan.n_fwin
+        job_ids = [(j // len(plan.extra["vms"])) * len(views) + g0 + j % len(plan.extra["vms"]) for j in plan.job_ids] \
+            if n_fw > 1 else [g0 + j for j in plan.job_ids]            # indices in the step's ordered job list
+        raw = mview = None
+        if use_renoise or use_prev:
+            shape = (plan.n_local, state.shape[0], state.shape[1], plan.f_len, plan.h, plan.w)
+            eps = eps_fn(step_i, job_ids, shape, state.device) if use_renoise else \
+                torch.zeros(shape, dtype=state.dtype, device=state.device)
+            x, raw, mview = stepper.gather_all(state, plan, renoise=dict(
+                eps=eps.contiguous(), c=rc, s=rs, ratio=renoise_ratio if use_renoise else 0.0,
+                want_raw=use_prev, want_mask=use_prev))
+        else:
+            x = stepper.gather_all(state, plan)
+        n = x.shape[0]
+        if n > 0:
+            xb = x.view(n * x.shape[1], *x.shape[2:])                   # [n*B, C, f, h, w]; B == 1 in every pipeline
+            if on_input is not None:
+                on_input(step_i, job_ids, xb)
+            ec, eu = unet_eval(model, xb, t, cond, frames, model_kwargs, uncond, cfg_batch)
+            ec = ec.view(x.shape)
+            eu = None if eu is None else eu.view(x.shape)
+        else:
+            ec, eu = x, (x if uncond is not None else None)
+        noise = noise_fn(step_i, job_ids, tuple(x.shape), state.device) if (noise_fn is not None and sigma > 0) else None
+        stepper.merge_denoised(state, x, ec, eu, coef, plan, noise=noise, prev=raw if use_prev else None,
+                               prev_mask=mview if use_prev else None, prev_ratio=prev_ratio if use_prev else None)
+
+
+def sphere_denoise_loop(stepper: PanoramaStepper, state: PanoramaState, *, model: Callable, schedule,
+                        views_fn: Callable, width: int, height: int, frames: int, cond: dict,
+                        uncond: Optional[dict], guidance_scale: float = 7.5, fov=120,
+                        timesteps: Optional[Sequence[int]] = None, group_size: Optional[int] = None,
+                        renoise_ratio: Optional[float] = None, prev_ratio_list: Optional[Sequence[float]] = None,
+                        eps_fn: Optional[Callable] = None, noise_fn: Optional[Callable] = None,
+                        model_kwargs: Optional[dict] = None, cfg_batch: bool = True, frame_begins_fn=None,
+                        on_input: Optional[Callable] = None):
+    """The whole DDIM loop (t2v_sphere_panorama_pipeline.py:164-293): ``timesteps`` defaults to the
+    flipped ``ddim_timesteps`` (:103); ``views_fn(i)`` returns the ordered (phi, theta) list of step i
+    (``geometry.sphere_views``).  The state's panorama 0 / 1 end up holding the final latents / the
+    denoised prediction (:295-296)."""
+    ddim_ts = [int(v) for v in _get(schedule, "ddim_timesteps")]
+    timesteps = list(reversed(ddim_ts)) if timesteps is None else list(timesteps)
+    kwargs = dict(model_kwargs or {})
+    kwargs.setdefault("clean_cond", True)                               # :232
+    for i, t in enumerate(timesteps):
+        sphere_denoise_step(stepper, state, views_fn(i), width, height, model=model, t=t, step_i=i, schedule=schedule,
+                            cond=cond, uncond=uncond, guidance_scale=guidance_scale, frames=frames, fov=fov,
+                            group_size=group_size, renoise_ratio=renoise_ratio,
+                            prev_ratio=None if prev_ratio_list is None else prev_ratio_list[i], eps_fn=eps_fn,
+                            noise_fn=noise_fn, model_kwargs=kwargs, cfg_batch=cfg_batch,
+                            frame_begins=None if frame_begins_fn is None else frame_begins_fn(i), on_input=on_input)
+    return state

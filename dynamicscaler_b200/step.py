@@ -49,6 +49,15 @@ def ddim_coefficients(alpha_t, alpha_prev, sigma_t, sqrt_one_minus_alpha_t, guid
     return (float(a_t.sqrt()), float(s1m), float(a_prev.sqrt()), float(sd), float(sig), float(f(guidance_scale)))
 
 
+def renoise_coefficients(alphas_cumprod, ddim_timesteps, step_a: int, step_b: int):
+    """float32 scalars (c, s) of ``re_noise(x_a, step_a, step_b)`` -- ``x_b = c*x_a + s*eps`` -- derived
+    with the float32 torch ops of the reference (pipeline/scheduler.py:98-110): ``alphas_cumprod`` is the
+    scheduler's float32 table, ``ddim_timesteps`` its integer DDIM time steps."""
+    ac = torch.as_tensor(alphas_cumprod, dtype=torch.float32)
+    a, b = ac[int(ddim_timesteps[step_a])], ac[int(ddim_timesteps[step_b])]
+    return float(torch.sqrt(b / a)), float(torch.sqrt(1 - b / a))
+
+
 def shard_range(n_jobs: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous, balanced split of the ordered job list: (begin, count) of ``rank``."""
     base, rem = divmod(n_jobs, world)
@@ -182,6 +191,14 @@ class PanoramaState:
         self.peer_table, self._peer_buf, self._peer_hdl = buf.data_ptr(), buf, hdl
         torch.cuda.synchronize(self.device)
         dist.barrier(group=group)                  # every table is filled before any kernel signals into it
+
+    def reset_mask(self):
+        """Zero the denoised-mask panorama: the reference builds a fresh zero mask every step
+        (t2v_sphere_panorama_pipeline.py:173, i2v_...:242).  With peer replicas every rank clears its
+        own replica; call it before the step's first gather on every rank."""
+        m = self.mask_plane if self.mask_plane is not None else self.mask_pm
+        if m is not None:
+            m.zero_()
 
     def peer_error(self) -> bool:
         """True if a cross-GPU wait of this state timed out (results are then undefined)."""
@@ -395,6 +412,38 @@ class PanoramaStepper:
                                        d_jobs.data_ptr(), 0, nj, 4, F, HW, plan.f_len, plan.hw, plan.w, peer,
                                        _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)), "ds_pm_gather")
 
+    def _pm_gather_renoise(self, st, plan, out, index, j0, nj, rn):
+        import ctypes as C
+        assert plan.kind == "sphere_nearest", "the re-noise mix follows the nearest read (the reference's call sites)"
+        eps = rn["eps"]
+        assert eps.is_contiguous() and eps.dtype == st.dtype and tuple(eps.shape) == tuple(out.shape)
+        mplan = rn.get("mask_plan") or plan
+        assert mplan.kind == "sphere_nearest" and mplan.hw == plan.hw and mplan.n_local == plan.n_local
+        if st.mask_plane is not None:
+            assert plan.d_ftab is None, "a [1, H, W] mask panorama has no frame axis"
+            mask, mode = st.mask_plane, _lib.DS_MASK_PLANE
+            mshape = (nj, plan.h, plan.w)
+        else:
+            assert st.mask_pm is not None, "the state has no denoised-mask panorama"
+            mask, mode = st.mask_pm, _lib.DS_MASK_FULL
+            mshape = tuple(out.shape)
+        raw = torch.empty_like(out) if rn.get("want_raw") else None
+        mview = torch.empty(mshape, dtype=st.dtype, device=st.device) if rn.get("want_mask") else None
+        r = float(rn["ratio"])
+        h_coef = (C.c_float * 4)(float(rn["c"]), float(rn["s"]), r, 1 - r)
+        F, HW = plan.F, plan.H * plan.W
+        if nj > 0 or st.peer_table is not None:
+            d_jobs = plan.d_jobs[j0:j0 + max(nj, 1)]
+            with _lib.on(st.device):
+                lib.check(lib.ds_pm_gather_renoise(st.pms[index].data_ptr(), out.data_ptr(), _lib.ptr(raw), _lib.ptr(mview),
+                                                   eps.data_ptr(), mask.data_ptr(), mode, plan.d_idx.data_ptr(),
+                                                   mplan.d_idx.data_ptr(), h_coef, d_jobs.data_ptr(), 0, nj, 4, F, HW,
+                                                   plan.f_len, plan.hw, st.peer_table, _lib.dtype_code(st.dtype),
+                                                   _lib.stream_ptr(st.device)), "ds_pm_gather_renoise")
+        if st.peer_table is not None:
+            self._peer_sync(st, _lib.DS_PEER_AFTER_GATHER)
+        return out, raw, mview
+
     def _pm_merge_into(self, pms, payloads, mask, mask_mode, plan, j0, nj, peer=None):
         if plan.T == 0:
             return                                 # none of this rank's views survives anywhere
@@ -466,9 +515,19 @@ class PanoramaStepper:
         _launch_gather_nearest(image, out, d_idx, None, 0, len(vms), C, 1, Hi * Wi, 1, width * height)
         return out
 
-    def gather_all(self, latent, plan: StepPlan, out: Optional[torch.Tensor] = None, index: int = 0) -> torch.Tensor:
+    def gather_all(self, latent, plan: StepPlan, out: Optional[torch.Tensor] = None, index: int = 0,
+                   renoise: Optional[dict] = None):
         """latent [B, C, F, H, W] -- or a :class:`PanoramaState` (panorama ``index``) -- ->
-        windows [n_local_jobs, B, C, f_len, h, w] (this rank's slice of the ordered job list)."""
+        windows [n_local_jobs, B, C, f_len, h, w] (this rank's slice of the ordered job list).
+
+        ``renoise`` (states, nearest plans): fuse what follows the read in the
+        reference's loops (t2v_sphere_panorama_pipeline.py:194-221) -- the nearest read of the state's
+        denoised-mask panorama, ``re_noise`` with INJECTED epsilon and ``mix_latents_with_mask`` -- into
+        the gather: ``dict(eps=<windows-shaped tensor>, c=, s=, ratio=, want_raw=False, want_mask=False,
+        mask_plan=None)`` with (c, s) from :func:`renoise_coefficients`.  Returns ``(windows, raw,
+        mask_view)``: the mixed windows, the unmixed ones (``want_raw``) and the mask view
+        (``want_mask``; [n, h, w] for a [1, H, W] mask, windows-shaped for a latent-shaped mask) -- the
+        last two feed ``merge_denoised(prev=, prev_mask=)``."""
         if isinstance(latent, PanoramaState):
             assert plan.kind != "ring", "planar ring windows run on reference-order tensors"
             st = latent
@@ -478,6 +537,8 @@ class PanoramaStepper:
             if out is None:
                 out = torch.empty(shape, dtype=st.dtype, device=st.device)
             assert tuple(out.shape) == shape and out.is_contiguous()
+            if renoise is not None:
+                return self._pm_gather_renoise(st, plan, out, index, j0, nj, renoise)
             if nj > 0:
                 self._pm_gather(st.pms[index], plan, out, j0, nj, st.peer_table)
             if st.peer_table is not None:            # replicas may be overwritten once every rank has read
@@ -556,14 +617,20 @@ class PanoramaStepper:
 
     def merge_denoised(self, st: PanoramaState, x: torch.Tensor, eps_cond: torch.Tensor,
                        eps_uncond: Optional[torch.Tensor], coef, plan: StepPlan,
-                       noise: Optional[torch.Tensor] = None):
+                       noise: Optional[torch.Tensor] = None, prev: Optional[torch.Tensor] = None,
+                       prev_mask: Optional[torch.Tensor] = None, prev_ratio: Optional[float] = None):
         """merge_all fused with the denoise epilogue: the latent panorama (state
         panorama 0) receives ``x_prev`` and the denoised panorama (1) ``pred_x0`` of
         ``ddim_step(x, eps_uncond + g*(eps_cond - eps_uncond))`` -- computed inside the merge kernel
         for the surviving pixels only, so the ~75 % of window pixels that lose to a later window are
         never denoised, and x_prev / pred_x0 are never materialised.  ``x``: this rank's windows as
         returned by ``gather_all``; ``eps_*``: UNet outputs of the same shape; ``coef``:
-        ``ddim_coefficients(...)``; ``noise``: the injected epsilon when sigma > 0."""
+        ``ddim_coefficients(...)``; ``noise``: the injected epsilon when sigma > 0.
+        ``prev`` / ``prev_mask`` / ``prev_ratio``: the merge prologue of the I2V loops
+        (i2v_sphere_panorama_pipeline.py:430-435): ``x_prev = mix_latents_with_mask(x_prev, prev,
+        prev_mask, prev_ratio)`` before the latent set, with ``prev`` the windows as gathered and
+        ``prev_mask`` the mask view read at gather time (``gather_all(..., renoise=dict(want_raw=True,
+        want_mask=True))`` returns both)."""
         import ctypes as C
         assert plan.kind != "ring" and len(st.pms) >= 2, "needs latent + denoised panoramas"
         assert self.world == 1 or st.peer_table is not None, "sharded fused merge needs peer replicas (make_state(peer=True))"
@@ -578,10 +645,19 @@ class PanoramaStepper:
         elif st.mask_pm is not None:
             mask, mask_mode = st.mask_pm, _lib.DS_MASK_FULL
         self._pm_merge_plan(plan)
-        h_coef = (C.c_float * 6)(*coef)
+        mview_full = 0
+        if prev is not None:
+            assert prev_mask is not None and prev_ratio is not None
+            assert prev.is_contiguous() and prev.dtype == st.dtype and prev.shape == x.shape
+            assert prev_mask.is_contiguous() and prev_mask.dtype == st.dtype
+            mview_full = 1 if prev_mask.numel() == x.numel() else 0
+            assert mview_full or prev_mask.numel() == nj * plan.hw, "mask view: [n, h, w] or windows-shaped"
+        pr = 0.0 if prev_ratio is None else float(prev_ratio)
+        h_coef = (C.c_float * 8)(*coef, pr, 1 - pr)
         F, HW = plan.F, plan.H * plan.W
         pms = st.pms[:2]
-        head = (_lib.ptr_array(pms), x.data_ptr(), eps_cond.data_ptr(), _lib.ptr(eps_uncond), _lib.ptr(noise), h_coef,
+        head = (_lib.ptr_array(pms), x.data_ptr(), eps_cond.data_ptr(), _lib.ptr(eps_uncond), _lib.ptr(noise),
+                _lib.ptr(prev), _lib.ptr(prev_mask if prev is not None else None), mview_full, h_coef,
                 _lib.ptr(mask), mask_mode)
         tail = (_lib.ptr(plan.d_ftab), _lib.ptr(plan.d_fbegin), plan.n_fwin, plan.vpf, j0, nj, 4, F, HW, plan.f_len,
                 plan.hw, st.peer_table, _lib.dtype_code(st.dtype), _lib.stream_ptr(st.device))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DS_ABI_VERSION 4
+#define DS_ABI_VERSION 5
 
 enum { DS_F32 = 0, DS_BF16 = 1 };
 
@@ -212,6 +212,26 @@ int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d
                  const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
                  int hw, int view_w, void* d_peer, int dtype, void* stream);
 
+/* Gather fused with the re-noise + mask mix that follows it in the reference's loops (SURVEY §8f-1;
+ * pipeline/t2v_sphere_panorama_pipeline.py:194-221, pipeline/i2v_sphere_panorama_pipeline.py:330-365):
+ *   view   = get_view_tensor_no_interpolate(latent panorama)         panorama_tensor_utils.py:53-70
+ *   m      = get_view_tensor_no_interpolate(denoised-mask panorama)
+ *   noised = c * view + s * eps                                       pipeline/scheduler.py:98-110
+ *   out    = mix_latents_with_mask(view, noised, m, ratio)           utils/tensor_utils.py:19-39
+ * for every job, each elementwise op rounded on its own like the reference's tensor ops.  eps is
+ * INJECTED (same layout as out; the reference draws randn_like inside re_noise).
+ * mask: DS_MASK_PLANE -> the [H*W] plane of the T2V loop (t2v_...:159); DS_MASK_FULL -> a
+ * pixel-major panorama (the latent-shaped I2V mask, i2v_...:220).  d_idx / d_midx: nearest read maps
+ * [n_maps][hw] of the latent and of the mask read (they differ only when phi_fov_dict gives the
+ * mask another fov, t2v_...:194,206).  h_coef: HOST float[4] = { c, s, ratio, 1 - ratio }.
+ * out_raw (or NULL): the unmixed view (view_latent_prev_denoise, i2v_...:345); out_mask (or NULL):
+ * m, as [jobs][hw] (DS_MASK_PLANE) or in window layout (DS_MASK_FULL) -- both feed the merge
+ * prologue of ds_pm_merge_*_ddim.  d_jobs, h_f0, d_peer as in ds_pm_gather. */
+int ds_pm_gather_renoise(const void* pm, void* out, void* out_raw, void* out_mask, const void* eps,
+                         const void* mask, int mask_mode, const int32_t* d_idx, const int32_t* d_midx,
+                         const float* h_coef, const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F,
+                         int HW, int f_len, int hw, void* d_peer, int dtype, void* stream);
+
 /* Ordered sequence of set_view_tensor_no_interpolation calls (panorama_tensor_utils.py:
  * 154-183; ring twin ring_panorama_tensor_utils.py:170-198), scatter form over the surviving
  * view pixels only ("last writer wins").  Entry e says: view pixel
@@ -282,21 +302,30 @@ int ds_mix_mask(const void* l1, const void* add, const void* mask, void* out,
  *                                                   pipeline/t2v_sphere_panorama_pipeline.py:256-261
  *   pred_x0 = (x - s1m * e) / sa                    pipeline/scheduler.py:84
  *   x_prev  = (sp * pred_x0 + sd * e) + sig * noise :86-89   (noise NULL: the term is skipped)
- * h_coef: HOST float[6] = { sa = sqrt(alpha_t), s1m = sqrt(1 - alpha_t), sp = sqrt(alpha_prev),
- *   sd = sqrt(1 - alpha_prev - sigma^2), sig = sigma_t, g = guidance scale }, each computed in
- *   float32 like the reference's torch.full(...) tensors.
+ * Optional merge prologue, the merge_prev_denoised_ratio mix of the I2V loops
+ * (pipeline/i2v_sphere_panorama_pipeline.py:430-435, :938-943) applied to x_prev before it is merged:
+ *   x_prev = mix_latents_with_mask(x_prev, prev, mask_view, r)       utils/tensor_utils.py:19-39
+ * prev: the window as gathered (view_latent_prev_denoise, :345), same layout as x; mask_view: the
+ * denoised-mask view read at gather time ([jobs][hw] if mask_view_full == 0, else window layout);
+ * both NULL: no mix.
+ * h_coef: HOST float[8] = { sa = sqrt(alpha_t), s1m = sqrt(1 - alpha_t), sp = sqrt(alpha_prev),
+ *   sd = sqrt(1 - alpha_prev - sigma^2), sig = sigma_t, g = guidance scale (each computed in float32
+ *   like the reference's torch.full(...) tensors), r = merge_prev ratio, 1 - r (formed in double
+ *   like the reference) }.
  * h_pms: exactly 2 panoramas: [0] <- x_prev (latent), [1] <- pred_x0 (denoised).
  * Plans, frame windows, sharding, mask and d_peer as in ds_pm_merge_nearest /
  * ds_pm_merge_bilinear_tiled. */
 int ds_pm_merge_nearest_ddim(void* const* h_pms, const void* x, const void* eps_cond, const void* eps_uncond,
-                             const void* noise, const float* h_coef, void* mask, int mask_mode,
+                             const void* noise, const void* prev, const void* mask_view, int mask_view_full,
+                             const float* h_coef, void* mask, int mask_mode,
                              const int32_t* d_view_ptr, const int32_t* d_ent_src,
                              const int32_t* d_ent_dst, int n_ent, const int32_t* d_ftab,
                              const int32_t* d_fbegin, int n_fwin, int views_per_fwin, int job_begin,
                              int job_count, int P, int F, int HW, int f_len, int hw, void* d_peer,
                              int dtype, void* stream);
 int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x, const void* eps_cond,
-                                    const void* eps_uncond, const void* noise, const float* h_coef,
+                                    const void* eps_uncond, const void* noise, const void* prev,
+                                    const void* mask_view, int mask_view_full, const float* h_coef,
                                     void* mask, int mask_mode, const int32_t* d_view_ptr,
                                     const int32_t* d_tile, int n_tiles, const int32_t* d_row_dst,
                                     const int32_t* d_row_start, int n_rows, const int32_t* d_ent_k,

@@ -1,0 +1,234 @@
+"""Golden vectors from the REAL reference denoising loop -> tests/golden/loop.npz.
+
+Runs the UNMODIFIED ``VC2_Pipeline_T2V_SpherePano.basic_sample_shift_shpere_panorama``
+(pipeline/t2v_sphere_panorama_pipeline.py:23-310) imported from /root/reference on CPU, with
+  * the reference's own ``DiffusionWrapper`` + ``UNetModel`` (lvdm/models/ddpm3d.py:696-712,
+    lvdm/modules/networks/openaimodel3d.py) at REDUCED width, seeded random init (the zero-initialised
+    output layers re-randomised),
+  * the reference's own ``lvdm_DDIM_Scheduler`` (pipeline/scheduler.py) incl. ``re_noise`` and ``ddim_step``,
+  * ``merge_renoised_overlap_latent_ratio`` set, so the re-noise + mask mix runs,
+  * ~30 lines of stubs for what is not installed here (diffusers, pytorch_lightning),
+and records, per UNet call, the digest of the input window and the model output.  The GPU box has no
+reference checkout: there the tests replay the recorded UNet outputs ("replay model") through
+dynamicscaler_b200's fused gather / merge calls and must reproduce the final panoramas bit for bit.
+
+The scheduler's internal RNG draws (re_noise: randn_like, ddim_step: randn) are replaced by
+seeded tensors ``randn(seed)`` that the tests regenerate.
+
+Also recorded (P9): the same windows pushed through the UNet as ONE batch with ``timesteps`` of length
+b*t -- the call the batched driver makes -- next to the per-window results.
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_loop.py
+"""
+import hashlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+sys.dont_write_bytecode = True
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("DS_REFERENCE", "/root/reference")
+sys.path.insert(0, REF)
+sys.path.insert(0, os.path.dirname(HERE))
+from conftest import randn  # noqa: E402
+
+# ---- stubs for packages that are not installed ---------------------------------
+_pl = types.ModuleType("pytorch_lightning")
+_pl.LightningModule = torch.nn.Module
+_pl.seed_everything = lambda *a, **k: None
+_plu = types.ModuleType("pytorch_lightning.utilities")
+_plu.rank_zero_only = lambda f: f
+sys.modules.setdefault("pytorch_lightning", _pl)
+sys.modules.setdefault("pytorch_lightning.utilities", _plu)
+
+
+class _Bar:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def update(self, *a):
+        pass
+
+
+class _DiffusionPipeline:
+    def __init__(self):
+        pass
+
+    def register_modules(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def _execution_device(self):
+        return torch.device("cpu")
+
+    def to(self, *a, **k):
+        return self
+
+    def progress_bar(self, *a, **k):
+        return _Bar()
+
+
+_df = types.ModuleType("diffusers")
+_df.DiffusionPipeline = _DiffusionPipeline
+_df.ConfigMixin = type("ConfigMixin", (), {})
+_df.SchedulerMixin = type("SchedulerMixin", (), {})
+_df.logging = types.SimpleNamespace(get_logger=lambda name: types.SimpleNamespace(
+    info=lambda *a, **k: None, warning=lambda *a, **k: None))
+_cu = types.ModuleType("diffusers.configuration_utils")
+_cu.ConfigMixin = _df.ConfigMixin
+_cu.register_to_config = lambda f: f
+_su = types.ModuleType("diffusers.schedulers.scheduling_utils")
+_su.SchedulerMixin = _df.SchedulerMixin
+_ut = types.ModuleType("diffusers.utils")
+_ut.BaseOutput = type("BaseOutput", (), {})
+_ut.logging = _df.logging
+_sc = types.ModuleType("diffusers.schedulers")
+for name, mod in (("diffusers", _df), ("diffusers.configuration_utils", _cu), ("diffusers.schedulers", _sc),
+                  ("diffusers.schedulers.scheduling_utils", _su), ("diffusers.utils", _ut)):
+    sys.modules.setdefault(name, mod)
+for missing in ("kornia", "open_clip", "imageio", "decord", "omegaconf"):
+    if missing not in sys.modules:
+        try:
+            __import__(missing)
+        except Exception:
+            sys.modules[missing] = types.ModuleType(missing)
+
+import builtins  # noqa: E402
+_print = builtins.print
+builtins.print = lambda *a, **k: None          # the reference prints one line per window
+try:
+    from lvdm.models.utils_diffusion import make_beta_schedule  # noqa: E402
+    from lvdm.models.ddpm3d import DiffusionWrapper  # noqa: E402
+    import pipeline.scheduler as ref_sched  # noqa: E402
+    from pipeline.t2v_sphere_panorama_pipeline import VC2_Pipeline_T2V_SpherePano  # noqa: E402
+finally:
+    builtins.print = _print
+
+
+def sha(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+
+
+# ---- reduced-width reference UNet ------------------------------------------------------------
+CTX = 32
+UNET = dict(in_channels=4, out_channels=4, model_channels=32, attention_resolutions=[2, 1], num_res_blocks=1,
+            channel_mult=[1, 2], num_head_channels=16, transformer_depth=1, context_dim=CTX, use_linear=True,
+            use_checkpoint=False, temporal_conv=True, temporal_attention=True, temporal_selfatt_only=True,
+            use_relative_position=False, use_causal_attention=False, temporal_length=4, addition_attention=True,
+            fps_cond=True)
+torch.manual_seed(0)
+torch.set_num_threads(1)
+wrapper = DiffusionWrapper({"target": "lvdm.modules.networks.openaimodel3d.UNetModel", "params": UNET}, "crossattn")
+g = torch.Generator().manual_seed(1)
+for name, p in wrapper.named_parameters():      # zero_module layers would make a random-init UNet output exactly 0
+    if p.abs().max() == 0:
+        p.data = torch.randn(p.shape, generator=g) * 0.05
+wrapper.eval()
+
+# ---- fake pretrained_t2v (only what the loop touches) ---------------------------
+betas = make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.012)
+ac = np.cumprod(1.0 - betas, axis=0)
+calls = []                                        # (input sha, input sample, output)
+
+
+def recording_model(x, t, **kw):
+    y = wrapper(x, t, **kw)
+    calls.append((sha(x.numpy()), x.numpy().reshape(-1)[::97].copy(), y.numpy().copy(), x.numpy().copy()))
+    return y
+
+
+def text_embed(prompts):
+    out = []
+    for pr in prompts:
+        seed = int(hashlib.sha256(pr.encode()).hexdigest()[:8], 16)
+        out.append(torch.from_numpy(randn(seed, 77, CTX)))
+    return torch.stack(out)
+
+
+fake = types.SimpleNamespace(
+    model=recording_model, first_stage_model=None, cond_stage_model=None, uncond_type="empty_seq",
+    temporal_length=4, device=torch.device("cpu"), get_learned_conditioning=text_embed,
+    num_timesteps=1000, betas=torch.tensor(betas, dtype=torch.float32),
+    alphas_cumprod=torch.tensor(ac, dtype=torch.float32),
+    alphas_cumprod_prev=torch.tensor(np.append(1.0, ac[:-1]), dtype=torch.float32), use_scale=False)
+sched = ref_sched.lvdm_DDIM_Scheduler(fake)
+pipe = VC2_Pipeline_T2V_SpherePano.__new__(VC2_Pipeline_T2V_SpherePano)
+pipe.pretrained_t2v, pipe.scheduler = fake, sched
+pipe.model_config = {"params": {"unet_config": {"params": UNET}}}
+pipe.vae_scale_factor = 8
+
+# ---- the run ----------------------------------------------------------------------------------
+CFG = dict(F=4, H=64, W=128, h=16, w=24, steps=3, fov=120, guidance=7.5, ratio=0.6, loop_step_theta=10, prompt="a test panorama")
+PHI_THETA = {90: [0], 0: [0, 120, 240], -45: [60, 300]}
+lat0 = randn(41, 1, 4, CFG["F"], CFG["H"], CFG["W"])
+
+draws = {"n": 0}
+real_randn, real_randn_like = torch.randn, torch.randn_like
+
+
+def seeded_randn_like(x, **k):
+    draws["n"] += 1
+    return torch.from_numpy(randn(5000 + draws["n"], *x.shape))
+
+
+def zero_randn(*shape, **k):                    # ddim_step: sigma = 0 (eta 0) multiplies this draw, any finite value works
+    if len(shape) == 1 and not isinstance(shape[0], int):
+        shape = tuple(shape[0])
+    return torch.zeros(shape)
+
+
+out = {"cfg": np.array([CFG[k] for k in ("F", "H", "W", "h", "w", "steps", "fov")], dtype=np.int64),
+       "guidance": np.array(CFG["guidance"]), "ratio": np.array(CFG["ratio"]),
+       "views": np.array([(ph, th) for ph, ths in PHI_THETA.items() for th in ths], dtype=np.float64)}
+builtins.print = lambda *a, **k: None
+ref_sched.torch.randn_like = seeded_randn_like
+ref_sched.torch.randn = zero_randn
+try:
+    videos, denoised = pipe.basic_sample_shift_shpere_panorama(
+        prompt=CFG["prompt"], height=CFG["h"] * 8, width=CFG["w"] * 8, frames=CFG["F"], fps=16,
+        guidance_scale=CFG["guidance"], init_sphere_latent=torch.from_numpy(lat0),
+        equirect_width=CFG["W"] * 8, equirect_height=CFG["H"] * 8, phi_theta_dict=PHI_THETA, view_fov=CFG["fov"],
+        loop_step_theta=CFG["loop_step_theta"], merge_renoised_overlap_latent_ratio=CFG["ratio"],
+        num_inference_steps=CFG["steps"], output_type="latent")
+finally:
+    ref_sched.torch.randn_like, ref_sched.torch.randn = real_randn_like, real_randn
+    builtins.print = _print
+
+n_views = len(out["views"])
+assert len(calls) == CFG["steps"] * n_views * 2, len(calls)
+out["final_latent"] = videos.numpy()
+out["final_denoised"] = denoised.numpy()
+out["unet_in_sha"] = np.stack([c[0] for c in calls[0::2]])           # cond call of every window (uncond sees the same x)
+out["unet_in_sample"] = np.stack([c[1] for c in calls[0::2]])
+out["eps_cond"] = np.stack([c[2] for c in calls[0::2]])
+out["eps_uncond"] = np.stack([c[2] for c in calls[1::2]])
+out["renoise_draws"] = np.array(draws["n"])
+out["text_emb"] = text_embed([CFG["prompt"]]).numpy()
+out["uncond_emb"] = text_embed([""]).numpy()
+# scheduler tables the loop driver needs (float64 numpy arrays in the reference)
+out["ddim_timesteps"] = np.asarray(sched.ddim_timesteps)
+out["alphas_cumprod"] = sched.alphas_cumprod.numpy()
+for k in ("ddim_alphas", "ddim_alphas_prev", "ddim_sigmas", "ddim_sqrt_one_minus_alphas"):
+    out[k] = np.asarray(getattr(sched, k), dtype=np.float64)
+
+# ---- P9: one batched UNet call (timesteps of length b*t) == the per-window calls ----------------
+step0 = [c[3] for c in calls[0:2 * n_views:2]]
+xb = torch.from_numpy(np.concatenate(step0, axis=0))               # [n, 4, F, h, w]
+t0 = int(np.flip(sched.ddim_timesteps)[0])
+ts = torch.full((xb.shape[0] * CFG["F"],), t0, dtype=torch.long)
+ctx = text_embed([CFG["prompt"]]).expand(xb.shape[0], -1, -1)
+with torch.no_grad():
+    yb = wrapper(xb, ts, c_crossattn=[ctx], fps=16, curr_time_steps=ts, temporal_length=CFG["F"], clean_cond=True)
+per = np.concatenate([c[2] for c in calls[0:2 * n_views:2]], axis=0)
+out["p9_batched_vs_looped_maxabs"] = np.array(np.abs(yb.numpy() - per).max())
+print("P9 batched vs looped max abs:", float(out["p9_batched_vs_looped_maxabs"]))
+np.savez_compressed(os.path.join(HERE, "loop.npz"), **out)
+print("loop.npz:", len(out), "arrays,", os.path.getsize(os.path.join(HERE, "loop.npz")) // 1024, "KiB;",
+      len(calls), "UNet calls,", draws["n"], "re_noise draws")
