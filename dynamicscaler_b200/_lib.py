@@ -47,6 +47,9 @@ PROTOTYPES = {
     "ds_pm_gather_renoise": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_resize_planes": [_vp, _vp, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_select_merged": [_vp, _vp, _vp, _ll, _ll, _ll, _i, _vp],
+    "ds_tile_accumulate": [_vp, _vp, _vp, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "ds_tile_normalise": [_vp, _vp, _vp, _ll, _ll, _ll, _vp],
+    "ds_repeat_renoise": [_vp, _vp, _vp, _f, _f, _ll, _i, _ll, _i, _vp],
 }
 
 

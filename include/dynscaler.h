@@ -341,6 +341,27 @@ enum { DS_RESIZE_NEAREST = 0, DS_RESIZE_BILINEAR = 1, DS_RESIZE_BICUBIC = 2 };
 int ds_resize_planes(const void* in, void* out, long long planes, int h, int w, int H, int W,
                      int mode, int align_corners, int dtype, void* stream);
 
+/* ------------------------------------------ pixel-side neighbours ---- */
+/* One tile of tiled_vae_encode_tensor_simple (pipeline/i2v_sphere_panorama_pipeline.py:505-562):
+ *   img_latent[:, :, :, dst_top:dst_top+ch, dst_left:dst_left+cw] += tile[:, :, :, top_cut:top_cut+ch, left_cut:left_cut+cw]
+ *   count[:, :, :, same region] += 1                                                     (:550-554)
+ * acc: float32 [planes][H][W] (the reference accumulates in float32 whatever the tile dtype, :521);
+ * count: float32 [planes / planes_per_count][H][W] (the reference's [B,1,1,H,W]: planes_per_count = 4*F);
+ * tile: [planes][th][tw] of `dtype`.  Calls on one stream are applied in order. */
+int ds_tile_accumulate(float* acc, float* count, const void* tile, long long planes, long long planes_per_count,
+                       int H, int W, int th, int tw, int top_cut, int left_cut, int ch, int cw,
+                       int dst_top, int dst_left, int dtype, void* stream);
+/* count = clamp(count, min=1); out = acc / count   (:556-558), float32, IEEE division. */
+int ds_tile_normalise(const float* acc, const float* count, float* out, long long planes,
+                      long long planes_per_count, long long HW, void* stream);
+
+/* paste_on_static (pipeline/i2v_sphere_panorama_pipeline.py:245-254): the frame-0 latent x0 [planes][HW]
+ * repeated over F frames (torch.cat([x0] * F, dim=2), :248) and re-noised with injected epsilon
+ * (pipeline/scheduler.py:98-110): out[pl][f][p] = c * x0[pl][p] + s * eps[pl][f][p], each op rounded
+ * on its own.  eps == NULL: the plain repeat. */
+int ds_repeat_renoise(const void* x0, const void* eps, void* out, float c, float s, long long planes, int F,
+                      long long HW, int dtype, void* stream);
+
 /* Final select of the sharded merge:
  *   pano[i] = weight[(i / weight_group) mod weight_period] > 0 ? sum[i] : pano[i]   for i < n.
  * weight has the panorama's dtype.  Reference layout: weight_group = 1 and weight_period =

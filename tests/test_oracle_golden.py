@@ -315,3 +315,30 @@ def test_denoise_loop_oracle_matches_real_pipeline():
     assert draws["n"] == int(g["renoise_draws"])
     assert np.array_equal(lat, g["final_latent"]) and np.array_equal(den, g["final_denoised"])
     assert float(g["p9_batched_vs_looped_maxabs"]) < 1e-4      # P9: one UNet call over all windows == looped calls
+
+
+def test_vae_tiling_oracle_matches_reference():
+    """oracle.tiled_encode / wrap_pad / crop_wrap_padded == the reference's tiled_vae_encode_tensor_simple
+    and the inline wrap-padded decode of i2v_sphere_panorama_pipeline.py:974-991 (tests/golden/vae.npz)."""
+    import torch.nn.functional as F
+    v = np.load(os.path.join(GOLDEN, "vae.npz"))
+    mix = torch.tensor([[0.5, -0.25, 0.125], [0.1, 0.2, 0.3], [-0.4, 0.3, 0.2], [0.05, 0.6, -0.35]])
+
+    def enc(a):
+        x = torch.from_numpy(np.ascontiguousarray(a))
+        B, C, Fr, H, W = x.shape
+        p = F.avg_pool2d(x.permute(0, 2, 1, 3, 4).reshape(B * Fr, C, H, W), 8)
+        y = torch.einsum("oc,nchw->nohw", mix, p) + 0.01 * p.mean(dim=(1, 2, 3), keepdim=True)
+        return y.view(B, Fr, 4, H // 8, W // 8).permute(0, 2, 1, 3, 4).numpy()
+
+    for n in range(3):
+        shape = tuple(int(x) for x in v[f"encode/{n}/shape"])
+        ht, wt, oh, ow = (int(x) for x in v[f"encode/{n}/kw"])
+        got = po.tiled_encode(randn(600 + n, *shape), enc, h_tile_num=ht, w_tile_num=wt, overlap_h=oh, overlap_w=ow)
+        assert np.array_equal(got, v[f"encode/{n}/latent"]), n
+        shape = tuple(int(x) for x in v[f"decode/{n}/shape"])
+        cn = int(v[f"decode/{n}/chunk_num"])
+        padded = po.wrap_pad(randn(700 + n, *shape), cn)
+        assert np.array_equal(padded, v[f"decode/{n}/padded"]), n
+        up = np.repeat(np.repeat(padded, 2, axis=-1), 2, axis=-2) * np.arange(1, shape[2] + 1, dtype=np.float32)[None, None, :, None, None]
+        assert np.array_equal(po.crop_wrap_padded(up, cn), v[f"decode/{n}/videos"]), n
