@@ -227,7 +227,7 @@ class Workset:
     """One rotating buffer set (panoramas + windows + payloads), so consecutive steps touch
     different memory and the aggregate footprint exceeds L2."""
 
-    def __init__(self, wl, n_local, dev, gen, st=None, peer=False, gen_pano=None, dtype=torch.float32):
+    def __init__(self, wl, n_local, dev, gen, st=None, peer=False, gen_pano=None, dtype=torch.float32, ring_st=None):
         shape = (1, wl["C"], wl["F"], wl["H"], wl["W"])
         vshape = (n_local, 1, wl["C"], wl["f_len"], wl["h"], wl["w"])
         self.lat = torch.randn(shape, device=dev, generator=gen_pano if gen_pano is not None else gen).to(dtype)
@@ -241,13 +241,23 @@ class Workset:
         self.x0 = torch.randn(vshape, device=dev, generator=gen).to(dtype)
         # resident pixel-major state (layout "pm"): gather/merge work on it in place
         self.state = st.make_state([self.lat, self.den], mask=self.mask, peer=peer) if st is not None else None
-        self.pano = self.state if self.state is not None else self.lat
+        # planar ring path on N > 1 GPUs: reference-order replicas in symmetric memory, peer-store exchange
+        self.ring_state = ring_st.make_ring_state([self.lat, self.den], mask=self.mask) if ring_st is not None else None
+        self.pano = self.state if self.state is not None else (self.ring_state if self.ring_state is not None else self.lat)
 
     def merge(self, st, plan):
         if self.state is not None:
             st.merge_all(self.state, [self.x_prev, self.x0], plan)
+        elif self.ring_state is not None:
+            st.merge_all(self.ring_state, [self.x_prev, self.x0], plan)
         else:
             st.merge_all([self.lat, self.den], [self.x_prev, self.x0], plan, mask=self.mask)
+
+    def peer_error(self):
+        for s_ in (self.state, self.ring_state):
+            if s_ is not None and getattr(s_, "peer_table", None) is not None and s_.peer_error():
+                return True
+        return False
 
     def nbytes(self):
         return sum(t.numel() * t.element_size() for t in (self.lat, self.den, self.mask, self.wins, self.x_prev, self.x0))
@@ -353,22 +363,24 @@ def parity_check(wl, mode, dev, rank, world, pm, peer, dtype, n_steps, multicast
         base_b = torch.randn((n_win,) + vshape, device=dev, generator=g2).to(dtype)
         lat, den, msk = lat0.clone(), torch.zeros_like(lat0), torch.zeros(mshape, device=dev, dtype=dtype)
         state = st.make_state([lat, den], mask=msk, peer=peer_) if pm else None
+        if not pm and peer_:
+            state = st.make_ring_state([lat, den], mask=msk)           # planar ring path, peer-store exchange
         for i in range(n_steps):
             plan = plans[i % len(plans)]
             ids = torch.tensor(plan.job_ids, device=dev, dtype=torch.long)
-            wins = st.gather_all(state if pm else lat, plan)
+            wins = st.gather_all(state if state is not None else lat, plan)
             xp = wins * 0.5 + base_a[ids] * float(1 + i % 3)
             x0 = wins * 0.25 - base_b[ids]
-            if pm:
+            if state is not None:
                 st.merge_all(state, [xp, x0], plan)
             else:
                 st.merge_all([lat, den], [xp, x0], plan, mask=msk)
-        outs = (state.export() + [state.export_mask()]) if pm else [lat, den, msk]
+        outs = (state.export() + [state.export_mask()]) if state is not None else [lat, den, msk]
         torch.cuda.synchronize()
         h = hashlib.sha256()
         for t in outs:
             h.update(t.contiguous().view(torch.uint8).cpu().numpy().tobytes())
-        if pm and state.peer_table is not None:
+        if state is not None and getattr(state, "peer_table", None) is not None:
             assert not state.peer_error(), "a cross-GPU wait timed out during the parity run"
         return h.digest()
 
@@ -419,19 +431,21 @@ def run_ours(args, wl, wl_name):
     n_win = plans[modes[0]][0].n_jobs
     st_pm = st if (args.layout == "pm" and wl["kind"] == "sphere") else None
     peer = dist_on and st_pm is not None and args.exchange == "peer"
+    ring_peer = dist_on and wl["kind"] == "ring" and args.exchange == "peer"
+    ring_st = st if ring_peer else None
     gen_pano = torch.Generator(device=dev).manual_seed(99)      # replicas start identical on every rank
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     esz = 2 if args.dtype == "bf16" else 4
     try:
-        one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano, dtype)
+        one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano, dtype, ring_st)
     except Exception as e:                                   # no symmetric memory on this system
-        if not peer:
+        if not (peer or ring_peer):
             raise
         print(f"[bench] peer exchange unavailable ({type(e).__name__}: {e}); using the NCCL all-reduce path", file=sys.stderr)
-        peer = False
+        peer, ring_peer, ring_st = False, False, None
         one = Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano, dtype)
     n_sets = max(2, min(4, -(-3 * L2_BYTES // one.nbytes())))   # aggregate footprint >= 3x L2
-    sets = [one] + [Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano, dtype) for _ in range(n_sets - 1)]
+    sets = [one] + [Workset(wl, n_local, dev, gen, st_pm, peer, gen_pano, dtype, ring_st) for _ in range(n_sets - 1)]
     combos = [(i % NP, i % n_sets) for i in range(NP * n_sets // np.gcd(NP, n_sets))]
 
     # --denoise-us T: a busy kernel of T microseconds per LOCAL window between gather and merge, the
@@ -551,6 +565,8 @@ def run_ours(args, wl, wl_name):
             main.wait_event(ready[b])                       # this step's inputs have arrived
             if ws.state is not None:
                 st.merge_all(ws.state, list(dev_pay[b]), plan)
+            elif ws.ring_state is not None:
+                st.merge_all(ws.ring_state, list(dev_pay[b]), plan)
             else:
                 st.merge_all([ws.lat, ws.den], list(dev_pay[b]), plan, mask=ws.mask)
             free[b] = torch.cuda.Event()
@@ -576,7 +592,7 @@ def run_ours(args, wl, wl_name):
 
     parity = None
     if dist_on and not args.no_parity:
-        parity = parity_check(wl, args.mode, dev, rank, world, st_pm is not None, peer, dtype,
+        parity = parity_check(wl, args.mode, dev, rank, world, st_pm is not None, peer or ring_peer, dtype,
                               max(4, min(K, 10)), st.use_multicast)
 
     if rank == 0:
@@ -600,10 +616,12 @@ def run_ours(args, wl, wl_name):
                                     "windows split over ranks; merge kernels push rows into every replica over NVLink ("
                                     + ("NVLS multicast stores" if st.use_multicast else "per-replica TMA row copies")
                                     + ", release/acquire counters)" if peer else
+                                    "windows split over ranks; merge kernel stores won elements into every reference-order "
+                                    "replica over NVLink, 2 cross-GPU barriers/step" if ring_peer else
                                     "windows split over ranks, 1 NCCL all-reduce/step")},
             "steps_per_s": 1e3 / head["ms_per_step"],
             "regions_ms_per_step": head["regions_ms_per_step"],
-            "peer_wait_timeouts": bool(peer and any(w.state.peer_error() for w in sets)),
+            "peer_wait_timeouts": bool((peer or ring_peer) and any(w.peer_error() for w in sets)),
             "gpu_launches": int(head["launches_per_step"] * K),
             "clocks": sampler.summary(),
             "e2e": {"value": n_win / (e2e_ms * 1e-3), "unit": "blends/s",

@@ -134,7 +134,26 @@ struct MergeArgs {
   int vpf;                  // views per frame window
   int job_begin, job_count; // sharding: only jobs in [job_begin, job_begin + job_count) are applied
   int P, F, HW, f_len, hw;
+  const ds_peer_table_t* peer;   // exchange mode: every write goes to the replicas listed there (pano / mask above unused)
 };
+
+// One element (or 16-byte vector) to the local panorama, or to every rank's replica over NVLink.
+template <typename V, typename T, bool PEER>
+__device__ __forceinline__ void merge_store(const MergeArgs& a, int q, size_t off, const V& v) {
+  if (!PEER) {
+    *reinterpret_cast<V*>(static_cast<T*>(a.pano[q]) + off) = v;
+  } else {
+    for (int r = 0; r < a.peer->world; ++r) *reinterpret_cast<V*>(reinterpret_cast<T*>(a.peer->pm[r][q]) + off) = v;
+  }
+}
+template <typename T, bool PEER>
+__device__ __forceinline__ void merge_store_mask(const MergeArgs& a, size_t off) {
+  if (!PEER) {
+    static_cast<T*>(a.mask)[off] = Elem<T>::one();
+  } else {
+    for (int r = 0; r < a.peer->world; ++r) reinterpret_cast<T*>(a.peer->mask[r])[off] = Elem<T>::one();
+  }
+}
 
 // Resolve panorama slice (pl, f) + view v to the local payload job and window frame.
 // Returns false when the frame is not written this step or the job belongs to another rank.
@@ -150,7 +169,7 @@ __device__ __forceinline__ bool merge_source(const MergeArgs& a, const int32_t* 
 
 // thread = one plan entry (VEC consecutive panorama pixels), CPT panorama (plane, frame)
 // slices, all Q payloads.
-template <typename T, int VEC, int CPT, int QMAX>
+template <typename T, int VEC, int CPT, int QMAX, bool PEER = false>
 __global__ void __launch_bounds__(kBlock)
 merge_nearest_kernel(MergeArgs a, const int32_t* __restrict__ d_dst,
                      const int32_t* __restrict__ d_src, const int32_t* __restrict__ d_ftab) {
@@ -185,10 +204,10 @@ merge_nearest_kernel(MergeArgs a, const int32_t* __restrict__ d_dst,
       const size_t off = (static_cast<size_t>(pl) * a.F + f) * a.HW + dst;
 #pragma unroll
       for (int q = 0; q < QMAX; ++q)
-        if (q < a.Q) *reinterpret_cast<V*>(static_cast<T*>(a.pano[q]) + off) = val[q][c];
+        if (q < a.Q) merge_store<V, T, PEER>(a, q, off, val[q][c]);
       if (a.mask_mode == DS_MASK_FULL && pl < a.mask_planes) {
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) static_cast<T*>(a.mask)[off + e] = Elem<T>::one();
+        for (int e = 0; e < VEC; ++e) merge_store_mask<T, PEER>(a, off + e);
       }
     }
     if (++f == a.F) { f = 0; ++pl; }
@@ -196,7 +215,7 @@ merge_nearest_kernel(MergeArgs a, const int32_t* __restrict__ d_dst,
   // DS_MASK_PLANE (host guarantees d_ftab == nullptr): one write per pixel, from slice 0
   if (a.mask_mode == DS_MASK_PLANE && blockIdx.y == 0 && live[0]) {
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) static_cast<T*>(a.mask)[dst + e] = Elem<T>::one();
+    for (int e = 0; e < VEC; ++e) merge_store_mask<T, PEER>(a, dst + e);
   }
 }
 
@@ -337,17 +356,18 @@ extern "C" int ds_gather_bilinear(const void* pano, void* out, const int32_t* d_
   return check_launch();
 }
 
-extern "C" int ds_merge_nearest(void* const* h_panos, const void* const* h_payloads, int Q,
-                                void* mask, int mask_mode, int mask_planes,
-                                const int32_t* d_dst, const int32_t* d_src, int T,
-                                const int32_t* d_ftab, int views_per_fwin, int job_begin,
-                                int job_count, int P, int F, int HW, int f_len, int hw, int vec,
-                                int dtype, void* stream) {
+static int merge_nearest_impl(void* const* h_panos, const void* const* h_payloads, int Q,
+                              void* mask, int mask_mode, int mask_planes,
+                              const int32_t* d_dst, const int32_t* d_src, int T,
+                              const int32_t* d_ftab, int views_per_fwin, int job_begin,
+                              int job_count, int P, int F, int HW, int f_len, int hw, int vec,
+                              void* d_peer, int dtype, void* stream) {
   using namespace ds;
   MergeArgs a;
   int rc = fill_merge_args(a, h_panos, h_payloads, Q, mask, mask_mode, mask_planes, T,
                            views_per_fwin, job_begin, job_count, d_ftab, P, F, HW, f_len, hw);
   if (rc != DS_OK) return rc;
+  a.peer = static_cast<const ds_peer_table_t*>(d_peer);
   DS_REQUIRE(d_src != nullptr, DS_ERR_NULL);
   DS_REQUIRE(vec == 1 || vec == 4, DS_ERR_DIM);
   if (T == 0) return DS_OK;
@@ -363,15 +383,38 @@ extern "C" int ds_merge_nearest(void* const* h_panos, const void* const* h_paylo
       constexpr int CPT = 4;
       DS_REQUIRE(div_up(PF, CPT) <= 65535, DS_ERR_DIM);
       dim3 grid(div_up(T, kBlock), div_up(PF, CPT));
-      merge_nearest_kernel<ET, 4, CPT, DS_MAX_PAYLOADS><<<grid, kBlock, 0, st>>>(a, d_dst, d_src, d_ftab);
+      if (d_peer != nullptr) merge_nearest_kernel<ET, 4, CPT, DS_MAX_PAYLOADS, true><<<grid, kBlock, 0, st>>>(a, d_dst, d_src, d_ftab);
+      else merge_nearest_kernel<ET, 4, CPT, DS_MAX_PAYLOADS><<<grid, kBlock, 0, st>>>(a, d_dst, d_src, d_ftab);
     } else {
       constexpr int CPT = 8;
       DS_REQUIRE(div_up(PF, CPT) <= 65535, DS_ERR_DIM);
       dim3 grid(div_up(T, kBlock), div_up(PF, CPT));
-      merge_nearest_kernel<ET, 1, CPT, DS_MAX_PAYLOADS><<<grid, kBlock, 0, st>>>(a, d_dst, d_src, d_ftab);
+      if (d_peer != nullptr) merge_nearest_kernel<ET, 1, CPT, DS_MAX_PAYLOADS, true><<<grid, kBlock, 0, st>>>(a, d_dst, d_src, d_ftab);
+      else merge_nearest_kernel<ET, 1, CPT, DS_MAX_PAYLOADS><<<grid, kBlock, 0, st>>>(a, d_dst, d_src, d_ftab);
     }
   });
   return check_launch();
+}
+
+extern "C" int ds_merge_nearest(void* const* h_panos, const void* const* h_payloads, int Q,
+                                void* mask, int mask_mode, int mask_planes,
+                                const int32_t* d_dst, const int32_t* d_src, int T,
+                                const int32_t* d_ftab, int views_per_fwin, int job_begin,
+                                int job_count, int P, int F, int HW, int f_len, int hw, int vec,
+                                int dtype, void* stream) {
+  return merge_nearest_impl(h_panos, h_payloads, Q, mask, mask_mode, mask_planes, d_dst, d_src, T, d_ftab,
+                            views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, vec, nullptr, dtype, stream);
+}
+
+extern "C" int ds_merge_nearest_peer(void* const* h_panos, const void* const* h_payloads, int Q,
+                                     void* mask, int mask_mode, int mask_planes,
+                                     const int32_t* d_dst, const int32_t* d_src, int T,
+                                     const int32_t* d_ftab, int views_per_fwin, int job_begin,
+                                     int job_count, int P, int F, int HW, int f_len, int hw, int vec,
+                                     void* d_peer, int dtype, void* stream) {
+  DS_REQUIRE(d_peer != nullptr, DS_ERR_NULL);
+  return merge_nearest_impl(h_panos, h_payloads, Q, mask, mask_mode, mask_planes, d_dst, d_src, T, d_ftab,
+                            views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, vec, d_peer, dtype, stream);
 }
 
 extern "C" int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q,

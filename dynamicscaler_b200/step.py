@@ -227,6 +227,73 @@ class PanoramaState:
         return None
 
 
+class RingPanoramaState:
+    """Reference-order [B, C, F, H, W] panoramas of the PLANAR ring path
+    (t2v_sphere_panorama_pipeline.py:537-632) replicated on every rank in symmetric (peer-mapped)
+    memory: ``merge_all`` then stores every element this rank's windows win straight into every
+    replica over NVLink (ds_merge_nearest_peer) instead of zero buffer + NCCL all-reduce + select.
+    Collective constructor (one rendezvous per state); ``tensors`` / ``mask`` alias the replica."""
+
+    def __init__(self, stepper, tensors, mask=None):
+        import ctypes as C
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        t0 = tensors[0]
+        _lib.require_cuda(t0, "panorama")
+        assert stepper.world > 1 and stepper.world <= _lib.DS_MAX_PEERS and len(tensors) <= _lib.DS_MAX_PAYLOADS
+        self.stepper, self.shape, self.dtype, self.device = stepper, tuple(t0.shape), t0.dtype, t0.device
+        esz, n = t0.element_size(), t0.numel()
+        align = lambda x: (x + 255) // 256 * 256
+        tab_bytes = align(lib.ds_peer_table_size())
+        t_bytes = align(n * esz)
+        m_bytes = 0 if mask is None else align(mask.numel() * esz)
+        group = stepper.group if stepper.group is not None else dist.group.WORLD
+        buf = symm.empty(tab_bytes + len(tensors) * t_bytes + m_bytes, dtype=torch.uint8, device=self.device)
+        hdl = symm.rendezvous(buf, group.group_name)
+        buf.zero_()
+        base = [int(p_) for p_ in hdl.buffer_ptrs]
+        self.tensors = []
+        for q, t in enumerate(tensors):
+            assert tuple(t.shape) == self.shape and t.dtype == self.dtype
+            off = tab_bytes + q * t_bytes
+            v = buf[off:off + n * esz].view(self.dtype).view(self.shape)
+            v.copy_(t)
+            self.tensors.append(v)
+        m_off = tab_bytes + len(tensors) * t_bytes
+        self.mask = None
+        if mask is not None:
+            assert mask.dtype == self.dtype
+            self.mask = buf[m_off:m_off + mask.numel() * esz].view(self.dtype).view(mask.shape)
+            self.mask.copy_(mask)
+        tab = _lib.PeerTable()
+        tab.rank, tab.world = stepper.rank, stepper.world
+        for r in range(stepper.world):
+            for q in range(len(tensors)):
+                tab.pm[r][q] = base[r] + tab_bytes + q * t_bytes
+            tab.mask[r] = base[r] + m_off if mask is not None else 0
+            tab.ctl[r] = base[r]
+        raw = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8)
+        buf[:raw.numel()].copy_(raw)
+        self.peer_table, self._peer_buf, self._peer_hdl = buf.data_ptr(), buf, hdl
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+
+    def peer_error(self) -> bool:
+        off = _lib.PeerTable.error.offset
+        return bool(self._peer_buf[off:off + 4].view(torch.int32).item())
+
+    def export(self):
+        """Clones of the replicated panoramas (collective: waits for every rank's stores)."""
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.stepper.group)
+        assert not self.peer_error(), "a cross-GPU wait timed out"
+        return [t.clone() for t in self.tensors]
+
+    def export_mask(self):
+        return None if self.mask is None else self.mask.clone()
+
+
 class PanoramaStepper:
     """Plans and runs gather_all / merge_all for one panorama geometry on one device."""
 
@@ -361,6 +428,11 @@ class PanoramaStepper:
         return 0, plan.n_local
 
     # ------------------------------------------------------- pixel-major residency ----
+    def make_ring_state(self, tensors: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None) -> RingPanoramaState:
+        """Planar ring path, world_size > 1 (collective): replicate reference-order panoramas in symmetric
+        memory so that ``merge_all`` exchanges rows by peer stores (see :class:`RingPanoramaState`)."""
+        return RingPanoramaState(self, list(tensors), mask)
+
     def make_state(self, tensors: Sequence[torch.Tensor], mask: Optional[torch.Tensor] = None,
                    peer: bool = False) -> PanoramaState:
         """Pack reference-order panoramas (latent, denoised, ...) into a resident
@@ -544,6 +616,10 @@ class PanoramaStepper:
             if st.peer_table is not None:            # replicas may be overwritten once every rank has read
                 self._peer_sync(st, _lib.DS_PEER_AFTER_GATHER)
             return out
+        ring_state = latent if isinstance(latent, RingPanoramaState) else None
+        if ring_state is not None:
+            assert plan.kind == "ring", "RingPanoramaState holds the planar ring path"
+            latent = ring_state.tensors[index]
         _lib.require_cuda(latent, "latent")
         assert latent.is_contiguous() and latent.dim() == 5
         B, C, F, H, W = latent.shape
@@ -553,15 +629,18 @@ class PanoramaStepper:
         if out is None:
             out = torch.empty(shape, dtype=latent.dtype, device=latent.device)
         assert tuple(out.shape) == shape and out.is_contiguous()
-        if nj == 0:
+        if nj == 0 and ring_state is None:
             return out
         if plan.kind == "ring":
             d_jobs = plan.d_jobs[j0:j0 + nj]
             with _lib.on(latent.device):
-                lib.check(lib.ds_ring_gather(latent.data_ptr(), out.data_ptr(), d_jobs.data_ptr(), nj, 0, 0, 0,
-                                             B * C, F, H, W, plan.f_len, plan.h, plan.w,
-                                             _lib.dtype_code(latent.dtype), _lib.stream_ptr(latent.device)),
-                          "ds_ring_gather")
+                if nj > 0:
+                    lib.check(lib.ds_ring_gather(latent.data_ptr(), out.data_ptr(), d_jobs.data_ptr(), nj, 0, 0, 0,
+                                                 B * C, F, H, W, plan.f_len, plan.h, plan.w,
+                                                 _lib.dtype_code(latent.dtype), _lib.stream_ptr(latent.device)),
+                              "ds_ring_gather")
+            if ring_state is not None:           # replicas may be overwritten once EVERY rank has read (full barrier)
+                self._peer_sync(ring_state, _lib.DS_PEER_AFTER_GATHER, wait=True)
         elif plan.kind == "sphere_nearest":
             _launch_gather_nearest(latent, out, plan.d_idx, plan.d_jobs[j0:j0 + nj], 0, nj, B * C, F, H * W,
                                    plan.f_len, plan.hw)
@@ -594,6 +673,8 @@ class PanoramaStepper:
         With world_size > 1 every rank ends up with the identical merged replica."""
         if isinstance(panos, PanoramaState):
             return self._merge_state(panos, payloads, plan)
+        if isinstance(panos, RingPanoramaState):
+            return self._merge_ring_state(panos, payloads, plan)
         assert len(panos) == len(payloads) and 0 < len(panos) <= _lib.DS_MAX_PAYLOADS
         B, C, F, H, W = panos[0].shape
         P = B * C
@@ -733,6 +814,33 @@ class PanoramaStepper:
                 else:
                     lib.check(lib.ds_select_merged(mask.data_ptr(), self._xbuf[okey].data_ptr(), weight.data_ptr(),
                                                    n, period, group, code, sp), "ds_select_merged")
+
+    def _merge_ring_state(self, rs: RingPanoramaState, payloads, plan: StepPlan):
+        """Planar ring merge in exchange mode: every element this rank's windows win goes into every
+        replica (peer stores), then a full cross-GPU barrier publishes the step."""
+        assert plan.kind == "ring" and 0 < len(payloads) <= len(rs.tensors)
+        panos = rs.tensors[:len(payloads)]
+        B, C, F, H, W = rs.shape
+        P = B * C
+        for y in payloads:
+            assert y.is_contiguous() and y.dtype == rs.dtype
+        j0, nj = self.local_jobs(plan)
+        mask, mask_mode, mask_planes = rs.mask, _lib.DS_MASK_NONE, 0
+        if mask is not None:
+            if mask.numel() == H * W:
+                assert plan.d_ftab is None, "a [1, H, W] mask panorama has no frame axis"
+                mask_mode = _lib.DS_MASK_PLANE
+            else:
+                mask_mode, mask_planes = _lib.DS_MASK_FULL, mask.numel() // (F * H * W)
+        if nj > 0 and plan.T > 0:
+            with _lib.on(rs.device):
+                lib.check(lib.ds_merge_nearest_peer(_lib.ptr_array(panos), _lib.ptr_array(payloads), len(panos),
+                                                    _lib.ptr(mask), mask_mode, mask_planes, None, plan.d_src.data_ptr(),
+                                                    plan.T, _lib.ptr(plan.d_ftab), plan.vpf, j0, nj, P, F, H * W,
+                                                    plan.f_len, plan.hw, plan.vec, rs.peer_table,
+                                                    _lib.dtype_code(rs.dtype), _lib.stream_ptr(rs.device)),
+                          "ds_merge_nearest_peer")
+        self._peer_sync(rs, _lib.DS_PEER_AFTER_MERGE, wait=True)
 
     def _merge_sharded(self, panos, payloads, mask, plan, P, j0, nj):
         """disjoint-support partial merge -> one all-reduce -> select."""

@@ -138,6 +138,18 @@ int ds_merge_nearest(void* const* h_panos, const void* const* h_payloads, int Q,
                      int views_per_fwin, int job_begin, int job_count,
                      int P, int F, int HW, int f_len, int hw, int vec, int dtype, void* stream);
 
+/* ds_merge_nearest in exchange mode (windows sharded over ranks; planar ring path of
+ * pipeline/t2v_sphere_panorama_pipeline.py:537-632): d_peer is the local ds_peer_table_t (below) whose
+ * pm[r][q] / mask[r] list every rank's REFERENCE-ORDER replica; every element this rank's jobs win is
+ * stored into all of them over NVLink (peer st.global, 16-byte vectors when vec == 4), so the sharded
+ * planar merge needs no zeroed sum buffer, all-reduce or select.  h_panos / mask are only validated.
+ * The host orders the phases with ds_pm_peer_sync(wait = 1) after the gather and after the merge. */
+int ds_merge_nearest_peer(void* const* h_panos, const void* const* h_payloads, int Q,
+                          void* mask, int mask_mode, int mask_planes,
+                          const int32_t* d_dst, const int32_t* d_src, int T,
+                          const int32_t* d_ftab, int views_per_fwin, int job_begin, int job_count,
+                          int P, int F, int HW, int f_len, int hw, int vec, void* d_peer, int dtype, void* stream);
+
 /* Weighted scatter-accumulate + per-pixel weight normalisation in gather form:
  * PanoramaTensor.set_view_tensor_bilinear (utils/panorama_tensor_utils.py:98-152; ring twin
  * ring_panorama_tensor_utils.py:107-166).  Row t owns panorama pixel d_row_dst[t] and

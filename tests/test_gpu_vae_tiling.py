@@ -114,7 +114,8 @@ def test_repeat_renoise_vs_oracle(dev, dtype):
     got = repeat_renoise(f0, 5, c, s, eps)
     rep = torch.cat([f0] * 5, dim=2)
     assert torch.equal(repeat_renoise(f0, 5, 1.0, 0.0, None), rep)
-    want = torch.tensor(c, dtype=dtype, device=dev) * rep + torch.tensor(s, dtype=dtype, device=dev) * eps   # the reference's ops
+    # the reference's ops: c, s are float32 0-dim tensors (pipeline/scheduler.py:104-105), x_a / eps have the latent dtype
+    want = torch.tensor(c, device=dev) * rep + torch.tensor(s, device=dev) * eps
     assert torch.equal(got, want)
     if dtype == torch.float32:
         oc, os_ = po.renoise_scalars(ac, np.array([1, 334, 667]), 0, 2)
