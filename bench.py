@@ -338,6 +338,39 @@ def sleep_cycles_per_us(dev):
     return _SLEEP_CAL[dev]
 
 
+def dropin_step_time(wl, dev, steps=10):
+    """Regime (i) of SURVEY §7: the reference's UNMODIFIED sequential call sites (per view: get latent, get
+    mask, mix, set latent / denoised / mask -- t2v_sphere_panorama_pipeline.py:176-291) through the drop-in
+    classes, one kernel launch per call, eager Python.  Returns (ms per step, calls per step)."""
+    from dynamicscaler_b200.panorama_tensor_utils import PanoramaLatentProxy, PanoramaTensor
+    from dynamicscaler_b200.tensor_utils import mix_latents_with_mask
+    H, W, F, C, h, w = wl["H"], wl["W"], wl["F"], wl["C"], wl["h"], wl["w"]
+    lat = torch.randn(1, C, F, H, W, device=dev)
+    h_lat, h_den = PanoramaLatentProxy(lat), PanoramaLatentProxy(torch.zeros_like(lat))
+    xp = torch.randn(1, C, F, h, w, device=dev)
+    x0 = torch.randn(1, C, F, h, w, device=dev)
+    ones = torch.ones(1, h, w, device=dev)
+
+    def step(i):
+        h_msk = PanoramaTensor(torch.zeros(1, H, W, device=dev))          # re-created every step (:173)
+        for ph, th in default_views(i):
+            vw, _ = h_lat.get_view_tensor_no_interpolate(fov=wl["fov"], theta=th, phi=ph, width=w, height=h)
+            mk, _ = h_msk.get_view_tensor_no_interpolate(fov=wl["fov"], theta=th, phi=ph, width=w, height=h)
+            vw = mix_latents_with_mask(latent_1=vw, latent_to_add=vw, mask=mk, mix_ratio=0.5)
+            h_lat.set_view_tensor_no_interpolation(view_tensor=xp, fov=wl["fov"], theta=th, phi=ph)
+            h_den.set_view_tensor_no_interpolation(view_tensor=x0, fov=wl["fov"], theta=th, phi=ph)
+            h_msk.set_view_tensor_no_interpolation(view_tensor=ones, fov=wl["fov"], theta=th, phi=ph)
+
+    for i in range(10):
+        step(i)                                                           # fills the map caches of the 10 offsets
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t) / steps * 1e3, len(default_views(0)) * 6
+
+
 # ---------------------------------------------------------------- multi-GPU parity ----
 def parity_check(wl, mode, dev, rank, world, pm, peer, dtype, n_steps, multicast):
     """N > 1: run ``n_steps`` steps of the sharded path on fresh, seeded inputs (identical on every
@@ -633,6 +666,13 @@ def run_ours(args, wl, wl_name):
         }
         if parity is not None:
             line["parity"] = parity
+        if not dist_on and wl["kind"] == "sphere" and not wl.get("frame_ring") and args.dtype == "f32" and not args.no_kernel_pass:
+            d_ms, d_calls = dropin_step_time(wl, dev)
+            line["variants"]["dropin_sequential"] = {
+                "ms_per_step": d_ms, "blends_per_s": n_win / (d_ms * 1e-3), "calls_per_step": d_calls,
+                "us_per_call": d_ms * 1e3 / d_calls,
+                "what": "the reference's unmodified per-view call sites through the drop-in classes (nearest), eager, "
+                        "one launch per call"}
         if not dist_on and not args.no_kernel_pass and not denoise_cycles:
             P = wl["C"]
             plan0 = plans[args.mode][0]

@@ -55,7 +55,7 @@ PROTOTYPES = {
 
 
 DS_MAX_PEERS = 8
-DS_PEER_AFTER_GATHER, DS_PEER_AFTER_MERGE = 0, 1
+DS_PEER_AFTER_GATHER, DS_PEER_AFTER_MERGE, DS_PEER_WAIT_MERGES = 0, 1, 2
 
 
 class PeerTable(C.Structure):
@@ -99,7 +99,9 @@ class _Lib:
 
     def __getattr__(self, name):
         if name.startswith("ds_"):
-            return getattr(self.load(), name)
+            fn = getattr(self.load(), name)
+            self.__dict__[name] = fn           # next lookup is a plain instance attribute
+            return fn
         raise AttributeError(name)
 
     def check(self, rc: int, what: str = ""):
@@ -146,7 +148,15 @@ def on(device):
     return torch.cuda.device(device)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device) -> int:
+    """cudaStream_t of torch's current stream on ``device`` (the raw C accessor when torch has it: the
+    unmodified call sites make ~300 launches per step, so every microsecond of host work counts)."""
+    if _raw_stream is not None:
+        idx = device.index
+        return _raw_stream(torch.cuda.current_device() if idx is None else idx)
     return torch.cuda.current_stream(device).cuda_stream
 
 

@@ -197,13 +197,14 @@ __global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, int wait, l
   int32_t* mine = phase == DS_PEER_AFTER_GATHER ? &tab->my_gathers : &tab->my_merges;
   const size_t off = phase == DS_PEER_AFTER_GATHER ? offsetof(ds_peer_table_t, gathers_done)
                                                    : offsetof(ds_peer_table_t, merges_done);
-  const int c = *mine + 1;
+  const bool publish = phase != DS_PEER_WAIT_MERGES;       // WAIT_MERGES: no new count, only the wait below
+  const int c = *mine + (publish ? 1 : 0);
   __syncwarp();
-  if (p == 0) *mine = c;
+  if (p == 0 && publish) *mine = c;
   __threadfence_system();
   if (p < tab->world && p != tab->rank) {
     char* peer = reinterpret_cast<char*>(tab->ctl[p]);
-    st_release_sys(reinterpret_cast<int32_t*>(peer + off) + tab->rank, c);
+    if (publish) st_release_sys(reinterpret_cast<int32_t*>(peer + off) + tab->rank, c);
     const int32_t* done = reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(tab) + off) + p;
     const unsigned long long t0 = global_ns();
     while (wait && ld_acquire_sys(done) < c) {
@@ -1530,7 +1531,8 @@ extern "C" int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x
 
 extern "C" int ds_pm_peer_sync(void* d_peer, int phase, int wait, void* stream) {
   DS_REQUIRE(d_peer != nullptr, DS_ERR_NULL);
-  DS_REQUIRE(phase == DS_PEER_AFTER_GATHER || phase == DS_PEER_AFTER_MERGE, DS_ERR_DIM);
+  DS_REQUIRE(phase == DS_PEER_AFTER_GATHER || phase == DS_PEER_AFTER_MERGE || phase == DS_PEER_WAIT_MERGES, DS_ERR_DIM);
+  if (phase == DS_PEER_WAIT_MERGES) wait = 1;
   ds::pm_peer_sync_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<ds_peer_table_t*>(d_peer), phase,
                                                                            wait, ds::g_peer_timeout_ns);
   return ds::check_launch();

@@ -66,6 +66,14 @@ def _frame_table(F, f0, f_len, device):
 
 
 _VIEW_CALL_CACHE = {}      # (kind, fov, theta, phi, w, h, H, W, device) -> (ViewMap, device arrays)
+_ONE = {}
+
+
+def _ones_view(height, width, dtype, device):
+    one = _ONE.get((dtype, device))
+    if one is None:
+        one = _ONE[(dtype, device)] = torch.ones((1, 1), dtype=dtype, device=device)
+    return one.expand(height, width)
 
 
 class _Block:
@@ -193,8 +201,14 @@ class PanoramaTensor:
                                     lambda vm, dev: maps.on_device(("idx_read", vm.key), dev, lambda: vm.idx_read))
         out = torch.empty(self._view_shape(blk, height, width), dtype=blk.store.dtype, device=dev)
         _launch_gather_nearest(blk.store, out, d_idx, None, blk.f0, 1, blk.P, blk.F, self.H * self.W, blk.f_len, vm.hw)
-        mask = torch.ones((height, width), dtype=self.dtype, device=dev)
-        if not vm.all_valid:                                              # :198-200 (never taken: u, v in range)
+        if vm.all_valid:
+            # second return value of the reference (:196-202): ones[h, w].  Every caller discards it
+            # (`view, _ = ...`); a fresh torch.ones would cost an allocation + a fill kernel per call, so
+            # hand out a broadcast view of one cached element (same shape, dtype, values; in-place
+            # writes to it raise instead of corrupting the cache)
+            mask = _ones_view(height, width, self.dtype, dev)
+        else:                                                             # :198-200 (never taken: u, v in range)
+            mask = torch.ones((height, width), dtype=self.dtype, device=dev)
             bad = torch.from_numpy(~vm.read_valid).to(dev)
             mask[bad] = 0
             out[..., bad] = 0

@@ -198,6 +198,10 @@ class PanoramaState:
         own replica; call it before the step's first gather on every rank."""
         m = self.mask_plane if self.mask_plane is not None else self.mask_pm
         if m is not None:
+            if self.peer_table is not None:
+                # the peers' previous merges push mask rows into THIS replica: they must have landed before it
+                # is cleared (the next gather would wait for them anyway, but the memset would not)
+                self.stepper._peer_sync(self, _lib.DS_PEER_WAIT_MERGES, wait=True)
             m.zero_()
 
     def peer_error(self) -> bool:

@@ -201,7 +201,10 @@ typedef struct ds_peer_table {
   uint64_t mc_mask;                             /* multicast alias of the mask, or 0 */
 } ds_peer_table_t;
 int ds_peer_table_size(void);                   /* sizeof(ds_peer_table_t), for bindings */
-enum { DS_PEER_AFTER_GATHER = 0, DS_PEER_AFTER_MERGE = 1 };
+enum { DS_PEER_AFTER_GATHER = 0, DS_PEER_AFTER_MERGE = 1,
+       DS_PEER_WAIT_MERGES = 2 /* publishes nothing: only waits until every peer has pushed as many merges as this
+                                  rank has issued -- before the host touches its replica outside the kernels above
+                                  (e.g. zeroing the mask panorama at the start of a step) */ };
 int ds_pm_peer_sync(void* d_peer, int phase, int wait, void* stream);
 
 /* The batched step driver keeps the panorama of a stage resident as pm[pixel][frame][plane]
