@@ -194,11 +194,15 @@ def _spawn(tmp_path, world, fn, *args):
     import time
     ctx = mp.spawn(fn, args=(world, _free_port(), str(tmp_path)) + tuple(args), nprocs=world, join=False)
     deadline = time.time() + 300
-    while not ctx.join(timeout=5):
-        if time.time() > deadline:
-            for p in ctx.processes:
-                p.kill()
-            pytest.fail("multi-GPU workers did not finish in 300 s")
+    try:
+        while not ctx.join(timeout=5):
+            if time.time() > deadline:
+                for p in ctx.processes:
+                    p.kill()
+                pytest.fail("multi-GPU workers did not finish in 300 s")
+    except Exception as e:                       # a worker exited non-zero: show what it recorded
+        notes = "".join(open(f).read() for f in sorted(str(x) for x in tmp_path.glob("rank*.txt")))
+        pytest.fail(f"{type(e).__name__}: {str(e)[:200]}\n{notes}")
     for r in range(world):
         assert np.load(tmp_path / f"rank{r}.npy")[0], f"rank {r} mismatch"
 
@@ -236,7 +240,8 @@ def _loop_worker(rank, world, port, out_dir, group_size):
                      ddim_sigmas=np.zeros(4), ddim_sqrt_one_minus_alphas=np.sqrt(1 - al))
 
         def model(x, ts_, c_crossattn=None, fps=None, **kw):          # elementwise: independent of the batch split
-            return torch.sin(x * 1.7) * 0.5 + c_crossattn[0].mean(dim=(1, 2)).view(-1, 1, 1, 1, 1) * 0.1
+            # (no reductions: a mean over the context would depend on the reduction shape, i.e. on the batch size)
+            return torch.sin(x * 1.7) * 0.5 + c_crossattn[0][:, 3, 5].reshape(-1, 1, 1, 1, 1) * 0.1
 
         def eps_fn(i, job_ids, shape, device):
             if not len(job_ids):
@@ -254,13 +259,18 @@ def _loop_worker(rank, world, port, out_dir, group_size):
                                 group_size=group_size, renoise_ratio=0.6, prev_ratio_list=[0.3, 0.4, 0.5, 0.6], eps_fn=eps_fn)
             outs.append(state.export() + [state.export_mask()])
         ok = all(torch.equal(a, b) for a, b in zip(*outs))
+        if not ok:
+            with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as fh:
+                for name, a, b in zip(("latent", "denoised", "mask"), *outs):
+                    d = (a.float() - b.float()).abs()
+                    fh.write(f"rank {rank} {name}: {int((d > 0).sum())} elements differ, max {float(d.max()):.3e}\n")
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.array([ok]))
         torch.cuda.synchronize()
         dist.barrier()
     except BaseException:
         import traceback
-        traceback.print_exc()
-        sys.stderr.flush()
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "a") as fh:
+            fh.write(traceback.format_exc())
         ok = False
     finally:
         os._exit(0 if ok else 1)
