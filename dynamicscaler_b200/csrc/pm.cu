@@ -54,6 +54,7 @@ constexpr int kWarps = kBlock / 32;
 static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
 static int g_gather_tile_w = 0;                 // 0: linear tiles of 64 view pixels; 8 / 16 / 32: 2-D tiles (64/w rows x w pixels)
 static int g_merge_weighted_minb = 0;           // 5: two-payload tiled weighted merge compiled for 5 CTAs per SM
+static int g_merge_publish = 1;                 // 1: exchange-mode merges publish their count themselves (last CTA), 0: host launches ds_pm_peer_sync
 static int g_gather_pipe = 2;                   // bit 1: copy-only gather, bit 2: 4-tap gather use the pipelined tile loop
 static long long g_peer_timeout_ns = 60000000000ll;  // a cross-GPU wait longer than this (60 s: first-step autotune,
                                                        // lazy module loads, stragglers are all far shorter) aborts the kernel
@@ -137,6 +138,13 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
   bulk_commit();
   bulk_wait_read();
 }
+// ... until the copies are COMPLETE (their global writes performed), not merely read from shared memory:
+// needed before this thread's release fence publishes rows it pushed into peer replicas.
+__device__ __forceinline__ void bulk_commit_and_wait_done() {
+  bulk_commit();
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
 
 // 4-byte asynchronous copy global -> shared (SASS LDGSTS): no register holds the value, so a
 // prefetch costs nothing while it is in flight.  bytes == 0 writes a zero instead.
@@ -211,6 +219,31 @@ __global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, int wait, l
       if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) pm_peer_timeout(tab);
     }
   }
+}
+
+// Publication folded into a data kernel: every CTA calls this once after its last access (after a
+// __syncthreads, by all threads); the LAST CTA to arrive bumps this rank's count and stores it into
+// every peer's table -- what pm_peer_sync_kernel does, without the extra launch.  Release pattern:
+// each CTA's thread 0 fences at system scope (cumulative over the accesses of its CTA, which the barrier
+// ordered before it) and then adds to the arrival counter; the last CTA's add observes them all, fences
+// again (acquire side) and issues the release stores.
+__device__ __forceinline__ void pm_peer_publish_last_cta(ds_peer_table_t* tab, int phase, unsigned n_ctas) {
+  if (threadIdx.x != 0) return;
+  __threadfence_system();
+  int32_t* arrivals = phase == DS_PEER_AFTER_GATHER ? &tab->gather_arrivals : &tab->merge_arrivals;
+  const unsigned prev = static_cast<unsigned>(atomicAdd(arrivals, 1));
+  if (prev != n_ctas - 1) return;
+  *arrivals = 0;                                   // next launch on this table starts from zero again
+  __threadfence_system();
+  int32_t* mine = phase == DS_PEER_AFTER_GATHER ? &tab->my_gathers : &tab->my_merges;
+  const size_t off = phase == DS_PEER_AFTER_GATHER ? offsetof(ds_peer_table_t, gathers_done)
+                                                   : offsetof(ds_peer_table_t, merges_done);
+  const int c = *mine + 1;
+  *mine = c;
+  __threadfence_system();
+  for (int p = 0; p < tab->world; ++p)
+    if (p != tab->rank)
+      st_release_sys(reinterpret_cast<int32_t*>(reinterpret_cast<char*>(tab->ctl[p]) + off) + tab->rank, c);
 }
 
 // In-kernel half of the ordering: lane p of every CTA waits until peer p's counter `done[p]` has
@@ -460,6 +493,12 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     }
   }
   if (PIPE && in_flight) bulk_wait_read();      // shared memory must outlive the last copy
+  if (peer != nullptr) {
+    // exchange mode: this rank has finished READING its replica once every CTA is past its last tap
+    // load -> the last CTA publishes the gather count (the peers' merges may then overwrite the rows)
+    __syncthreads();
+    pm_peer_publish_last_cta(peer, DS_PEER_AFTER_GATHER, gridDim.x);
+  }
 }
 
 // -------------------------------------------------- gather + re-noise + mask mix ----
@@ -593,6 +632,10 @@ pm_gather_renoise_kernel(const typename Atom<T>::type* __restrict__ pm, T* __res
     if (MM == DS_MASK_FULL && e.out_mask != nullptr)
       pm_renoise_pass<T, MM, 2>(pm, static_cast<T*>(e.out_mask), s_idx, s_midx, tile, a, e, job, k0, f0);
   }
+  if (peer != nullptr) {
+    __syncthreads();
+    pm_peer_publish_last_cta(peer, DS_PEER_AFTER_GATHER, gridDim.x);
+  }
 }
 
 // ------------------------------------------------------------------------ merges ----
@@ -666,6 +709,7 @@ struct PmMergeArgs {
   int vpf, job_begin, job_count;
   int F, HW, f_len, hw;
   ds_peer_table_t* peer;         // NULL: single replica (pm / mask above)
+  int publish;                   // exchange mode: the kernel publishes this rank's merge count itself (last CTA)
   long long peer_timeout_ns;
   PmDdim dd;                     // DD kernels only
 };
@@ -748,6 +792,16 @@ __device__ __forceinline__ void pm_store_mask_plane(const PmMergeArgs& a, const 
   } else {
     for (int r = 0; r < rep.world; ++r) reinterpret_cast<T*>(rep.ptr[r][DS_MAX_PAYLOADS])[dst] = Elem<T>::one();
   }
+}
+
+// Last statement of every exchange-mode merge CTA (also of CTAs that found no work): the rows this CTA
+// pushed are complete (bulk copies waited for by their issuing threads), then the last CTA of the grid
+// publishes the merge count -- the peers' next gather may then read the replicas.
+template <bool PEER>
+__device__ __forceinline__ void pm_merge_end(const PmMergeArgs& a) {
+  if (!PEER || !a.publish) return;
+  __syncthreads();
+  pm_peer_publish_last_cta(a.peer, DS_PEER_AFTER_MERGE, gridDim.x * gridDim.y);
 }
 
 struct PmRange {
@@ -901,7 +955,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
                    tile + (q * kPmET + i) * SA, row_bytes);
         issued = true;
       }
-      if (issued) bulk_commit_and_wait_read();
+      if (issued) { if (a.publish) bulk_commit_and_wait_done(); else bulk_commit_and_wait_read(); }
     } else {
       const int per_q = cnt * f_len;
       const int n_units = (a.Q > 0 ? a.Q : 1) * per_q;
@@ -917,6 +971,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
       }
     }
   }
+  pm_merge_end<PEER>(a);
 }
 
 // Tiled weighted merge (fast path): the host pads the CSR entry list so that tile t owns
@@ -949,7 +1004,10 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   const int v_hi = min(max(a.job_begin + a.job_count - s * a.vpf, 0), a.vpf);
   const int t = __ldg(d_view_ptr + v_lo) + blockIdx.x;
   pdl_launch_dependents();
-  if (t >= __ldg(d_view_ptr + v_hi)) return;
+  if (t >= __ldg(d_view_ptr + v_hi)) {
+    pm_merge_end<PEER>(a);                         // a CTA without a tile still arrives for the publication
+    return;
+  }
   __shared__ PmReplicas rep;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int e_base = t * kPmEC;
@@ -1137,8 +1195,9 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
         issued = true;
       }
     }
-    if (issued) bulk_commit_and_wait_read();
+    if (issued) { if (a.publish) bulk_commit_and_wait_done(); else bulk_commit_and_wait_read(); }
   }
+  pm_merge_end<PEER>(a);
 }
 
 // Generic (runtime f_len, any row length) weighted merge.  CTA = 32 panorama rows; each lane
@@ -1214,6 +1273,7 @@ pm_merge_bilinear_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view
       }
     }
   }
+  pm_merge_end<PEER>(a);
 }
 
 static bool pm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -1252,6 +1312,7 @@ static int pm_fill_merge_args(PmMergeArgs& a, void* const* h_pms, const void* co
   a.vpf = vpf; a.job_begin = job_begin; a.job_count = job_count;
   a.F = F; a.HW = HW; a.f_len = f_len; a.hw = hw;
   a.peer = static_cast<ds_peer_table_t*>(d_peer);
+  a.publish = d_peer != nullptr ? g_merge_publish : 0;
   a.peer_timeout_ns = g_peer_timeout_ns;
   return DS_OK;
 }
@@ -1548,6 +1609,7 @@ extern "C" int ds_tune(int knob, long long value) {
     case DS_TUNE_PM_GATHER_PIPELINE: ds::g_gather_pipe = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PM_GATHER_TILE_W: ds::g_gather_tile_w = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PM_MERGE_WEIGHTED_MINB: ds::g_merge_weighted_minb = static_cast<int>(value); return DS_OK;
+    case DS_TUNE_PEER_MERGE_PUBLISH: ds::g_merge_publish = value != 0 ? 1 : 0; return DS_OK;
     default: return DS_ERR_DIM;
   }
 }

@@ -308,8 +308,21 @@ class PanoramaStepper:
         # peer states: NVLS multicast stores win from 4 GPUs up (one store instead of world-1 copies);
         # at 2 GPUs the per-replica TMA row copies are faster (tools/peer_probe.py)
         self.use_multicast = world > 2
+        # exchange-mode merges publish their merge count in-kernel (DS_TUNE_PEER_MERGE_PUBLISH); False: one
+        # ds_pm_peer_sync launch after every merge instead
+        self._merge_publish = True
         self._plans = {}
         self._xbuf = {}
+
+    @property
+    def merge_publish_in_kernel(self) -> bool:
+        return self._merge_publish
+
+    @merge_publish_in_kernel.setter
+    def merge_publish_in_kernel(self, on: bool):
+        """Process-wide switch (ds_tune DS_TUNE_PEER_MERGE_PUBLISH): every stepper of the process follows it."""
+        self._merge_publish = bool(on)
+        lib.check(lib.ds_tune(6, 1 if on else 0), "ds_tune")
 
     # ------------------------------------------------------------------ planning ----
     def _frames(self, frame_begins, frames):
@@ -516,13 +529,12 @@ class PanoramaStepper:
                                                    mplan.d_idx.data_ptr(), h_coef, d_jobs.data_ptr(), 0, nj, 4, F, HW,
                                                    plan.f_len, plan.hw, st.peer_table, _lib.dtype_code(st.dtype),
                                                    _lib.stream_ptr(st.device)), "ds_pm_gather_renoise")
-        if st.peer_table is not None:
-            self._peer_sync(st, _lib.DS_PEER_AFTER_GATHER)
-        return out, raw, mview
+        return out, raw, mview                        # (peer states: the kernel published the gather count itself)
 
     def _pm_merge_into(self, pms, payloads, mask, mask_mode, plan, j0, nj, peer=None):
-        if plan.T == 0:
-            return                                 # none of this rank's views survives anywhere
+        """Returns True when a merge kernel was launched (in exchange mode it then publishes the merge count)."""
+        if plan.T == 0 or nj == 0:
+            return False                           # none of this rank's views survives anywhere
         mp = self._pm_merge_plan(plan)
         F, HW = plan.F, plan.H * plan.W
         ref = pms[0] if pms else mask
@@ -550,6 +562,7 @@ class PanoramaStepper:
                                                    row_dst.data_ptr(), row_ptr.data_ptr(), row_dst.numel(),
                                                    ent_src.data_ptr(), ent_w.data_ptr(), *common),
                           "ds_pm_merge_bilinear")
+        return True
 
     # ---------------------------------------------- condition-image windows (§8f-3) ----
     def gather_image_windows(self, image: torch.Tensor, windows: Sequence[Tuple[int, int]], w: int, h: int
@@ -615,10 +628,8 @@ class PanoramaStepper:
             assert tuple(out.shape) == shape and out.is_contiguous()
             if renoise is not None:
                 return self._pm_gather_renoise(st, plan, out, index, j0, nj, renoise)
-            if nj > 0:
+            if nj > 0 or st.peer_table is not None:  # an idle rank still publishes its gather count (in-kernel)
                 self._pm_gather(st.pms[index], plan, out, j0, nj, st.peer_table)
-            if st.peer_table is not None:            # replicas may be overwritten once every rank has read
-                self._peer_sync(st, _lib.DS_PEER_AFTER_GATHER)
             return out
         ring_state = latent if isinstance(latent, RingPanoramaState) else None
         if ring_state is not None:
@@ -746,6 +757,7 @@ class PanoramaStepper:
                 _lib.ptr(mask), mask_mode)
         tail = (_lib.ptr(plan.d_ftab), _lib.ptr(plan.d_fbegin), plan.n_fwin, plan.vpf, j0, nj, 4, F, HW, plan.f_len,
                 plan.hw, st.peer_table, _lib.dtype_code(st.dtype), _lib.stream_ptr(st.device))
+        launched = nj > 0 and plan.T > 0
         with _lib.on(st.device):
             if nj > 0 and plan.T > 0 and plan.kind == "sphere_nearest":
                 view_ptr, ent_src, ent_dst = plan.pm_merge
@@ -759,7 +771,7 @@ class PanoramaStepper:
                                                               row_dst.data_ptr(), row_start.data_ptr(), row_dst.numel(),
                                                               ent_k.data_ptr(), ent_w.data_ptr(), *tail),
                           "ds_pm_merge_bilinear_tiled_ddim")
-        if st.peer_table is not None:
+        if st.peer_table is not None and not (launched and self.merge_publish_in_kernel):
             self._peer_sync(st, _lib.DS_PEER_AFTER_MERGE)
 
     def _merge_state(self, st: PanoramaState, payloads, plan: StepPlan):
@@ -781,9 +793,9 @@ class PanoramaStepper:
             return
         if st.peer_table is not None:
             # fused exchange: this rank's surviving rows go straight into every replica (csrc/pm.cu)
-            if nj > 0:
-                self._pm_merge_into(pms, payloads, mask, mask_mode, plan, j0, nj, st.peer_table)
-            self._peer_sync(st, _lib.DS_PEER_AFTER_MERGE)   # replicas are complete once every rank has pushed
+            launched = self._pm_merge_into(pms, payloads, mask, mask_mode, plan, j0, nj, st.peer_table)
+            if not (launched and self.merge_publish_in_kernel):  # an idle rank (or the host-sync protocol) publishes here
+                self._peer_sync(st, _lib.DS_PEER_AFTER_MERGE)   # replicas are complete once every rank has pushed
             return
         # sharded: disjoint-support partial merge into zeroed buffers -> all-reduce -> select
         import torch.distributed as dist

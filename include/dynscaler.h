@@ -60,6 +60,9 @@ enum {
   DS_TUNE_PM_GATHER_TILE_W = 4         /* gather tile shape: 0 = 64 consecutive view pixels; 8 / 16 / 32 = 2-D tiles of
                                           (64 / value) view rows x value pixels when ds_pm_gather knows the view width */
   , DS_TUNE_PM_MERGE_WEIGHTED_MINB = 5 /* 5: the two-payload tiled weighted merge runs the variant compiled for 5 CTAs/SM */
+  , DS_TUNE_PEER_MERGE_PUBLISH = 6     /* 1 (default): exchange-mode pixel-major merges publish their merge count themselves
+                                          (last CTA, after their pushes are complete); 0: the host must enqueue
+                                          ds_pm_peer_sync(DS_PEER_AFTER_MERGE) after every such merge */
 };
 int ds_tune(int knob, long long value);
 
@@ -175,14 +178,15 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
  * -- one multimem.st to the NVLS multicast alias (mc_pm[q], mc_mask) when the host provides it,
  * else one peer store / TMA bulk copy per replica (pm[r][q], mask[r]) -- so there is no sum
  * buffer, all-reduce or select.
- * Ordering across GPUs is two monotonic counters per peer.  The host enqueues ds_pm_peer_sync (one
- * 32-thread kernel) after every gather (DS_PEER_AFTER_GATHER) and every merge
- * (DS_PEER_AFTER_MERGE): it bumps this rank's count and publishes it into every peer's table
- * (st.release.sys) and, if wait != 0, also waits for the peers' counts.  With d_peer the data
- * kernels do the waiting themselves (ld.acquire.sys, overlapped with their first loads): a
- * gather starts reading only when every peer has published as many merges as this rank (replicas
- * complete), a merge starts storing only when every peer has published as many gathers
- * (replicas may be overwritten) -- so wait = 0 is enough between them.
+ * Ordering across GPUs is two monotonic counters per peer: a rank's gather count and merge count, each
+ * published into every peer's table with st.release.sys.  The pixel-major gathers (ds_pm_gather,
+ * ds_pm_gather_renoise) publish their count THEMSELVES (the last CTA to finish does it); after every
+ * pixel-major merge -- and around the reference-order ring calls -- the host enqueues ds_pm_peer_sync
+ * (one 32-thread kernel; DS_PEER_AFTER_MERGE / DS_PEER_AFTER_GATHER): it bumps this rank's count,
+ * publishes it and, if wait != 0, also waits for the peers' counts.  With d_peer the data kernels do
+ * the waiting themselves (ld.acquire.sys, overlapped with their first loads): a gather starts reading
+ * only when every peer has published as many merges as this rank (replicas complete), a merge starts
+ * storing only when every peer has published as many gathers (replicas may be overwritten).
  * All ranks must issue the same gather / merge sequence on a state.  A wait that exceeds
  * DS_TUNE_PEER_TIMEOUT_NS sets `error`.  The host zero-fills the table, then writes rank,
  * world, pm, mask and ctl (the address of every rank's table, own included) and makes sure
@@ -192,7 +196,7 @@ typedef struct ds_peer_table {
   int32_t merges_done[DS_MAX_PEERS];            /* [p]: written by peer p */
   int32_t gathers_done[DS_MAX_PEERS];           /* [p]: written by peer p */
   int32_t my_merges, my_gathers;                /* this rank's own counts */
-  int32_t reserved0, reserved1;
+  int32_t gather_arrivals, merge_arrivals;      /* CTA arrival counters of the in-kernel publication (zero between launches) */
   int32_t error, rank, world, reserved;
   uint64_t pm[DS_MAX_PEERS][DS_MAX_PAYLOADS];   /* replica r, panorama q */
   uint64_t mask[DS_MAX_PEERS];                  /* replica r of the mask panorama (or 0) */
