@@ -372,7 +372,7 @@ def dropin_step_time(wl, dev, steps=10):
 
 
 # ---------------------------------------------------------------- multi-GPU parity ----
-def parity_check(wl, mode, dev, rank, world, pm, peer, dtype, n_steps, multicast, publish_in_kernel=True):
+def parity_check(wl, mode, dev, rank, world, pm, peer, dtype, n_steps, multicast, publish_in_kernel=False):
     """N > 1: run ``n_steps`` steps of the sharded path on fresh, seeded inputs (identical on every
     rank), export every rank's panoramas + mask, and compare their sha256 with a SINGLE-rank run of
     the same steps done locally on every rank.  Payloads depend on the gathered windows, so a wrong
@@ -454,8 +454,8 @@ def run_ours(args, wl, wl_name):
     st = PanoramaStepper(wl["H"], wl["W"], wl["F"], device=dev, rank=rank, world=world)
     if args.multicast != "auto":
         st.use_multicast = args.multicast == "on"
-    if args.merge_publish == "host":
-        st.merge_publish_in_kernel = False
+    if args.merge_publish == "kernel":
+        st.merge_publish_in_kernel = True
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     modes, NP = modes_of(wl), n_phases(wl)
     if args.mode not in modes:
@@ -751,7 +751,7 @@ def main():
                     help="N > 1: fused peer-store exchange in the merge kernels, or NCCL all-reduce + select")
     ap.add_argument("--multicast", default="auto", choices=["auto", "on", "off"],
                     help="peer exchange: NVLS multicast stores (one store reaches every replica) or per-replica copies")
-    ap.add_argument("--merge-publish", default="kernel", choices=["kernel", "host"],
+    ap.add_argument("--merge-publish", default="host", choices=["kernel", "host"],
                     help="peer exchange: merge kernels publish their merge count themselves (last CTA) or the host "
                          "launches one ds_pm_peer_sync kernel after every merge")
     ap.add_argument("--workload", default="cfg2_sphere_128x256", choices=list(WORKLOADS))

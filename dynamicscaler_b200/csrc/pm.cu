@@ -54,7 +54,10 @@ constexpr int kWarps = kBlock / 32;
 static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
 static int g_gather_tile_w = 0;                 // 0: linear tiles of 64 view pixels; 8 / 16 / 32: 2-D tiles (64/w rows x w pixels)
 static int g_merge_weighted_minb = 0;           // 5: two-payload tiled weighted merge compiled for 5 CTAs per SM
-static int g_merge_publish = 1;                 // 1: exchange-mode merges publish their count themselves (last CTA), 0: host launches ds_pm_peer_sync
+static int g_merge_publish = 0;                 // 1: exchange-mode gathers / merges publish their counts themselves (last CTA).  Measured at
+                                                // 2 GPUs (cfg2, us/step): merges 71.5 vs 52.2 (every CTA pays a system-scope fence that waits
+                                                // for its NVLink acknowledgements), gathers 46.0 vs 46.2 (no gain).  0 (default): the host
+                                                // launches ds_pm_peer_sync after each of them
 static int g_gather_pipe = 2;                   // bit 1: copy-only gather, bit 2: 4-tap gather use the pipelined tile loop
 static long long g_peer_timeout_ns = 60000000000ll;  // a cross-GPU wait longer than this (60 s: first-step autotune,
                                                        // lazy module loads, stragglers are all far shorter) aborts the kernel
@@ -229,7 +232,11 @@ __global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, int wait, l
 // again (acquire side) and issues the release stores.
 __device__ __forceinline__ void pm_peer_publish_last_cta(ds_peer_table_t* tab, int phase, unsigned n_ctas) {
   if (threadIdx.x != 0) return;
-  __threadfence_system();
+  // merges: this CTA's peer stores must be performed before the arrival (a system-scope fence per CTA: it
+  // waits for the NVLink acknowledgements, which is why the host-side publication is the default for
+  // merges).  gathers only READ the replica and every loaded value was consumed before the barrier the
+  // caller just passed, so their arrival needs no fence at all.
+  if (phase != DS_PEER_AFTER_GATHER) __threadfence_system();
   int32_t* arrivals = phase == DS_PEER_AFTER_GATHER ? &tab->gather_arrivals : &tab->merge_arrivals;
   const unsigned prev = static_cast<unsigned>(atomicAdd(arrivals, 1));
   if (prev != n_ctas - 1) return;
@@ -270,6 +277,7 @@ struct PmGatherArgs {
   // 2-D tiles keep the 2x2 tap footprints of neighbouring view rows in one CTA, so the panorama
   // rows they share are fetched from L2 once per tile instead of once per view row.
   int tw_shift, w, tiles_x;
+  int publish;                   // exchange mode: the last CTA publishes this rank's gather count (DS_TUNE_PEER_PUBLISH)
 };
 
 // first view pixel of segment r (a run of TW pixels) of tile tj of a job
@@ -493,7 +501,7 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     }
   }
   if (PIPE && in_flight) bulk_wait_read();      // shared memory must outlive the last copy
-  if (peer != nullptr) {
+  if (peer != nullptr && a.publish) {
     // exchange mode: this rank has finished READING its replica once every CTA is past its last tap
     // load -> the last CTA publishes the gather count (the peers' merges may then overwrite the rows)
     __syncthreads();
@@ -632,7 +640,7 @@ pm_gather_renoise_kernel(const typename Atom<T>::type* __restrict__ pm, T* __res
     if (MM == DS_MASK_FULL && e.out_mask != nullptr)
       pm_renoise_pass<T, MM, 2>(pm, static_cast<T*>(e.out_mask), s_idx, s_midx, tile, a, e, job, k0, f0);
   }
-  if (peer != nullptr) {
+  if (peer != nullptr && a.publish) {
     __syncthreads();
     pm_peer_publish_last_cta(peer, DS_PEER_AFTER_GATHER, gridDim.x);
   }
@@ -1379,7 +1387,7 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   const long long n_tiles = static_cast<long long>(n_jobs) * tpj;
   DS_REQUIRE(n_tiles < (1ll << 31) && static_cast<long long>(n_jobs) * P * f_len * hw < (1ll << 40), DS_ERR_DIM);
   DS_REQUIRE(static_cast<long long>(n_jobs) * taps * hw < (1ll << 31), DS_ERR_DIM);
-  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj, tw_shift, geo_w, tiles_x};
+  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj, tw_shift, geo_w, tiles_x, d_peer != nullptr ? g_merge_publish : 0};
   const bool pipe = (g_gather_pipe & (taps == 1 ? 1 : 2)) != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DS_DISPATCH_DTYPE(dtype, {
@@ -1419,7 +1427,7 @@ extern "C" int ds_pm_gather_renoise(const void* pm, void* out, void* out_raw, vo
   const int tpj = static_cast<int>(div_up(hw, kPmKT));
   const long long n_tiles = static_cast<long long>(n_jobs) * tpj;
   DS_REQUIRE(n_tiles < (1ll << 31) && static_cast<long long>(n_jobs) * P * f_len * hw < (1ll << 40), DS_ERR_DIM);
-  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj, 6, kPmKT, 1};
+  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj, 6, kPmKT, 1, d_peer != nullptr ? g_merge_publish : 0};
   PmRenoiseArgs e{eps, mask, out_raw, out_mask, h_coef[0], h_coef[1], h_coef[2], h_coef[3]};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DS_DISPATCH_DTYPE(dtype, {

@@ -308,9 +308,9 @@ class PanoramaStepper:
         # peer states: NVLS multicast stores win from 4 GPUs up (one store instead of world-1 copies);
         # at 2 GPUs the per-replica TMA row copies are faster (tools/peer_probe.py)
         self.use_multicast = world > 2
-        # exchange-mode merges publish their merge count in-kernel (DS_TUNE_PEER_MERGE_PUBLISH); False: one
-        # ds_pm_peer_sync launch after every merge instead
-        self._merge_publish = True
+        # True: exchange-mode merges publish their merge count in-kernel (DS_TUNE_PEER_MERGE_PUBLISH; measured
+        # slower); False (default): one ds_pm_peer_sync launch after every merge
+        self._merge_publish = False
         self._plans = {}
         self._xbuf = {}
 
@@ -521,7 +521,7 @@ class PanoramaStepper:
         r = float(rn["ratio"])
         h_coef = (C.c_float * 4)(float(rn["c"]), float(rn["s"]), r, 1 - r)
         F, HW = plan.F, plan.H * plan.W
-        if nj > 0 or st.peer_table is not None:
+        if nj > 0 or (st.peer_table is not None and self.merge_publish_in_kernel):
             d_jobs = plan.d_jobs[j0:j0 + max(nj, 1)]
             with _lib.on(st.device):
                 lib.check(lib.ds_pm_gather_renoise(st.pms[index].data_ptr(), out.data_ptr(), _lib.ptr(raw), _lib.ptr(mview),
@@ -529,7 +529,9 @@ class PanoramaStepper:
                                                    mplan.d_idx.data_ptr(), h_coef, d_jobs.data_ptr(), 0, nj, 4, F, HW,
                                                    plan.f_len, plan.hw, st.peer_table, _lib.dtype_code(st.dtype),
                                                    _lib.stream_ptr(st.device)), "ds_pm_gather_renoise")
-        return out, raw, mview                        # (peer states: the kernel published the gather count itself)
+        if st.peer_table is not None and not self.merge_publish_in_kernel:
+            self._peer_sync(st, _lib.DS_PEER_AFTER_GATHER)
+        return out, raw, mview
 
     def _pm_merge_into(self, pms, payloads, mask, mask_mode, plan, j0, nj, peer=None):
         """Returns True when a merge kernel was launched (in exchange mode it then publishes the merge count)."""
@@ -628,8 +630,11 @@ class PanoramaStepper:
             assert tuple(out.shape) == shape and out.is_contiguous()
             if renoise is not None:
                 return self._pm_gather_renoise(st, plan, out, index, j0, nj, renoise)
-            if nj > 0 or st.peer_table is not None:  # an idle rank still publishes its gather count (in-kernel)
+            launched = nj > 0 or (st.peer_table is not None and self.merge_publish_in_kernel)
+            if launched:                             # (in-kernel publication: an idle rank launches too)
                 self._pm_gather(st.pms[index], plan, out, j0, nj, st.peer_table)
+            if st.peer_table is not None and not self.merge_publish_in_kernel:
+                self._peer_sync(st, _lib.DS_PEER_AFTER_GATHER)   # replicas may be overwritten once every rank has read
             return out
         ring_state = latent if isinstance(latent, RingPanoramaState) else None
         if ring_state is not None:

@@ -60,9 +60,10 @@ enum {
   DS_TUNE_PM_GATHER_TILE_W = 4         /* gather tile shape: 0 = 64 consecutive view pixels; 8 / 16 / 32 = 2-D tiles of
                                           (64 / value) view rows x value pixels when ds_pm_gather knows the view width */
   , DS_TUNE_PM_MERGE_WEIGHTED_MINB = 5 /* 5: the two-payload tiled weighted merge runs the variant compiled for 5 CTAs/SM */
-  , DS_TUNE_PEER_MERGE_PUBLISH = 6     /* 1 (default): exchange-mode pixel-major merges publish their merge count themselves
-                                          (last CTA, after their pushes are complete); 0: the host must enqueue
-                                          ds_pm_peer_sync(DS_PEER_AFTER_MERGE) after every such merge */
+  , DS_TUNE_PEER_MERGE_PUBLISH = 6     /* 0 (default): the host enqueues ds_pm_peer_sync after every exchange-mode pixel-major
+                                          gather / merge; 1: those kernels publish their gather / merge count themselves
+                                          (last CTA; merges only after their pushes are complete -- slower: one system-scope
+                                          fence per CTA) */
 };
 int ds_tune(int knob, long long value);
 
@@ -179,14 +180,15 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
  * else one peer store / TMA bulk copy per replica (pm[r][q], mask[r]) -- so there is no sum
  * buffer, all-reduce or select.
  * Ordering across GPUs is two monotonic counters per peer: a rank's gather count and merge count, each
- * published into every peer's table with st.release.sys.  The pixel-major gathers (ds_pm_gather,
- * ds_pm_gather_renoise) publish their count THEMSELVES (the last CTA to finish does it); after every
- * pixel-major merge -- and around the reference-order ring calls -- the host enqueues ds_pm_peer_sync
- * (one 32-thread kernel; DS_PEER_AFTER_MERGE / DS_PEER_AFTER_GATHER): it bumps this rank's count,
- * publishes it and, if wait != 0, also waits for the peers' counts.  With d_peer the data kernels do
- * the waiting themselves (ld.acquire.sys, overlapped with their first loads): a gather starts reading
- * only when every peer has published as many merges as this rank (replicas complete), a merge starts
- * storing only when every peer has published as many gathers (replicas may be overwritten).
+ * published into every peer's table with st.release.sys.  The host enqueues ds_pm_peer_sync (one
+ * 32-thread kernel) after every gather (DS_PEER_AFTER_GATHER) and every merge (DS_PEER_AFTER_MERGE): it
+ * bumps this rank's count, publishes it and, if wait != 0, also waits for the peers' counts (with
+ * DS_TUNE_PEER_MERGE_PUBLISH = 1 the pixel-major kernels publish themselves instead -- their last CTA
+ * does it -- and the host must NOT enqueue the sync).  With d_peer the data kernels do the waiting
+ * themselves (ld.acquire.sys, overlapped with their first loads): a gather starts reading only when
+ * every peer has published as many merges as this rank (replicas complete), a merge starts storing
+ * only when every peer has published as many gathers (replicas may be overwritten) -- so wait = 0 is
+ * enough between them.
  * All ranks must issue the same gather / merge sequence on a state.  A wait that exceeds
  * DS_TUNE_PEER_TIMEOUT_NS sets `error`.  The host zero-fills the table, then writes rank,
  * world, pm, mask and ctl (the address of every rank's table, own included) and makes sure

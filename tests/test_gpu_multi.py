@@ -45,8 +45,8 @@ def _worker(rank, world, port, exchange, out_dir, multicast=None, dtype_name="fl
             st = PanoramaStepper(H, W, F, device=dev, rank=rank, world=world)
             if multicast is not None:
                 st.use_multicast = multicast
-            if os.environ.get("DS_TEST_HOST_PUBLISH"):                       # the host-side publication protocol
-                st.merge_publish_in_kernel = False
+            if os.environ.get("DS_TEST_KERNEL_PUBLISH"):                     # in-kernel publication of the merge count
+                st.merge_publish_in_kernel = True
             mk_mask = (lambda: torch.zeros_like(lat0)) if frame_ring else (lambda: torch.zeros(1, H, W, device=dev, dtype=dtype))
             ref = ref_st.make_state([lat0, torch.zeros_like(lat0)], mask=mk_mask())
             state = st.make_state([lat0, torch.zeros_like(lat0)], mask=mk_mask(), peer=(exchange == "peer"))
