@@ -752,8 +752,8 @@ def main():
     ap.add_argument("--multicast", default="auto", choices=["auto", "on", "off"],
                     help="peer exchange: NVLS multicast stores (one store reaches every replica) or per-replica copies")
     ap.add_argument("--merge-publish", default="host", choices=["kernel", "host"],
-                    help="peer exchange: merge kernels publish their merge count themselves (last CTA) or the host "
-                         "launches one ds_pm_peer_sync kernel after every merge")
+                    help="peer exchange ordering: 'host' = one ds_pm_peer_sync launch after every gather / merge; 'kernel' = "
+                         "deferred: kernels count themselves as issued, the next kernel publishes the count in its prologue")
     ap.add_argument("--workload", default="cfg2_sphere_128x256", choices=list(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

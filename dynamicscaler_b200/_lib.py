@@ -62,8 +62,8 @@ class PeerTable(C.Structure):
     """Mirror of ``ds_peer_table_t`` (include/dynscaler.h); tests/test_abi.py checks the layout
     against the header."""
     _fields_ = [("merges_done", C.c_int32 * DS_MAX_PEERS), ("gathers_done", C.c_int32 * DS_MAX_PEERS),
-                ("my_merges", C.c_int32), ("my_gathers", C.c_int32), ("gather_arrivals", C.c_int32),
-                ("merge_arrivals", C.c_int32), ("error", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
+                ("my_merges", C.c_int32), ("my_gathers", C.c_int32), ("issued_gathers", C.c_int32),
+                ("issued_merges", C.c_int32), ("error", C.c_int32), ("rank", C.c_int32), ("world", C.c_int32),
                 ("reserved", C.c_int32),
                 ("pm", (C.c_uint64 * DS_MAX_PAYLOADS) * DS_MAX_PEERS), ("mask", C.c_uint64 * DS_MAX_PEERS),
                 ("ctl", C.c_uint64 * DS_MAX_PEERS), ("mc_pm", C.c_uint64 * DS_MAX_PAYLOADS), ("mc_mask", C.c_uint64)]

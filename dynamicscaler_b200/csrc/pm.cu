@@ -54,10 +54,8 @@ constexpr int kWarps = kBlock / 32;
 static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
 static int g_gather_tile_w = 0;                 // 0: linear tiles of 64 view pixels; 8 / 16 / 32: 2-D tiles (64/w rows x w pixels)
 static int g_merge_weighted_minb = 0;           // 5: two-payload tiled weighted merge compiled for 5 CTAs per SM
-static int g_merge_publish = 0;                 // 1: exchange-mode gathers / merges publish their counts themselves (last CTA).  Measured at
-                                                // 2 GPUs (cfg2, us/step): merges 71.5 vs 52.2 (every CTA pays a system-scope fence that waits
-                                                // for its NVLink acknowledgements), gathers 46.0 vs 46.2 (no gain).  0 (default): the host
-                                                // launches ds_pm_peer_sync after each of them
+static int g_merge_publish = 0;                 // exchange mode: 0 = the host enqueues ds_pm_peer_sync after every gather / merge; 1 = deferred:
+                                                // a data kernel counts itself as issued and the next kernel publishes it in its prologue
 static int g_gather_pipe = 2;                   // bit 1: copy-only gather, bit 2: 4-tap gather use the pipelined tile loop
 static long long g_peer_timeout_ns = 60000000000ll;  // a cross-GPU wait longer than this (60 s: first-step autotune,
                                                        // lazy module loads, stragglers are all far shorter) aborts the kernel
@@ -141,14 +139,6 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
   bulk_commit();
   bulk_wait_read();
 }
-// ... until the copies are COMPLETE (their global writes performed), not merely read from shared memory:
-// needed before this thread's release fence publishes rows it pushed into peer replicas.
-__device__ __forceinline__ void bulk_commit_and_wait_done() {
-  bulk_commit();
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  asm volatile("fence.proxy.async;" ::: "memory");
-}
-
 // 4-byte asynchronous copy global -> shared (SASS LDGSTS): no register holds the value, so a
 // prefetch costs nothing while it is in flight.  bytes == 0 writes a zero instead.
 __device__ __forceinline__ void cp_async4(void* sdst, const void* gsrc, int bytes) {
@@ -195,62 +185,69 @@ __device__ __forceinline__ void pm_peer_timeout(ds_peer_table_t* tab) {
   asm volatile("trap;");
 }
 
-// One tiny kernel after each data kernel of a step (stream order does the rest):
-//   phase DS_PEER_AFTER_GATHER: this rank has finished reading its replica -> bump my_gathers and
-//     publish it into gathers_done[rank] of every peer (their merges may then overwrite it);
-//   phase DS_PEER_AFTER_MERGE: this rank's rows have been pushed (the merge kernel has retired,
-//     so its peer stores are performed) -> same with my_merges / merges_done.
-// wait != 0 additionally blocks until every peer has published as much (a full barrier); the
-// data kernels normally do that part themselves (pm_peer_spin).  lane p talks to peer p.  A wait
-// longer than timeout_ns sets tab->error and traps (pm_peer_timeout) instead of hanging.
+// Counters of the exchange (ds_peer_table_t): issued_gathers / issued_merges count the gather / merge
+// launches of this rank that have COMPLETED (bumped by the launch itself or by the sync kernel below);
+// my_gathers / my_merges are how many of them have been PUBLISHED into every peer's table
+// (st.release.sys into gathers_done[rank] / merges_done[rank] there).  Two protocols:
+//   host-side (default)  the host enqueues ds_pm_peer_sync after every data kernel: it bumps the
+//                        issued count and publishes it at once;
+//   deferred (DS_TUNE_PEER_MERGE_PUBLISH = 1)  a data kernel bumps the issued count as its last act and
+//                        the NEXT kernel on the state publishes it in its prologue (pm_publish_pending, CTA 0,
+//                        after griddepcontrol.wait: the predecessor has retired, so its reads are done
+//                        and its peer stores performed) -- no extra launches in the step.
+// Either way a data kernel waits on `issued`: a gather reads the replica only when every peer has
+// published as many merges as this rank has issued, a merge stores rows only when every peer has
+// published as many gathers.
+
+// Warp 0 of one CTA: publish whatever is issued but not yet published.  lane p talks to peer p.
+__device__ __forceinline__ void pm_publish_pending(ds_peer_table_t* tab, bool gathers) {
+  if (threadIdx.x >= 32) return;
+  int32_t* pub = gathers ? &tab->my_gathers : &tab->my_merges;
+  const int issued = gathers ? tab->issued_gathers : tab->issued_merges;
+  const int have = *pub;
+  __syncwarp();
+  if (have >= issued) return;
+  const size_t off = gathers ? offsetof(ds_peer_table_t, gathers_done) : offsetof(ds_peer_table_t, merges_done);
+  __threadfence_system();
+  const int p = threadIdx.x;
+  if (p < tab->world && p != tab->rank)
+    st_release_sys(reinterpret_cast<int32_t*>(reinterpret_cast<char*>(tab->ctl[p]) + off) + tab->rank, issued);
+  if (p == 0) *pub = issued;
+}
+
+// Host-enqueued ordering kernel (32 threads; stream order does the rest):
+//   DS_PEER_AFTER_GATHER / DS_PEER_AFTER_MERGE: one more gather / merge of this rank has completed ->
+//     bump the issued count and publish it;
+//   DS_PEER_WAIT_MERGES: bump nothing, publish what is pending and wait for the peers' merges.
+// wait != 0 additionally blocks until every peer has published as much (a full barrier); the data
+// kernels normally do that part themselves (pm_peer_spin).  A wait longer than timeout_ns sets
+// tab->error and traps (pm_peer_timeout) instead of hanging.
 __global__ void pm_peer_sync_kernel(ds_peer_table_t* tab, int phase, int wait, long long timeout_ns) {
   const int p = threadIdx.x;
-  int32_t* mine = phase == DS_PEER_AFTER_GATHER ? &tab->my_gathers : &tab->my_merges;
-  const size_t off = phase == DS_PEER_AFTER_GATHER ? offsetof(ds_peer_table_t, gathers_done)
-                                                   : offsetof(ds_peer_table_t, merges_done);
-  const bool publish = phase != DS_PEER_WAIT_MERGES;       // WAIT_MERGES: no new count, only the wait below
-  const int c = *mine + (publish ? 1 : 0);
+  const bool gathers = phase == DS_PEER_AFTER_GATHER;
+  int32_t* issued = gathers ? &tab->issued_gathers : &tab->issued_merges;
+  const int c = *issued + (phase != DS_PEER_WAIT_MERGES ? 1 : 0);
   __syncwarp();
-  if (p == 0 && publish) *mine = c;
-  __threadfence_system();
-  if (p < tab->world && p != tab->rank) {
-    char* peer = reinterpret_cast<char*>(tab->ctl[p]);
-    if (publish) st_release_sys(reinterpret_cast<int32_t*>(peer + off) + tab->rank, c);
-    const int32_t* done = reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(tab) + off) + p;
+  if (p == 0) *issued = c;
+  __syncwarp();
+  if (phase == DS_PEER_WAIT_MERGES) pm_publish_pending(tab, true);
+  pm_publish_pending(tab, gathers);
+  if (wait && p < tab->world && p != tab->rank) {
+    const int32_t* done = (gathers ? tab->gathers_done : tab->merges_done) + p;
     const unsigned long long t0 = global_ns();
-    while (wait && ld_acquire_sys(done) < c) {
+    while (ld_acquire_sys(done) < c) {
       if (global_ns() - t0 > static_cast<unsigned long long>(timeout_ns)) pm_peer_timeout(tab);
     }
   }
 }
 
-// Publication folded into a data kernel: every CTA calls this once after its last access (after a
-// __syncthreads, by all threads); the LAST CTA to arrive bumps this rank's count and stores it into
-// every peer's table -- what pm_peer_sync_kernel does, without the extra launch.  Release pattern:
-// each CTA's thread 0 fences at system scope (cumulative over the accesses of its CTA, which the barrier
-// ordered before it) and then adds to the arrival counter; the last CTA's add observes them all, fences
-// again (acquire side) and issues the release stores.
-__device__ __forceinline__ void pm_peer_publish_last_cta(ds_peer_table_t* tab, int phase, unsigned n_ctas) {
-  if (threadIdx.x != 0) return;
-  // merges: this CTA's peer stores must be performed before the arrival (a system-scope fence per CTA: it
-  // waits for the NVLink acknowledgements, which is why the host-side publication is the default for
-  // merges).  gathers only READ the replica and every loaded value was consumed before the barrier the
-  // caller just passed, so their arrival needs no fence at all.
-  if (phase != DS_PEER_AFTER_GATHER) __threadfence_system();
-  int32_t* arrivals = phase == DS_PEER_AFTER_GATHER ? &tab->gather_arrivals : &tab->merge_arrivals;
-  const unsigned prev = static_cast<unsigned>(atomicAdd(arrivals, 1));
-  if (prev != n_ctas - 1) return;
-  *arrivals = 0;                                   // next launch on this table starts from zero again
-  __threadfence_system();
-  int32_t* mine = phase == DS_PEER_AFTER_GATHER ? &tab->my_gathers : &tab->my_merges;
-  const size_t off = phase == DS_PEER_AFTER_GATHER ? offsetof(ds_peer_table_t, gathers_done)
-                                                   : offsetof(ds_peer_table_t, merges_done);
-  const int c = *mine + 1;
-  *mine = c;
-  __threadfence_system();
-  for (int p = 0; p < tab->world; ++p)
-    if (p != tab->rank)
-      st_release_sys(reinterpret_cast<int32_t*>(reinterpret_cast<char*>(tab->ctl[p]) + off) + tab->rank, c);
+// Deferred protocol: last act of a data kernel (one thread of the grid): this launch is done as far as
+// the NEXT kernel on the stream is concerned, which is the one that publishes it.
+__device__ __forceinline__ void pm_count_issued(ds_peer_table_t* tab, bool gathers) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) {
+    int32_t* issued = gathers ? &tab->issued_gathers : &tab->issued_merges;
+    *issued = *issued + 1;
+  }
 }
 
 // In-kernel half of the ordering: lane p of every CTA waits until peer p's counter `done[p]` has
@@ -277,7 +274,7 @@ struct PmGatherArgs {
   // 2-D tiles keep the 2x2 tap footprints of neighbouring view rows in one CTA, so the panorama
   // rows they share are fetched from L2 once per tile instead of once per view row.
   int tw_shift, w, tiles_x;
-  int publish;                   // exchange mode: the last CTA publishes this rank's gather count (DS_TUNE_PEER_PUBLISH)
+  int publish;                   // exchange mode, deferred protocol: count this gather as issued at the end (DS_TUNE_PEER_MERGE_PUBLISH)
 };
 
 // first view pixel of segment r (a run of TW pixels) of tile tj of a job
@@ -396,8 +393,10 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     if (!waited) {
       // the map entries above are static; everything below reads the panorama
       pdl_wait_predecessors();
-      if (peer != nullptr)   // exchange mode: every peer must have pushed the previous step's rows too
-        pm_peer_spin(peer, peer->merges_done, -1, peer->my_merges, peer_timeout_ns);
+      if (peer != nullptr) {  // exchange mode: every peer must have pushed the previous step's rows too
+        if (blockIdx.x == 0) pm_publish_pending(peer, false);      // deferred protocol: my own last merge first
+        pm_peer_spin(peer, peer->merges_done, -1, peer->issued_merges, peer_timeout_ns);
+      }
       waited = true;
     }
     __syncthreads();        // also orders the previous tile's bulk-store reads before the STS below
@@ -501,12 +500,11 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     }
   }
   if (PIPE && in_flight) bulk_wait_read();      // shared memory must outlive the last copy
-  if (peer != nullptr && a.publish) {
-    // exchange mode: this rank has finished READING its replica once every CTA is past its last tap
-    // load -> the last CTA publishes the gather count (the peers' merges may then overwrite the rows)
-    __syncthreads();
-    pm_peer_publish_last_cta(peer, DS_PEER_AFTER_GATHER, gridDim.x);
+  if (peer != nullptr && !waited && blockIdx.x == 0) {             // an idle rank (no tile): still publish its last merge
+    pdl_wait_predecessors();
+    pm_publish_pending(peer, false);
   }
+  if (peer != nullptr && a.publish) pm_count_issued(peer, true);   // deferred protocol: the next kernel publishes it
 }
 
 // -------------------------------------------------- gather + re-noise + mask mix ----
@@ -616,7 +614,10 @@ pm_gather_renoise_kernel(const typename Atom<T>::type* __restrict__ pm, T* __res
   T* tile = reinterpret_cast<T*>(smem_raw);                                   // [R][S]
   int32_t* s_idx = reinterpret_cast<int32_t*>(tile + R * S);                  // [KT] latent map
   int32_t* s_midx = s_idx + kPmKT;                                            // [KT] mask map
-  if (peer != nullptr) pm_peer_spin(peer, peer->merges_done, -1, peer->my_merges, peer_timeout_ns);
+  if (peer != nullptr) {
+    if (blockIdx.x == 0) pm_publish_pending(peer, false);
+    pm_peer_spin(peer, peer->merges_done, -1, peer->issued_merges, peer_timeout_ns);
+  }
   for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     const int job = t / a.tiles_per_job;
     const int k0 = (t - job * a.tiles_per_job) * kPmKT;
@@ -640,10 +641,7 @@ pm_gather_renoise_kernel(const typename Atom<T>::type* __restrict__ pm, T* __res
     if (MM == DS_MASK_FULL && e.out_mask != nullptr)
       pm_renoise_pass<T, MM, 2>(pm, static_cast<T*>(e.out_mask), s_idx, s_midx, tile, a, e, job, k0, f0);
   }
-  if (peer != nullptr && a.publish) {
-    __syncthreads();
-    pm_peer_publish_last_cta(peer, DS_PEER_AFTER_GATHER, gridDim.x);
-  }
+  if (peer != nullptr && a.publish) pm_count_issued(peer, true);
 }
 
 // ------------------------------------------------------------------------ merges ----
@@ -717,7 +715,7 @@ struct PmMergeArgs {
   int vpf, job_begin, job_count;
   int F, HW, f_len, hw;
   ds_peer_table_t* peer;         // NULL: single replica (pm / mask above)
-  int publish;                   // exchange mode: the kernel publishes this rank's merge count itself (last CTA)
+  int publish;                   // exchange mode, deferred protocol: count this merge as issued at the end
   long long peer_timeout_ns;
   PmDdim dd;                     // DD kernels only
 };
@@ -756,8 +754,9 @@ __device__ __forceinline__ PmPeerFlag pm_merge_begin(const PmMergeArgs& a, PmRep
     const int r = threadIdx.x / (DS_MAX_PAYLOADS + 1), q = threadIdx.x % (DS_MAX_PAYLOADS + 1);
     rep.ptr[r][q] = q < DS_MAX_PAYLOADS ? a.peer->pm[r][q] : a.peer->mask[r];
   }
+  if (blockIdx.x == 0 && blockIdx.y == 0) pm_publish_pending(a.peer, true);   // deferred protocol: my own last gather first
   if (static_cast<int>(threadIdx.x) < a.peer->world && static_cast<int>(threadIdx.x) != a.peer->rank) {
-    f.want = a.peer->my_gathers;
+    f.want = a.peer->issued_gathers;
     f.v = ld_acquire_sys(a.peer->gathers_done + threadIdx.x);
   }
   return f;
@@ -802,14 +801,11 @@ __device__ __forceinline__ void pm_store_mask_plane(const PmMergeArgs& a, const 
   }
 }
 
-// Last statement of every exchange-mode merge CTA (also of CTAs that found no work): the rows this CTA
-// pushed are complete (bulk copies waited for by their issuing threads), then the last CTA of the grid
-// publishes the merge count -- the peers' next gather may then read the replicas.
+// Last statement of every exchange-mode merge CTA (also of CTAs that found no work).  Deferred protocol:
+// count this merge as issued; the next kernel on the state publishes it once this one has retired.
 template <bool PEER>
 __device__ __forceinline__ void pm_merge_end(const PmMergeArgs& a) {
-  if (!PEER || !a.publish) return;
-  __syncthreads();
-  pm_peer_publish_last_cta(a.peer, DS_PEER_AFTER_MERGE, gridDim.x * gridDim.y);
+  if (PEER && a.publish) pm_count_issued(a.peer, false);
 }
 
 struct PmRange {
@@ -963,7 +959,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
                    tile + (q * kPmET + i) * SA, row_bytes);
         issued = true;
       }
-      if (issued) { if (a.publish) bulk_commit_and_wait_done(); else bulk_commit_and_wait_read(); }
+      if (issued) bulk_commit_and_wait_read();
     } else {
       const int per_q = cnt * f_len;
       const int n_units = (a.Q > 0 ? a.Q : 1) * per_q;
@@ -1203,7 +1199,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
         issued = true;
       }
     }
-    if (issued) { if (a.publish) bulk_commit_and_wait_done(); else bulk_commit_and_wait_read(); }
+    if (issued) bulk_commit_and_wait_read();
   }
   pm_merge_end<PEER>(a);
 }

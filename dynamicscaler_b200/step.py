@@ -308,8 +308,9 @@ class PanoramaStepper:
         # peer states: NVLS multicast stores win from 4 GPUs up (one store instead of world-1 copies);
         # at 2 GPUs the per-replica TMA row copies are faster (tools/peer_probe.py)
         self.use_multicast = world > 2
-        # True: exchange-mode merges publish their merge count in-kernel (DS_TUNE_PEER_MERGE_PUBLISH; measured
-        # slower); False (default): one ds_pm_peer_sync launch after every merge
+        # exchange-mode ordering protocol (DS_TUNE_PEER_MERGE_PUBLISH): False = one ds_pm_peer_sync launch after every
+        # gather / merge; True = deferred: the kernels count themselves as issued and the NEXT kernel on the state
+        # publishes the count in its prologue (no ordering launches inside a step)
         self._merge_publish = False
         self._plans = {}
         self._xbuf = {}

@@ -60,10 +60,8 @@ enum {
   DS_TUNE_PM_GATHER_TILE_W = 4         /* gather tile shape: 0 = 64 consecutive view pixels; 8 / 16 / 32 = 2-D tiles of
                                           (64 / value) view rows x value pixels when ds_pm_gather knows the view width */
   , DS_TUNE_PM_MERGE_WEIGHTED_MINB = 5 /* 5: the two-payload tiled weighted merge runs the variant compiled for 5 CTAs/SM */
-  , DS_TUNE_PEER_MERGE_PUBLISH = 6     /* 0 (default): the host enqueues ds_pm_peer_sync after every exchange-mode pixel-major
-                                          gather / merge; 1: those kernels publish their gather / merge count themselves
-                                          (last CTA; merges only after their pushes are complete -- slower: one system-scope
-                                          fence per CTA) */
+  , DS_TUNE_PEER_MERGE_PUBLISH = 6     /* exchange-mode ordering protocol: 0 = host-side (ds_pm_peer_sync after every pixel-major
+                                          gather / merge), 1 = deferred (kernels count themselves, the next kernel publishes) */
 };
 int ds_tune(int knob, long long value);
 
@@ -180,15 +178,16 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
  * else one peer store / TMA bulk copy per replica (pm[r][q], mask[r]) -- so there is no sum
  * buffer, all-reduce or select.
  * Ordering across GPUs is two monotonic counters per peer: a rank's gather count and merge count, each
- * published into every peer's table with st.release.sys.  The host enqueues ds_pm_peer_sync (one
- * 32-thread kernel) after every gather (DS_PEER_AFTER_GATHER) and every merge (DS_PEER_AFTER_MERGE): it
- * bumps this rank's count, publishes it and, if wait != 0, also waits for the peers' counts (with
- * DS_TUNE_PEER_MERGE_PUBLISH = 1 the pixel-major kernels publish themselves instead -- their last CTA
- * does it -- and the host must NOT enqueue the sync).  With d_peer the data kernels do the waiting
- * themselves (ld.acquire.sys, overlapped with their first loads): a gather starts reading only when
- * every peer has published as many merges as this rank (replicas complete), a merge starts storing
- * only when every peer has published as many gathers (replicas may be overwritten) -- so wait = 0 is
- * enough between them.
+ * published into every peer's table with st.release.sys.  Host-side protocol (default): the host enqueues
+ * ds_pm_peer_sync (one 32-thread kernel) after every gather (DS_PEER_AFTER_GATHER) and every merge
+ * (DS_PEER_AFTER_MERGE); it counts the launch as issued, publishes the count and, if wait != 0, also waits
+ * for the peers' counts.  Deferred protocol (DS_TUNE_PEER_MERGE_PUBLISH = 1): the pixel-major kernels count
+ * themselves as issued when they finish and the NEXT kernel on the state publishes the count in its
+ * prologue, so a step has no ordering launches at all (the host must then NOT enqueue the sync, except
+ * DS_PEER_WAIT_MERGES before it touches a replica itself).  With d_peer the data kernels do the waiting
+ * themselves (ld.acquire.sys, overlapped with their first loads): a gather starts reading only when every
+ * peer has published as many merges as this rank has issued (replicas complete), a merge starts storing
+ * only when every peer has published as many gathers (replicas may be overwritten).
  * All ranks must issue the same gather / merge sequence on a state.  A wait that exceeds
  * DS_TUNE_PEER_TIMEOUT_NS sets `error`.  The host zero-fills the table, then writes rank,
  * world, pm, mask and ctl (the address of every rank's table, own included) and makes sure
@@ -197,8 +196,8 @@ int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q
 typedef struct ds_peer_table {
   int32_t merges_done[DS_MAX_PEERS];            /* [p]: written by peer p */
   int32_t gathers_done[DS_MAX_PEERS];           /* [p]: written by peer p */
-  int32_t my_merges, my_gathers;                /* this rank's own counts */
-  int32_t gather_arrivals, merge_arrivals;      /* CTA arrival counters of the in-kernel publication (zero between launches) */
+  int32_t my_merges, my_gathers;                /* this rank's counts as PUBLISHED to the peers */
+  int32_t issued_gathers, issued_merges;        /* gather / merge launches of this rank that have completed (>= published) */
   int32_t error, rank, world, reserved;
   uint64_t pm[DS_MAX_PEERS][DS_MAX_PAYLOADS];   /* replica r, panorama q */
   uint64_t mask[DS_MAX_PEERS];                  /* replica r of the mask panorama (or 0) */
@@ -208,9 +207,9 @@ typedef struct ds_peer_table {
 } ds_peer_table_t;
 int ds_peer_table_size(void);                   /* sizeof(ds_peer_table_t), for bindings */
 enum { DS_PEER_AFTER_GATHER = 0, DS_PEER_AFTER_MERGE = 1,
-       DS_PEER_WAIT_MERGES = 2 /* publishes nothing: only waits until every peer has pushed as many merges as this
-                                  rank has issued -- before the host touches its replica outside the kernels above
-                                  (e.g. zeroing the mask panorama at the start of a step) */ };
+       DS_PEER_WAIT_MERGES = 2 /* counts nothing: publishes what is pending and waits until every peer has pushed as many
+                                  merges as this rank has issued -- before the host touches its replica outside the
+                                  kernels above (e.g. zeroing the mask panorama at the start of a step) */ };
 int ds_pm_peer_sync(void* d_peer, int phase, int wait, void* stream);
 
 /* The batched step driver keeps the panorama of a stage resident as pm[pixel][frame][plane]
