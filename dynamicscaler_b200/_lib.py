@@ -13,7 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdynscaler_sm100.so")
 
-DS_F32, DS_BF16 = 0, 1
+DS_F32, DS_BF16, DS_F16 = 0, 1, 2
 DS_MASK_NONE, DS_MASK_PLANE, DS_MASK_FULL = 0, 1, 2
 DS_MAX_PAYLOADS = 4
 ABI_VERSION = 5
@@ -119,7 +119,9 @@ def dtype_code(dtype: torch.dtype) -> int:
         return DS_F32
     if dtype == torch.bfloat16:
         return DS_BF16
-    raise TypeError(f"dynamicscaler_b200 supports float32 and bfloat16 latents, got {dtype}")
+    if dtype == torch.float16:                 # the reference's use_fp16 mode (gen_pano_360.py:191-213)
+        return DS_F16
+    raise TypeError(f"dynamicscaler_b200 supports float32, bfloat16 and float16 latents, got {dtype}")
 
 
 def require_cuda(t: torch.Tensor, what: str = "tensor"):

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -27,10 +28,21 @@ template <> struct Elem<__nv_bfloat16> {
   static __device__ __forceinline__ __nv_bfloat16 one() { return __float2bfloat16_rn(1.0f); }
 };
 
+template <> struct Elem<__half> {                          // the reference's use_fp16 mode (gen_pano_360.py:191-213)
+  using vec4 = uint2;
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ __half one() { return __float2half_rn(1.0f); }
+};
+
 // read-only (LDG.NC) scalar / vector loads
 template <typename T> __device__ __forceinline__ T ldg(const T* p) { return __ldg(p); }
 template <> __device__ __forceinline__ __nv_bfloat16 ldg(const __nv_bfloat16* p) {
   return __ushort_as_bfloat16(__ldg(reinterpret_cast<const unsigned short*>(p)));
+}
+
+template <> __device__ __forceinline__ __half ldg(const __half* p) {
+  return __ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(p)));
 }
 
 __device__ __forceinline__ int pos_mod(int a, int m) {   // a in [0, 2m)
@@ -59,6 +71,9 @@ inline unsigned div_up(long long a, long long b) { return static_cast<unsigned>(
       __VA_ARGS__                                       \
     } else if ((dtype) == DS_BF16) {                    \
       using ET = __nv_bfloat16;                          \
+      __VA_ARGS__                                       \
+    } else if ((dtype) == DS_F16) {                     \
+      using ET = __half;                                 \
       __VA_ARGS__                                       \
     } else {                                            \
       return DS_ERR_DTYPE;                              \

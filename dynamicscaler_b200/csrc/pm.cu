@@ -84,6 +84,19 @@ template <> struct Atom<__nv_bfloat16> {
   }
 };
 
+template <> struct Atom<__half> {
+  using type = uint2;
+  static __device__ __forceinline__ void unpack(const uint2& a, float (&v)[4]) {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&a.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+    v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+  }
+  static __device__ __forceinline__ uint2 pack(const float (&v)[4]) {
+    const __half2 lo = __floats2half2_rn(v[0], v[1]), hi = __floats2half2_rn(v[2], v[3]);
+    return make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+  }
+};
+
 // raw element <-> atom component without a float round trip (pure copies)
 template <typename T> __device__ __forceinline__ void atom_split(const typename Atom<T>::type& a, T (&v)[4]);
 template <> __device__ __forceinline__ void atom_split<float>(const float4& a, float (&v)[4]) { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; }
@@ -91,15 +104,24 @@ template <> __device__ __forceinline__ void atom_split<__nv_bfloat16>(const uint
   v[0] = __ushort_as_bfloat16(static_cast<unsigned short>(a.x & 0xffffu)); v[1] = __ushort_as_bfloat16(static_cast<unsigned short>(a.x >> 16));
   v[2] = __ushort_as_bfloat16(static_cast<unsigned short>(a.y & 0xffffu)); v[3] = __ushort_as_bfloat16(static_cast<unsigned short>(a.y >> 16));
 }
+template <> __device__ __forceinline__ void atom_split<__half>(const uint2& a, __half (&v)[4]) {
+  v[0] = __ushort_as_half(static_cast<unsigned short>(a.x & 0xffffu)); v[1] = __ushort_as_half(static_cast<unsigned short>(a.x >> 16));
+  v[2] = __ushort_as_half(static_cast<unsigned short>(a.y & 0xffffu)); v[3] = __ushort_as_half(static_cast<unsigned short>(a.y >> 16));
+}
 template <typename T> __device__ __forceinline__ typename Atom<T>::type atom_join(const T (&v)[4]);
 template <> __device__ __forceinline__ float4 atom_join<float>(const float (&v)[4]) { return make_float4(v[0], v[1], v[2], v[3]); }
 template <> __device__ __forceinline__ uint2 atom_join<__nv_bfloat16>(const __nv_bfloat16 (&v)[4]) {
   return make_uint2(__bfloat16_as_ushort(v[0]) | (static_cast<unsigned>(__bfloat16_as_ushort(v[1])) << 16),
                     __bfloat16_as_ushort(v[2]) | (static_cast<unsigned>(__bfloat16_as_ushort(v[3])) << 16));
 }
+template <> __device__ __forceinline__ uint2 atom_join<__half>(const __half (&v)[4]) {
+  return make_uint2(__half_as_ushort(v[0]) | (static_cast<unsigned>(__half_as_ushort(v[1])) << 16),
+                    __half_as_ushort(v[2]) | (static_cast<unsigned>(__half_as_ushort(v[3])) << 16));
+}
 template <typename T> __device__ __forceinline__ typename Atom<T>::type atom_ones();
 template <> __device__ __forceinline__ float4 atom_ones<float>() { return make_float4(1.f, 1.f, 1.f, 1.f); }
 template <> __device__ __forceinline__ uint2 atom_ones<__nv_bfloat16>() { return make_uint2(0x3f803f80u, 0x3f803f80u); }
+template <> __device__ __forceinline__ uint2 atom_ones<__half>() { return make_uint2(0x3c003c00u, 0x3c003c00u); }
 
 template <typename A> __device__ __forceinline__ A ldg_atom(const A* p) { return __ldg(p); }
 
@@ -1368,7 +1390,7 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   DS_REQUIRE(pm_aligned16(pm) && pm_aligned16(out), DS_ERR_ALIGN);
   // tile geometry: 2-D tiles when the view is a whole number of tile widths and every segment is a
   // 16-byte multiple, else (and by default) linear tiles of 64 consecutive view pixels
-  const int elem = dtype == DS_BF16 ? 2 : 4;
+  const int elem = dtype == DS_F32 ? 4 : 2;
   const int tw = g_gather_tile_w;
   const bool two_d = view_w > 0 && (tw == 8 || tw == 16 || tw == 32) && view_w % tw == 0 && (tw * elem) % 16 == 0 &&
                      hw % (16 / elem) == 0;

@@ -13,7 +13,7 @@
  *   - The library allocates nothing, keeps no state besides the ds_tune knobs, and is stream-ordered and
  *     re-entrant: every call only enqueues kernels on `stream` (a cudaStream_t).
  *   - Return value: 0 = ok; < 0 = argument error (DS_ERR_*); > 0 = a cudaError_t.
- *   - dtype: DS_F32 or DS_BF16 for every latent/payload/window buffer of one call.
+ *   - dtype: DS_F32, DS_BF16 or DS_F16 (the reference's use_fp16 mode) for every latent/payload/window buffer of one call.
  *   - A panorama latent is addressed as planes [P][F][H*W] (P = B*C, frame-major, W
  *     fastest) -- the reference's own [B,C,F,H,W] memory order
  *     (shift_window_utils.py:42).  A window/view batch is [n_jobs][P][f_len][h*w].
@@ -32,7 +32,7 @@ extern "C" {
 
 #define DS_ABI_VERSION 5
 
-enum { DS_F32 = 0, DS_BF16 = 1 };
+enum { DS_F32 = 0, DS_BF16 = 1, DS_F16 = 2 };
 
 enum {
   DS_OK = 0,

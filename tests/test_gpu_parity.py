@@ -396,22 +396,23 @@ def test_sphere_full_size_vs_oracle_all_offsets(dev):
         assert 0.5 < plan.coverage < 0.6
 
 
-# ----------------------------------------------------------------------- bf16 ----
-def test_bf16_within_tolerance(dev):
-    """bf16 latents, fp32 maps: vs the fp32 oracle on bf16-rounded inputs at 1e-2 (nearest
-    paths are pure copies and stay bit-exact)."""
+# ---------------------------------------------------------------- bf16 / fp16 ----
+@pytest.mark.parametrize("half_dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_bf16_within_tolerance(dev, half_dtype):
+    """bf16 / fp16 latents (the reference's use_fp16 mode, gen_pano_360.py:191-213), fp32 maps: vs the fp32
+    oracle on the rounded inputs at 1e-2 (nearest paths are pure copies and stay bit-exact)."""
     from dynamicscaler_b200.step import PanoramaStepper
     from dynamicscaler_b200.tensor_utils import mix_latents_with_mask
     H, W, F = 32, 64, 4
     views = po.default_sphere_views(1)[:10]
-    lat_bf = G(randn(13, 1, 4, F, H, W), dev).to(torch.bfloat16)
+    lat_bf = G(randn(13, 1, 4, F, H, W), dev).to(half_dtype)
     lat0 = lat_bf.float().cpu().numpy()
     st = PanoramaStepper(H, W, F, device=dev)
     for mode in ("nearest", "bilinear"):
         plan = st.plan_sphere(views, 16, 10, fov=120, mode=mode)
         lat = lat_bf.clone()
         wins = st.gather_all(lat, plan)
-        pays = G(np.stack([randn(50 + n, 1, 4, F, 10, 16) for n in range(10)]), dev).to(torch.bfloat16)
+        pays = G(np.stack([randn(50 + n, 1, 4, F, 10, 16) for n in range(10)]), dev).to(half_dtype)
         st.merge_all([lat], [pays], plan)
         ref = lat0.copy()
         pay_np = pays.float().cpu().numpy()
@@ -420,7 +421,7 @@ def test_bf16_within_tolerance(dev):
         assert np.abs(wins.float().cpu().numpy() - np.stack(ref_wins)).max() <= (0 if mode == "nearest" else BF16_TOL * 4)
         assert np.abs(lat.float().cpu().numpy() - ref).max() <= (0 if mode == "nearest" else BF16_TOL * 4)
     a, b = lat_bf, (lat_bf * 0.5)
-    m = (torch.rand(1, H, W, device=dev) > 0.5).to(torch.bfloat16)
+    m = (torch.rand(1, H, W, device=dev) > 0.5).to(half_dtype)
     got = mix_latents_with_mask(a, b, m, 0.25).float().cpu().numpy()
     want = po.mix_mask(a.float().cpu().numpy(), b.float().cpu().numpy(), m.float().cpu().numpy(), 0.25)
     assert np.abs(got - want).max() <= BF16_TOL * 4

@@ -29,14 +29,14 @@ def G(a, dev):
 
 
 def N(t):
-    return t.detach().float().cpu().numpy() if t.dtype == torch.bfloat16 else t.detach().cpu().numpy()
+    return t.detach().float().cpu().numpy() if t.dtype in (torch.bfloat16, torch.float16) else t.detach().cpu().numpy()
 
 
 def sha(a):
     return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("F,H,W", [(16, 128, 256), (3, 6, 12), (5, 10, 20), (64, 16, 32), (2, 3, 6), (1, 1, 2)])
 def test_pack_unpack_round_trip(dev, dtype, F, H, W):
     """pack = ds_pm_merge_nearest(identity plan), unpack = ds_pm_gather(identity map); ragged
@@ -154,18 +154,19 @@ def test_state_equals_plane_major_ragged(dev, mode, h, w):
         assert torch.equal(state.export_mask(), msk)
 
 
-def test_state_bf16_within_tolerance(dev):
+@pytest.mark.parametrize("half_dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_state_bf16_within_tolerance(dev, half_dtype):
     from dynamicscaler_b200.step import PanoramaStepper
     H, W, F = 32, 64, 4
     views = po.default_sphere_views(1)[:10]
-    lat_bf = G(randn(13, 1, 4, F, H, W), dev).to(torch.bfloat16)
+    lat_bf = G(randn(13, 1, 4, F, H, W), dev).to(half_dtype)
     lat0 = lat_bf.float().cpu().numpy()
     st = PanoramaStepper(H, W, F, device=dev)
     for mode in ("nearest", "bilinear"):
         plan = st.plan_sphere(views, 16, 10, fov=120, mode=mode)
         state = st.make_state([lat_bf])
         wins = st.gather_all(state, plan)
-        pays = G(np.stack([randn(50 + n, 1, 4, F, 10, 16) for n in range(10)]), dev).to(torch.bfloat16)
+        pays = G(np.stack([randn(50 + n, 1, 4, F, 10, 16) for n in range(10)]), dev).to(half_dtype)
         st.merge_all(state, [pays], plan)
         ref = lat0.copy()
         pay_np = pays.float().cpu().numpy()
