@@ -52,8 +52,6 @@ constexpr int kWarps = kBlock / 32;
 
 // Launch-shape knobs (ds_tune); defaults are the measured best on B200 for the bench workload.
 static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
-static int g_gather_tile_w = 0;                 // 0: linear tiles of 64 view pixels; 8 / 16 / 32: 2-D tiles (64/w rows x w pixels)
-static int g_merge_weighted_minb = 0;           // 5: two-payload tiled weighted merge compiled for 5 CTAs per SM
 static int g_merge_publish = 0;                 // exchange mode: 0 = the host enqueues ds_pm_peer_sync after every gather / merge; 1 = deferred:
                                                 // a data kernel counts itself as issued and the next kernel publishes it in its prologue
 static int g_gather_pipe = 2;                   // bit 1: copy-only gather, bit 2: 4-tap gather use the pipelined tile loop
@@ -290,24 +288,8 @@ __device__ __forceinline__ void pm_peer_spin(ds_peer_table_t* tab, const int32_t
 struct PmGatherArgs {
   int F, HW, f_len, hw;
   int n_tiles, tiles_per_job;
-  // Tile geometry.  A tile is 64 view pixels: TR = 64 / TW rows of TW consecutive pixels of a view
-  // that is `w` pixels wide; tile (ty, tx) of a job starts at view pixel (ty*TR)*w + tx*TW.
-  // Linear tiles (64 consecutive k, any hw) are the case TW = 64, w = 64, tiles_x = 1.
-  // 2-D tiles keep the 2x2 tap footprints of neighbouring view rows in one CTA, so the panorama
-  // rows they share are fetched from L2 once per tile instead of once per view row.
-  int tw_shift, w, tiles_x;
   int publish;                   // exchange mode, deferred protocol: count this gather as issued at the end (DS_TUNE_PEER_MERGE_PUBLISH)
 };
-
-// first view pixel of segment r (a run of TW pixels) of tile tj of a job
-__device__ __forceinline__ int pm_tile_seg(const PmGatherArgs& a, int tj, int r) {
-  const int ty = tj / a.tiles_x, tx = tj - ty * a.tiles_x;
-  return (ty * (kPmKT >> a.tw_shift) + r) * a.w + (tx << a.tw_shift);
-}
-// view pixel of position kl of tile tj
-__device__ __forceinline__ int pm_tile_k(const PmGatherArgs& a, int tj, int kl) {
-  return pm_tile_seg(a, tj, kl >> a.tw_shift) + (kl & ((1 << a.tw_shift) - 1));
-}
 
 // Persistent CTAs; work item = (tile of kPmKT view pixels, job).
 // Load: warp lanes = 4 pixel groups x 8 frames; a lane loads the atoms of 4 CONSECUTIVE view
@@ -365,7 +347,7 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
   auto stage_async = [&](int tt, int map, int b) {
     if (threadIdx.x < TAPS * kPmKT) {
       const int tap = threadIdx.x / kPmKT, kl = threadIdx.x % kPmKT;
-      const int k = pm_tile_k(a, tt % a.tiles_per_job, kl);
+      const int k = (tt % a.tiles_per_job) * kPmKT + kl;
       const int ok = k < a.hw ? 4 : 0;                                   // ragged last tile: zero-fill
       const size_t e = static_cast<size_t>(map * TAPS + tap) * a.hw + min(k, a.hw - 1);
       int32_t* di = s_idx0 + b * TAPS * kPmKT + threadIdx.x;
@@ -386,7 +368,7 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
 
   for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
     const int job = t / a.tiles_per_job;
-    const int tj = t - job * a.tiles_per_job;
+    const int k0 = (t - job * a.tiles_per_job) * kPmKT;
     const int32_t* s_idx = s_idx0 + buf * TAPS * kPmKT;
     const float* s_wt = s_wt0 + buf * TAPS * kPmKT;
     int f0;
@@ -400,7 +382,7 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
       f0 %= a.F;
       for (int i = threadIdx.x; i < TAPS * kPmKT; i += kBlock) {
         const int tap = i / kPmKT, kl = i % kPmKT;
-        const int k = pm_tile_k(a, tj, kl);
+        const int k = k0 + kl;
         int idx = 0;
         float w = 0.f;
         if (k < a.hw) {
@@ -436,7 +418,7 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
       const int kgb = it / n_fblk, fb = it - kgb * n_fblk;
       const int kl = (kgb * 4 + kgl) * 4;         // first of this lane's 4 consecutive view pixels
       const int fo = fb * 8 + fl;
-      if (fo >= f_len || pm_tile_k(a, tj, kl) >= a.hw) continue;
+      if (fo >= f_len || k0 + kl >= a.hw) continue;
       int f = f0 + fo;
       f = f >= a.F ? f - a.F : f;
       A v[TAPS][4];
@@ -490,29 +472,22 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     fence_proxy_async_smem();
     __syncthreads();
 
-    T* __restrict__ o = out + static_cast<size_t>(job) * R * a.hw;
+    T* __restrict__ o = out + static_cast<size_t>(job) * R * a.hw + k0;
     if (a.hw % VE != 0) {
-      // window rows are not 16-byte multiples (odd view sizes; linear tiles only): element-wise copy
-      const int k0 = tj * kPmKT;
+      // window rows are not 16-byte multiples (odd view sizes): element-wise copy of the tile
       const int kt = min(kPmKT, a.hw - k0);
       for (int u = threadIdx.x; u < R * kPmKT; u += kBlock) {
         const int row = u / kPmKT, c = u - row * kPmKT;
-        if (c < kt) o[static_cast<size_t>(row) * a.hw + k0 + c] = tile[row * S + c];
+        if (c < kt) o[static_cast<size_t>(row) * a.hw + c] = tile[row * S + c];
       }
       __syncthreads();                            // the tile is rewritten by the next work item
       continue;
     }
-    // every (tile row, segment) is one contiguous run of the window tensor: one bulk copy each
-    const int tw = 1 << a.tw_shift, n_seg = kPmKT >> a.tw_shift;
+    const uint32_t row_bytes = static_cast<uint32_t>(min(kPmKT, a.hw - k0) * sizeof(T));
     bool issued = false;
-    for (int u = threadIdx.x; u < R * n_seg; u += kBlock) {
-      const int row = u >> (6 - a.tw_shift), r = u & (n_seg - 1);
-      const int ks = pm_tile_seg(a, tj, r);
-      const int n = min(tw, a.hw - ks);
-      if (n > 0) {
-        bulk_store(o + static_cast<size_t>(row) * a.hw + ks, tile + row * S + r * tw, static_cast<uint32_t>(n * sizeof(T)));
-        issued = true;
-      }
+    for (int row = threadIdx.x; row < R; row += kBlock) {
+      bulk_store(o + static_cast<size_t>(row) * a.hw, tile + row * S, row_bytes);
+      issued = true;
     }
     if (PIPE) {
       if (issued) bulk_commit();
@@ -600,7 +575,9 @@ __device__ __forceinline__ void pm_renoise_pass(const typename Atom<T>::type* __
         } else {
           const float ep = Elem<T>::to_f(ldg(static_cast<const T*>(e.eps) +
                                              (static_cast<size_t>(job) * R + p * f_len + fo) * a.hw + k));
-          const float noised = rt(__fadd_rn(rt(__fmul_rn(e.c, x[p])), rt(__fmul_rn(e.s, ep))));
+          // c, s: 0-dim float32 tensors in the reference, cast to the latent dtype by the multiply (python-float
+          // ratios of the mix are NOT: torch keeps wrapped scalars in the op's float math type)
+          const float noised = rt(__fadd_rn(rt(__fmul_rn(rt(e.c), x[p])), rt(__fmul_rn(rt(e.s), ep))));
           val[j][p] = pm_mix1<T>(x[p], noised, m[p], e.r, e.omr);
         }
       }
@@ -1006,10 +983,8 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
 // on nothing but blockIdx: global dependency depth 2 (entries -> payload) instead of 3, and
 // every loop bound of phase A is a compile-time constant.  d_view_ptr[v] = first tile of view
 // v; d_row_start[r] = first (padded) entry of row r, rows of a tile being contiguous.
-// MINB: min resident CTAs per SM (register budget; 0 = unconstrained).  At 5 the two-payload kernel fits 48 registers
-// without spilling and the cfg2 grid of 1090 tiles is 1.47 waves instead of 1.84.
-template <typename T, int FL, int QN, bool DD, bool PEER, int MINB = 0>
-__global__ void __launch_bounds__(kBlock, MINB)
+template <typename T, int FL, int QN, bool DD, bool PEER>
+__global__ void __launch_bounds__(kBlock)
 pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                                const int4* __restrict__ d_tile, const int32_t* __restrict__ d_row_dst,
                                const int32_t* __restrict__ d_row_start, const int32_t* __restrict__ d_ent_k,
@@ -1377,10 +1352,9 @@ static int pm_launch(K kernel, int pdl_bit, long long items, int ctas_per_sm, un
 
 extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d_wt, int taps,
                             const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
-                            int hw, int view_w, void* d_peer, int dtype, void* stream) {
+                            int hw, void* d_peer, int dtype, void* stream) {
   using namespace ds;
   DS_REQUIRE(pm != nullptr && (out != nullptr || n_jobs == 0), DS_ERR_NULL);
-  DS_REQUIRE(view_w >= 0 && (view_w == 0 || hw % view_w == 0), DS_ERR_DIM);
   DS_REQUIRE(taps == 1 || taps == 4, DS_ERR_DIM);
   DS_REQUIRE(taps == 1 || (d_idx != nullptr && d_wt != nullptr), DS_ERR_NULL);
   DS_REQUIRE(P == kPmPlanes, DS_ERR_DIM);
@@ -1388,24 +1362,11 @@ extern "C" int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, con
   DS_REQUIRE(n_jobs > 0 || d_peer != nullptr, DS_ERR_DIM);        // an idle rank still takes part in the exchange
   DS_REQUIRE(d_idx != nullptr || hw <= HW, DS_ERR_DIM);
   DS_REQUIRE(pm_aligned16(pm) && pm_aligned16(out), DS_ERR_ALIGN);
-  // tile geometry: 2-D tiles when the view is a whole number of tile widths and every segment is a
-  // 16-byte multiple, else (and by default) linear tiles of 64 consecutive view pixels
-  const int elem = dtype == DS_F32 ? 4 : 2;
-  const int tw = g_gather_tile_w;
-  const bool two_d = view_w > 0 && (tw == 8 || tw == 16 || tw == 32) && view_w % tw == 0 && (tw * elem) % 16 == 0 &&
-                     hw % (16 / elem) == 0;
-  int tw_shift = 6, geo_w = kPmKT, tiles_x = 1;
-  int tpj = static_cast<int>(div_up(hw, kPmKT));
-  if (two_d) {
-    tw_shift = tw == 8 ? 3 : tw == 16 ? 4 : 5;
-    geo_w = view_w;
-    tiles_x = view_w / tw;
-    tpj = tiles_x * static_cast<int>(div_up(hw / view_w, kPmKT / tw));
-  }
+  const int tpj = static_cast<int>(div_up(hw, kPmKT));
   const long long n_tiles = static_cast<long long>(n_jobs) * tpj;
   DS_REQUIRE(n_tiles < (1ll << 31) && static_cast<long long>(n_jobs) * P * f_len * hw < (1ll << 40), DS_ERR_DIM);
   DS_REQUIRE(static_cast<long long>(n_jobs) * taps * hw < (1ll << 31), DS_ERR_DIM);
-  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj, tw_shift, geo_w, tiles_x, d_peer != nullptr ? g_merge_publish : 0};
+  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj, d_peer != nullptr ? g_merge_publish : 0};
   const bool pipe = (g_gather_pipe & (taps == 1 ? 1 : 2)) != 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DS_DISPATCH_DTYPE(dtype, {
@@ -1445,7 +1406,7 @@ extern "C" int ds_pm_gather_renoise(const void* pm, void* out, void* out_raw, vo
   const int tpj = static_cast<int>(div_up(hw, kPmKT));
   const long long n_tiles = static_cast<long long>(n_jobs) * tpj;
   DS_REQUIRE(n_tiles < (1ll << 31) && static_cast<long long>(n_jobs) * P * f_len * hw < (1ll << 40), DS_ERR_DIM);
-  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj, 6, kPmKT, 1, d_peer != nullptr ? g_merge_publish : 0};
+  PmGatherArgs a{F, HW, f_len, hw, static_cast<int>(n_tiles), tpj, d_peer != nullptr ? g_merge_publish : 0};
   PmRenoiseArgs e{eps, mask, out_raw, out_mask, h_coef[0], h_coef[1], h_coef[2], h_coef[3]};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DS_DISPATCH_DTYPE(dtype, {
@@ -1534,7 +1495,7 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
   const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmTR + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
     if (Q == 1) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
-    if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); if (g_merge_weighted_minb == 5) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false, 5>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
     { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
@@ -1633,8 +1594,6 @@ extern "C" int ds_tune(int knob, long long value) {
     case DS_TUNE_PEER_TIMEOUT_NS: ds::g_peer_timeout_ns = value; return DS_OK;
     case DS_TUNE_PDL: ds::g_pdl = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PM_GATHER_PIPELINE: ds::g_gather_pipe = static_cast<int>(value); return DS_OK;
-    case DS_TUNE_PM_GATHER_TILE_W: ds::g_gather_tile_w = static_cast<int>(value); return DS_OK;
-    case DS_TUNE_PM_MERGE_WEIGHTED_MINB: ds::g_merge_weighted_minb = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PEER_MERGE_PUBLISH: ds::g_merge_publish = value != 0 ? 1 : 0; return DS_OK;
     default: return DS_ERR_DIM;
   }

@@ -62,6 +62,10 @@ repeat_renoise_kernel(const T* __restrict__ x0, const T* __restrict__ eps, T* __
   const long long n = planes * F * HW;
   const long long stride = static_cast<long long>(gridDim.x) * kBlock;
   auto rt = [](float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); };
+  // the reference's c and s are 0-dim float32 tensors (scheduler.py:104-105): in `c * x_a` torch casts a 0-dim
+  // operand to the dimensioned operand's dtype first, so for half latents the coefficients are rounded to T
+  c = rt(c);
+  s = rt(s);
   for (long long i = static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x; i < n; i += stride) {
     const long long pl = i / (F * HW), p = i % HW;
     const float a = rt(__fmul_rn(c, Elem<T>::to_f(ldg(x0 + pl * HW + p))));

@@ -477,7 +477,7 @@ class PanoramaStepper:
         out = torch.empty(shape, dtype=pm.dtype, device=pm.device)
         with _lib.on(pm.device):
             lib.check(lib.ds_pm_gather(pm.data_ptr(), out.data_ptr(), None, None, 1, None, 0, 1, 4, F, H * W, F,
-                                       H * W, 0, None, _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)),
+                                       H * W, None, _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)),
                       "ds_pm_gather(unpack)")
         return out
 
@@ -499,7 +499,7 @@ class PanoramaStepper:
             (d_idx, d_wt), taps = plan.d_taps, 4
         with _lib.on(pm.device):
             lib.check(lib.ds_pm_gather(pm.data_ptr(), out.data_ptr(), d_idx.data_ptr(), _lib.ptr(d_wt), taps,
-                                       d_jobs.data_ptr(), 0, nj, 4, F, HW, plan.f_len, plan.hw, plan.w, peer,
+                                       d_jobs.data_ptr(), 0, nj, 4, F, HW, plan.f_len, plan.hw, peer,
                                        _lib.dtype_code(pm.dtype), _lib.stream_ptr(pm.device)), "ds_pm_gather")
 
     def _pm_gather_renoise(self, st, plan, out, index, j0, nj, rn):

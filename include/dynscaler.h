@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DS_ABI_VERSION 5
+#define DS_ABI_VERSION 6
 
 enum { DS_F32 = 0, DS_BF16 = 1, DS_F16 = 2 };
 
@@ -55,11 +55,10 @@ enum {
   DS_TUNE_PEER_TIMEOUT_NS = 1,         /* cross-GPU waits give up (and set ds_peer_table_t.error) after this */
   DS_TUNE_PDL = 2,                     /* programmatic dependent launch, bit mask: 1 copy-only gather, 2 4-tap gather,
                                           4 nearest merge, 8 weighted merges (default: 11) */
-  DS_TUNE_PM_GATHER_PIPELINE = 3,      /* software-pipelined gather tile loop (next tile's map entries prefetched with
+  DS_TUNE_PM_GATHER_PIPELINE = 3       /* software-pipelined gather tile loop (next tile's map entries prefetched with
                                           cp.async, deferred bulk-copy wait), bit mask: 1 copy-only gather, 2 4-tap gather */
-  DS_TUNE_PM_GATHER_TILE_W = 4         /* gather tile shape: 0 = 64 consecutive view pixels; 8 / 16 / 32 = 2-D tiles of
-                                          (64 / value) view rows x value pixels when ds_pm_gather knows the view width */
-  , DS_TUNE_PM_MERGE_WEIGHTED_MINB = 5 /* 5: the two-payload tiled weighted merge runs the variant compiled for 5 CTAs/SM */
+                                       /* (4, 5: retired -- 2-D gather tiles and the 5-CTA/SM weighted merge, both measured
+                                          slower, profiles/r02a_kbench_*.jsonl) */
   , DS_TUNE_PEER_MERGE_PUBLISH = 6     /* exchange-mode ordering protocol: 0 = host-side (ds_pm_peer_sync after every pixel-major
                                           gather / merge), 1 = deferred (kernels count themselves, the next kernel publishes) */
 };
@@ -225,12 +224,10 @@ int ds_pm_peer_sync(void* d_peer, int phase, int wait, void* stream);
  * d_idx == NULL (taps == 1): identity map, i.e. the unpack pm -> [P][F][hw], hw <= H*W.
  * d_jobs as in ds_gather_nearest.  Window rows that are 16-byte multiples (hw % (16 / elem_size) == 0)
  * leave through TMA bulk copies, other sizes through plain stores.
- * view_w: width of the view in pixels (hw = h*view_w), or 0 if unknown / not a 2-D view; it only
- * lets the kernel cut 2-D tiles (DS_TUNE_PM_GATHER_TILE_W), the result does not depend on it.
  * d_peer: NULL, or the local ds_peer_table_t: the kernel first waits for the peers' merges. */
 int ds_pm_gather(const void* pm, void* out, const int32_t* d_idx, const float* d_wt, int taps,
                  const int32_t* d_jobs, int h_f0, int n_jobs, int P, int F, int HW, int f_len,
-                 int hw, int view_w, void* d_peer, int dtype, void* stream);
+                 int hw, void* d_peer, int dtype, void* stream);
 
 /* Gather fused with the re-noise + mask mix that follows it in the reference's loops (SURVEY §8f-1;
  * pipeline/t2v_sphere_panorama_pipeline.py:194-221, pipeline/i2v_sphere_panorama_pipeline.py:330-365):

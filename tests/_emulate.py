@@ -216,35 +216,3 @@ def pm_merge_bilinear_tiled(pms, payloads, plan, ftab, fbegin, vpf, f_len, hw, m
                         pms[q][d, f, :] = acc / ws_
                     if mask_mode == 2:
                         mask[d, f, :] = 1
-
-
-# ------------------------------------------------------- gather tile geometry (pm.cu) ----
-def pm_gather_geometry(hw, view_w, tile_w, elem=4):
-    """Host side of ds_pm_gather: (tw_shift, geo_w, tiles_x, tiles_per_job)."""
-    two_d = (view_w > 0 and tile_w in (8, 16, 32) and view_w % tile_w == 0 and (tile_w * elem) % 16 == 0
-             and hw % (16 // elem) == 0)
-    if not two_d:
-        return 6, 64, 1, -(-hw // 64)
-    return {8: 3, 16: 4, 32: 5}[tile_w], view_w, view_w // tile_w, (view_w // tile_w) * -(-(hw // view_w) // (64 // tile_w))
-
-
-def pm_tile_seg(geo, tj, r):
-    tw_shift, w, tiles_x, _ = geo
-    ty, tx = divmod(tj, tiles_x)
-    return (ty * (64 >> tw_shift) + r) * w + (tx << tw_shift)
-
-
-def pm_tile_k(geo, tj, kl):
-    return pm_tile_seg(geo, tj, kl >> geo[0]) + (kl & ((1 << geo[0]) - 1))
-
-
-def pm_tile_store_segments(geo, tj, hw):
-    """(first view pixel, tile offset, pixels) of the bulk copies of one tile row."""
-    tw = 1 << geo[0]
-    out = []
-    for r in range(64 >> geo[0]):
-        ks = pm_tile_seg(geo, tj, r)
-        n = min(tw, hw - ks)
-        if n > 0:
-            out.append((ks, r * tw, n))
-    return out

@@ -350,38 +350,3 @@ def test_random_view_lists_merge_plans_property():
             assert np.array_equal(pm_unpack(got).reshape(P, H, W), want_b)
 
     check()
-
-
-@pytest.mark.parametrize("elem", [4, 2])
-def test_gather_tile_geometry_covers_every_view_pixel_once(elem):
-    """Tile geometry of ds_pm_gather (csrc/pm.cu pm_tile_k / pm_tile_seg, mirrored in _emulate):
-    linear and 2-D tiles visit every view pixel exactly once, a lane's 4 consecutive positions
-    stay on one view row, and the bulk-copy segments tile the window row with 16-byte alignment."""
-    from _emulate import pm_gather_geometry, pm_tile_k, pm_tile_seg, pm_tile_store_segments
-    for (h, w) in [(40, 64), (6, 10), (5, 7), (40, 48), (3, 32), (17, 16), (9, 8), (64, 128)]:
-        hw = h * w
-        for tile_w in (0, 8, 16, 32):
-            geo = pm_gather_geometry(hw, w, tile_w, elem)
-            tw_shift, geo_w, tiles_x, tpj = geo
-            if tw_shift != 6:
-                assert w % tile_w == 0 and (tile_w * elem) % 16 == 0
-            seen = np.zeros(hw, np.int32)
-            stored = np.zeros(hw, np.int32)
-            for tj in range(tpj):
-                ks = np.array([pm_tile_k(geo, tj, kl) for kl in range(64)])
-                valid = ks < hw
-                np.add.at(seen, ks[valid], 1)
-                grp = ks.reshape(16, 4)
-                assert np.all(np.diff(grp, axis=1) == 1)                   # a lane's 4 pixels are consecutive
-                if tw_shift != 6:
-                    assert np.all(valid.reshape(16, 4).all(1) | ~valid.reshape(16, 4).any(1))
-                    assert np.all(grp[:, 0] // w == grp[:, 3] // w)        # ... and on one view row
-                if hw % (16 // elem) == 0:
-                    for k0, off, n in pm_tile_store_segments(geo, tj, hw):
-                        assert (k0 * elem) % 16 == 0 and (off * elem) % 16 == 0
-                        assert tw_shift == 6 or (n * elem) % 16 == 0
-                        assert np.array_equal(ks[off:off + n], np.arange(k0, k0 + n))
-                        stored[k0:k0 + n] += 1
-            assert np.all(seen == 1), (h, w, tile_w)
-            if hw % (16 // elem) == 0:
-                assert np.all(stored == 1), (h, w, tile_w)

@@ -46,14 +46,12 @@ def main():
     settings = [{"gather_cps": 0, "pdl": m} for m in (11, 0, 15)]
     if os.environ.get("KBENCH_DEFAULT_ONLY"):
         settings = settings[:1]
-    if os.environ.get("KBENCH_SETTINGS"):                                 # JSON list of {gather_cps, pdl, pipe, tile_w}
+    if os.environ.get("KBENCH_SETTINGS"):                                 # JSON list of {gather_cps, pdl, pipe}
         settings = json.loads(os.environ["KBENCH_SETTINGS"])
     for cfg in settings:
         lib.check(lib.ds_tune(GATHER_CPS, cfg.get("gather_cps", 0)))
         lib.check(lib.ds_tune(2, cfg.get("pdl", 11)))                     # DS_TUNE_PDL
         lib.check(lib.ds_tune(3, cfg.get("pipe", 2)))                     # DS_TUNE_PM_GATHER_PIPELINE
-        lib.check(lib.ds_tune(4, cfg.get("tile_w", 0)))                   # DS_TUNE_PM_GATHER_TILE_W
-        lib.check(lib.ds_tune(5, cfg.get("merge_minb", 0)))               # DS_TUNE_PM_MERGE_WEIGHTED_MINB
         res = dict(cfg, workload=wl_name)
         for mode in modes:                                  # whole steps (gather -> merge chains)
             fns = []
