@@ -357,6 +357,10 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     }
   };
 
+  if (peer != nullptr && a.n_tiles == 0) {       // an idle rank (no window of its own): still publish its last merge
+    pdl_wait_predecessors();
+    pm_publish_pending(peer, false);
+  }
   int cur_f0 = 0, nxt_map = 0, nxt_f0 = 0, buf = 0;
   bool in_flight = false;                        // PIPE: this thread's bulk copies of the previous tile
   if (PIPE && static_cast<int>(blockIdx.x) < a.n_tiles) {
@@ -497,10 +501,6 @@ pm_gather_kernel(const typename Atom<T>::type* __restrict__ pm, T* __restrict__ 
     }
   }
   if (PIPE && in_flight) bulk_wait_read();      // shared memory must outlive the last copy
-  if (peer != nullptr && !waited && blockIdx.x == 0) {             // an idle rank (no tile): still publish its last merge
-    pdl_wait_predecessors();
-    pm_publish_pending(peer, false);
-  }
   if (peer != nullptr && a.publish) pm_count_issued(peer, true);   // deferred protocol: the next kernel publishes it
 }
 

@@ -37,8 +37,19 @@ with open(f"{P}/{label}_launches_summary.md", "w") as f:
         f.write(f"| `{k[:110]}` | {len(v)} | {sum(v) / len(v) / 1e3:.2f} | {sum(v) / tot * 100:.1f}% |\n")
 os.replace(f"{G}/launches_{tag}.csv", f"{P}/{label}_launches.csv") if False else None
 
-rows = list(csv.reader(open(f"{G}/raw_{tag}.csv")))
-hdr, units = rows[0], rows[1]
+# one or several raw exports (raw_<tag>.csv, raw_<tag>_<mode>.csv): merged by column NAME
+import glob
+hdr, units, merged = [], {}, []
+for path in sorted(glob.glob(f"{G}/raw_{tag}.csv") + glob.glob(f"{G}/raw_{tag}_*.csv")):
+    rr = list(csv.reader(open(path)))
+    for h, u in zip(rr[0], rr[1]):
+        if h not in units:
+            hdr.append(h)
+            units[h] = u
+    merged += [dict(zip(rr[0], r)) for r in rr[2:]]
+assert merged, f"no raw_{tag}*.csv under {G}"
+rows = [hdr, [units[h] for h in hdr]] + [[d.get(h, "") for h in hdr] for d in merged]
+units = rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
@@ -50,7 +61,13 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__waves_per_multiprocessor", "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio"]
 data = rows[2:]
 names = [short(r[idx["Kernel Name"]]) for r in data]
 with open(f"{P}/{label}_ncu_full_summary.md", "w") as f:
