@@ -147,6 +147,43 @@ def test_panorama_tensor_image_and_mask_golden(small, dev):
         assert np.array_equal(N(pm.equirect_tensor), small[f"sph/mask_set/{i}"])
 
 
+def test_cpu_condition_image_is_uploaded_once(small, dev):
+    """The I2V pipeline wraps the CPU condition image (torch.from_numpy, i2v_sphere_panorama_pipeline.py:
+    223-224) in a PanoramaTensor and reads a view from it per window (:367): the image is uploaded once,
+    views equal the reference's (computed from the same CPU tensor) bit for bit."""
+    from dynamicscaler_b200.panorama_tensor_utils import PanoramaTensor
+    img = torch.from_numpy(randn(22, 3, 16, 32))                       # stays on the CPU, like the reference's
+    pt = PanoramaTensor(img)
+    stores = set()
+    for i, (fov, th, ph) in enumerate(small["sph/views"][:3]):
+        view, mask = pt.get_view_tensor_no_interpolate(fov, th, ph, 10, 6)
+        assert view.is_cuda and np.array_equal(N(view), small[f"sph/img_get/{i}"])
+        assert mask.shape == (6, 10) and bool((mask == 1).all())
+        stores.add(pt.equirect_tensor.data_ptr())
+    assert len(stores) == 1 and pt.equirect_tensor.is_cuda             # one upload, then resident
+
+
+def test_proxy_single_frame_and_single_channel(dev):
+    """N == 1 or C == 1 latents: the permuted [B,N,C,H,W] alias is then itself contiguous, so proxy layout
+    must come from the explicit flag, not from strides.  Shapes and values vs the oracle."""
+    from dynamicscaler_b200.panorama_tensor_utils import PanoramaLatentProxy
+    for (C, Fn) in ((4, 1), (1, 5), (1, 1)):
+        lat0 = randn(70 + C + Fn, 1, C, Fn, 16, 32)
+        px = PanoramaLatentProxy(G(lat0, dev))
+        view, _ = px.get_view_tensor_no_interpolate(fov=100, theta=30, phi=20, width=10, height=6)
+        ref, _ = po.proxy_get_nearest(lat0, 100, 30, 20, 10, 6)
+        assert tuple(view.shape) == (1, C, Fn, 6, 10) and np.array_equal(N(view), ref), (C, Fn)
+        new = randn(80 + C + Fn, 1, C, Fn, 6, 10)
+        px.set_view_tensor_no_interpolation(G(new, dev), fov=100, theta=30, phi=20)
+        want = lat0.copy()
+        po.proxy_set_nearest(want, new, 100, 30, 20)
+        out = px.get_equirect_tensor()
+        assert tuple(out.shape) == (1, C, Fn, 16, 32) and np.array_equal(N(out), want), (C, Fn)
+        got_b = px.get_view_tensor_interpolate(fov=100, theta=30, phi=20, width=10, height=6)
+        assert tuple(got_b.shape) == (1, C, Fn, 6, 10)
+        assert np.abs(N(got_b) - po.proxy_get_bilinear(want, 100, 30, 20, 10, 6)).max() <= FP32_TOL
+
+
 def test_frame_ring_sphere_golden(small, dev):
     from dynamicscaler_b200.ring_panorama_tensor_utils import RingPanoramaLatentProxy
     rp5 = randn(31, 1, 2, 7, 16, 32)
