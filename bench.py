@@ -492,14 +492,36 @@ def run_ours(args, wl, wl_name):
     # --denoise-us T: a busy kernel of T microseconds per LOCAL window between gather and merge, the
     # stand-in for the UNet + ddim_step of BASELINE config 3 (the reference module cannot travel here)
     denoise_cycles = int(args.denoise_us * n_local * sleep_cycles_per_us(dev)) if args.denoise_us > 0 else 0
+    # --balance-evals (with --denoise-us, N > 1): T is the time of the TWO CFG evaluations of a window; single uncond
+    # evaluations move between ranks exactly as loop.sphere_denoise_loop(balance_evals=True) moves them (the window
+    # travels to the receiver, the result back: real NCCL point-to-point transfers inside the step)
+    balance = None
+    if args.balance_evals and denoise_cycles and dist_on and wl["kind"] == "sphere":
+        from dynamicscaler_b200.loop import exchange_windows, plan_eval_balance
+        n_views = len(default_views(0))
+        n_fw = plans[modes[0]][0].n_fwin
+        per_rank = [len(range(r, n_views, world)) * n_fw for r in range(world)]
+        moves = plan_eval_balance(per_rank)
+        evals = 2 * n_local - sum(1 for d, q, j in moves if d == rank) + sum(1 for d, q, j in moves if q == rank)
+        denoise_cycles = int(args.denoise_us / 2 * evals * sleep_cycles_per_us(dev))
+        balance = dict(out=[(j, q) for d, q, j in moves if d == rank], inn=[d for d, q, j in moves if q == rank], evals=evals)
+        vshape1 = (1, wl["C"], wl["f_len"], wl["h"], wl["w"])
+        balance["x_in"] = [torch.empty(vshape1, device=dev, dtype=dtype) for _ in balance["inn"]]
+        balance["eu_in"] = [torch.empty(vshape1, device=dev, dtype=dtype) for _ in balance["out"]]
 
     def make_step(mode, off, s):
         ws, plan = sets[s], plans[mode][off]
 
         def step():
             st.gather_all(ws.pano, plan, out=ws.wins)
+            if balance is not None:                     # donated windows travel to their receivers
+                exchange_windows([(ws.wins[j], q) for j, q in balance["out"]],
+                                 [(t, d) for t, d in zip(balance["x_in"], balance["inn"])])
             if denoise_cycles:
                 torch.cuda._sleep(denoise_cycles)
+            if balance is not None:                     # ... and the uncond results back to the owners
+                exchange_windows([(t, d) for t, d in zip(balance["x_in"], balance["inn"])],
+                                 [(t, q) for t, (j, q) in zip(balance["eu_in"], balance["out"])])
             ws.merge(st, plan)
         return step
 
@@ -653,6 +675,9 @@ def run_ours(args, wl, wl_name):
                                  else "reference [B,C,F,H,W] (csrc/sphere.cu, csrc/ring.cu)",
                        "maps": "precomputed on host (static geometry), cached on device",
                        "denoise_us_per_window": args.denoise_us,
+                       "balance_evals": (None if balance is None else
+                                         f"{balance['evals']} CFG evaluations on rank 0 after moving single uncond evaluations "
+                                         "between ranks (NCCL P2P inside the step)"),
                        "host_plan_build_ms": {"total": plan_build_ms, "plans": NP * len(modes),
                                               "note": "index maps + merge plans of all distinct window lists, built once per "
                                                       "stage before the loop and cached (outside the timed region)"},
@@ -770,6 +795,8 @@ def main():
     ap.add_argument("--denoise-us", type=float, default=0.0,
                     help="busy kernel of this many microseconds per local window between gather and merge "
                          "(UNet + ddim_step stand-in for the scaling study; 0 = the blend-only headline)")
+    ap.add_argument("--balance-evals", action="store_true",
+                    help="with --denoise-us and N > 1: move single uncond evaluations between ranks (88 = 8 x 11)")
     ap.add_argument("--only-mode", action="store_true", help="time only --mode (skip the other variant)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the sharded-vs-single-rank parity run")
     ap.add_argument("--no-kernel-pass", action="store_true",

@@ -13,8 +13,10 @@ launches per group:
 ``None`` = the whole step (the batched order BASELINE.json config 3 shards over GPUs); ``1`` = the
 reference's own sequential order, reproduced bit for bit (tests/golden/loop.npz comes from the real
 ``basic_sample_shift_shpere_panorama``).  With ``stepper.world > 1`` the views of every group are dealt
-round-robin over the ranks, each rank runs the UNet on its own windows only, and the merge kernels
-push the surviving rows into every replica (step.py).
+round-robin over the ranks, each rank runs the UNet on its own windows only (``balance_evals=True``
+additionally moves single uncond evaluations between ranks so that 44 views x 2 CFG branches are 11
+evaluations on each of 8 ranks instead of 12 / 10), and the merge kernels push the surviving rows into
+every replica (step.py).
 
 The model is called exactly like the reference calls ``self.pretrained_t2v.model`` (:236-254):
 ``model(x, ts, c_crossattn=[ctx], fps=fps, curr_time_steps=ts, temporal_length=frames, **kwargs)``.
@@ -31,22 +33,64 @@ import torch
 from .step import PanoramaState, PanoramaStepper, ddim_coefficients, renoise_coefficients
 
 
+def plan_eval_balance(n_local_per_rank: Sequence[int]):
+    """Classifier-free guidance doubles every window into two UNet evaluations (cond, uncond).  Views are dealt
+    round-robin, so ranks own n or n+1 windows -- 2n or 2n+2 evaluations (44 views on 8 ranks: 12,12,12,12,10,10,
+    10,10).  Moving single UNCOND evaluations from the ranks with more to the ranks with fewer evens that out
+    (88 = 8 x 11).  Returns the list of transfers ``(donor rank, receiver rank, local window index at the donor)``
+    -- the donor's LAST windows first -- identical on every rank."""
+    world = len(n_local_per_rank)
+    evals = [2 * n for n in n_local_per_rank]
+    base, extra = divmod(sum(evals), world)
+    order = sorted(range(world), key=lambda r: (-evals[r], r))
+    target = {r: base + (1 if i < extra else 0) for i, r in enumerate(order)}
+    surplus = {r: evals[r] - target[r] for r in range(world)}
+    donors = [r for r in order if surplus[r] > 0]
+    receivers = [r for r in reversed(order) if surplus[r] < 0]
+    transfers, given = [], {r: 0 for r in range(world)}
+    for d in donors:
+        while surplus[d] > 0 and receivers:
+            q = receivers[0]
+            if given[d] >= n_local_per_rank[d]:
+                break                                          # nothing left to donate (every uncond already given away)
+            given[d] += 1
+            transfers.append((d, q, n_local_per_rank[d] - given[d]))
+            surplus[d] -= 1
+            surplus[q] += 1
+            if surplus[q] == 0:
+                receivers.pop(0)
+    return transfers
+
+
+def exchange_windows(tensors_out, tensors_in, group=None):
+    """One batch of point-to-point transfers: ``tensors_out`` = [(tensor, peer rank)] to send, ``tensors_in`` =
+    [(tensor, peer rank)] to receive into (torch.distributed P2P: NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    ops = [dist.P2POp(dist.isend, t, peer, group) for t, peer in tensors_out]
+    ops += [dist.P2POp(dist.irecv, t, peer, group) for t, peer in tensors_in]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+
 def _get(schedule, name):
     return schedule[name] if isinstance(schedule, dict) else getattr(schedule, name)
 
 
 def unet_eval(model: Callable, x: torch.Tensor, t: int, cond: dict, frames: int, model_kwargs: Optional[dict] = None,
-              uncond: Optional[dict] = None, cfg_batch: bool = True):
+              uncond: Optional[dict] = None, cfg_batch: bool = True, x_uncond: Optional[torch.Tensor] = None):
     """Run the UNet on ``x`` [n, C, f, h, w] for the conditional and (if ``uncond`` is given) the
     unconditional branch.  ``cond`` / ``uncond``: the reference's dicts ``{"c_crossattn": [emb], "fps": fps}``
     with ``emb`` [1 or n, L, D].  ``cfg_batch``: evaluate both branches as ONE batch of 2n windows.
     Returns (eps_cond, eps_uncond or None), each [n, C, f, h, w] contiguous."""
     n = x.shape[0]
     kwargs = dict(model_kwargs or {})
+    xu = x if x_uncond is None else x_uncond        # eval balancing: the uncond branch may run on another window set
 
-    def ctx_of(c):
+    def ctx_of(c, count=None):
+        count = n if count is None else count
         emb = torch.cat(c["c_crossattn"], dim=1)
-        return emb.expand(n, -1, -1) if emb.shape[0] == 1 and n > 1 else emb
+        return emb.expand(count, -1, -1) if emb.shape[0] == 1 and count != 1 else emb
 
     def call(xx, ctx, fps):
         b = xx.shape[0]
@@ -55,11 +99,13 @@ def unet_eval(model: Callable, x: torch.Tensor, t: int, cond: dict, frames: int,
 
     if uncond is None:
         return call(x, ctx_of(cond), cond.get("fps", 16)).contiguous(), None
-    if cfg_batch:
-        y = call(torch.cat([x, x], dim=0), torch.cat([ctx_of(cond), ctx_of(uncond)], dim=0), cond.get("fps", 16))
+    nu = xu.shape[0]
+    if cfg_batch and n + nu > 0:
+        y = call(torch.cat([x, xu], dim=0), torch.cat([ctx_of(cond), ctx_of(uncond, nu)], dim=0), cond.get("fps", 16))
         return y[:n].contiguous(), y[n:].contiguous()
-    return (call(x, ctx_of(cond), cond.get("fps", 16)).contiguous(),
-            call(x, ctx_of(uncond), uncond.get("fps", 16)).contiguous())
+    ec = call(x, ctx_of(cond), cond.get("fps", 16)).contiguous() if n else x
+    eu = call(xu, ctx_of(uncond, nu), uncond.get("fps", 16)).contiguous() if nu else xu
+    return ec, eu
 
 
 def sphere_denoise_step(stepper: PanoramaStepper, state: PanoramaState, views: Sequence, width: int, height: int, *,
@@ -68,7 +114,7 @@ def sphere_denoise_step(stepper: PanoramaStepper, state: PanoramaState, views: S
                         renoise_ratio: Optional[float] = None, prev_ratio: Optional[float] = None,
                         eps_fn: Optional[Callable] = None, noise_fn: Optional[Callable] = None,
                         model_kwargs: Optional[dict] = None, cfg_batch: bool = True, frame_begins=None,
-                        on_input: Optional[Callable] = None):
+                        on_input: Optional[Callable] = None, balance_evals: bool = False):
     """One DDIM step i over ``views`` (ordered (phi, theta) list of the step).  ``schedule``: object or
     dict with the reference scheduler's ``ddim_timesteps, alphas_cumprod, ddim_alphas, ddim_alphas_prev,
     ddim_sigmas, ddim_sqrt_one_minus_alphas`` (pipeline/scheduler.py:17-57).  ``eps_fn(step_i, job_ids,
@@ -107,10 +153,13 @@ def sphere_denoise_step(stepper: PanoramaStepper, state: PanoramaState, views: S
         else:
             x = stepper.gather_all(state, plan)
         n = x.shape[0]
-        if n > 0:
-            xb = x.view(n * x.shape[1], *x.shape[2:])                   # [n*B, C, f, h, w]; B == 1 in every pipeline
-            if on_input is not None:
-                on_input(step_i, job_ids, xb)
+        xb = x.view(n * x.shape[1], *x.shape[2:])                       # [n*B, C, f, h, w]; B == 1 in every pipeline
+        if on_input is not None and n > 0:
+            on_input(step_i, job_ids, xb)
+        if balance_evals and stepper.world > 1 and uncond is not None:
+            ec, eu = _balanced_eval(stepper, plan, model, xb, t, cond, uncond, frames, model_kwargs, cfg_batch)
+            ec, eu = ec.view(x.shape), eu.view(x.shape)
+        elif n > 0:
             ec, eu = unet_eval(model, xb, t, cond, frames, model_kwargs, uncond, cfg_batch)
             ec = ec.view(x.shape)
             eu = None if eu is None else eu.view(x.shape)
@@ -121,6 +170,36 @@ def sphere_denoise_step(stepper: PanoramaStepper, state: PanoramaState, views: S
                                prev_mask=mview if use_prev else None, prev_ratio=prev_ratio if use_prev else None)
 
 
+def _balanced_eval(stepper, plan, model, xb, t, cond, uncond, frames, model_kwargs, cfg_batch):
+    """UNet evaluations of one group with single uncond evaluations moved between ranks
+    (:func:`plan_eval_balance`): donors ship the window to the receiver, the receiver evaluates the uncond
+    branch in its own batch and ships the result back; the merge stays at the window's owner."""
+    n_views = len(plan.extra["vms"])
+    n_fwin = plan.n_fwin
+    per_rank = [len(range(r, n_views, stepper.world)) * n_fwin for r in range(stepper.world)]
+    moves = plan_eval_balance(per_rank)
+    mine_out = [j for (d, q, j) in moves if d == stepper.rank]
+    peers_out = [q for (d, q, j) in moves if d == stepper.rank]
+    mine_in = [(d, j) for (d, q, j) in moves if q == stepper.rank]
+    n = xb.shape[0]
+    x_in = xb.new_empty((len(mine_in),) + tuple(xb.shape[1:]))
+    exchange_windows([(xb[j].contiguous(), q) for j, q in zip(mine_out, peers_out)],
+                     [(x_in[i], d) for i, (d, j) in enumerate(mine_in)], stepper.group)
+    keep = [j for j in range(n) if j not in set(mine_out)]
+    xu = torch.cat([xb[keep], x_in], dim=0) if (len(keep) != n or len(mine_in)) else xb
+    ec, eu_mix = unet_eval(model, xb, t, cond, frames, model_kwargs, uncond, cfg_batch, x_uncond=xu)
+    eu = torch.empty_like(xb)
+    if keep:
+        eu[keep] = eu_mix[:len(keep)]
+    back = eu_mix[len(keep):]
+    recv = [eu.new_empty(xb.shape[1:]) for _ in mine_out]
+    exchange_windows([(back[i].contiguous(), d) for i, (d, j) in enumerate(mine_in)],
+                     [(recv[i], q) for i, q in enumerate(peers_out)], stepper.group)
+    for j, r in zip(mine_out, recv):
+        eu[j] = r
+    return ec, eu
+
+
 def sphere_denoise_loop(stepper: PanoramaStepper, state: PanoramaState, *, model: Callable, schedule,
                         views_fn: Callable, width: int, height: int, frames: int, cond: dict,
                         uncond: Optional[dict], guidance_scale: float = 7.5, fov=120,
@@ -128,7 +207,7 @@ def sphere_denoise_loop(stepper: PanoramaStepper, state: PanoramaState, *, model
                         renoise_ratio: Optional[float] = None, prev_ratio_list: Optional[Sequence[float]] = None,
                         eps_fn: Optional[Callable] = None, noise_fn: Optional[Callable] = None,
                         model_kwargs: Optional[dict] = None, cfg_batch: bool = True, frame_begins_fn=None,
-                        on_input: Optional[Callable] = None):
+                        on_input: Optional[Callable] = None, balance_evals: bool = False):
     """The whole DDIM loop (t2v_sphere_panorama_pipeline.py:164-293): ``timesteps`` defaults to the
     flipped ``ddim_timesteps`` (:103); ``views_fn(i)`` returns the ordered (phi, theta) list of step i
     (``geometry.sphere_views``).  The state's panorama 0 / 1 end up holding the final latents / the
@@ -143,5 +222,6 @@ def sphere_denoise_loop(stepper: PanoramaStepper, state: PanoramaState, *, model
                             group_size=group_size, renoise_ratio=renoise_ratio,
                             prev_ratio=None if prev_ratio_list is None else prev_ratio_list[i], eps_fn=eps_fn,
                             noise_fn=noise_fn, model_kwargs=kwargs, cfg_batch=cfg_batch,
-                            frame_begins=None if frame_begins_fn is None else frame_begins_fn(i), on_input=on_input)
+                            frame_begins=None if frame_begins_fn is None else frame_begins_fn(i), on_input=on_input,
+                            balance_evals=balance_evals)
     return state

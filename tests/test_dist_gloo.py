@@ -178,3 +178,63 @@ def test_peer_replica_exchange_world2_gloo(tmp_path, mode):
         assert np.array_equal(g["lat"], pm_unpack(want[0]))
         assert np.array_equal(g["den"], pm_unpack(want[1]))
         assert np.array_equal(g["owners"], pm_unpack(wmask))
+
+
+# ------------------------------------------------ CFG evaluation balancing of the loop driver ----
+def test_plan_eval_balance_schedule():
+    """88 evaluations of 44 views on 8 ranks become 11 each; schedules are valid for every split."""
+    from dynamicscaler_b200.loop import plan_eval_balance
+    for per in ([6, 6, 6, 6, 5, 5, 5, 5], [6, 5], [3, 3, 3, 2], [1, 1, 1, 0, 0, 0, 0, 0], [22, 22], [2, 1, 1, 1, 1, 1, 1, 1],
+                [7, 7, 7, 6, 6, 6, 6, 6]):
+        moves = plan_eval_balance(per)
+        evals = [2 * n for n in per]
+        seen = set()
+        for d, q, j in moves:
+            assert d != q and 0 <= j < per[d] and (d, j) not in seen      # an uncond evaluation moves at most once
+            seen.add((d, j))
+            evals[d] -= 1
+            evals[q] += 1
+        assert max(evals) - min(evals) <= 1, (per, evals)
+    assert plan_eval_balance([6, 6, 6, 6, 5, 5, 5, 5]) == [(0, 7, 5), (1, 6, 5), (2, 5, 5), (3, 4, 5)]
+
+
+def _balance_worker(rank, world, port, out_dir):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import types
+    from conftest import randn
+    from dynamicscaler_b200 import loop
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_views, F = 7, 3                                                  # rank 0 owns 4 views, rank 1 owns 3: 8 / 6 evals -> 7 / 7
+        local = list(range(rank, n_views, world))
+        stepper = types.SimpleNamespace(world=world, rank=rank, group=None)
+        plan = types.SimpleNamespace(extra={"vms": [None] * n_views}, n_fwin=1)
+        xb = torch.stack([torch.from_numpy(randn(300 + v, 4, F, 5, 6)) for v in local])
+        calls = []
+
+        def model(x, ts, c_crossattn=None, fps=None, **kw):                # elementwise, depends on the context row
+            calls.append(x.shape[0])
+            assert ts.numel() == (x.shape[0] * F if x.shape[0] > 1 else 1)
+            return torch.sin(x) + c_crossattn[0][:, 0, 0].reshape(-1, 1, 1, 1, 1)
+
+        cond = {"c_crossattn": [torch.full((1, 2, 2), 0.25)], "fps": 16}
+        uncond = {"c_crossattn": [torch.full((1, 2, 2), -0.5)], "fps": 16}
+        ec, eu = loop._balanced_eval(stepper, plan, model, xb, 500, cond, uncond, F, None, True)
+        ok = torch.equal(ec, torch.sin(xb) + 0.25) and torch.equal(eu, torch.sin(xb) - 0.5)
+        ok = ok and calls == [7]                                           # 4 + 3 resp. 3 + 4 windows in ONE batch on both ranks
+        np.save(os.path.join(out_dir, f"balance{rank}.npy"), np.array([ok]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_balanced_eval_world2_gloo(tmp_path):
+    """loop._balanced_eval over gloo: one uncond evaluation travels from rank 0 to rank 1 and its result back;
+    every window ends up with both branches at its owner, each rank evaluates 7 windows."""
+    mp.spawn(_balance_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(tmp_path / f"balance{r}.npy")[0], f"rank {r}"

@@ -217,7 +217,7 @@ def test_ring_peer_exchange(tmp_path, world, dtype_name):
 
 
 # ------------------------------------------------ denoising-loop driver, sharded ----
-def _loop_worker(rank, world, port, out_dir, group_size):
+def _loop_worker(rank, world, port, out_dir, group_size, balance=False):
     for p in (ROOT, HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
@@ -258,7 +258,8 @@ def _loop_worker(rank, world, port, out_dir, group_size):
             state = st.make_state([lat0, torch.zeros_like(lat0)], mask=torch.zeros(1, H, W, device=dev), peer=peer)
             sphere_denoise_loop(st, state, model=model, schedule=sched, views_fn=lambda i: geo.sphere_views(i)[:11],
                                 width=w, height=h, frames=F, cond=cond, uncond=uncond, guidance_scale=7.5,
-                                group_size=group_size, renoise_ratio=0.6, prev_ratio_list=[0.3, 0.4, 0.5, 0.6], eps_fn=eps_fn)
+                                group_size=group_size, renoise_ratio=0.6, prev_ratio_list=[0.3, 0.4, 0.5, 0.6], eps_fn=eps_fn,
+                                balance_evals=balance and peer)
             outs.append(state.export() + [state.export_mask()])
         ok = all(torch.equal(a, b) for a, b in zip(*outs))
         if not ok:
@@ -276,6 +277,13 @@ def _loop_worker(rank, world, port, out_dir, group_size):
         ok = False
     finally:
         os._exit(0 if ok else 1)
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_sharded_denoise_loop_balanced_evals(tmp_path, world):
+    """The same with single uncond evaluations moved between ranks (11 views on 2 ranks: 12 / 10 -> 11 / 11
+    evaluations; NCCL point-to-point): still bit-identical to the single-GPU loop."""
+    _spawn(tmp_path, world, _loop_worker, None, True)
 
 
 @pytest.mark.parametrize("world,group_size", [(2, None), (2, 3), (4, None), (8, None)])
