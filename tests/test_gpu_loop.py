@@ -188,3 +188,49 @@ def test_merge_prev_mix_full_mask_vs_oracle(dev, mode):
     tol = 0.0 if mode == "nearest" else 1e-5
     assert np.abs(N(out_lat) - ref_lat).max() <= tol and np.abs(N(out_den) - ref_den).max() <= tol
     assert np.array_equal(N(state.export_mask()), ref_mask)
+
+
+def test_dropin_classes_replay_the_real_reference_pipeline(dev):
+    """The reference's own call sites, one view at a time, through the DROP-IN classes (regime (i)): the body of
+    the real loop (pipeline/t2v_sphere_panorama_pipeline.py:166-291) mirrored call for call -- PanoramaLatentProxy /
+    PanoramaTensor gets, re_noise with the recorded epsilon, mix_latents_with_mask, the recorded UNet outputs,
+    CFG and ddim_step as plain torch ops, the three sets -- must land on the REAL pipeline's final panoramas
+    (tests/golden/loop.npz) bit for bit, and feed the UNet bit-identical windows on the way."""
+    from dynamicscaler_b200.panorama_tensor_utils import PanoramaLatentProxy, PanoramaTensor
+    from dynamicscaler_b200.tensor_utils import mix_latents_with_mask
+    g, (F, H, W, h, w, steps, fov), views0, sched, views_fn = load_loop()
+    nv = len(views0)
+    lat0 = G(randn(41, 1, 4, F, H, W), dev)
+    h_lat = PanoramaLatentProxy(equirect_tensor=lat0)
+    h_den = PanoramaLatentProxy(equirect_tensor=torch.zeros_like(lat0))
+    ac = torch.from_numpy(np.asarray(sched["alphas_cumprod"], dtype=np.float32)).to(dev)
+    ddim_ts = [int(v) for v in sched["ddim_timesteps"]]
+    total, ratio, gscale = len(ddim_ts), float(g["ratio"]), float(g["guidance"])
+    draws = 0
+    for i in range(steps):
+        h_msk = PanoramaTensor(equirect_tensor=torch.zeros_like(lat0[0, 0, [0]]))          # :173
+        for n, (ph, th) in enumerate(views_fn(i)):
+            view, _ = h_lat.get_view_tensor_no_interpolate(fov=fov, theta=th, phi=ph, width=w, height=h)
+            m, _ = h_msk.get_view_tensor_no_interpolate(fov=fov, theta=th, phi=ph, width=w, height=h)
+            if i < total - 1:                                                             # :212-221
+                a_a, a_b = ac[ddim_ts[total - i - 2]], ac[ddim_ts[total - i - 1]]         # scheduler.py:99-105
+                c, s = torch.sqrt(a_b / a_a), torch.sqrt(1 - a_b / a_a)
+                draws += 1
+                noised = c * view.clone() + s * G(randn(5000 + draws, *view.shape), dev)
+                view = mix_latents_with_mask(latent_1=view, latent_to_add=noised, mask=m, mix_ratio=ratio)
+            j = i * nv + n
+            assert np.array_equal(sha(N(view.contiguous())), g["unet_in_sha"][j]), (i, n)
+            ec, eu = G(g["eps_cond"][j], dev), G(g["eps_uncond"][j], dev)
+            e = eu + gscale * (ec - eu)                                                   # :258
+            idx = total - i - 1
+            f32 = lambda v: torch.full((1, 1, 1, 1, 1), float(v), device=dev)            # scheduler.py:78-81
+            a_t, a_prev, sig, s1m = (f32(sched[k][idx]) for k in ("ddim_alphas", "ddim_alphas_prev", "ddim_sigmas",
+                                                                  "ddim_sqrt_one_minus_alphas"))
+            pred_x0 = (view - s1m * e) / a_t.sqrt()                                       # :84-89 (sigma = 0)
+            x_prev = a_prev.sqrt() * pred_x0 + (1. - a_prev - sig ** 2).sqrt() * e
+            h_lat.set_view_tensor_no_interpolation(view_tensor=x_prev, fov=fov, theta=th, phi=ph)
+            h_den.set_view_tensor_no_interpolation(view_tensor=pred_x0, fov=fov, theta=th, phi=ph)
+            h_msk.set_view_tensor_no_interpolation(view_tensor=torch.ones_like(x_prev[0, 0, [0]]), fov=fov, theta=th, phi=ph)
+    assert draws == int(g["renoise_draws"])
+    assert np.array_equal(N(h_lat.get_equirect_tensor()), g["final_latent"])
+    assert np.array_equal(N(h_den.get_equirect_tensor()), g["final_denoised"])
