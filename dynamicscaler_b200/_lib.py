@@ -54,6 +54,7 @@ PROTOTYPES = {
 }
 
 
+PEER_DEFERRED_PUBLISH = [False]   # mirror of the library's DS_TUNE_PEER_MERGE_PUBLISH switch (set through PanoramaStepper)
 DS_MAX_PEERS = 8
 DS_PEER_AFTER_GATHER, DS_PEER_AFTER_MERGE, DS_PEER_WAIT_MERGES = 0, 1, 2
 

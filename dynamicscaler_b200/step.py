@@ -308,22 +308,21 @@ class PanoramaStepper:
         # peer states: NVLS multicast stores win from 4 GPUs up (one store instead of world-1 copies);
         # at 2 GPUs the per-replica TMA row copies are faster (tools/peer_probe.py)
         self.use_multicast = world > 2
-        # exchange-mode ordering protocol (DS_TUNE_PEER_MERGE_PUBLISH): False = one ds_pm_peer_sync launch after every
-        # gather / merge; True = deferred: the kernels count themselves as issued and the NEXT kernel on the state
-        # publishes the count in its prologue (no ordering launches inside a step)
-        self._merge_publish = False
         self._plans = {}
         self._xbuf = {}
 
     @property
     def merge_publish_in_kernel(self) -> bool:
-        return self._merge_publish
+        """Exchange ordering protocol: False = host-side (one ds_pm_peer_sync launch after every gather / merge),
+        True = deferred (kernels count themselves as issued, the next kernel publishes).  PROCESS-WIDE: the switch
+        lives in the library (ds_tune DS_TUNE_PEER_MERGE_PUBLISH) and every stepper of the process reads the one
+        copy kept next to the binding, so host and kernels can never disagree about who publishes."""
+        return _lib.PEER_DEFERRED_PUBLISH[0]
 
     @merge_publish_in_kernel.setter
     def merge_publish_in_kernel(self, on: bool):
-        """Process-wide switch (ds_tune DS_TUNE_PEER_MERGE_PUBLISH): every stepper of the process follows it."""
-        self._merge_publish = bool(on)
         lib.check(lib.ds_tune(6, 1 if on else 0), "ds_tune")
+        _lib.PEER_DEFERRED_PUBLISH[0] = bool(on)
 
     # ------------------------------------------------------------------ planning ----
     def _frames(self, frame_begins, frames):
