@@ -738,23 +738,32 @@ def run_ours(args, wl, wl_name):
                                  / (results[m][kn + "_us"] * 1e-6) / 1e9} for kn in ("gather", "merge")}
                         for m in results},
             }
-            # context for the fraction: what a PLAIN device copy (torch's copy kernel) of the same necessary byte count
-            # reaches in the same harness (CUDA graph, rotating buffers larger than L2) -- at 10-15 us per launch even
-            # a memcpy is far from the 6.5 TB/s it reaches on gigabyte transfers
-            try:
-                half = max(int(nec_launch) // 8 * 4, 1 << 20)                       # bytes read = bytes written = half
+            # context for the fractions: what a PLAIN device copy (torch's copy kernel) of the same necessary byte
+            # count reaches in the same harness (CUDA graph, rotating buffers larger than L2) -- at 10-15 us per launch
+            # even a memcpy is far from the 6.5 TB/s it reaches on gigabyte transfers
+            def plain_copy_us(nbytes):
+                half = max(int(nbytes) // 8 * 4, 1 << 20)                           # bytes read = bytes written = half
                 n_pairs = max(2, -(-3 * L2_BYTES // (2 * half)))
                 pairs = [(torch.empty(half // 4, device=dev), torch.empty(half // 4, device=dev)) for _ in range(n_pairs)]
                 cfns = [(lambda a=a, b=b: b.copy_(a)) for a, b in pairs]
                 iters = max(K, 5 * len(cfns))
                 crun = make_runner(cfns, iters, use_graph, side)
                 crun()
-                copy_us = statistics.median(timed_regions(crun, False, 5, dev)) / iters * 1e3
+                return statistics.median(timed_regions(crun, False, 5, dev)) / iters * 1e3
+
+            try:
+                for m in results:
+                    nb = st.necessary_bytes(plans[m][0], P, esz)
+                    for kn, nbytes in (("gather", nb[0]), ("merge", nb[1])):
+                        cu = plain_copy_us(nbytes)
+                        line["roofline"]["all"][m][kn]["plain_copy_same_bytes_us"] = cu
+                        line["roofline"]["all"][m][kn]["kernel_vs_plain_copy"] = cu / results[m][kn + "_us"]
+                dom = line["roofline"]["all"][args.mode][kern]
                 line["roofline"]["plain_copy_same_bytes"] = {
-                    "us": copy_us, "GBps": 2 * half / (copy_us * 1e-6) / 1e9,
-                    "kernel_vs_copy": copy_us / (dur * 1e6),
-                    "what": "torch copy kernel moving the dominant kernel's necessary bytes (half read, half written), same harness"}
-                del pairs, cfns, crun
+                    "us": dom["plain_copy_same_bytes_us"], "GBps": nec_launch / (dom["plain_copy_same_bytes_us"] * 1e-6) / 1e9,
+                    "kernel_vs_copy": dom["kernel_vs_plain_copy"],
+                    "what": "torch copy kernel moving the same necessary byte count (half read, half written) in the same "
+                            "harness; kernel_vs_copy = copy time / kernel time"}
             except Exception as e:                                                  # never let the calibration break the line
                 print(f"[bench] plain-copy calibration skipped ({type(e).__name__}: {e})", file=sys.stderr)
             if not args.no_cpu and args.dtype == "f32":
