@@ -738,14 +738,16 @@ def run_ours(args, wl, wl_name):
                                  / (results[m][kn + "_us"] * 1e-6) / 1e9} for kn in ("gather", "merge")}
                         for m in results},
             }
-            # context for the fractions: what a PLAIN device copy (torch's copy kernel) of the same necessary byte
+            # context for the fractions: what a PLAIN elementwise copy kernel moving the same necessary byte
             # count reaches in the same harness (CUDA graph, rotating buffers larger than L2) -- at 10-15 us per launch
             # even a memcpy is far from the 6.5 TB/s it reaches on gigabyte transfers
             def plain_copy_us(nbytes):
                 half = max(int(nbytes) // 8 * 4, 1 << 20)                           # bytes read = bytes written = half
                 n_pairs = max(2, -(-3 * L2_BYTES // (2 * half)))
                 pairs = [(torch.empty(half // 4, device=dev), torch.empty(half // 4, device=dev)) for _ in range(n_pairs)]
-                cfns = [(lambda a=a, b=b: b.copy_(a)) for a, b in pairs]
+                # an SM copy kernel: b.copy_(a) would become a driver memcpy node, which only reaches 2.6 TB/s inside
+                # a graph at these sizes (tools/calib_copy_sweep.py, profiles/r02e_copy_sweep.jsonl)
+                cfns = [(lambda a=a, b=b: torch.add(a, 0.0, out=b)) for a, b in pairs]
                 iters = max(K, 5 * len(cfns))
                 crun = make_runner(cfns, iters, use_graph, side)
                 crun()
@@ -762,8 +764,8 @@ def run_ours(args, wl, wl_name):
                 line["roofline"]["plain_copy_same_bytes"] = {
                     "us": dom["plain_copy_same_bytes_us"], "GBps": nec_launch / (dom["plain_copy_same_bytes_us"] * 1e-6) / 1e9,
                     "kernel_vs_copy": dom["kernel_vs_plain_copy"],
-                    "what": "torch copy kernel moving the same necessary byte count (half read, half written) in the same "
-                            "harness; kernel_vs_copy = copy time / kernel time"}
+                    "what": "elementwise SM copy kernel (torch.add(src, 0, out=dst)) moving the same necessary byte count (half "
+                            "read, half written) in the same harness; kernel_vs_copy = copy time / kernel time"}
             except Exception as e:                                                  # never let the calibration break the line
                 print(f"[bench] plain-copy calibration skipped ({type(e).__name__}: {e})", file=sys.stderr)
             if not args.no_cpu and args.dtype == "f32":
