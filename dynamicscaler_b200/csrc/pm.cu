@@ -54,6 +54,7 @@ constexpr int kWarps = kBlock / 32;
 static int g_gather_ctas_per_sm = 0;            // 0: occupancy limit
 static int g_merge_publish = 0;                 // exchange mode: 0 = the host enqueues ds_pm_peer_sync after every gather / merge; 1 = deferred:
                                                 // a data kernel counts itself as issued and the next kernel publishes it in its prologue
+static int g_hw_const = 1;                      // 40 x 64 windows: kernels specialised on the window size (immediate load offsets)
 static int g_gather_pipe = 2;                   // bit 1: copy-only gather, bit 2: 4-tap gather use the pipelined tile loop
 static long long g_peer_timeout_ns = 60000000000ll;  // a cross-GPU wait longer than this (60 s: first-step autotune,
                                                        // lazy module loads, stragglers are all far shorter) aborts the kernel
@@ -849,7 +850,8 @@ __device__ __forceinline__ int pm_job_offset(const PmMergeArgs& a, int s, int sr
 // CTA = 32 surviving view pixels.
 // Load: warp <-> (payload q, window frame fo), lane <-> entry: 4 plane loads -> one atom ->
 // shared tile[q][entry][fo].  Store: f_len consecutive lanes write one full panorama row.
-template <typename T, int FL, bool DD, bool PEER>
+// HWC: as in the weighted merge below -- 40 x 64 windows known at compile time, payload offsets become immediates.
+template <typename T, int FL, bool DD, bool PEER, int HWC = 0>
 __global__ void __launch_bounds__(kBlock, 5)
 pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                         const int32_t* __restrict__ d_ent_src, const int32_t* __restrict__ d_ent_dst,
@@ -866,14 +868,19 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
     int32_t* s_dst = reinterpret_cast<int32_t*>(tile + (a.Q > 0 ? a.Q : 1) * kPmET * SA);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int plane_stride = f_len * a.hw;
+    const int plane_stride = f_len * (HWC > 0 ? HWC : a.hw);
     const int n_pairs = a.Q * f_len;
     const int cnt = rg.hi - rg.lo;
     const bool have = lane < cnt;
     int off = 0;
     if (have) {
       const int src = d_ent_src != nullptr ? __ldg(d_ent_src + rg.lo + lane) : rg.lo + lane;
-      off = pm_job_offset(a, rg.s, src, plane_stride);
+      if (HWC > 0) {
+        const int v = src / HWC, k = src - v * HWC;
+        off = (rg.s * a.vpf + v - a.job_begin) * kPmPlanes * plane_stride + k;
+      } else {
+        off = pm_job_offset(a, rg.s, src, plane_stride);
+      }
       if (warp == 0) {
         const int dst = d_ent_dst != nullptr ? __ldg(d_ent_dst + rg.lo + lane) : rg.lo + lane;
         s_dst[lane] = dst;
@@ -915,6 +922,26 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
             tile[(1 * kPmET + lane) * SA + f0 + u] = Atom<T>::pack(x0);
           }
       }
+    } else if (HWC > 0 && FL == 16 && a.Q == 2) {
+      // two payloads x 16 frames = 32 (payload, frame) pairs = 4 per warp: payload q = warp / 4, frames
+      // (warp % 4) * 4 + u.  One base pointer per thread; (frame, plane) offsets are immediates.
+      constexpr int U = 4;
+      const int q = warp >> 2, fo0 = (warp & 3) * U;
+      const T* __restrict__ b = static_cast<const T*>(q == 0 ? a.pay[0] : a.pay[1]) + off + fo0 * HWC;
+      T e[U][4];
+      bool live[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        int f;
+        live[u] = have && pm_frame_live(a, d_ftab, rg, fo0 + u, FL, f);
+        if (live[u]) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) e[u][p] = ldg(b + (u + p * FL) * HWC);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (live[u]) tile[(q * kPmET + lane) * SA + fo0 + u] = atom_join<T>(e[u]);
     } else {
     constexpr int U = 4;
     for (int p0 = warp * U; p0 < n_pairs; p0 += kWarps * U) {
@@ -983,7 +1010,10 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
 // on nothing but blockIdx: global dependency depth 2 (entries -> payload) instead of 3, and
 // every loop bound of phase A is a compile-time constant.  d_view_ptr[v] = first tile of view
 // v; d_row_start[r] = first (padded) entry of row r, rows of a tile being contiguous.
-template <typename T, int FL, int QN, bool DD, bool PEER>
+// HWC: view pixels per window known at compile time (40 x 64 = 2560, the one window size of the reference's
+// pipelines: 320 x 512 pixels / 8), else 0 = runtime.  With HWC every (frame, plane) offset of a payload element is
+// an immediate of the load instruction, so the 32 loads of a thread need 4 address computations instead of 32.
+template <typename T, int FL, int QN, bool DD, bool PEER, int HWC = 0>
 __global__ void __launch_bounds__(kBlock)
 pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_ptr,
                                const int4* __restrict__ d_tile, const int32_t* __restrict__ d_row_dst,
@@ -1052,7 +1082,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
   const PmPeerFlag pflag = pm_merge_begin<PEER>(a, rep);
 
   // ---- phase A: products (level-2 loads) ----
-  const int plane_stride = FL * a.hw;
+  const int plane_stride = FL * (HWC > 0 ? HWC : a.hw);
   const int job_off = (s * a.vpf + view - a.job_begin) * kPmPlanes * plane_stride;
   if (DD) {
     static_assert(!DD || QN == 2, "the fused denoise epilogue produces exactly x_prev and pred_x0");
@@ -1090,26 +1120,47 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
         }
     }
   } else {
+  // HWC path: branch-free, one base pointer per (half, payload) and immediates for everything else.  Padding entries
+  // (k < 0, w = 0) read view pixel 0 instead of being predicated off: their products are never consumed (phase B
+  // only walks the real entries of a row); dead window frames of a frame ring are skipped per warp (uniform).
+  const unsigned koff[2] = {static_cast<unsigned>(max(k[0], 0)), static_cast<unsigned>(max(k[1], 0))};
   T x[2][QN][2][4];                               // [half][payload][frame j][plane]
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
+  if (HWC > 0) {
+    // one base pointer per (half, payload): (job, plane 0, frame `warp`, pixel k); the rest are immediates
 #pragma unroll
     for (int q = 0; q < QN; ++q)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (k[h] >= 0 && liveA[j]) {
-          const T* __restrict__ src = static_cast<const T*>(a.pay[q]) + job_off + (warp + j * kWarps) * a.hw + k[h];
+      for (int h = 0; h < 2; ++h) {
+        const T* __restrict__ b = static_cast<const T*>(a.pay[q]) + job_off + warp * HWC + koff[h];
 #pragma unroll
-          for (int p = 0; p < 4; ++p) x[h][q][j][p] = ldg(src + p * plane_stride);
-        }
+        for (int j = 0; j < 2; ++j)
+          if (liveA[j]) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) x[h][q][j][p] = ldg(b + (j * kWarps + p * FL) * HWC);
+          }
       }
+  } else {
+    // generic window size: predicated per entry (measured faster than the branch-free form at runtime strides)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int q = 0; q < QN; ++q)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (k[h] >= 0 && liveA[j]) {
+            const T* __restrict__ src = static_cast<const T*>(a.pay[q]) + job_off + (warp + j * kWarps) * a.hw + k[h];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) x[h][q][j][p] = ldg(src + p * plane_stride);
+          }
+        }
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
     for (int q = 0; q < QN; ++q)
 #pragma unroll
       for (int j = 0; j < 2; ++j)
-        if (k[h] >= 0 && liveA[j])
+        if ((HWC > 0 || k[h] >= 0) && liveA[j])
           prod[(q * kPmEC + h * 32 + lane) * SA + warp + j * kWarps] =
               make_float4(__fmul_rn(Elem<T>::to_f(x[h][q][j][0]), w[h]), __fmul_rn(Elem<T>::to_f(x[h][q][j][1]), w[h]),
                           __fmul_rn(Elem<T>::to_f(x[h][q][j][2]), w[h]), __fmul_rn(Elem<T>::to_f(x[h][q][j][3]), w[h]));
@@ -1444,7 +1495,15 @@ extern "C" int ds_pm_merge_nearest(void* const* h_pms, const void* const* h_payl
   DS_DISPATCH_DTYPE(dtype, {
     using AT = typename Atom<ET>::type;
     const size_t smem = static_cast<size_t>(Q > 0 ? Q : 1) * kPmET * (f_len | 1) * sizeof(AT) + kPmET * sizeof(int32_t);
-    if (f_len == 16) { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, false, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 16, false, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
+    if (f_len == 16) {
+      if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, false, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+      // (38 registers: 6 CTAs fit an SM instead of 5.  Holding it at 5 by padding the shared-memory request was measured
+      // and is far WORSE -- 24.7 vs 15.2 us -- because the larger carve-out shrinks L1, which the scattered 4-byte payload
+      // loads depend on: profiles/r02f_kbench_hw_const.jsonl)
+      if (hw == 2560 && Q == 2 && g_hw_const && d_view_ptr != nullptr)
+        return pm_launch(pm_merge_nearest_kernel<ET, 16, false, false, 2560>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+      return pm_launch(pm_merge_nearest_kernel<ET, 16, false, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    }
     { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 0, false, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 0, false, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
   });
   return DS_OK;
@@ -1495,7 +1554,7 @@ extern "C" int ds_pm_merge_bilinear_tiled(void* const* h_pms, const void* const*
   const size_t smem = static_cast<size_t>(Q) * kPmEC * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmTR + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
     if (Q == 1) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 1, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
-    if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    if (Q == 2) { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); if (hw == 2560 && g_hw_const) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false, 2560>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
     { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 4, false, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
@@ -1594,6 +1653,7 @@ extern "C" int ds_tune(int knob, long long value) {
     case DS_TUNE_PEER_TIMEOUT_NS: ds::g_peer_timeout_ns = value; return DS_OK;
     case DS_TUNE_PDL: ds::g_pdl = static_cast<int>(value); return DS_OK;
     case DS_TUNE_PM_GATHER_PIPELINE: ds::g_gather_pipe = static_cast<int>(value); return DS_OK;
+    case DS_TUNE_PM_HW_CONST: ds::g_hw_const = value != 0 ? 1 : 0; return DS_OK;
     case DS_TUNE_PEER_MERGE_PUBLISH: ds::g_merge_publish = value != 0 ? 1 : 0; return DS_OK;
     default: return DS_ERR_DIM;
   }

@@ -57,8 +57,10 @@ enum {
                                           4 nearest merge, 8 weighted merges (default: 11) */
   DS_TUNE_PM_GATHER_PIPELINE = 3       /* software-pipelined gather tile loop (next tile's map entries prefetched with
                                           cp.async, deferred bulk-copy wait), bit mask: 1 copy-only gather, 2 4-tap gather */
-                                       /* (4, 5: retired -- 2-D gather tiles and the 5-CTA/SM weighted merge, both measured
-                                          slower, profiles/r02a_kbench_*.jsonl) */
+  , DS_TUNE_PM_HW_CONST = 4            /* 1 (default): 40 x 64 windows (the reference's only window size) run kernels
+                                          specialised on hw = 2560 (payload offsets become load immediates); 0: generic kernels */
+                                       /* (5: retired -- the 5-CTA/SM weighted merge and, formerly 4, the 2-D gather tiles, both
+                                          measured slower, profiles/r02a_kbench_*.jsonl) */
   , DS_TUNE_PEER_MERGE_PUBLISH = 6     /* exchange-mode ordering protocol: 0 = host-side (ds_pm_peer_sync after every pixel-major
                                           gather / merge), 1 = deferred (kernels count themselves, the next kernel publishes) */
 };

@@ -52,6 +52,7 @@ def main():
         lib.check(lib.ds_tune(GATHER_CPS, cfg.get("gather_cps", 0)))
         lib.check(lib.ds_tune(2, cfg.get("pdl", 11)))                     # DS_TUNE_PDL
         lib.check(lib.ds_tune(3, cfg.get("pipe", 2)))                     # DS_TUNE_PM_GATHER_PIPELINE
+        lib.check(lib.ds_tune(4, cfg.get("hw_const", 1)))                 # DS_TUNE_PM_HW_CONST
         res = dict(cfg, workload=wl_name)
         for mode in modes:                                  # whole steps (gather -> merge chains)
             fns = []
