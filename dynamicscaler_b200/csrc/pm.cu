@@ -902,7 +902,7 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
           int f;
           live[u] = fo < f_len && have && pm_frame_live(a, d_ftab, rg, fo, f_len, f);
           if (live[u]) {
-            const int o = fo * a.hw + off;
+            const int o = fo * (HWC > 0 ? HWC : a.hw) + off;          // HWC: (frame, plane) offsets fold into immediates
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
               x[u][p] = ldg(static_cast<const T*>(a.pay[0]) + o + p * plane_stride);
@@ -917,7 +917,8 @@ pm_merge_nearest_kernel(const PmMergeArgs a, const int32_t* __restrict__ d_view_
           if (live[u]) {
             float xp[4], x0[4];
             pm_ddim<T>(a.dd, x[u], ec[u], eu[u], nz[u], has_eu, has_nz, xp, x0);
-            if (a.dd.prev != nullptr) pm_prev_mix<T>(a.dd, (f0 + u) * a.hw + off, off, plane_stride, a.hw, xp);
+            if (a.dd.prev != nullptr)
+              pm_prev_mix<T>(a.dd, (f0 + u) * (HWC > 0 ? HWC : a.hw) + off, off, plane_stride, HWC > 0 ? HWC : a.hw, xp);
             tile[(0 * kPmET + lane) * SA + f0 + u] = Atom<T>::pack(xp);
             tile[(1 * kPmET + lane) * SA + f0 + u] = Atom<T>::pack(x0);
           }
@@ -1093,7 +1094,7 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 2; ++j)
         if (k[h] >= 0 && liveA[j]) {
-          const int o = job_off + (warp + j * kWarps) * a.hw + k[h];
+          const int o = job_off + (warp + j * kWarps) * (HWC > 0 ? HWC : a.hw) + k[h];
 #pragma unroll
           for (int p = 0; p < 4; ++p) {
             x[j][p] = ldg(static_cast<const T*>(a.pay[0]) + o + p * plane_stride);
@@ -1108,7 +1109,8 @@ pm_merge_weighted_tiled_kernel(const PmMergeArgs a, const int32_t* __restrict__ 
           float xp[4], x0[4];
           pm_ddim<T>(a.dd, x[j], ec[j], eu[j], nz[j], has_eu, has_nz, xp, x0);
           if (a.dd.prev != nullptr)
-            pm_prev_mix<T>(a.dd, job_off + (warp + j * kWarps) * a.hw + k[h], job_off + k[h], plane_stride, a.hw, xp);
+            pm_prev_mix<T>(a.dd, job_off + (warp + j * kWarps) * (HWC > 0 ? HWC : a.hw) + k[h], job_off + k[h], plane_stride,
+                           HWC > 0 ? HWC : a.hw, xp);
           // the reference merges the ROUNDED payload tensors: round to T before the weighting
           const int e = h * 32 + lane, fo = warp + j * kWarps;
           prod[(0 * kPmEC + e) * SA + fo] = make_float4(
@@ -1602,7 +1604,11 @@ extern "C" int ds_pm_merge_nearest_ddim(void* const* h_pms, const void* x, const
   DS_DISPATCH_DTYPE(dtype, {
     using AT = typename Atom<ET>::type;
     const size_t smem = 2 * static_cast<size_t>(kPmET) * (f_len | 1) * sizeof(AT) + kPmET * sizeof(int32_t);
-    if (f_len == 16) { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, true, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 16, true, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
+    if (f_len == 16) {
+      if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 16, true, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+      if (hw == 2560 && g_hw_const) return pm_launch(pm_merge_nearest_kernel<ET, 16, true, false, 2560>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+      return pm_launch(pm_merge_nearest_kernel<ET, 16, true, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin);
+    }
     { if (d_peer != nullptr) return pm_launch(pm_merge_nearest_kernel<ET, 0, true, true>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); return pm_launch(pm_merge_nearest_kernel<ET, 0, true, false>, 4, items, -1, n_fwin, smem, st, a, d_view_ptr, d_ent_src, d_ent_dst, d_ftab, d_fbegin); }
   });
   return DS_OK;
@@ -1631,7 +1637,7 @@ extern "C" int ds_pm_merge_bilinear_tiled_ddim(void* const* h_pms, const void* x
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t smem = 2 * static_cast<size_t>(kPmEC) * 17 * sizeof(float4) + kPmEC * sizeof(float) + (2 * kPmTR + 1) * sizeof(int32_t);
   DS_DISPATCH_DTYPE(dtype, {
-    { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
+    { if (d_peer != nullptr) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, true>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); if (hw == 2560 && g_hw_const) return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, false, 2560>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); return pm_launch(pm_merge_weighted_tiled_kernel<ET, 16, 2, true, false>, 8, n_tiles, -1, n_fwin, smem, st, a, d_view_ptr, d_tile4, d_row_dst, d_row_start, d_ent_k, d_ent_w, d_ftab, d_fbegin); }
   });
   return DS_OK;
 }
