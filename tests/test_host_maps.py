@@ -350,3 +350,35 @@ def test_random_view_lists_merge_plans_property():
             assert np.array_equal(pm_unpack(got).reshape(P, H, W), want_b)
 
     check()
+
+
+def test_chunk_sizes_match_torch_chunk():
+    """vae_tiling._chunk_sizes mirrors torch.chunk (i2v_sphere_panorama_pipeline.py:977,990 rely on its
+    uneven-tail behaviour): chunk size, number of chunks, size of the last one."""
+    import torch
+    from dynamicscaler_b200.vae_tiling import _chunk_sizes
+    for n in (1, 5, 16, 17, 36, 40, 64, 100, 128, 255, 256, 1024):
+        for chunks in (1, 2, 8, 16, 18, 33):
+            parts = torch.chunk(torch.arange(n), chunks)
+            size, count, last = _chunk_sizes(n, chunks)
+            assert (size, count, last) == (parts[0].numel(), len(parts), parts[-1].numel()), (n, chunks)
+
+
+def test_necessary_bytes_accounting():
+    """necessary_bytes (the honest roofline numerator): a gather writes every window and reads each touched
+    panorama row once; a merge never needs more payload than the SURVEY formula charges, and exactly the rows the
+    plan owns are written."""
+    from dynamicscaler_b200.geometry import frame_windows, sphere_views
+    from dynamicscaler_b200.step import PanoramaStepper
+    for (H, W, F, kw) in ((128, 256, 16, {}), (64, 128, 32, dict(frame_begins=frame_windows(1, total_f=32), frames=16))):
+        st = PanoramaStepper(H, W, F, device="cpu")
+        for mode in ("nearest", "bilinear"):
+            plan = st.plan_sphere(sphere_views(2), 64, 40, mode=mode, **kw)
+            ga, ma = st.algorithmic_bytes(plan, 4, 4, k=2)
+            gn, mn, detail = st.necessary_bytes(plan, 4, 4, k=2)
+            n_win_bytes = plan.n_jobs * 4 * plan.f_len * plan.hw * 4
+            assert gn >= n_win_bytes and gn <= ga * 1.25
+            assert detail["payload_bytes"] <= 2 * n_win_bytes            # never more payload than exists
+            assert mn <= ma * 1.05                                        # pruned views only ever remove bytes (+ plan arrays)
+            assert detail["rows_written"] == plan.extra["host_plan"][0].size
+            assert detail["rows_written"] == int(round(plan.coverage * H * W))
