@@ -5,8 +5,12 @@ package; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
 ``cpu_baseline`` / ``--impl reference`` legs do, and there only as the checker /
 the timed CPU baseline.
 
-Parity status: the reference ships no tests or golden vectors, so
+Parity status: PINNED.  The reference ships no tests or golden vectors, so
 the oracle is pinned against outputs of the reference itself, imported from
-``/root/reference`` in the build container by ``tests/golden/make_golden.py``
-and committed as ``tests/golden/*.npz``.
+``/root/reference`` in the build container by the committed generators
+``tests/golden/make_golden*.py`` and stored as ``tests/golden/*.npz``: every §8a function,
+the five BASELINE configs at full size (sha256), ``ddim_step``, ``resize_video_latent``,
+``tiled_vae_encode_tensor_simple`` and a run of the REAL
+``basic_sample_shift_shpere_panorama`` loop (``loop.npz``).  ``tests/test_oracle_golden.py``
+checks ``panorama_oracle`` and ``torch_port`` against all of them on the CPU.
 """
