@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libdynscaler_sm100.so")
 DS_F32, DS_BF16, DS_F16 = 0, 1, 2
 DS_MASK_NONE, DS_MASK_PLANE, DS_MASK_FULL = 0, 1, 2
 DS_MAX_PAYLOADS = 4
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _vp, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
@@ -35,6 +35,8 @@ PROTOTYPES = {
     "ds_gather_bilinear": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_merge_nearest": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_merge_nearest_peer": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "ds_merge_nearest_ddim": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                              _vp, _i, _vp],
     "ds_merge_bilinear": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_pm_gather": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_pm_merge_nearest": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],

@@ -49,6 +49,29 @@ __device__ __forceinline__ int pos_mod(int a, int m) {   // a in [0, 2m)
   return a >= m ? a - m : a;
 }
 
+// ---- denoise epilogue of the fused reference-order merge (sphere.cu) ---------------------
+// (csrc/pm.cu pm_ddim is the same chain over the 4 planes of a pixel-major atom.)
+// float32 scalars of one ddim_step (pipeline/scheduler.py:78-86), formed on the host with the
+// reference's torch ops: sqrt(a_t), sqrt(1 - a_t), sqrt(a_prev), sqrt(1 - a_prev - sigma^2), sigma,
+// and the classifier-free guidance scale.
+struct DdimCoef {
+  float sa, s1m, sp, sd, sig, g;
+};
+
+// One element of  e = eu + g*(ec - eu)  (t2v_sphere_panorama_pipeline.py:258, t2v_normal_pipeline.py:603),
+// pred_x0 = (x - s1m*e)/sa,  x_prev = sp*pred_x0 + sd*e [+ sig*noise]  (scheduler.py:84-94); every
+// product / sum / quotient rounded on its own like the reference's elementwise chain.
+__device__ __forceinline__ void ddim_point(const DdimCoef& c, float x, float ec, float eu, float nz,
+                                           bool has_eu, bool has_nz, float& x_prev, float& pred_x0) {
+  float e = ec;
+  if (has_eu) e = __fadd_rn(eu, __fmul_rn(c.g, __fsub_rn(ec, eu)));
+  const float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(c.s1m, e)), c.sa);
+  float xp = __fadd_rn(__fmul_rn(c.sp, x0), __fmul_rn(c.sd, e));
+  if (has_nz) xp = __fadd_rn(xp, __fmul_rn(c.sig, nz));
+  pred_x0 = x0;
+  x_prev = xp;
+}
+
 // Host-side launch helpers ----------------------------------------------------------
 inline int check_launch() {
   cudaError_t e = cudaGetLastError();

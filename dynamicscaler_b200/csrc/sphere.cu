@@ -219,6 +219,77 @@ merge_nearest_kernel(MergeArgs a, const int32_t* __restrict__ d_dst,
   }
 }
 
+// The nearest merge fused with the denoise epilogue, reference-order tensors (the planar ring loop,
+// t2v_normal_pipeline.py:526-557, and any nearest plan): pay[0] = x (the windows as gathered),
+// pay[1] = eps_cond, pay[2] = eps_uncond or NULL, pay[3] = ddim noise or NULL; pano[0] receives
+// x_prev and pano[1] pred_x0 of ddim_step, computed for the winning elements only -- elements
+// that lose to a later window are never denoised and x_prev / pred_x0 never exist as tensors.
+// Same thread mapping as merge_nearest_kernel.
+template <typename T, int VEC, int CPT, bool PEER = false>
+__global__ void __launch_bounds__(kBlock)
+merge_nearest_ddim_kernel(MergeArgs a, DdimCoef dc, const int32_t* __restrict__ d_dst,
+                          const int32_t* __restrict__ d_src, const int32_t* __restrict__ d_ftab) {
+  using V = typename std::conditional<VEC == 4, typename Elem<T>::vec4, T>::type;
+  const int t = blockIdx.x * kBlock + threadIdx.x;
+  if (t >= a.T) return;
+  const int dst = d_dst != nullptr ? __ldg(d_dst + t) : t * VEC;
+  const int src = __ldg(d_src + (d_dst != nullptr ? t : t * VEC));
+  if (src < 0) return;
+  const int v = src / a.hw, k = src - v * a.hw;
+  const bool has_eu = a.pay[2] != nullptr, has_nz = a.pay[3] != nullptr;
+  const int PF = a.P * a.F;
+  const int pf0 = blockIdx.y * CPT;
+  int pl = pf0 / a.F, f = pf0 - pl * a.F;
+  V val[4][CPT];
+  bool live[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    int job, fo;
+    live[c] = pf0 + c < PF && merge_source(a, d_ftab, f, v, job, fo);
+    if (live[c]) {
+      const size_t off = ((static_cast<size_t>(job) * a.P + pl) * a.f_len + fo) * a.hw + k;
+      val[0][c] = __ldg(reinterpret_cast<const V*>(static_cast<const T*>(a.pay[0]) + off));
+      val[1][c] = __ldg(reinterpret_cast<const V*>(static_cast<const T*>(a.pay[1]) + off));
+      if (has_eu) val[2][c] = __ldg(reinterpret_cast<const V*>(static_cast<const T*>(a.pay[2]) + off));
+      if (has_nz) val[3][c] = __ldg(reinterpret_cast<const V*>(static_cast<const T*>(a.pay[3]) + off));
+    }
+    if (++f == a.F) { f = 0; ++pl; }
+  }
+  pl = pf0 / a.F; f = pf0 - pl * a.F;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    if (live[c]) {
+      V xp, x0;
+      const T* ex = reinterpret_cast<const T*>(&val[0][c]);
+      const T* ec = reinterpret_cast<const T*>(&val[1][c]);
+      const T* eu = reinterpret_cast<const T*>(&val[2][c]);
+      const T* nz = reinterpret_cast<const T*>(&val[3][c]);
+      T* oxp = reinterpret_cast<T*>(&xp);
+      T* ox0 = reinterpret_cast<T*>(&x0);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float fxp, fx0;
+        ddim_point(dc, Elem<T>::to_f(ex[e]), Elem<T>::to_f(ec[e]), has_eu ? Elem<T>::to_f(eu[e]) : 0.f,
+                   has_nz ? Elem<T>::to_f(nz[e]) : 0.f, has_eu, has_nz, fxp, fx0);
+        oxp[e] = Elem<T>::from_f(fxp);
+        ox0[e] = Elem<T>::from_f(fx0);
+      }
+      const size_t off = (static_cast<size_t>(pl) * a.F + f) * a.HW + dst;
+      merge_store<V, T, PEER>(a, 0, off, xp);
+      merge_store<V, T, PEER>(a, 1, off, x0);
+      if (a.mask_mode == DS_MASK_FULL && pl < a.mask_planes) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) merge_store_mask<T, PEER>(a, off + e);
+      }
+    }
+    if (++f == a.F) { f = 0; ++pl; }
+  }
+  if (a.mask_mode == DS_MASK_PLANE && blockIdx.y == 0 && live[0]) {
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) merge_store_mask<T, PEER>(a, dst + e);
+  }
+}
+
 // thread = one CSR row (one panorama pixel), CPT panorama (plane, frame) slices, Q payloads.
 template <typename T, int CPT, int QMAX>
 __global__ void __launch_bounds__(kBlock)
@@ -415,6 +486,53 @@ extern "C" int ds_merge_nearest_peer(void* const* h_panos, const void* const* h_
   DS_REQUIRE(d_peer != nullptr, DS_ERR_NULL);
   return merge_nearest_impl(h_panos, h_payloads, Q, mask, mask_mode, mask_planes, d_dst, d_src, T, d_ftab,
                             views_per_fwin, job_begin, job_count, P, F, HW, f_len, hw, vec, d_peer, dtype, stream);
+}
+
+extern "C" int ds_merge_nearest_ddim(void* const* h_panos, const void* x, const void* eps_cond,
+                                     const void* eps_uncond, const void* noise, const float* h_coef,
+                                     void* mask, int mask_mode, int mask_planes,
+                                     const int32_t* d_dst, const int32_t* d_src, int T,
+                                     const int32_t* d_ftab, int views_per_fwin, int job_begin,
+                                     int job_count, int P, int F, int HW, int f_len, int hw, int vec,
+                                     void* d_peer, int dtype, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(x != nullptr && eps_cond != nullptr && h_coef != nullptr, DS_ERR_NULL);
+  const void* pays[2] = {x, eps_cond};
+  MergeArgs a;
+  int rc = fill_merge_args(a, h_panos, pays, 2, mask, mask_mode, mask_planes, T, views_per_fwin,
+                           job_begin, job_count, d_ftab, P, F, HW, f_len, hw);
+  if (rc != DS_OK) return rc;
+  a.pay[2] = eps_uncond;
+  a.pay[3] = noise;
+  a.peer = static_cast<const ds_peer_table_t*>(d_peer);
+  const DdimCoef dc{h_coef[0], h_coef[1], h_coef[2], h_coef[3], h_coef[4], h_coef[5]};
+  DS_REQUIRE(d_src != nullptr, DS_ERR_NULL);
+  DS_REQUIRE(vec == 1 || vec == 4, DS_ERR_DIM);
+  if (T == 0) return DS_OK;
+  if (vec == 4) {
+    DS_REQUIRE(HW % 4 == 0 && hw % 4 == 0, DS_ERR_ALIGN);
+    for (int q = 0; q < 2; ++q) DS_REQUIRE(aligned16(a.pano[q]), DS_ERR_ALIGN);
+    for (int q = 0; q < 4; ++q) DS_REQUIRE(aligned16(a.pay[q]), DS_ERR_ALIGN);
+    if (mask_mode != DS_MASK_NONE) DS_REQUIRE(aligned16(mask), DS_ERR_ALIGN);
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int PF = P * F;
+  DS_DISPATCH_DTYPE(dtype, {
+    if (vec == 4) {
+      constexpr int CPT = 2;
+      DS_REQUIRE(div_up(PF, CPT) <= 65535, DS_ERR_DIM);
+      dim3 grid(div_up(T, kBlock), div_up(PF, CPT));
+      if (d_peer != nullptr) merge_nearest_ddim_kernel<ET, 4, CPT, true><<<grid, kBlock, 0, st>>>(a, dc, d_dst, d_src, d_ftab);
+      else merge_nearest_ddim_kernel<ET, 4, CPT><<<grid, kBlock, 0, st>>>(a, dc, d_dst, d_src, d_ftab);
+    } else {
+      constexpr int CPT = 8;
+      DS_REQUIRE(div_up(PF, CPT) <= 65535, DS_ERR_DIM);
+      dim3 grid(div_up(T, kBlock), div_up(PF, CPT));
+      if (d_peer != nullptr) merge_nearest_ddim_kernel<ET, 1, CPT, true><<<grid, kBlock, 0, st>>>(a, dc, d_dst, d_src, d_ftab);
+      else merge_nearest_ddim_kernel<ET, 1, CPT><<<grid, kBlock, 0, st>>>(a, dc, d_dst, d_src, d_ftab);
+    }
+  });
+  return check_launch();
 }
 
 extern "C" int ds_merge_bilinear(void* const* h_panos, const void* const* h_payloads, int Q,

@@ -225,3 +225,130 @@ def sphere_denoise_loop(stepper: PanoramaStepper, state: PanoramaState, *, model
                             frame_begins=None if frame_begins_fn is None else frame_begins_fn(i), on_input=on_input,
                             balance_evals=balance_evals)
     return state
+
+
+# ------------------------------------------------------------------ planar shift-window loop ----
+def shift_window_schedule(step_i: int, *, frames: int, latent_height: int, latent_width: int, num_windows_f: int,
+                          num_windows_h: int, num_windows_w: int, loop_step: int, vae_scale_factor: int = 8,
+                          shift_jump_odd_w: bool = False, shift_jump_odd_h: bool = False, shift_jump_odd_f: bool = False,
+                          docking_w: bool = False, docking_h: bool = False, docking_f: bool = False,
+                          docking_step_range=None):
+    """Window positions of DDIM step ``step_i`` of ``basic_sample_shift_multi_windows``
+    (pipeline/t2v_normal_pipeline.py:420-432 step sizes, :438-440 and :473-478 per-step starts, :483-524
+    the three nested index loops with docking).  Returns ``(windows, frame_begins)``: the ordered
+    (left, top) list (w outer, h inner) and the ordered frame-window begins -- the reference visits
+    ``for f: for w: for h``, which is ``plan_ring(windows, ..., frame_begins=frame_begins)``'s job order.
+
+    Kept as the reference has them: the per-axis shift is ``(size_px // loop_step) // vae`` latent cells
+    (frames: ``frames // loop_step``), zero for a single window on that axis; ``shift_jump_odd_h`` moves
+    the LEFT start by half the panorama width and ``shift_jump_odd_w`` the TOP start by half its height
+    (:473-476, the names are crossed there); at a docking step the extra window -1 sits at 0 and the
+    last window at ``size * (n - 1)``, the others stay shifted."""
+    def shift(size_latent, n):
+        return 0 if n == 1 else (size_latent * vae_scale_factor // loop_step) // vae_scale_factor
+
+    odd = step_i % 2 == 1
+    k = step_i % loop_step
+    left0 = k * shift(latent_width, num_windows_w)
+    top0 = k * shift(latent_height, num_windows_h)
+    f0 = k * (0 if num_windows_f == 1 else frames // loop_step)
+    assert num_windows_f == 1 or frames // loop_step > 0, f"loop_step {loop_step} > frames {frames}"
+    if odd and shift_jump_odd_h and num_windows_h > 1:
+        left0 += latent_width * num_windows_w // 2
+    if odd and shift_jump_odd_w and num_windows_w > 1:
+        top0 += latent_height * num_windows_h // 2
+    if odd and shift_jump_odd_f and num_windows_f > 1:
+        f0 += frames * num_windows_f // 2
+    assert not (docking_w or docking_h or docking_f) or docking_step_range is not None, "docking needs docking_step_range"
+
+    def axis(start, n, size, docking):
+        dock_now = docking and step_i in docking_step_range
+        out = []
+        for idx in (range(-1, n) if docking else range(n)):
+            b = start + idx * size
+            if dock_now:
+                if idx == -1:
+                    b = 0
+                if idx == n - 1:
+                    b = size * (n - 1)
+            elif idx == -1:
+                continue
+            out.append(b)
+        return out
+
+    lefts = axis(left0, num_windows_w, latent_width, docking_w)
+    tops = axis(top0, num_windows_h, latent_height, docking_h)
+    return [(l, t) for l in lefts for t in tops], axis(f0, num_windows_f, frames, docking_f)
+
+
+def ring_denoise_step(stepper: PanoramaStepper, target, windows: Sequence, frame_begins: Sequence[int], w: int, h: int,
+                      frames: int, *, model: Callable, t: int, index: int, step_i: int, schedule, cond: dict,
+                      uncond: Optional[dict], guidance_scale: float, group_size: Optional[int] = None,
+                      noise_fn: Optional[Callable] = None, model_kwargs: Optional[dict] = None, cfg_batch: bool = True,
+                      on_input: Optional[Callable] = None):
+    """One DDIM step of the planar shift-window loop (pipeline/t2v_normal_pipeline.py:481-557) over the
+    ordered job list ``frame_begins x windows``: ring gather (ds_ring_gather) -> ONE UNet call per group
+    -> nearest merge fused with CFG + ddim_step (ds_merge_nearest_ddim).  ``target``: ``[latent,
+    denoised]`` reference-order tensors, or a ``RingPanoramaState`` (world_size > 1, peer stores).
+    ``index``: the scheduler index ``total_steps - i - 1`` (:611).  ``group_size`` None: the whole step is
+    one group (for a step without docking the windows tile the torus without overlap, so this IS the
+    reference's result); an integer g: g consecutive windows of one frame window (1 = the reference's
+    sequential order, needed only when docked windows overlap)."""
+    coef = ddim_coefficients(_get(schedule, "ddim_alphas")[index], _get(schedule, "ddim_alphas_prev")[index],
+                             _get(schedule, "ddim_sigmas")[index], _get(schedule, "ddim_sqrt_one_minus_alphas")[index],
+                             guidance_scale if uncond is not None else 1.0)
+    sigma = float(_get(schedule, "ddim_sigmas")[index])
+    nw = len(windows)
+    if group_size is None:
+        groups = [(list(windows), list(frame_begins), None)]
+    else:
+        gs = int(group_size)
+        groups = [(list(windows[g0:g0 + gs]), [fb], s * nw + g0) for s, fb in enumerate(frame_begins)
+                  for g0 in range(0, nw, gs)]
+    source = target if not isinstance(target, (list, tuple)) else target[0]
+    for wins, fbs, base in groups:
+        plan = stepper.plan_ring(wins, w, h, frame_begins=fbs, frames=frames)
+        x = stepper.gather_all(source, plan)
+        job_ids = list(plan.job_ids) if base is None else [base + j for j in plan.job_ids]
+        n = x.shape[0]
+        xb = x.view(n * x.shape[1], *x.shape[2:])
+        if on_input is not None and n > 0:
+            on_input(step_i, job_ids, xb)
+        if n > 0:
+            ec, eu = unet_eval(model, xb, t, cond, frames, model_kwargs, uncond, cfg_batch)
+            ec = ec.view(x.shape)
+            eu = None if eu is None else eu.view(x.shape)
+        else:
+            ec, eu = x, (x if uncond is not None else None)
+        noise = noise_fn(step_i, job_ids, tuple(x.shape), x.device) if (noise_fn is not None and sigma > 0) else None
+        stepper.merge_denoised_ref(target, x, ec, eu, coef, plan, noise=noise)
+
+
+def ring_denoise_loop(stepper: PanoramaStepper, target, *, model: Callable, schedule, schedule_fn: Callable, width: int,
+                      height: int, frames: int, cond: dict, uncond: Optional[dict], guidance_scale: float = 7.5,
+                      timesteps: Optional[Sequence[int]] = None, group_size=None, noise_fn: Optional[Callable] = None,
+                      model_kwargs: Optional[dict] = None, cfg_batch: bool = True, on_input: Optional[Callable] = None,
+                      before_step: Optional[Callable] = None):
+    """The planar DDIM loop of ``basic_sample_shift_multi_windows`` (pipeline/t2v_normal_pipeline.py:434-561).
+    ``target``: ``[latent, denoised]`` ([B, C, F_total, H_total, W_total]; the reference starts the denoised
+    panorama at zero, :417) or a ``RingPanoramaState``; both are updated in place, ``target[1]`` is what
+    the reference returns (:561).  ``schedule_fn(i)`` -> ``(windows, frame_begins)`` of step i
+    (:func:`shift_window_schedule`); ``width`` / ``height``: the window in latent cells.  ``timesteps``
+    defaults to the flipped ``ddim_timesteps`` (:300); a shorter list is the reference's ``use_skip_time``
+    tail (:303).  ``group_size``: see :func:`ring_denoise_step`; a callable ``group_size(i)`` picks it per
+    step (e.g. 1 on docking steps only).  ``before_step(i, target)``: hook for the residual mix of
+    :442-470 (whole-panorama elementwise, outside the tiling path)."""
+    ddim_ts = [int(v) for v in _get(schedule, "ddim_timesteps")]
+    timesteps = list(reversed(ddim_ts)) if timesteps is None else [int(v) for v in timesteps]
+    total = len(timesteps)
+    kwargs = dict(model_kwargs or {})
+    kwargs.setdefault("clean_cond", True)                               # :581
+    for i, t in enumerate(timesteps):
+        if before_step is not None:
+            before_step(i, target)
+        windows, frame_begins = schedule_fn(i)
+        ring_denoise_step(stepper, target, windows, frame_begins, width, height, frames, model=model, t=t,
+                          index=total - i - 1, step_i=i, schedule=schedule, cond=cond, uncond=uncond,
+                          guidance_scale=guidance_scale, group_size=group_size(i) if callable(group_size) else group_size,
+                          noise_fn=noise_fn, model_kwargs=kwargs, cfg_batch=cfg_batch, on_input=on_input)
+    return target

@@ -779,6 +779,64 @@ class PanoramaStepper:
         if st.peer_table is not None and not (launched and self.merge_publish_in_kernel):
             self._peer_sync(st, _lib.DS_PEER_AFTER_MERGE)
 
+    def merge_denoised_ref(self, target, x: torch.Tensor, eps_cond: torch.Tensor, eps_uncond: Optional[torch.Tensor],
+                           coef, plan: StepPlan, noise: Optional[torch.Tensor] = None,
+                           mask: Optional[torch.Tensor] = None):
+        """:meth:`merge_denoised` for REFERENCE-ORDER panoramas and nearest plans (planar ring windows,
+        ``plan_ring``; also ``plan_sphere(mode="nearest")``) -- the write side of the planar shift-window
+        loop (pipeline/t2v_normal_pipeline.py:526-557): CFG + ``ddim_step`` run inside the merge kernel
+        (ds_merge_nearest_ddim) for the winning elements only.  ``target``: ``[latent, denoised]`` tensors
+        [B, C, F, H, W] (world_size > 1: every rank ends with the identical merged replica, all-reduce
+        exchange) or a :class:`RingPanoramaState` (peer-store exchange).  ``mask`` as in ``merge_all``."""
+        import ctypes as C
+        assert plan.kind in ("ring", "sphere_nearest"), "the reference-order fused merge takes nearest plans"
+        j0, nj = self.local_jobs(plan)
+        for t in (x, eps_cond, eps_uncond, noise):
+            assert t is None or (t.is_contiguous() and t.dtype == x.dtype and t.shape == x.shape)
+        assert x.shape[0] == nj
+        h_coef = (C.c_float * 6)(*coef)
+        ring_state = target if isinstance(target, RingPanoramaState) else None
+        if ring_state is not None:
+            assert mask is None, "a RingPanoramaState carries its own mask"
+            panos, mask = ring_state.tensors[:2], ring_state.mask
+        else:
+            panos = list(target)
+        assert len(panos) == 2, "needs the latent and the denoised panorama"
+        B, Cc, F, H, W = panos[0].shape
+        P = B * Cc
+        for p_ in panos:
+            _lib.require_cuda(p_, "panorama")
+            assert p_.is_contiguous() and p_.shape == panos[0].shape and p_.dtype == x.dtype
+        assert (F, H, W) == (plan.F, plan.H, plan.W)
+        mask_mode, mask_planes = _lib.DS_MASK_NONE, 0
+        if mask is not None:
+            assert mask.is_contiguous() and mask.dtype == x.dtype
+            if mask.numel() == H * W:
+                assert plan.d_ftab is None, "a [1, H, W] mask panorama has no frame axis"
+                mask_mode = _lib.DS_MASK_PLANE
+            else:
+                assert mask.numel() % (F * H * W) == 0
+                mask_mode, mask_planes = _lib.DS_MASK_FULL, mask.numel() // (F * H * W)
+
+        def launch(dst_panos, m, m_mode, m_planes, peer):
+            if nj == 0 or plan.T == 0:
+                return
+            with _lib.on(x.device):
+                lib.check(lib.ds_merge_nearest_ddim(_lib.ptr_array(dst_panos), x.data_ptr(), eps_cond.data_ptr(),
+                                                    _lib.ptr(eps_uncond), _lib.ptr(noise), h_coef, _lib.ptr(m), m_mode,
+                                                    m_planes, _lib.ptr(plan.d_dst), plan.d_src.data_ptr(), plan.T,
+                                                    _lib.ptr(plan.d_ftab), plan.vpf, j0, nj, P, F, H * W, plan.f_len,
+                                                    plan.hw, plan.vec, peer, _lib.dtype_code(x.dtype),
+                                                    _lib.stream_ptr(x.device)), "ds_merge_nearest_ddim")
+
+        if ring_state is not None:
+            launch(panos, mask, mask_mode, mask_planes, ring_state.peer_table)
+            self._peer_sync(ring_state, _lib.DS_PEER_AFTER_MERGE, wait=True)
+        elif self.world == 1:
+            launch(panos, mask, mask_mode, mask_planes, None)
+        else:
+            self._merge_sharded(panos, None, mask, plan, P, j0, nj, launch=launch)
+
     def _merge_state(self, st: PanoramaState, payloads, plan: StepPlan):
         """merge_all on a resident state: payloads[q] -> st.pms[q]; the state's mask receives 1."""
         assert plan.kind != "ring", "planar ring windows run on reference-order tensors"
@@ -863,8 +921,9 @@ class PanoramaStepper:
                           "ds_merge_nearest_peer")
         self._peer_sync(rs, _lib.DS_PEER_AFTER_MERGE, wait=True)
 
-    def _merge_sharded(self, panos, payloads, mask, plan, P, j0, nj):
-        """disjoint-support partial merge -> one all-reduce -> select."""
+    def _merge_sharded(self, panos, payloads, mask, plan, P, j0, nj, launch=None):
+        """disjoint-support partial merge -> one all-reduce -> select.  ``launch(sums, weight,
+        mask_mode, mask_planes, peer)``: the fused-epilogue merge in place of the payload merge."""
         import torch.distributed as dist
         Q = len(panos)
         n = panos[0].numel()
@@ -877,7 +936,10 @@ class PanoramaStepper:
         buf.zero_()
         sums = [buf[q * n:(q + 1) * n] for q in range(Q)]
         weight = buf[Q * n:]
-        if nj > 0:
+        if launch is not None:
+            launch([t.view(panos[0].shape) for t in sums], weight, _lib.DS_MASK_FULL if per_frame else _lib.DS_MASK_PLANE,
+                   1 if per_frame else 0, None)
+        elif nj > 0:
             self._merge_into(sums, payloads, weight, _lib.DS_MASK_FULL if per_frame else _lib.DS_MASK_PLANE,
                              1 if per_frame else 0, plan, P, j0, nj)
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DS_ABI_VERSION 6
+#define DS_ABI_VERSION 7
 
 enum { DS_F32 = 0, DS_BF16 = 1, DS_F16 = 2 };
 
@@ -152,6 +152,21 @@ int ds_merge_nearest_peer(void* const* h_panos, const void* const* h_payloads, i
                           const int32_t* d_dst, const int32_t* d_src, int T,
                           const int32_t* d_ftab, int views_per_fwin, int job_begin, int job_count,
                           int P, int F, int HW, int f_len, int hw, int vec, void* d_peer, int dtype, void* stream);
+
+/* ds_merge_nearest fused with the denoise epilogue on REFERENCE-ORDER tensors -- the write side of the
+ * planar shift-window loop, pipeline/t2v_normal_pipeline.py:526-557 (``_basic_denoise_one_step`` :572-617
+ * followed by the two ``set_window_latent`` calls), and of any nearest plan:
+ *     e = eps_uncond + g*(eps_cond - eps_uncond)            (:603; eps_uncond NULL: e = eps_cond)
+ *     pred_x0 = (x - s1m*e)/sa;  x_prev = sp*pred_x0 + sd*e [+ sig*noise]     (pipeline/scheduler.py:84-94)
+ * h_panos[0] receives x_prev, h_panos[1] pred_x0, for the winning elements only.  x / eps_* / noise:
+ * [n_jobs][P][f_len][hw] like the payloads of ds_merge_nearest; h_coef = {sa, s1m, sp, sd, sig, g}
+ * (float32, formed like the reference's torch.full tensors).  d_peer NULL: local stores; else the
+ * exchange mode of ds_merge_nearest_peer.  Everything else as ds_merge_nearest. */
+int ds_merge_nearest_ddim(void* const* h_panos, const void* x, const void* eps_cond, const void* eps_uncond,
+                          const void* noise, const float* h_coef, void* mask, int mask_mode, int mask_planes,
+                          const int32_t* d_dst, const int32_t* d_src, int T, const int32_t* d_ftab,
+                          int views_per_fwin, int job_begin, int job_count, int P, int F, int HW, int f_len,
+                          int hw, int vec, void* d_peer, int dtype, void* stream);
 
 /* Weighted scatter-accumulate + per-pixel weight normalisation in gather form:
  * PanoramaTensor.set_view_tensor_bilinear (utils/panorama_tensor_utils.py:98-152; ring twin

@@ -292,3 +292,80 @@ def test_sharded_denoise_loop(tmp_path, world, group_size):
     gather / merge launches), views dealt over the ranks, UNet stand-in evaluated on local windows only:
     every rank's replica equals the single-GPU loop bit for bit."""
     _spawn(tmp_path, world, _loop_worker, group_size)
+
+
+# ------------------------------------------------ planar shift-window loop, sharded ----
+def _ring_loop_worker(rank, world, port, out_dir, exchange, dtype_name="float32"):
+    for p in (ROOT, HERE):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import torch.distributed as dist
+    from conftest import randn
+    from dynamicscaler_b200.loop import ring_denoise_loop, shift_window_schedule
+    from dynamicscaler_b200.step import PanoramaStepper
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    ok = True
+    try:
+        dtype = getattr(torch, dtype_name)
+        frames, h, w, nf, nh, nw = 4, 8, 12, 2, 2, 3
+        F, H, W = frames * nf, h * nh, w * nw
+        lat0 = torch.from_numpy(randn(71, 1, 4, F, H, W)).to(dev).to(dtype)
+        ac = np.cumprod(1 - np.linspace(0.00085, 0.012, 1000)).astype(np.float32)
+        ts = np.array([1, 251, 501, 751])
+        al = ac[ts].astype(np.float64)
+        sched = dict(ddim_timesteps=ts, alphas_cumprod=ac, ddim_alphas=al, ddim_alphas_prev=np.append(ac[0], al[:-1]),
+                     ddim_sigmas=np.full(4, 0.02), ddim_sqrt_one_minus_alphas=np.sqrt(1 - al))
+        kw = dict(frames=frames, latent_height=h, latent_width=w, num_windows_f=nf, num_windows_h=nh, num_windows_w=nw,
+                  loop_step=4, shift_jump_odd_w=True, docking_w=True, docking_f=True, docking_step_range=[1, 3])
+
+        def model(x, ts_, c_crossattn=None, fps=None, **kw_):         # elementwise: independent of the batch split
+            return (torch.sin(x.float() * 1.7) * 0.5 + c_crossattn[0][:, 3, 5].reshape(-1, 1, 1, 1, 1) * 0.1).to(x.dtype)
+
+        def noise_fn(i, job_ids, shape, device):
+            if not len(job_ids):
+                return torch.empty(shape, device=device, dtype=dtype)
+            return torch.stack([torch.from_numpy(randn(8000 + 50 * i + j, *shape[1:])).to(device) for j in job_ids]).to(dtype)
+
+        cond = {"c_crossattn": [torch.from_numpy(randn(72, 1, 77, 16)).to(dev)], "fps": 16}
+        uncond = {"c_crossattn": [torch.from_numpy(randn(73, 1, 77, 16)).to(dev)], "fps": 16}
+        outs = []
+        for (r, wsz) in ((0, 1), (rank, world)):
+            st = PanoramaStepper(H, W, F, device=dev, rank=r, world=wsz)
+            target = [lat0.clone(), torch.zeros_like(lat0)]
+            if wsz > 1 and exchange == "peer":
+                target = st.make_ring_state(target)
+            # whole-step groups on the steps whose windows tile the torus, 2 windows at a time on the docked ones
+            ring_denoise_loop(st, target, model=model, schedule=sched, schedule_fn=lambda i: shift_window_schedule(i, **kw),
+                              width=w, height=h, frames=frames, cond=cond, uncond=uncond, guidance_scale=7.5,
+                              group_size=lambda i: 2 if i in (1, 3) else None, noise_fn=noise_fn)
+            outs.append(target.export() if hasattr(target, "export") else target)
+        ok = all(torch.equal(a, b) for a, b in zip(*outs)) and not torch.equal(outs[0][0], lat0)
+        if not ok:
+            with open(os.path.join(out_dir, f"rank{rank}.txt"), "w") as fh:
+                for name, a, b in zip(("latent", "denoised"), *outs):
+                    d = (a.float() - b.float()).abs()
+                    fh.write(f"rank {rank} {name}: {int((d > 0).sum())} elements differ, max {float(d.max()):.3e}\n")
+        np.save(os.path.join(out_dir, f"rank{rank}.npy"), np.array([ok]))
+        torch.cuda.synchronize()
+        dist.barrier()
+    except BaseException:
+        import traceback
+        with open(os.path.join(out_dir, f"rank{rank}.txt"), "a") as fh:
+            fh.write(traceback.format_exc())
+        ok = False
+    finally:
+        os._exit(0 if ok else 1)
+
+
+@pytest.mark.parametrize("world,exchange,dtype_name", [(2, "peer", "float32"), (2, "allreduce", "float32"),
+                                                        (2, "peer", "bfloat16"), (4, "peer", "float32"), (8, "peer", "float32")])
+def test_sharded_ring_denoise_loop(tmp_path, world, exchange, dtype_name):
+    """4 DDIM steps of the planar shift-window loop (ring gather -> stand-in UNet on the local windows -> nearest merge
+    fused with CFG + ddim_step incl. eta > 0 noise, ds_merge_nearest_ddim), windows split over the ranks, docked steps
+    with overlapping windows: every rank's replica equals the single-GPU loop bit for bit -- through peer stores
+    into reference-order replicas and through the zero-buffer all-reduce."""
+    _spawn(tmp_path, world, _ring_loop_worker, exchange, dtype_name)

@@ -382,3 +382,25 @@ def test_necessary_bytes_accounting():
             assert mn <= ma * 1.05                                        # pruned views only ever remove bytes (+ plan arrays)
             assert detail["rows_written"] == plan.extra["host_plan"][0].size
             assert detail["rows_written"] == int(round(plan.coverage * H * W))
+
+
+def test_shift_window_schedule_matches_oracle():
+    """loop.shift_window_schedule (windows x frame_begins, the product plan_ring takes) == the reference's triple
+    loop restated in oracle.shift_window_jobs (pipeline/t2v_normal_pipeline.py:420-524) for every step, incl. the
+    odd-step jumps (crossed w/h names kept), single-window axes and docking on any axis."""
+    import itertools
+    from dynamicscaler_b200.loop import shift_window_schedule
+    from oracle import panorama_oracle as po
+    cases = 0
+    for nf, nh, nw in ((1, 1, 1), (2, 2, 3), (1, 3, 1), (3, 1, 2)):
+        for jump, dock in itertools.product(((False, False, False), (True, False, True), (False, True, False)),
+                                            ((False, False, False), (True, False, False), (False, True, True))):
+            kw = dict(frames=8, latent_height=8, latent_width=12, num_windows_f=nf, num_windows_h=nh, num_windows_w=nw,
+                      loop_step=4, shift_jump_odd_w=jump[0], shift_jump_odd_h=jump[1], shift_jump_odd_f=jump[2],
+                      docking_w=dock[0], docking_h=dock[1], docking_f=dock[2], docking_step_range=[0, 3, 5])
+            for i in range(9):
+                windows, fbs = shift_window_schedule(i, **kw)
+                got = [(l, t, fb) for fb in fbs for (l, t) in windows]
+                assert got == po.shift_window_jobs(i, **kw), (nf, nh, nw, jump, dock, i)
+                cases += 1
+    assert cases == 4 * 9 * 9

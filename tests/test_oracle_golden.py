@@ -317,6 +317,52 @@ def test_denoise_loop_oracle_matches_real_pipeline():
     assert float(g["p9_batched_vs_looped_maxabs"]) < 1e-4      # P9: one UNet call over all windows == looped calls
 
 
+def ring_loop_golden():
+    g = np.load(os.path.join(GOLDEN, "ring_loop.npz"))
+    frames, h, w, nw, nh, nf, loop_step, steps = [int(v) for v in g["cfg"]]
+    sched = {k: g[k] for k in ("ddim_timesteps", "alphas_cumprod", "ddim_alphas", "ddim_alphas_prev", "ddim_sigmas",
+                               "ddim_sqrt_one_minus_alphas")}
+    kw = dict(frames=frames, latent_height=h, latent_width=w, num_windows_f=nf, num_windows_h=nh, num_windows_w=nw,
+              loop_step=loop_step, shift_jump_odd_w=True, docking_w=True, docking_step_range=[int(v) for v in g["dock_steps"]])
+    return g, (frames, h, w, nw, nh, nf, steps), sched, kw
+
+
+def test_ring_loop_oracle_matches_real_pipeline():
+    """oracle.ring_denoise_loop + oracle.shift_window_jobs == the REAL ``VC2_Pipeline_T2V.
+    basic_sample_shift_multi_windows`` run (tests/golden/ring_loop.npz: 3 DDIM steps, 3 x 2 x 2 windows,
+    odd-step jump, docking with overlapping windows at the last step): every UNet input, the latent and
+    denoised panoramas after EVERY step and the returned denoised panorama, bit for bit -- in the
+    reference's one-window-at-a-time order, and with whole-step groups on the steps whose windows tile the
+    torus (the batched order the driver runs)."""
+    import hashlib
+    sha = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+    g, (frames, h, w, nw, nh, nf, steps), sched, kw = ring_loop_golden()
+    jobs_fn = lambda i: po.shift_window_jobs(i, **kw)
+    counts = [len(jobs_fn(i)) for i in range(steps)]
+    assert counts == [12, 12, 16] and sum(counts) == len(g["unet_in_sha"])
+    base = np.concatenate([[0], np.cumsum(counts)])
+    dock = [int(v) for v in g["dock_steps"]]
+
+    def model_fn(i, n, x):
+        j = int(base[i]) + n
+        assert np.array_equal(sha(x), g["unet_in_sha"][j]), (i, n)
+        return g["eps_cond"][j], g["eps_uncond"][j]
+
+    def on_step(i, lat, den):
+        assert np.array_equal(sha(lat), g["step_latent_sha"][i]), i
+        assert np.array_equal(sha(den), g["step_denoised_sha"][i]), i
+
+    lat0 = randn(51, 1, 4, frames * nf, h * nh, w * nw)
+    for groups_fn in (None, lambda i, n: [[k] for k in range(n)] if i in dock else [list(range(n))]):
+        _, den, _ = po.ring_denoise_loop(lat0, sched, jobs_fn, model_fn, float(g["guidance"]), w, h, frames,
+                                         groups_fn=groups_fn, on_step=on_step)
+        assert np.array_equal(den, g["final_denoised"])
+    # ... and whole-step groups on the docked step do NOT reproduce it (overlapping windows read stale data)
+    with pytest.raises(AssertionError):
+        po.ring_denoise_loop(lat0, sched, jobs_fn, model_fn, float(g["guidance"]), w, h, frames,
+                             groups_fn=lambda i, n: [list(range(n))], on_step=on_step)
+
+
 def test_vae_tiling_oracle_matches_reference():
     """oracle.tiled_encode / wrap_pad / crop_wrap_padded == the reference's tiled_vae_encode_tensor_simple
     and the inline wrap-padded decode of i2v_sphere_panorama_pipeline.py:974-991 (tests/golden/vae.npz)."""
