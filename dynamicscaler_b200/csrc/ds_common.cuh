@@ -49,6 +49,19 @@ __device__ __forceinline__ int pos_mod(int a, int m) {   // a in [0, 2m)
   return a >= m ? a - m : a;
 }
 
+// mix_latents_with_mask (utils/tensor_utils.py:19-39) on one element, every op rounded on its own and -- like
+// the reference's elementwise tensor ops -- in the tensor dtype T:
+//   mixed = l1*(1-r) + add*r;  out = l1*(1-m) + mixed*m.   (csrc/pm.cu pm_mix1 is the same chain.)
+template <typename T>
+__device__ __forceinline__ float mix_point(float l1, float add, float m, float r, float omr) {
+  auto rt = [](float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); };
+  const float a = rt(__fmul_rn(l1, omr));
+  const float b = rt(__fmul_rn(add, r));
+  const float mixed = rt(__fadd_rn(a, b));
+  const float keep = rt(__fmul_rn(l1, rt(__fsub_rn(1.0f, m))));
+  return rt(__fadd_rn(keep, rt(__fmul_rn(mixed, m))));
+}
+
 // ---- denoise epilogue of the fused reference-order merge (sphere.cu) ---------------------
 // (csrc/pm.cu pm_ddim is the same chain over the 4 planes of a pixel-major atom.)
 // float32 scalars of one ddim_step (pipeline/scheduler.py:78-86), formed on the host with the

@@ -1,6 +1,8 @@
 // Elementwise steps either side of the tiling path: mix_latents_with_mask
 // (reference utils/tensor_utils.py:19-39) and the final select of the sharded merge
 // (SURVEY §8e).  Grid-stride, 16-byte vectors when everything is aligned.
+#include <type_traits>
+
 #include "ds_common.cuh"
 
 namespace ds {
@@ -39,6 +41,38 @@ mix_mask_f32x4_kernel(const float4* __restrict__ l1, const float4* __restrict__ 
     o.z = mix_one(a.z, b.z, m.z, r, omr);
     o.w = mix_one(a.w, b.w, m.w, r, omr);
     out[i] = o;
+  }
+}
+
+// The read side of the planar I2V loop after the two window gathers (i2v_sphere_panorama_pipeline.py:875-884):
+//   noised = c*x + s*eps              re_noise, pipeline/scheduler.py:98-110, epsilon injected
+//   out    = mix_latents_with_mask(x, noised, m, r)
+// in ONE pass over the window tensors.  c, s are 0-dim float32 tensors in the reference and are cast to the
+// latent dtype by the multiply; every op is rounded on its own in T (csrc/pm.cu pm_renoise_pass is the same chain).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kBlock)
+renoise_mix_kernel(const T* __restrict__ x, const T* __restrict__ eps, const T* __restrict__ mask,
+                   T* __restrict__ out, float c, float s, float r, float omr, long long n_vec) {
+  using V = typename std::conditional<VEC == 4, typename Elem<T>::vec4, T>::type;
+  auto rt = [](float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); };
+  const float ct = rt(c), st = rt(s);
+  const long long stride = static_cast<long long>(gridDim.x) * kBlock;
+  for (long long i = static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x; i < n_vec; i += stride) {
+    const V vx = __ldg(reinterpret_cast<const V*>(x) + i);
+    const V ve = __ldg(reinterpret_cast<const V*>(eps) + i);
+    const V vm = __ldg(reinterpret_cast<const V*>(mask) + i);
+    V vo;
+    const T* ex = reinterpret_cast<const T*>(&vx);
+    const T* ee = reinterpret_cast<const T*>(&ve);
+    const T* em = reinterpret_cast<const T*>(&vm);
+    T* eo = reinterpret_cast<T*>(&vo);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+      const float xv = Elem<T>::to_f(ex[e]);
+      const float noised = rt(__fadd_rn(rt(__fmul_rn(ct, xv)), rt(__fmul_rn(st, Elem<T>::to_f(ee[e])))));
+      eo[e] = Elem<T>::from_f(mix_point<T>(xv, noised, Elem<T>::to_f(em[e]), r, omr));
+    }
+    reinterpret_cast<V*>(out)[i] = vo;
   }
 }
 
@@ -114,6 +148,28 @@ extern "C" int ds_mix_mask(const void* l1, const void* add, const void* mask, vo
     mix_mask_kernel<ET><<<stride_grid(n), kBlock, 0, st>>>(static_cast<const ET*>(l1), static_cast<const ET*>(add),
                                                             static_cast<const ET*>(mask), static_cast<ET*>(out),
                                                             ratio, one_minus_ratio, n, mask_hw);
+  });
+  return check_launch();
+}
+
+extern "C" int ds_renoise_mix(const void* x, const void* eps, const void* mask, void* out, float c, float s,
+                              float ratio, float one_minus_ratio, long long n, int dtype, void* stream) {
+  using namespace ds;
+  DS_REQUIRE(x != nullptr && eps != nullptr && mask != nullptr && out != nullptr, DS_ERR_NULL);
+  DS_REQUIRE(n > 0, DS_ERR_DIM);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DS_DISPATCH_DTYPE(dtype, {
+    const uintptr_t al = sizeof(typename Elem<ET>::vec4) - 1;
+    const bool vec = n % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps) |
+                                     reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(out)) & al) == 0;
+    if (vec)
+      renoise_mix_kernel<ET, 4><<<stride_grid(n / 4), kBlock, 0, st>>>(
+          static_cast<const ET*>(x), static_cast<const ET*>(eps), static_cast<const ET*>(mask), static_cast<ET*>(out),
+          c, s, ratio, one_minus_ratio, n / 4);
+    else
+      renoise_mix_kernel<ET, 1><<<stride_grid(n), kBlock, 0, st>>>(
+          static_cast<const ET*>(x), static_cast<const ET*>(eps), static_cast<const ET*>(mask), static_cast<ET*>(out),
+          c, s, ratio, one_minus_ratio, n);
   });
   return check_launch();
 }

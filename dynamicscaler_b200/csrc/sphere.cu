@@ -225,9 +225,18 @@ merge_nearest_kernel(MergeArgs a, const int32_t* __restrict__ d_dst,
 // x_prev and pano[1] pred_x0 of ddim_step, computed for the winning elements only -- elements
 // that lose to a later window are never denoised and x_prev / pred_x0 never exist as tensors.
 // Same thread mapping as merge_nearest_kernel.
-template <typename T, int VEC, int CPT, bool PEER = false>
+// merge_prev_denoised_ratio mix between ddim_step and the latent set (i2v_sphere_panorama_pipeline.py:938-943):
+//   x_prev <- mix_latents_with_mask(x_prev, prev, m, r);  prev = the window as gathered (:866), m = the
+// denoised-mask window read at gather time (:868-873); both in window layout like x.  prev NULL: off.
+struct PrevMix {
+  const void* prev;
+  const void* mview;
+  float r, omr;
+};
+
+template <typename T, int VEC, int CPT, bool PEER, bool PV>
 __global__ void __launch_bounds__(kBlock)
-merge_nearest_ddim_kernel(MergeArgs a, DdimCoef dc, const int32_t* __restrict__ d_dst,
+merge_nearest_ddim_kernel(MergeArgs a, DdimCoef dc, PrevMix pv, const int32_t* __restrict__ d_dst,
                           const int32_t* __restrict__ d_src, const int32_t* __restrict__ d_ftab) {
   using V = typename std::conditional<VEC == 4, typename Elem<T>::vec4, T>::type;
   const int t = blockIdx.x * kBlock + threadIdx.x;
@@ -240,7 +249,8 @@ merge_nearest_ddim_kernel(MergeArgs a, DdimCoef dc, const int32_t* __restrict__ 
   const int PF = a.P * a.F;
   const int pf0 = blockIdx.y * CPT;
   int pl = pf0 / a.F, f = pf0 - pl * a.F;
-  V val[4][CPT];
+  constexpr bool has_pv = PV;
+  V val[PV ? 6 : 4][CPT];
   bool live[CPT];
 #pragma unroll
   for (int c = 0; c < CPT; ++c) {
@@ -252,6 +262,10 @@ merge_nearest_ddim_kernel(MergeArgs a, DdimCoef dc, const int32_t* __restrict__ 
       val[1][c] = __ldg(reinterpret_cast<const V*>(static_cast<const T*>(a.pay[1]) + off));
       if (has_eu) val[2][c] = __ldg(reinterpret_cast<const V*>(static_cast<const T*>(a.pay[2]) + off));
       if (has_nz) val[3][c] = __ldg(reinterpret_cast<const V*>(static_cast<const T*>(a.pay[3]) + off));
+      if constexpr (PV) {
+        val[4][c] = __ldg(reinterpret_cast<const V*>(static_cast<const T*>(pv.prev) + off));
+        val[5][c] = __ldg(reinterpret_cast<const V*>(static_cast<const T*>(pv.mview) + off));
+      }
     }
     if (++f == a.F) { f = 0; ++pl; }
   }
@@ -264,6 +278,8 @@ merge_nearest_ddim_kernel(MergeArgs a, DdimCoef dc, const int32_t* __restrict__ 
       const T* ec = reinterpret_cast<const T*>(&val[1][c]);
       const T* eu = reinterpret_cast<const T*>(&val[2][c]);
       const T* nz = reinterpret_cast<const T*>(&val[3][c]);
+      const T* pr = reinterpret_cast<const T*>(&val[PV ? 4 : 0][c]);
+      const T* mv = reinterpret_cast<const T*>(&val[PV ? 5 : 0][c]);
       T* oxp = reinterpret_cast<T*>(&xp);
       T* ox0 = reinterpret_cast<T*>(&x0);
 #pragma unroll
@@ -271,6 +287,8 @@ merge_nearest_ddim_kernel(MergeArgs a, DdimCoef dc, const int32_t* __restrict__ 
         float fxp, fx0;
         ddim_point(dc, Elem<T>::to_f(ex[e]), Elem<T>::to_f(ec[e]), has_eu ? Elem<T>::to_f(eu[e]) : 0.f,
                    has_nz ? Elem<T>::to_f(nz[e]) : 0.f, has_eu, has_nz, fxp, fx0);
+        if constexpr (PV)                      // the reference mixes the ROUNDED x_prev tensor
+          fxp = mix_point<T>(Elem<T>::to_f(Elem<T>::from_f(fxp)), Elem<T>::to_f(pr[e]), Elem<T>::to_f(mv[e]), pv.r, pv.omr);
         oxp[e] = Elem<T>::from_f(fxp);
         ox0[e] = Elem<T>::from_f(fx0);
       }
@@ -489,7 +507,8 @@ extern "C" int ds_merge_nearest_peer(void* const* h_panos, const void* const* h_
 }
 
 extern "C" int ds_merge_nearest_ddim(void* const* h_panos, const void* x, const void* eps_cond,
-                                     const void* eps_uncond, const void* noise, const float* h_coef,
+                                     const void* eps_uncond, const void* noise, const void* prev,
+                                     const void* mask_view, const float* h_coef,
                                      void* mask, int mask_mode, int mask_planes,
                                      const int32_t* d_dst, const int32_t* d_src, int T,
                                      const int32_t* d_ftab, int views_per_fwin, int job_begin,
@@ -506,6 +525,8 @@ extern "C" int ds_merge_nearest_ddim(void* const* h_panos, const void* x, const 
   a.pay[3] = noise;
   a.peer = static_cast<const ds_peer_table_t*>(d_peer);
   const DdimCoef dc{h_coef[0], h_coef[1], h_coef[2], h_coef[3], h_coef[4], h_coef[5]};
+  DS_REQUIRE(prev == nullptr || mask_view != nullptr, DS_ERR_NULL);
+  const PrevMix pv{prev, mask_view, h_coef[6], h_coef[7]};
   DS_REQUIRE(d_src != nullptr, DS_ERR_NULL);
   DS_REQUIRE(vec == 1 || vec == 4, DS_ERR_DIM);
   if (T == 0) return DS_OK;
@@ -513,25 +534,26 @@ extern "C" int ds_merge_nearest_ddim(void* const* h_panos, const void* x, const 
     DS_REQUIRE(HW % 4 == 0 && hw % 4 == 0, DS_ERR_ALIGN);
     for (int q = 0; q < 2; ++q) DS_REQUIRE(aligned16(a.pano[q]), DS_ERR_ALIGN);
     for (int q = 0; q < 4; ++q) DS_REQUIRE(aligned16(a.pay[q]), DS_ERR_ALIGN);
+    DS_REQUIRE(aligned16(prev) && aligned16(mask_view), DS_ERR_ALIGN);
     if (mask_mode != DS_MASK_NONE) DS_REQUIRE(aligned16(mask), DS_ERR_ALIGN);
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int PF = P * F;
+  const bool peer = d_peer != nullptr, mix = prev != nullptr;
+#define DS_LAUNCH_DDIM(VEC_, CPT_)                                                                          \
+  do {                                                                                                      \
+    DS_REQUIRE(div_up(PF, CPT_) <= 65535, DS_ERR_DIM);                                                      \
+    dim3 grid(div_up(T, kBlock), div_up(PF, CPT_));                                                         \
+    if (peer && mix) merge_nearest_ddim_kernel<ET, VEC_, CPT_, true, true><<<grid, kBlock, 0, st>>>(a, dc, pv, d_dst, d_src, d_ftab);   \
+    else if (peer) merge_nearest_ddim_kernel<ET, VEC_, CPT_, true, false><<<grid, kBlock, 0, st>>>(a, dc, pv, d_dst, d_src, d_ftab);    \
+    else if (mix) merge_nearest_ddim_kernel<ET, VEC_, CPT_, false, true><<<grid, kBlock, 0, st>>>(a, dc, pv, d_dst, d_src, d_ftab);     \
+    else merge_nearest_ddim_kernel<ET, VEC_, CPT_, false, false><<<grid, kBlock, 0, st>>>(a, dc, pv, d_dst, d_src, d_ftab);             \
+  } while (0)
   DS_DISPATCH_DTYPE(dtype, {
-    if (vec == 4) {
-      constexpr int CPT = 2;
-      DS_REQUIRE(div_up(PF, CPT) <= 65535, DS_ERR_DIM);
-      dim3 grid(div_up(T, kBlock), div_up(PF, CPT));
-      if (d_peer != nullptr) merge_nearest_ddim_kernel<ET, 4, CPT, true><<<grid, kBlock, 0, st>>>(a, dc, d_dst, d_src, d_ftab);
-      else merge_nearest_ddim_kernel<ET, 4, CPT><<<grid, kBlock, 0, st>>>(a, dc, d_dst, d_src, d_ftab);
-    } else {
-      constexpr int CPT = 8;
-      DS_REQUIRE(div_up(PF, CPT) <= 65535, DS_ERR_DIM);
-      dim3 grid(div_up(T, kBlock), div_up(PF, CPT));
-      if (d_peer != nullptr) merge_nearest_ddim_kernel<ET, 1, CPT, true><<<grid, kBlock, 0, st>>>(a, dc, d_dst, d_src, d_ftab);
-      else merge_nearest_ddim_kernel<ET, 1, CPT><<<grid, kBlock, 0, st>>>(a, dc, d_dst, d_src, d_ftab);
-    }
+    if (vec == 4) DS_LAUNCH_DDIM(4, 2);
+    else DS_LAUNCH_DDIM(1, 8);
   });
+#undef DS_LAUNCH_DDIM
   return check_launch();
 }
 

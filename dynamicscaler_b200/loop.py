@@ -281,19 +281,45 @@ def shift_window_schedule(step_i: int, *, frames: int, latent_height: int, laten
     return [(l, t) for l in lefts for t in tops], axis(f0, num_windows_f, frames, docking_f)
 
 
+def i2v_planar_schedule(step_i: int, *, width: int, height: int, frames: int, total_w: int, total_h: int, total_f: int,
+                        num_windows_w: int, num_windows_h: int, loop_step: int, overlap_ratio_f: float,
+                        loop_step_frame: int, dock_at_f: bool = False, begin_index_offset: int = 0,
+                        vae_scale_factor: int = 8):
+    """Window positions of DDIM step ``step_i`` of the planar I2V loop (``VC2_Pipeline_I2V_SpherePano.
+    basic_sample_shift_multi_windows``, pipeline/i2v_sphere_panorama_pipeline.py:732-855): overlapping spatial
+    windows at ``round(k * stride)`` plus the per-step offset (``begin_index_offset`` included), frame windows with
+    optional docking.  Pixel sizes in; returns ``(windows, frame_begins)`` in latent cells / frames, the
+    ``for f: for w: for h`` order of the reference as ``plan_ring``'s job order."""
+    from .geometry import frame_windows, ring_windows
+    windows = ring_windows(step_i, num_windows_w, num_windows_h, total_w, total_h, width=width, height=height,
+                           loop_step=loop_step, vae_scale=vae_scale_factor, begin_index_offset=begin_index_offset)
+    return windows, frame_windows(step_i, frames=frames, total_f=total_f, overlap=overlap_ratio_f,
+                                  loop_step_frame=loop_step_frame, dock_at_f=dock_at_f)
+
+
 def ring_denoise_step(stepper: PanoramaStepper, target, windows: Sequence, frame_begins: Sequence[int], w: int, h: int,
-                      frames: int, *, model: Callable, t: int, index: int, step_i: int, schedule, cond: dict,
+                      frames: int, *, model: Callable, t: int, index: int, step_i: int, schedule, cond,
                       uncond: Optional[dict], guidance_scale: float, group_size: Optional[int] = None,
                       noise_fn: Optional[Callable] = None, model_kwargs: Optional[dict] = None, cfg_batch: bool = True,
-                      on_input: Optional[Callable] = None):
-    """One DDIM step of the planar shift-window loop (pipeline/t2v_normal_pipeline.py:481-557) over the
-    ordered job list ``frame_begins x windows``: ring gather (ds_ring_gather) -> ONE UNet call per group
-    -> nearest merge fused with CFG + ddim_step (ds_merge_nearest_ddim).  ``target``: ``[latent,
-    denoised]`` reference-order tensors, or a ``RingPanoramaState`` (world_size > 1, peer stores).
-    ``index``: the scheduler index ``total_steps - i - 1`` (:611).  ``group_size`` None: the whole step is
-    one group (for a step without docking the windows tile the torus without overlap, so this IS the
-    reference's result); an integer g: g consecutive windows of one frame window (1 = the reference's
-    sequential order, needed only when docked windows overlap)."""
+                      on_input: Optional[Callable] = None, mask: Optional[torch.Tensor] = None,
+                      renoise: Optional[tuple] = None, prev_ratio: Optional[float] = None,
+                      eps_fn: Optional[Callable] = None):
+    """One DDIM step of the planar shift-window loops (pipeline/t2v_normal_pipeline.py:481-557; I2V twin
+    pipeline/i2v_sphere_panorama_pipeline.py:812-968) over the ordered job list ``frame_begins x windows``:
+
+        gather  ds_ring_gather (+ the mask windows + ds_renoise_mix: re_noise and the mask mix, one pass)
+        UNet    ONE call per group
+        merge   ds_merge_nearest_ddim: CFG + ddim_step (+ merge_prev mix) + latent / denoised / mask sets
+
+    ``target``: ``[latent, denoised]`` reference-order tensors, or a ``RingPanoramaState`` (world_size > 1, peer
+    stores).  ``index``: the scheduler index ``total_steps - i - 1`` (:611).  ``group_size`` None: the whole step is
+    one group (for a T2V step without docking the windows tile the torus without overlap, so this IS the reference's
+    result); an integer g: g consecutive windows of one frame window (1 = the reference's sequential order, needed
+    whenever windows overlap).  I2V extras: ``mask`` = the latent-shaped denoised-mask panorama of this step (already
+    zeroed, i2v :810; a RingPanoramaState carries its own); ``renoise`` = ``(c, s, ratio)`` switches the re-noise mix
+    on (i2v :875-884, epsilon from ``eps_fn(step_i, job_ids, shape, device)``); ``prev_ratio`` the merge_prev mix
+    (i2v :938-943); ``cond`` may be a callable ``cond(step_i, job_ids, boxes)`` -> dict with one context row per
+    window (``boxes``: the (left, top, frame_begin) of each job; i2v :886-895 builds one image embedding per window)."""
     coef = ddim_coefficients(_get(schedule, "ddim_alphas")[index], _get(schedule, "ddim_alphas_prev")[index],
                              _get(schedule, "ddim_sigmas")[index], _get(schedule, "ddim_sqrt_one_minus_alphas")[index],
                              guidance_scale if uncond is not None else 1.0)
@@ -305,50 +331,86 @@ def ring_denoise_step(stepper: PanoramaStepper, target, windows: Sequence, frame
         gs = int(group_size)
         groups = [(list(windows[g0:g0 + gs]), [fb], s * nw + g0) for s, fb in enumerate(frame_begins)
                   for g0 in range(0, nw, gs)]
-    source = target if not isinstance(target, (list, tuple)) else target[0]
+    is_state = not isinstance(target, (list, tuple))
+    source = target if is_state else target[0]
+    use_prev = prev_ratio is not None
+    assert renoise is None or eps_fn is not None, "re_noise needs an epsilon source (eps_fn)"
     for wins, fbs, base in groups:
         plan = stepper.plan_ring(wins, w, h, frame_begins=fbs, frames=frames)
-        x = stepper.gather_all(source, plan)
         job_ids = list(plan.job_ids) if base is None else [base + j for j in plan.job_ids]
+        raw = mview = None
+        if renoise is not None or use_prev:
+            shape = (plan.n_local,) + tuple(source.shape[:2]) + (plan.f_len, plan.h, plan.w)
+            rn = dict(want_raw=use_prev, want_mask=use_prev, mask=mask)
+            if renoise is not None:
+                eps = eps_fn(step_i, job_ids, shape, stepper.device)
+                rn.update(eps=eps.contiguous(), c=renoise[0], s=renoise[1], ratio=renoise[2])
+            x, raw, mview = stepper.gather_all(source, plan, renoise=rn)
+        else:
+            x = stepper.gather_all(source, plan)
         n = x.shape[0]
         xb = x.view(n * x.shape[1], *x.shape[2:])
         if on_input is not None and n > 0:
             on_input(step_i, job_ids, xb)
         if n > 0:
-            ec, eu = unet_eval(model, xb, t, cond, frames, model_kwargs, uncond, cfg_batch)
+            c = cond
+            if callable(cond):
+                boxes = [(wins[j % len(wins)][0], wins[j % len(wins)][1], fbs[j // len(wins)]) for j in plan.job_ids]
+                c = cond(step_i, job_ids, boxes)
+            ec, eu = unet_eval(model, xb, t, c, frames, model_kwargs, uncond, cfg_batch)
             ec = ec.view(x.shape)
             eu = None if eu is None else eu.view(x.shape)
         else:
             ec, eu = x, (x if uncond is not None else None)
         noise = noise_fn(step_i, job_ids, tuple(x.shape), x.device) if (noise_fn is not None and sigma > 0) else None
-        stepper.merge_denoised_ref(target, x, ec, eu, coef, plan, noise=noise)
+        stepper.merge_denoised_ref(target, x, ec, eu, coef, plan, noise=noise, mask=None if is_state else mask,
+                                   prev=raw if use_prev else None, prev_mask=mview if use_prev else None,
+                                   prev_ratio=prev_ratio)
 
 
 def ring_denoise_loop(stepper: PanoramaStepper, target, *, model: Callable, schedule, schedule_fn: Callable, width: int,
-                      height: int, frames: int, cond: dict, uncond: Optional[dict], guidance_scale: float = 7.5,
+                      height: int, frames: int, cond, uncond: Optional[dict], guidance_scale: float = 7.5,
                       timesteps: Optional[Sequence[int]] = None, group_size=None, noise_fn: Optional[Callable] = None,
                       model_kwargs: Optional[dict] = None, cfg_batch: bool = True, on_input: Optional[Callable] = None,
-                      before_step: Optional[Callable] = None):
-    """The planar DDIM loop of ``basic_sample_shift_multi_windows`` (pipeline/t2v_normal_pipeline.py:434-561).
-    ``target``: ``[latent, denoised]`` ([B, C, F_total, H_total, W_total]; the reference starts the denoised
-    panorama at zero, :417) or a ``RingPanoramaState``; both are updated in place, ``target[1]`` is what
-    the reference returns (:561).  ``schedule_fn(i)`` -> ``(windows, frame_begins)`` of step i
-    (:func:`shift_window_schedule`); ``width`` / ``height``: the window in latent cells.  ``timesteps``
-    defaults to the flipped ``ddim_timesteps`` (:300); a shorter list is the reference's ``use_skip_time``
-    tail (:303).  ``group_size``: see :func:`ring_denoise_step`; a callable ``group_size(i)`` picks it per
-    step (e.g. 1 on docking steps only).  ``before_step(i, target)``: hook for the residual mix of
-    :442-470 (whole-panorama elementwise, outside the tiling path)."""
+                      before_step: Optional[Callable] = None, mask: Optional[torch.Tensor] = None,
+                      renoise_ratio: Optional[float] = None, prev_ratio_list: Optional[Sequence[float]] = None,
+                      eps_fn: Optional[Callable] = None):
+    """The planar DDIM loops: ``basic_sample_shift_multi_windows`` of pipeline/t2v_normal_pipeline.py:434-561 and, with
+    ``mask`` / ``renoise_ratio`` / ``prev_ratio_list`` / a callable ``cond``, of pipeline/i2v_sphere_panorama_pipeline.py:
+    777-970 (stages 2 / 3 of gen_pano_360.py).  ``target``: ``[latent, denoised]`` ([B, C, F_total, H_total, W_total];
+    the reference starts the denoised panorama at zero, :417) or a ``RingPanoramaState``; both are updated in place,
+    ``target[1]`` is what the reference returns (:561).  ``schedule_fn(i)`` -> ``(windows, frame_begins)`` of step i
+    (:func:`shift_window_schedule` / :func:`i2v_planar_schedule`); ``width`` / ``height``: the window in latent cells.
+    ``timesteps`` defaults to the flipped ``ddim_timesteps`` (:300); a shorter list is the reference's
+    ``use_skip_time`` tail (:303).  ``group_size``: see :func:`ring_denoise_step`; a callable ``group_size(i)`` picks
+    it per step (e.g. 1 on docking steps only).  ``mask``: a latent-shaped tensor that serves as the denoised-mask
+    panorama (zeroed here at every step, i2v :810; required for the re-noise / merge_prev mixes on plain tensors).
+    ``before_step(i, target)``: hook for the whole-panorama residual mix of t2v :442-470 (outside the tiling path)."""
     ddim_ts = [int(v) for v in _get(schedule, "ddim_timesteps")]
     timesteps = list(reversed(ddim_ts)) if timesteps is None else [int(v) for v in timesteps]
     total = len(timesteps)
     kwargs = dict(model_kwargs or {})
     kwargs.setdefault("clean_cond", True)                               # :581
+    is_state = not isinstance(target, (list, tuple))
+    step_mask = target.mask if is_state else mask
     for i, t in enumerate(timesteps):
         if before_step is not None:
             before_step(i, target)
+        mixing = i < total - 1                                          # i2v :875, :938
+        renoise = None
+        if renoise_ratio is not None and mixing:
+            rc, rs = renoise_coefficients(_get(schedule, "alphas_cumprod"), _get(schedule, "ddim_timesteps"),
+                                          total - i - 2, total - i - 1)
+            renoise = (rc, rs, renoise_ratio)
+        prev_ratio = prev_ratio_list[i] if (prev_ratio_list is not None and mixing) else None
+        if step_mask is not None:
+            step_mask.zero_()                                           # i2v :810 fresh mask panorama every step
+        else:
+            assert renoise is None and prev_ratio is None, "the re-noise / merge_prev mixes read a mask panorama"
         windows, frame_begins = schedule_fn(i)
         ring_denoise_step(stepper, target, windows, frame_begins, width, height, frames, model=model, t=t,
                           index=total - i - 1, step_i=i, schedule=schedule, cond=cond, uncond=uncond,
                           guidance_scale=guidance_scale, group_size=group_size(i) if callable(group_size) else group_size,
-                          noise_fn=noise_fn, model_kwargs=kwargs, cfg_batch=cfg_batch, on_input=on_input)
+                          noise_fn=noise_fn, model_kwargs=kwargs, cfg_batch=cfg_batch, on_input=on_input,
+                          mask=step_mask, renoise=renoise, prev_ratio=prev_ratio, eps_fn=eps_fn)
     return target

@@ -618,7 +618,9 @@ class PanoramaStepper:
         mask_plan=None)`` with (c, s) from :func:`renoise_coefficients`.  Returns ``(windows, raw,
         mask_view)``: the mixed windows, the unmixed ones (``want_raw``) and the mask view
         (``want_mask``; [n, h, w] for a [1, H, W] mask, windows-shaped for a latent-shaped mask) -- the
-        last two feed ``merge_denoised(prev=, prev_mask=)``."""
+        last two feed ``merge_denoised(prev=, prev_mask=)``.  Planar ring plans on reference-order tensors take the
+        same dict plus ``mask=<latent-shaped mask panorama>`` (a ``RingPanoramaState`` uses its own); ``eps`` None
+        skips the re-noise mix and only reads the mask windows (-> ``merge_denoised_ref(prev=, prev_mask=)``)."""
         if isinstance(latent, PanoramaState):
             assert plan.kind != "ring", "planar ring windows run on reference-order tensors"
             st = latent
@@ -649,18 +651,47 @@ class PanoramaStepper:
         if out is None:
             out = torch.empty(shape, dtype=latent.dtype, device=latent.device)
         assert tuple(out.shape) == shape and out.is_contiguous()
+        assert renoise is None or plan.kind == "ring", "fused re-noise on reference-order tensors: planar ring plans only"
         if nj == 0 and ring_state is None:
-            return out
+            if renoise is None:
+                return out
+            return (out, out if renoise.get("want_raw") else None, torch.empty_like(out) if renoise.get("want_mask") else None)
         if plan.kind == "ring":
             d_jobs = plan.d_jobs[j0:j0 + nj]
-            with _lib.on(latent.device):
+
+            def ring_gather(src, dst):
                 if nj > 0:
-                    lib.check(lib.ds_ring_gather(latent.data_ptr(), out.data_ptr(), d_jobs.data_ptr(), nj, 0, 0, 0,
-                                                 B * C, F, H, W, plan.f_len, plan.h, plan.w,
-                                                 _lib.dtype_code(latent.dtype), _lib.stream_ptr(latent.device)),
-                              "ds_ring_gather")
+                    with _lib.on(src.device):
+                        lib.check(lib.ds_ring_gather(src.data_ptr(), dst.data_ptr(), d_jobs.data_ptr(), nj, 0, 0, 0,
+                                                     B * C, F, H, W, plan.f_len, plan.h, plan.w,
+                                                     _lib.dtype_code(src.dtype), _lib.stream_ptr(src.device)),
+                                  "ds_ring_gather")
+
+            ring_gather(latent, out)
+            mview = None
+            if renoise is not None:
+                # planar I2V read side (i2v_sphere_panorama_pipeline.py:859-884): the latent-shaped denoised-mask
+                # panorama is read through the same windows, then re_noise + mask mix run as one pass
+                mask = ring_state.mask if ring_state is not None else renoise.get("mask")
+                assert mask is not None and tuple(mask.shape) == tuple(latent.shape) and mask.dtype == latent.dtype \
+                    and mask.is_contiguous(), "the planar loops keep a latent-shaped denoised-mask panorama"
+                mview = torch.empty_like(out)
+                ring_gather(mask, mview)
             if ring_state is not None:           # replicas may be overwritten once EVERY rank has read (full barrier)
                 self._peer_sync(ring_state, _lib.DS_PEER_AFTER_GATHER, wait=True)
+            if renoise is not None:
+                mixed = out
+                eps = renoise.get("eps")
+                if eps is not None and nj > 0:
+                    assert eps.shape == out.shape and eps.dtype == out.dtype and eps.is_contiguous()
+                    r = float(renoise["ratio"])
+                    mixed = torch.empty_like(out)
+                    with _lib.on(out.device):
+                        lib.check(lib.ds_renoise_mix(out.data_ptr(), eps.data_ptr(), mview.data_ptr(), mixed.data_ptr(),
+                                                     float(renoise["c"]), float(renoise["s"]), r, 1 - r, out.numel(),
+                                                     _lib.dtype_code(out.dtype), _lib.stream_ptr(out.device)),
+                                  "ds_renoise_mix")
+                return (mixed, out if renoise.get("want_raw") else None, mview if renoise.get("want_mask") else None)
         elif plan.kind == "sphere_nearest":
             _launch_gather_nearest(latent, out, plan.d_idx, plan.d_jobs[j0:j0 + nj], 0, nj, B * C, F, H * W,
                                    plan.f_len, plan.hw)
@@ -781,20 +812,28 @@ class PanoramaStepper:
 
     def merge_denoised_ref(self, target, x: torch.Tensor, eps_cond: torch.Tensor, eps_uncond: Optional[torch.Tensor],
                            coef, plan: StepPlan, noise: Optional[torch.Tensor] = None,
-                           mask: Optional[torch.Tensor] = None):
+                           mask: Optional[torch.Tensor] = None, prev: Optional[torch.Tensor] = None,
+                           prev_mask: Optional[torch.Tensor] = None, prev_ratio: Optional[float] = None):
         """:meth:`merge_denoised` for REFERENCE-ORDER panoramas and nearest plans (planar ring windows,
         ``plan_ring``; also ``plan_sphere(mode="nearest")``) -- the write side of the planar shift-window
         loop (pipeline/t2v_normal_pipeline.py:526-557): CFG + ``ddim_step`` run inside the merge kernel
         (ds_merge_nearest_ddim) for the winning elements only.  ``target``: ``[latent, denoised]`` tensors
         [B, C, F, H, W] (world_size > 1: every rank ends with the identical merged replica, all-reduce
-        exchange) or a :class:`RingPanoramaState` (peer-store exchange).  ``mask`` as in ``merge_all``."""
+        exchange) or a :class:`RingPanoramaState` (peer-store exchange).  ``mask`` as in ``merge_all``.
+        ``prev`` / ``prev_mask`` / ``prev_ratio``: the ``merge_prev_denoised_ratio`` mix of the planar I2V loop
+        (pipeline/i2v_sphere_panorama_pipeline.py:938-943) between ``ddim_step`` and the latent set, with the
+        windows and mask windows as read at gather time (``gather_all(..., renoise=dict(want_raw=True,
+        want_mask=True, ...))``), both shaped like ``x``."""
         import ctypes as C
         assert plan.kind in ("ring", "sphere_nearest"), "the reference-order fused merge takes nearest plans"
         j0, nj = self.local_jobs(plan)
-        for t in (x, eps_cond, eps_uncond, noise):
+        if prev is not None:
+            assert prev_mask is not None and prev_ratio is not None, "prev needs prev_mask and prev_ratio"
+        for t in (x, eps_cond, eps_uncond, noise, prev, prev_mask if prev is not None else None):
             assert t is None or (t.is_contiguous() and t.dtype == x.dtype and t.shape == x.shape)
         assert x.shape[0] == nj
-        h_coef = (C.c_float * 6)(*coef)
+        pr = 0.0 if prev_ratio is None else float(prev_ratio)
+        h_coef = (C.c_float * 8)(*coef, pr, 1 - pr)
         ring_state = target if isinstance(target, RingPanoramaState) else None
         if ring_state is not None:
             assert mask is None, "a RingPanoramaState carries its own mask"
@@ -823,7 +862,9 @@ class PanoramaStepper:
                 return
             with _lib.on(x.device):
                 lib.check(lib.ds_merge_nearest_ddim(_lib.ptr_array(dst_panos), x.data_ptr(), eps_cond.data_ptr(),
-                                                    _lib.ptr(eps_uncond), _lib.ptr(noise), h_coef, _lib.ptr(m), m_mode,
+                                                    _lib.ptr(eps_uncond), _lib.ptr(noise), _lib.ptr(prev),
+                                                    _lib.ptr(prev_mask if prev is not None else None), h_coef,
+                                                    _lib.ptr(m), m_mode,
                                                     m_planes, _lib.ptr(plan.d_dst), plan.d_src.data_ptr(), plan.T,
                                                     _lib.ptr(plan.d_ftab), plan.vpf, j0, nj, P, F, H * W, plan.f_len,
                                                     plan.hw, plan.vec, peer, _lib.dtype_code(x.dtype),

@@ -159,11 +159,16 @@ int ds_merge_nearest_peer(void* const* h_panos, const void* const* h_payloads, i
  *     e = eps_uncond + g*(eps_cond - eps_uncond)            (:603; eps_uncond NULL: e = eps_cond)
  *     pred_x0 = (x - s1m*e)/sa;  x_prev = sp*pred_x0 + sd*e [+ sig*noise]     (pipeline/scheduler.py:84-94)
  * h_panos[0] receives x_prev, h_panos[1] pred_x0, for the winning elements only.  x / eps_* / noise:
- * [n_jobs][P][f_len][hw] like the payloads of ds_merge_nearest; h_coef = {sa, s1m, sp, sd, sig, g}
- * (float32, formed like the reference's torch.full tensors).  d_peer NULL: local stores; else the
- * exchange mode of ds_merge_nearest_peer.  Everything else as ds_merge_nearest. */
+ * [n_jobs][P][f_len][hw] like the payloads of ds_merge_nearest; h_coef = {sa, s1m, sp, sd, sig, g, r, 1-r}
+ * (float32, formed like the reference's torch.full tensors).  prev != NULL: the merge_prev_denoised_ratio
+ * mix of the planar I2V loop (pipeline/i2v_sphere_panorama_pipeline.py:938-943) between ddim_step and the
+ * latent set: x_prev <- mix_latents_with_mask(x_prev, prev, mask_view, r), prev / mask_view in window layout
+ * like x (the window as gathered, :866, and the denoised-mask window read at gather time, :868-873).
+ * d_peer NULL: local stores; else the exchange mode of ds_merge_nearest_peer.  Everything else as
+ * ds_merge_nearest. */
 int ds_merge_nearest_ddim(void* const* h_panos, const void* x, const void* eps_cond, const void* eps_uncond,
-                          const void* noise, const float* h_coef, void* mask, int mask_mode, int mask_planes,
+                          const void* noise, const void* prev, const void* mask_view, const float* h_coef,
+                          void* mask, int mask_mode, int mask_planes,
                           const int32_t* d_dst, const int32_t* d_src, int T, const int32_t* d_ftab,
                           int views_per_fwin, int job_begin, int job_count, int P, int F, int HW, int f_len,
                           int hw, int vec, void* d_peer, int dtype, void* stream);
@@ -395,6 +400,13 @@ int ds_tile_normalise(const float* acc, const float* count, float* out, long lon
  * on its own.  eps == NULL: the plain repeat. */
 int ds_repeat_renoise(const void* x0, const void* eps, void* out, float c, float s, long long planes, int F,
                       long long HW, int dtype, void* stream);
+
+/* The read side of the planar I2V loop after its two window gathers (pipeline/i2v_sphere_panorama_pipeline.py:
+ * 875-884), one pass:  noised = c*x + s*eps  (re_noise, pipeline/scheduler.py:98-110, epsilon injected; c, s
+ * cast to the tensor dtype like the reference's 0-dim tensors);  out = mix_latents_with_mask(x, noised, mask,
+ * ratio) (utils/tensor_utils.py:19-39).  x / eps / mask / out: n elements each; every op rounded on its own. */
+int ds_renoise_mix(const void* x, const void* eps, const void* mask, void* out, float c, float s, float ratio,
+                   float one_minus_ratio, long long n, int dtype, void* stream);
 
 /* Final select of the sharded merge:
  *   pano[i] = weight[(i / weight_group) mod weight_period] > 0 ? sum[i] : pano[i]   for i < n.

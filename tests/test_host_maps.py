@@ -404,3 +404,26 @@ def test_shift_window_schedule_matches_oracle():
                 assert got == po.shift_window_jobs(i, **kw), (nf, nh, nw, jump, dock, i)
                 cases += 1
     assert cases == 4 * 9 * 9
+
+
+def test_i2v_planar_schedule_matches_oracle():
+    """loop.i2v_planar_schedule == the reference's f / w / h loops restated in oracle.i2v_planar_jobs
+    (pipeline/i2v_sphere_panorama_pipeline.py:732-855): overlapping strides with round(), begin_index_offset,
+    frame windows with and without docking (docked windows first / last, skipped when the shift is 0, windows past
+    the end dropped)."""
+    from dynamicscaler_b200.loop import i2v_planar_schedule
+    from oracle import panorama_oracle as po
+    n = 0
+    spatial = ((128, 64, 384, 128, 3, 3, 4), (96, 64, 240, 128, 3, 3, 4), (512, 320, 8192, 4096, 16, 16, 16),
+               (512, 320, 1024, 512, 4, 3, 8))                   # (width, height, total_w, total_h, nw, nh, loop_step)
+    for (width, height, tw, th, nw, nh, loop_step) in spatial:
+        for (frames, total_f, ov, lsf) in ((4, 8, 0.5, 2), (16, 64, 0.75, 8), (16, 16, 0.75, 8), (16, 32, 0.25, 4)):
+            for dock in (False, True):
+                kw = dict(width=width, height=height, frames=frames, total_w=tw, total_h=th, total_f=total_f,
+                          num_windows_w=nw, num_windows_h=nh, loop_step=loop_step, overlap_ratio_f=ov, loop_step_frame=lsf,
+                          dock_at_f=dock, begin_index_offset=n % 3)
+                for i in range(10):
+                    windows, fbs = i2v_planar_schedule(i, **kw)
+                    assert [(l, t, fb) for fb in fbs for (l, t) in windows] == po.i2v_planar_jobs(i, **kw), (kw, i)
+                    n += 1
+    assert n == 4 * 4 * 2 * 10

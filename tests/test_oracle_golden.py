@@ -363,6 +363,61 @@ def test_ring_loop_oracle_matches_real_pipeline():
                              groups_fn=lambda i, n: [list(range(n))], on_step=on_step)
 
 
+def ring_loop_i2v_golden():
+    g = np.load(os.path.join(GOLDEN, "ring_loop_i2v.npz"))
+    names = ("frames", "height", "width", "total_h", "total_w", "total_f", "nw", "nh", "loop_step", "steps",
+             "loop_step_frame", "begin_index_offset")
+    c = {k: int(v) for k, v in zip(names, g["cfg"])}
+    sched = {k: g[k] for k in ("ddim_timesteps", "alphas_cumprod", "ddim_alphas", "ddim_alphas_prev", "ddim_sigmas",
+                               "ddim_sqrt_one_minus_alphas")}
+    jobs_kw = dict(width=c["width"], height=c["height"], frames=c["frames"], total_w=c["total_w"], total_h=c["total_h"],
+                   total_f=c["total_f"], num_windows_w=c["nw"], num_windows_h=c["nh"], loop_step=c["loop_step"],
+                   overlap_ratio_f=float(g["overlap_f"]), loop_step_frame=c["loop_step_frame"], dock_at_f=True,
+                   begin_index_offset=c["begin_index_offset"])
+    return g, c, sched, jobs_kw
+
+
+def test_i2v_ring_loop_oracle_matches_real_pipeline():
+    """oracle.ring_denoise_loop (mask panorama + re_noise mix + merge_prev mix) over oracle.i2v_planar_jobs == the REAL
+    ``VC2_Pipeline_I2V_SpherePano.basic_sample_shift_multi_windows`` run (tests/golden/ring_loop_i2v.npz: 3 DDIM steps,
+    3 x 3 spatial windows overlapping on H, 3-4 frame windows with docking, 90 windows): every UNet input, every
+    condition-image window, the panoramas after every step and the returned denoised panorama, bit for bit."""
+    import hashlib
+    sha = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+    g, c, sched, jobs_kw = ring_loop_i2v_golden()
+    jobs_fn = lambda i: po.i2v_planar_jobs(i, **jobs_kw)
+    counts = [len(jobs_fn(i)) for i in range(c["steps"])]
+    assert counts == [27, 36, 27] and sum(counts) == len(g["unet_in_sha"])
+    base = np.concatenate([[0], np.cumsum(counts)])
+    h, w, frames = c["height"] // 8, c["width"] // 8, c["frames"]
+    image = ((g["image_u8"].astype(np.float32).transpose(2, 0, 1) / np.float32(255.)) - np.float32(0.5)) * np.float32(2)
+    assert np.array_equal(sha(image), g["image_f32_sha"])
+    draws = {"n": 0}
+
+    def eps_fn(i, n, shape):
+        draws["n"] += 1
+        return randn(6000 + draws["n"], *shape)
+
+    def model_fn(i, n, x):
+        j = int(base[i]) + n
+        assert np.array_equal(sha(x), g["unet_in_sha"][j]), (i, n)
+        left, top, _ = jobs_fn(i)[n]
+        win = po.image_ring_get(image, left * 8, left * 8 + c["width"], top * 8, top * 8 + c["height"])   # :814-817
+        assert np.array_equal(sha(win), g["img_win_sha"][j]), (i, n)
+        return g["eps_cond"][j], g["eps_uncond"][j]
+
+    def on_step(i, lat, den):
+        assert np.array_equal(sha(lat), g["step_latent_sha"][i]), i
+        assert np.array_equal(sha(den), g["step_denoised_sha"][i]), i
+
+    lat0 = randn(81, 1, 4, c["total_f"], c["total_h"] // 8, c["total_w"] // 8)
+    _, den, _ = po.ring_denoise_loop(lat0, sched, jobs_fn, model_fn, float(g["guidance"]), w, h, frames, on_step=on_step,
+                                     renoise_ratio=float(g["ratio"]), prev_ratio_list=[float(v) for v in g["prev_ratios"]],
+                                     eps_fn=eps_fn, use_mask=True)
+    assert draws["n"] == int(g["renoise_draws"])
+    assert np.array_equal(den, g["final_denoised"])
+
+
 def test_vae_tiling_oracle_matches_reference():
     """oracle.tiled_encode / wrap_pad / crop_wrap_padded == the reference's tiled_vae_encode_tensor_simple
     and the inline wrap-padded decode of i2v_sphere_panorama_pipeline.py:974-991 (tests/golden/vae.npz)."""
