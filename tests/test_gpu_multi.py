@@ -295,13 +295,13 @@ def test_sharded_denoise_loop(tmp_path, world, group_size):
 
 
 # ------------------------------------------------ planar shift-window loop, sharded ----
-def _ring_loop_worker(rank, world, port, out_dir, exchange, dtype_name="float32"):
+def _ring_loop_worker(rank, world, port, out_dir, exchange, dtype_name="float32", i2v=False):
     for p in (ROOT, HERE):
         if p not in sys.path:
             sys.path.insert(0, p)
     import torch.distributed as dist
     from conftest import randn
-    from dynamicscaler_b200.loop import ring_denoise_loop, shift_window_schedule
+    from dynamicscaler_b200.loop import i2v_planar_schedule, ring_denoise_loop, shift_window_schedule
     from dynamicscaler_b200.step import PanoramaStepper
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -313,6 +313,11 @@ def _ring_loop_worker(rank, world, port, out_dir, exchange, dtype_name="float32"
         dtype = getattr(torch, dtype_name)
         frames, h, w, nf, nh, nw = 4, 8, 12, 2, 2, 3
         F, H, W = frames * nf, h * nh, w * nw
+        if i2v:                                  # overlapping windows on W, H and F (the I2V planar loop)
+            h, w, H, W, nw, nh = 8, 16, 16, 48, 3, 3
+            i2v_kw = dict(width=128, height=64, frames=frames, total_w=384, total_h=128, total_f=F, num_windows_w=nw,
+                          num_windows_h=nh, loop_step=4, overlap_ratio_f=0.5, loop_step_frame=2, dock_at_f=True,
+                          begin_index_offset=1)
         lat0 = torch.from_numpy(randn(71, 1, 4, F, H, W)).to(dev).to(dtype)
         ac = np.cumprod(1 - np.linspace(0.00085, 0.012, 1000)).astype(np.float32)
         ts = np.array([1, 251, 501, 751])
@@ -332,16 +337,32 @@ def _ring_loop_worker(rank, world, port, out_dir, exchange, dtype_name="float32"
 
         cond = {"c_crossattn": [torch.from_numpy(randn(72, 1, 77, 16)).to(dev)], "fps": 16}
         uncond = {"c_crossattn": [torch.from_numpy(randn(73, 1, 77, 16)).to(dev)], "fps": 16}
+        def eps_fn(i, job_ids, shape, device):
+            if not len(job_ids):
+                return torch.empty(shape, device=device, dtype=dtype)
+            return torch.stack([torch.from_numpy(randn(8800 + 50 * i + j, *shape[1:])).to(device) for j in job_ids]).to(dtype)
+
+        def cond_fn(i, job_ids, boxes):          # one context row per window, a function of the window position
+            base = cond["c_crossattn"][0]
+            rows = [base + 0.01 * (l + 3 * t + 7 * fb) for (l, t, fb) in boxes]
+            return {"c_crossattn": [torch.cat(rows, dim=0)], "fps": 16}
+
         outs = []
         for (r, wsz) in ((0, 1), (rank, world)):
             st = PanoramaStepper(H, W, F, device=dev, rank=r, world=wsz)
             target = [lat0.clone(), torch.zeros_like(lat0)]
+            mask = torch.zeros_like(lat0) if i2v else None
             if wsz > 1 and exchange == "peer":
-                target = st.make_ring_state(target)
-            # whole-step groups on the steps whose windows tile the torus, 2 windows at a time on the docked ones
-            ring_denoise_loop(st, target, model=model, schedule=sched, schedule_fn=lambda i: shift_window_schedule(i, **kw),
-                              width=w, height=h, frames=frames, cond=cond, uncond=uncond, guidance_scale=7.5,
-                              group_size=lambda i: 2 if i in (1, 3) else None, noise_fn=noise_fn)
+                target = st.make_ring_state(target, mask=mask)
+            if i2v:     # whole-step groups and 4-window groups on alternating steps, all mixes on
+                ring_denoise_loop(st, target, model=model, schedule=sched, schedule_fn=lambda i: i2v_planar_schedule(i, **i2v_kw),
+                                  width=w, height=h, frames=frames, cond=cond_fn, uncond=uncond, guidance_scale=7.5,
+                                  group_size=lambda i: 4 if i % 2 else None, noise_fn=noise_fn, mask=mask, renoise_ratio=0.6,
+                                  prev_ratio_list=[0.3, 0.4, 0.5, 0.6], eps_fn=eps_fn)
+            else:       # whole-step groups on the steps whose windows tile the torus, 2 windows at a time on the docked ones
+                ring_denoise_loop(st, target, model=model, schedule=sched, schedule_fn=lambda i: shift_window_schedule(i, **kw),
+                                  width=w, height=h, frames=frames, cond=cond, uncond=uncond, guidance_scale=7.5,
+                                  group_size=lambda i: 2 if i in (1, 3) else None, noise_fn=noise_fn)
             outs.append(target.export() if hasattr(target, "export") else target)
         ok = all(torch.equal(a, b) for a, b in zip(*outs)) and not torch.equal(outs[0][0], lat0)
         if not ok:
@@ -369,3 +390,12 @@ def test_sharded_ring_denoise_loop(tmp_path, world, exchange, dtype_name):
     with overlapping windows: every rank's replica equals the single-GPU loop bit for bit -- through peer stores
     into reference-order replicas and through the zero-buffer all-reduce."""
     _spawn(tmp_path, world, _ring_loop_worker, exchange, dtype_name)
+
+
+@pytest.mark.parametrize("world,exchange,dtype_name", [(2, "peer", "float32"), (2, "allreduce", "float32"),
+                                                        (2, "peer", "bfloat16"), (4, "peer", "float32"), (8, "peer", "float32")])
+def test_sharded_i2v_ring_denoise_loop(tmp_path, world, exchange, dtype_name):
+    """The planar I2V loop sharded: overlapping windows on W, H and F with frame docking, latent-shaped mask panorama in
+    the replicas, re-noise mix on the read side (mask windows gathered before the cross-GPU barrier), merge_prev mix
+    inside the fused merge, one context row per window: every rank's replica equals the single-GPU loop bit for bit."""
+    _spawn(tmp_path, world, _ring_loop_worker, exchange, dtype_name, True)
