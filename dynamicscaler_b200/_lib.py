@@ -37,7 +37,7 @@ PROTOTYPES = {
     "ds_merge_nearest_peer": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_merge_nearest_ddim": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i,
                               _i, _i, _vp, _i, _vp],
-    "ds_renoise_mix": [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _ll, _i, _vp],
+    "ds_renoise_mix": [_vp, _vp, _vp, _vp, _f, _f, _f, _f, _ll, _ll, _i, _i, _vp],
     "ds_merge_bilinear": [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "ds_pm_gather": [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "ds_pm_merge_nearest": [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp],

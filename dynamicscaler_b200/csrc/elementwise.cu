@@ -52,7 +52,8 @@ mix_mask_f32x4_kernel(const float4* __restrict__ l1, const float4* __restrict__ 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kBlock)
 renoise_mix_kernel(const T* __restrict__ x, const T* __restrict__ eps, const T* __restrict__ mask,
-                   T* __restrict__ out, float c, float s, float r, float omr, long long n_vec) {
+                   T* __restrict__ out, float c, float s, float r, float omr, long long n_vec,
+                   long long win_vec, int hw_vec) {
   using V = typename std::conditional<VEC == 4, typename Elem<T>::vec4, T>::type;
   auto rt = [](float v) { return Elem<T>::to_f(Elem<T>::from_f(v)); };
   const float ct = rt(c), st = rt(s);
@@ -60,7 +61,9 @@ renoise_mix_kernel(const T* __restrict__ x, const T* __restrict__ eps, const T* 
   for (long long i = static_cast<long long>(blockIdx.x) * kBlock + threadIdx.x; i < n_vec; i += stride) {
     const V vx = __ldg(reinterpret_cast<const V*>(x) + i);
     const V ve = __ldg(reinterpret_cast<const V*>(eps) + i);
-    const V vm = __ldg(reinterpret_cast<const V*>(mask) + i);
+    // hw_vec > 0: every window is mixed with plane (batch 0, channel 0, frame 0) of its own mask window
+    const long long mi = hw_vec > 0 ? (i / win_vec) * win_vec + i % hw_vec : i;
+    const V vm = __ldg(reinterpret_cast<const V*>(mask) + mi);
     V vo;
     const T* ex = reinterpret_cast<const T*>(&vx);
     const T* ee = reinterpret_cast<const T*>(&ve);
@@ -153,23 +156,27 @@ extern "C" int ds_mix_mask(const void* l1, const void* add, const void* mask, vo
 }
 
 extern "C" int ds_renoise_mix(const void* x, const void* eps, const void* mask, void* out, float c, float s,
-                              float ratio, float one_minus_ratio, long long n, int dtype, void* stream) {
+                              float ratio, float one_minus_ratio, long long n, long long window_elems,
+                              int mask_plane_hw, int dtype, void* stream) {
   using namespace ds;
   DS_REQUIRE(x != nullptr && eps != nullptr && mask != nullptr && out != nullptr, DS_ERR_NULL);
-  DS_REQUIRE(n > 0, DS_ERR_DIM);
+  DS_REQUIRE(n > 0 && mask_plane_hw >= 0, DS_ERR_DIM);
+  DS_REQUIRE(mask_plane_hw == 0 || (window_elems > 0 && n % window_elems == 0 && window_elems % mask_plane_hw == 0),
+             DS_ERR_DIM);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DS_DISPATCH_DTYPE(dtype, {
     const uintptr_t al = sizeof(typename Elem<ET>::vec4) - 1;
-    const bool vec = n % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps) |
-                                     reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(out)) & al) == 0;
+    const bool vec = n % 4 == 0 && mask_plane_hw % 4 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(eps) |
+                       reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(out)) & al) == 0;
     if (vec)
       renoise_mix_kernel<ET, 4><<<stride_grid(n / 4), kBlock, 0, st>>>(
           static_cast<const ET*>(x), static_cast<const ET*>(eps), static_cast<const ET*>(mask), static_cast<ET*>(out),
-          c, s, ratio, one_minus_ratio, n / 4);
+          c, s, ratio, one_minus_ratio, n / 4, mask_plane_hw > 0 ? window_elems / 4 : 1, mask_plane_hw / 4);
     else
       renoise_mix_kernel<ET, 1><<<stride_grid(n), kBlock, 0, st>>>(
           static_cast<const ET*>(x), static_cast<const ET*>(eps), static_cast<const ET*>(mask), static_cast<ET*>(out),
-          c, s, ratio, one_minus_ratio, n);
+          c, s, ratio, one_minus_ratio, n, mask_plane_hw > 0 ? window_elems : 1, mask_plane_hw);
   });
   return check_launch();
 }

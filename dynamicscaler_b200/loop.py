@@ -297,13 +297,42 @@ def i2v_planar_schedule(step_i: int, *, width: int, height: int, frames: int, to
                                   loop_step_frame=loop_step_frame, dock_at_f=dock_at_f)
 
 
+def t2v_planar_schedule(step_i: int, *, width: int, height: int, frames: int, total_w: int, total_h: int,
+                        num_windows_w: int, num_windows_h: int, num_windows_f: int, loop_step: int,
+                        dock_at_h: bool = False, vae_scale_factor: int = 8):
+    """Window positions of DDIM step ``step_i`` of the T2V planar loop (``VC2_Pipeline_T2V_SpherePano.
+    basic_sample_shift_multi_windows``, pipeline/t2v_sphere_panorama_pipeline.py:436-535): integer strides
+    ``int(size * (1 - overlap)) // vae``, per-step offsets, non-overlapping frame windows shifted by
+    ``frames // loop_step`` per step, and -- ``dock_at_h`` -- extra windows docked at the top edge (first) and the
+    bottom edge (last) on every step whose shift is not 0, with windows running past the bottom edge dropped.
+    Pixel sizes in; returns ``(windows, frame_begins)`` in latent cells / frames (``for f: for w: for h``)."""
+    vae = vae_scale_factor
+
+    def axis(num, total, size):
+        overlap = 1 - (total / size - 1) / (num - 1)
+        return int(size * (1 - overlap)) // vae, int((1 - overlap) * size / loop_step) // vae
+
+    stride_w, off_w = axis(num_windows_w, total_w, width)
+    stride_h, off_h = axis(num_windows_h, total_h, height)
+    phase = step_i % loop_step
+    lat_h, lat_total_h = height // vae, total_h // vae
+    tops = [phase * off_h + k * stride_h for k in range(num_windows_h)]
+    if dock_at_h:
+        if phase != 0:
+            tops = [0] + tops + [lat_total_h - lat_h]
+        tops = [t for t in tops if t + lat_h <= lat_total_h]
+    lefts = [phase * off_w + k * stride_w for k in range(num_windows_w)]
+    step_f = 0 if num_windows_f == 1 else frames // loop_step
+    return [(l, t) for l in lefts for t in tops], [phase * step_f + k * frames for k in range(num_windows_f)]
+
+
 def ring_denoise_step(stepper: PanoramaStepper, target, windows: Sequence, frame_begins: Sequence[int], w: int, h: int,
                       frames: int, *, model: Callable, t: int, index: int, step_i: int, schedule, cond,
                       uncond: Optional[dict], guidance_scale: float, group_size: Optional[int] = None,
                       noise_fn: Optional[Callable] = None, model_kwargs: Optional[dict] = None, cfg_batch: bool = True,
                       on_input: Optional[Callable] = None, mask: Optional[torch.Tensor] = None,
                       renoise: Optional[tuple] = None, prev_ratio: Optional[float] = None,
-                      eps_fn: Optional[Callable] = None):
+                      eps_fn: Optional[Callable] = None, mask_frame0: bool = False):
     """One DDIM step of the planar shift-window loops (pipeline/t2v_normal_pipeline.py:481-557; I2V twin
     pipeline/i2v_sphere_panorama_pipeline.py:812-968) over the ordered job list ``frame_begins x windows``:
 
@@ -319,7 +348,9 @@ def ring_denoise_step(stepper: PanoramaStepper, target, windows: Sequence, frame
     zeroed, i2v :810; a RingPanoramaState carries its own); ``renoise`` = ``(c, s, ratio)`` switches the re-noise mix
     on (i2v :875-884, epsilon from ``eps_fn(step_i, job_ids, shape, device)``); ``prev_ratio`` the merge_prev mix
     (i2v :938-943); ``cond`` may be a callable ``cond(step_i, job_ids, boxes)`` -> dict with one context row per
-    window (``boxes``: the (left, top, frame_begin) of each job; i2v :886-895 builds one image embedding per window)."""
+    window (``boxes``: the (left, top, frame_begin) of each job; i2v :886-895 builds one image embedding per window).
+    ``mask_frame0``: the T2V sphere pipeline's planar loop mixes with ``mask_window[0, 0, [0]]`` broadcast over the
+    window (pipeline/t2v_sphere_panorama_pipeline.py:553)."""
     coef = ddim_coefficients(_get(schedule, "ddim_alphas")[index], _get(schedule, "ddim_alphas_prev")[index],
                              _get(schedule, "ddim_sigmas")[index], _get(schedule, "ddim_sqrt_one_minus_alphas")[index],
                              guidance_scale if uncond is not None else 1.0)
@@ -341,7 +372,7 @@ def ring_denoise_step(stepper: PanoramaStepper, target, windows: Sequence, frame
         raw = mview = None
         if renoise is not None or use_prev:
             shape = (plan.n_local,) + tuple(source.shape[:2]) + (plan.f_len, plan.h, plan.w)
-            rn = dict(want_raw=use_prev, want_mask=use_prev, mask=mask)
+            rn = dict(want_raw=use_prev, want_mask=use_prev, mask=mask, mask_frame0=mask_frame0)
             if renoise is not None:
                 eps = eps_fn(step_i, job_ids, shape, stepper.device)
                 rn.update(eps=eps.contiguous(), c=renoise[0], s=renoise[1], ratio=renoise[2])
@@ -374,17 +405,19 @@ def ring_denoise_loop(stepper: PanoramaStepper, target, *, model: Callable, sche
                       model_kwargs: Optional[dict] = None, cfg_batch: bool = True, on_input: Optional[Callable] = None,
                       before_step: Optional[Callable] = None, mask: Optional[torch.Tensor] = None,
                       renoise_ratio: Optional[float] = None, prev_ratio_list: Optional[Sequence[float]] = None,
-                      eps_fn: Optional[Callable] = None):
+                      eps_fn: Optional[Callable] = None, mask_frame0: bool = False):
     """The planar DDIM loops: ``basic_sample_shift_multi_windows`` of pipeline/t2v_normal_pipeline.py:434-561 and, with
     ``mask`` / ``renoise_ratio`` / ``prev_ratio_list`` / a callable ``cond``, of pipeline/i2v_sphere_panorama_pipeline.py:
     777-970 (stages 2 / 3 of gen_pano_360.py).  ``target``: ``[latent, denoised]`` ([B, C, F_total, H_total, W_total];
     the reference starts the denoised panorama at zero, :417) or a ``RingPanoramaState``; both are updated in place,
     ``target[1]`` is what the reference returns (:561).  ``schedule_fn(i)`` -> ``(windows, frame_begins)`` of step i
-    (:func:`shift_window_schedule` / :func:`i2v_planar_schedule`); ``width`` / ``height``: the window in latent cells.
+    (:func:`shift_window_schedule` / :func:`i2v_planar_schedule` / :func:`t2v_planar_schedule`); ``width`` / ``height``: the window in latent cells.
     ``timesteps`` defaults to the flipped ``ddim_timesteps`` (:300); a shorter list is the reference's
     ``use_skip_time`` tail (:303).  ``group_size``: see :func:`ring_denoise_step`; a callable ``group_size(i)`` picks
     it per step (e.g. 1 on docking steps only).  ``mask``: a latent-shaped tensor that serves as the denoised-mask
     panorama (zeroed here at every step, i2v :810; required for the re-noise / merge_prev mixes on plain tensors).
+    ``mask_frame0=True`` selects the T2V sphere pipeline's planar loop (pipeline/t2v_sphere_panorama_pipeline.py:
+    481-632: re-noise mix with ``mask_window[0, 0, [0]]``, no merge_prev mix).
     ``before_step(i, target)``: hook for the whole-panorama residual mix of t2v :442-470 (outside the tiling path)."""
     ddim_ts = [int(v) for v in _get(schedule, "ddim_timesteps")]
     timesteps = list(reversed(ddim_ts)) if timesteps is None else [int(v) for v in timesteps]
@@ -412,5 +445,5 @@ def ring_denoise_loop(stepper: PanoramaStepper, target, *, model: Callable, sche
                           index=total - i - 1, step_i=i, schedule=schedule, cond=cond, uncond=uncond,
                           guidance_scale=guidance_scale, group_size=group_size(i) if callable(group_size) else group_size,
                           noise_fn=noise_fn, model_kwargs=kwargs, cfg_batch=cfg_batch, on_input=on_input,
-                          mask=step_mask, renoise=renoise, prev_ratio=prev_ratio, eps_fn=eps_fn)
+                          mask=step_mask, renoise=renoise, prev_ratio=prev_ratio, eps_fn=eps_fn, mask_frame0=mask_frame0)
     return target

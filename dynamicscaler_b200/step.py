@@ -619,7 +619,8 @@ class PanoramaStepper:
         mask_view)``: the mixed windows, the unmixed ones (``want_raw``) and the mask view
         (``want_mask``; [n, h, w] for a [1, H, W] mask, windows-shaped for a latent-shaped mask) -- the
         last two feed ``merge_denoised(prev=, prev_mask=)``.  Planar ring plans on reference-order tensors take the
-        same dict plus ``mask=<latent-shaped mask panorama>`` (a ``RingPanoramaState`` uses its own); ``eps`` None
+        same dict plus ``mask=<latent-shaped mask panorama>`` (a ``RingPanoramaState`` uses its own) and
+        ``mask_frame0=True`` for the T2V planar loop's ``mask[0, 0, [0]]`` broadcast; ``eps`` None
         skips the re-noise mix and only reads the mask windows (-> ``merge_denoised_ref(prev=, prev_mask=)``)."""
         if isinstance(latent, PanoramaState):
             assert plan.kind != "ring", "planar ring windows run on reference-order tensors"
@@ -686,11 +687,13 @@ class PanoramaStepper:
                     assert eps.shape == out.shape and eps.dtype == out.dtype and eps.is_contiguous()
                     r = float(renoise["ratio"])
                     mixed = torch.empty_like(out)
+                    plane = plan.hw if renoise.get("mask_frame0") else 0     # t2v_sphere_...:553 mask[0, 0, [0]]
+                    assert not plane or B == 1, "the plane-mask variant indexes batch 0"
                     with _lib.on(out.device):
                         lib.check(lib.ds_renoise_mix(out.data_ptr(), eps.data_ptr(), mview.data_ptr(), mixed.data_ptr(),
                                                      float(renoise["c"]), float(renoise["s"]), r, 1 - r, out.numel(),
-                                                     _lib.dtype_code(out.dtype), _lib.stream_ptr(out.device)),
-                                  "ds_renoise_mix")
+                                                     out.numel() // nj, plane, _lib.dtype_code(out.dtype),
+                                                     _lib.stream_ptr(out.device)), "ds_renoise_mix")
                 return (mixed, out if renoise.get("want_raw") else None, mview if renoise.get("want_mask") else None)
         elif plan.kind == "sphere_nearest":
             _launch_gather_nearest(latent, out, plan.d_idx, plan.d_jobs[j0:j0 + nj], 0, nj, B * C, F, H * W,

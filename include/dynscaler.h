@@ -404,9 +404,13 @@ int ds_repeat_renoise(const void* x0, const void* eps, void* out, float c, float
 /* The read side of the planar I2V loop after its two window gathers (pipeline/i2v_sphere_panorama_pipeline.py:
  * 875-884), one pass:  noised = c*x + s*eps  (re_noise, pipeline/scheduler.py:98-110, epsilon injected; c, s
  * cast to the tensor dtype like the reference's 0-dim tensors);  out = mix_latents_with_mask(x, noised, mask,
- * ratio) (utils/tensor_utils.py:19-39).  x / eps / mask / out: n elements each; every op rounded on its own. */
+ * ratio) (utils/tensor_utils.py:19-39).  x / eps / mask / out: n elements each; every op rounded on its own.
+ * mask_plane_hw > 0: the T2V planar loop's variant (pipeline/t2v_sphere_panorama_pipeline.py:552-556,
+ * ``window_denoised_mask[0, 0, [0]]``): each window of window_elems elements is mixed with the first h*w =
+ * mask_plane_hw elements (batch 0, channel 0, frame 0) of its own mask window, broadcast over C and F. */
 int ds_renoise_mix(const void* x, const void* eps, const void* mask, void* out, float c, float s, float ratio,
-                   float one_minus_ratio, long long n, int dtype, void* stream);
+                   float one_minus_ratio, long long n, long long window_elems, int mask_plane_hw, int dtype,
+                   void* stream);
 
 /* Final select of the sharded merge:
  *   pano[i] = weight[(i / weight_group) mod weight_period] > 0 ? sum[i] : pano[i]   for i < n.

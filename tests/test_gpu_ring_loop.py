@@ -385,18 +385,129 @@ def test_i2v_ring_loop_batched_order_vs_oracle(dev, group_size):
 def test_renoise_mix_vs_reference_chain(dev, dtype):
     """ds_renoise_mix == re_noise (pipeline/scheduler.py:98-110, epsilon injected, 0-dim float32 c and s) followed by
     mix_latents_with_mask (utils/tensor_utils.py:30-39) as torch CPU ops in the tensor dtype, bit for bit; vector and
-    scalar paths."""
+    scalar paths; window-shaped mask (I2V planar loop) and the [0, 0, [0]] plane of every mask window (T2V planar loop)."""
     from dynamicscaler_b200 import _lib, lib
-    for shape in ((3, 1, 4, 4, 8, 12), (1, 1, 4, 3, 5, 7)):
+    from dynamicscaler_b200.tensor_utils import mix_latents_with_mask
+    for shape in ((3, 1, 4, 4, 8, 12), (2, 1, 4, 3, 5, 7)):
         x, eps = (torch.from_numpy(randn(s, *shape)).to(dtype) for s in (91, 92))
         m = (torch.from_numpy(randn(93, *shape)) > 0.3).to(dtype)
         c_t, s_t, r = torch.tensor(0.9721), torch.tensor(0.2346), 0.6
         noised = c_t * x + s_t * eps
         mixed = x * (1 - r) + noised * r
-        want = x * (1 - m) + mixed * m
-        assert want.dtype == dtype
         dx, de, dm = x.to(dev), eps.to(dev), m.to(dev)
-        out = torch.empty_like(dx)
-        lib.check(lib.ds_renoise_mix(dx.data_ptr(), de.data_ptr(), dm.data_ptr(), out.data_ptr(), float(c_t), float(s_t),
-                                     r, 1 - r, dx.numel(), _lib.dtype_code(dtype), _lib.stream_ptr(dev)), "ds_renoise_mix")
-        assert torch.equal(out.cpu(), want), (dtype, shape, float((out.cpu().float() - want.float()).abs().max()))
+        for plane in (False, True):
+            if plane:                       # per window n: mask[n][0, 0, [0]] -> [1, h, w], repeated over B, C, F (tensor_utils.py:21-23)
+                me = torch.stack([m[n][0, 0, [0]].unsqueeze(0).unsqueeze(0).repeat(*shape[1:4], 1, 1) for n in range(shape[0])])
+            else:
+                me = m
+            want = x * (1 - me) + mixed * me
+            assert want.dtype == dtype
+            out = torch.empty_like(dx)
+            hw = shape[-1] * shape[-2]
+            lib.check(lib.ds_renoise_mix(dx.data_ptr(), de.data_ptr(), dm.data_ptr(), out.data_ptr(), float(c_t), float(s_t),
+                                         r, 1 - r, dx.numel(), dx.numel() // shape[0], hw if plane else 0,
+                                         _lib.dtype_code(dtype), _lib.stream_ptr(dev)), "ds_renoise_mix")
+            assert torch.equal(out.cpu(), want), (dtype, shape, plane, float((out.cpu().float() - want.float()).abs().max()))
+
+
+# ------------------------------------------ the planar loop of the T2V sphere pipeline ----
+def load_ring_loop_t2v():
+    g = np.load(os.path.join(GOLDEN, "ring_loop_t2v.npz"))
+    names = ("frames", "height", "width", "total_h", "total_w", "nw", "nh", "nf", "loop_step", "steps")
+    c = {k: int(v) for k, v in zip(names, g["cfg"])}
+    sched = {k: g[k] for k in ("ddim_timesteps", "alphas_cumprod", "ddim_alphas", "ddim_alphas_prev", "ddim_sigmas",
+                               "ddim_sqrt_one_minus_alphas")}
+    kw = dict(width=c["width"], height=c["height"], frames=c["frames"], total_w=c["total_w"], total_h=c["total_h"],
+              num_windows_w=c["nw"], num_windows_h=c["nh"], num_windows_f=c["nf"], loop_step=c["loop_step"], dock_at_h=True)
+    counts = [len(po.t2v_planar_jobs(i, **kw)) for i in range(c["steps"])]
+    return g, c, sched, kw, [0] + [int(v) for v in np.cumsum(counts)]
+
+
+def test_t2v_ring_loop_replays_the_real_reference_pipeline(dev):
+    """3 DDIM steps of the T2V sphere pipeline's planar loop (18 + 24 + 24 overlapping windows, windows docked at the
+    top / bottom edge, latent-shaped mask panorama whose [0, 0, [0]] plane drives the re-noise mix): every UNet input
+    and the latent / denoised panoramas after every step equal the real pipeline's, bit for bit."""
+    from dynamicscaler_b200.loop import ring_denoise_loop, t2v_planar_schedule
+    from dynamicscaler_b200.step import PanoramaStepper
+    g, c, sched, kw, base = load_ring_loop_t2v()
+    frames, h, w = c["frames"], c["height"] // 8, c["width"] // 8
+    F, H, W = frames * c["nf"], c["total_h"] // 8, c["total_w"] // 8
+    st = PanoramaStepper(H, W, F, device=dev)
+    lat = G(randn(95, 1, 4, F, H, W), dev)
+    den, mask = torch.zeros_like(lat), torch.ones_like(lat)
+    cur = {"calls": 0, "draws": 0}
+
+    def on_input(i, job_ids, xb):
+        cur.update(i=i, jobs=list(job_ids), branch=0)
+        for q, job in enumerate(job_ids):
+            assert np.array_equal(sha(N(xb[q:q + 1])), g["unet_in_sha"][base[i] + job]), (i, job)
+
+    def replay_model(x, ts, c_crossattn=None, fps=None, **kw_):
+        src = g["eps_cond"] if cur["branch"] == 0 else g["eps_uncond"]
+        cur["branch"] += 1
+        cur["calls"] += x.shape[0]
+        return torch.cat([G(src[base[cur["i"]] + job], dev) for job in cur["jobs"]], dim=0)
+
+    def eps_fn(i, job_ids, shape, device):
+        cur["draws"] += 1
+        return G(randn(7000 + cur["draws"], *shape[1:]), device).view(shape)
+
+    def check_step(i, target):
+        if i > 0:
+            assert np.array_equal(sha(N(target[0])), g["step_latent_sha"][i - 1]), i - 1
+            assert np.array_equal(sha(N(target[1])), g["step_denoised_sha"][i - 1]), i - 1
+
+    ring_denoise_loop(st, [lat, den], model=replay_model, schedule=sched,
+                      schedule_fn=lambda i: t2v_planar_schedule(i, **kw), width=w, height=h, frames=frames,
+                      cond={"c_crossattn": [G(g["text_emb"], dev)], "fps": 16},
+                      uncond={"c_crossattn": [G(g["uncond_emb"], dev)], "fps": 16}, guidance_scale=float(g["guidance"]),
+                      group_size=1, cfg_batch=False, on_input=on_input, before_step=check_step, mask=mask,
+                      renoise_ratio=float(g["ratio"]), eps_fn=eps_fn, mask_frame0=True)
+    assert cur["calls"] == 2 * base[-1] and cur["draws"] == int(g["renoise_draws"])
+    check_step(c["steps"], [lat, den])
+    assert np.array_equal(N(den), g["final_denoised"])
+
+
+def test_t2v_ring_loop_dropin_classes_replay_the_real_reference_pipeline(dev):
+    """The same run call for call through the DROP-IN ``RingLatent`` / ``mix_latents_with_mask`` (the loop body of
+    pipeline/t2v_sphere_panorama_pipeline.py:537-632, incl. the [1, h, w] mask plane of :553)."""
+    from dynamicscaler_b200.shift_window_utils import RingLatent
+    from dynamicscaler_b200.tensor_utils import mix_latents_with_mask
+    g, c, sched, kw, base = load_ring_loop_t2v()
+    frames, h, w = c["frames"], c["height"] // 8, c["width"] // 8
+    lat0 = G(randn(95, 1, 4, frames * c["nf"], c["total_h"] // 8, c["total_w"] // 8), dev)
+    h_lat = RingLatent(init_latent=lat0)
+    h_den = RingLatent(init_latent=torch.zeros_like(lat0))
+    ac = torch.from_numpy(np.asarray(sched["alphas_cumprod"], dtype=np.float32)).to(dev)
+    ddim_ts = [int(v) for v in sched["ddim_timesteps"]]
+    total, ratio, gscale = c["steps"], float(g["ratio"]), float(g["guidance"])
+    draws = 0
+    for i in range(total):
+        idx = total - i - 1
+        f32 = lambda v: torch.full((1, 1, 1, 1, 1), float(v), device=dev)
+        a_t, a_prev, sig, s1m = (f32(sched[k][idx]) for k in ("ddim_alphas", "ddim_alphas_prev", "ddim_sigmas",
+                                                              "ddim_sqrt_one_minus_alphas"))
+        h_msk = RingLatent(init_latent=torch.zeros_like(lat0))                            # :494
+        for n, (left, top, fb) in enumerate(po.t2v_planar_jobs(i, **kw)):
+            box = dict(pos_left=left, pos_right=left + w, pos_top=top, pos_down=top + h, frame_begin=fb, frame_end=fb + frames)
+            x = h_lat.get_window_latent(**box)
+            m = h_msk.get_window_latent(**box)
+            if i < total - 1:                                                             # :548-559
+                a_a, a_b = ac[ddim_ts[total - i - 2]], ac[ddim_ts[total - i - 1]]
+                cc, ss = torch.sqrt(a_b / a_a), torch.sqrt(1 - a_b / a_a)
+                draws += 1
+                noised = cc * x.clone() + ss * G(randn(7000 + draws, *x.shape), dev)
+                x = mix_latents_with_mask(latent_1=x, latent_to_add=noised, mask=m[0, 0, [0]], mix_ratio=ratio)
+            j = base[i] + n
+            assert np.array_equal(sha(N(x)), g["unet_in_sha"][j]), (i, n)
+            ec, eu = G(g["eps_cond"][j], dev), G(g["eps_uncond"][j], dev)
+            e = eu + gscale * (ec - eu)
+            pred_x0 = (x - s1m * e) / a_t.sqrt()
+            x_prev = a_prev.sqrt() * pred_x0 + (1. - a_prev - sig ** 2).sqrt() * e
+            h_lat.set_window_latent(x_prev, **box)
+            h_den.set_window_latent(pred_x0, **box)
+            h_msk.set_window_latent(torch.ones_like(x_prev), **box)
+        assert np.array_equal(sha(N(h_lat.torch_latent)), g["step_latent_sha"][i]), i
+        assert np.array_equal(sha(N(h_den.torch_latent)), g["step_denoised_sha"][i]), i
+    assert draws == int(g["renoise_draws"])
+    assert np.array_equal(N(h_den.torch_latent), g["final_denoised"])

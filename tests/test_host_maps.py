@@ -427,3 +427,25 @@ def test_i2v_planar_schedule_matches_oracle():
                     assert [(l, t, fb) for fb in fbs for (l, t) in windows] == po.i2v_planar_jobs(i, **kw), (kw, i)
                     n += 1
     assert n == 4 * 4 * 2 * 10
+
+
+def test_t2v_planar_schedule_matches_oracle():
+    """loop.t2v_planar_schedule == the reference's f / w / h loops restated in oracle.t2v_planar_jobs
+    (pipeline/t2v_sphere_panorama_pipeline.py:436-535): integer strides, per-step offsets, shifted frame windows,
+    docking at the top / bottom edge (skipped when the shift is 0, windows past the bottom edge dropped)."""
+    from dynamicscaler_b200.loop import t2v_planar_schedule
+    from oracle import panorama_oracle as po
+    n = 0
+    for (width, height, tw, th, nw, nh, ls) in ((96, 64, 240, 128, 3, 3, 4), (128, 64, 384, 128, 3, 3, 4),
+                                                (512, 320, 8192, 4096, 16, 16, 16), (512, 320, 1024, 512, 4, 3, 8)):
+        for nf, frames in ((1, 16), (2, 4), (4, 16)):
+            if nf > 1 and frames // ls == 0:
+                continue
+            for dock in (False, True):
+                kw = dict(width=width, height=height, frames=frames, total_w=tw, total_h=th, num_windows_w=nw,
+                          num_windows_h=nh, num_windows_f=nf, loop_step=ls, dock_at_h=dock)
+                for i in range(10):
+                    windows, fbs = t2v_planar_schedule(i, **kw)
+                    assert [(l, t, fb) for fb in fbs for (l, t) in windows] == po.t2v_planar_jobs(i, **kw), (kw, i)
+                    n += 1
+    assert n == 200

@@ -418,6 +418,54 @@ def test_i2v_ring_loop_oracle_matches_real_pipeline():
     assert np.array_equal(den, g["final_denoised"])
 
 
+def ring_loop_t2v_golden():
+    g = np.load(os.path.join(GOLDEN, "ring_loop_t2v.npz"))
+    names = ("frames", "height", "width", "total_h", "total_w", "nw", "nh", "nf", "loop_step", "steps")
+    c = {k: int(v) for k, v in zip(names, g["cfg"])}
+    sched = {k: g[k] for k in ("ddim_timesteps", "alphas_cumprod", "ddim_alphas", "ddim_alphas_prev", "ddim_sigmas",
+                               "ddim_sqrt_one_minus_alphas")}
+    jobs_kw = dict(width=c["width"], height=c["height"], frames=c["frames"], total_w=c["total_w"], total_h=c["total_h"],
+                   num_windows_w=c["nw"], num_windows_h=c["nh"], num_windows_f=c["nf"], loop_step=c["loop_step"],
+                   dock_at_h=True)
+    return g, c, sched, jobs_kw
+
+
+def test_t2v_ring_loop_oracle_matches_real_pipeline():
+    """oracle.ring_denoise_loop (mask panorama, re-noise mix with the mask window's [0, 0, [0]] plane) over
+    oracle.t2v_planar_jobs == the REAL ``VC2_Pipeline_T2V_SpherePano.basic_sample_shift_multi_windows`` run
+    (tests/golden/ring_loop_t2v.npz: 3 DDIM steps, 3 x 3 overlapping windows + windows docked at the top / bottom
+    edge, 2 frame windows; 66 windows): every UNet input, the panoramas after every step and the returned denoised
+    panorama, bit for bit."""
+    import hashlib
+    sha = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+    g, c, sched, jobs_kw = ring_loop_t2v_golden()
+    jobs_fn = lambda i: po.t2v_planar_jobs(i, **jobs_kw)
+    counts = [len(jobs_fn(i)) for i in range(c["steps"])]
+    assert counts == [18, 24, 24] and sum(counts) == len(g["unet_in_sha"])
+    base = np.concatenate([[0], np.cumsum(counts)])
+    draws = {"n": 0}
+
+    def eps_fn(i, n, shape):
+        draws["n"] += 1
+        return randn(7000 + draws["n"], *shape)
+
+    def model_fn(i, n, x):
+        j = int(base[i]) + n
+        assert np.array_equal(sha(x), g["unet_in_sha"][j]), (i, n)
+        return g["eps_cond"][j], g["eps_uncond"][j]
+
+    def on_step(i, lat, den):
+        assert np.array_equal(sha(lat), g["step_latent_sha"][i]), i
+        assert np.array_equal(sha(den), g["step_denoised_sha"][i]), i
+
+    lat0 = randn(95, 1, 4, c["frames"] * c["nf"], c["total_h"] // 8, c["total_w"] // 8)
+    _, den, _ = po.ring_denoise_loop(lat0, sched, jobs_fn, model_fn, float(g["guidance"]), c["width"] // 8, c["height"] // 8,
+                                     c["frames"], on_step=on_step, renoise_ratio=float(g["ratio"]), eps_fn=eps_fn,
+                                     use_mask=True, mask_frame0=True)
+    assert draws["n"] == int(g["renoise_draws"])
+    assert np.array_equal(den, g["final_denoised"])
+
+
 def test_vae_tiling_oracle_matches_reference():
     """oracle.tiled_encode / wrap_pad / crop_wrap_padded == the reference's tiled_vae_encode_tensor_simple
     and the inline wrap-padded decode of i2v_sphere_panorama_pipeline.py:974-991 (tests/golden/vae.npz)."""
