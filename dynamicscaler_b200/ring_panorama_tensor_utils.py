@@ -7,9 +7,6 @@ same gather / merge kernels: ``(frame_begin + fo) mod F``.
 """
 from __future__ import annotations
 
-import torch
-
-from . import _lib
 from .panorama_tensor_utils import PanoramaTensor, _Block
 from .shift_window_utils import RingLatent
 
