@@ -7,7 +7,9 @@ Runs the UNMODIFIED ``VC2_Pipeline_T2V_SpherePano.basic_sample_shift_shpere_pano
     output layers re-randomised),
   * the reference's own ``lvdm_DDIM_Scheduler`` (pipeline/scheduler.py) incl. ``re_noise`` and ``ddim_step``,
   * ``merge_renoised_overlap_latent_ratio`` set, so the re-noise + mask mix runs,
-  * ~30 lines of stubs for what is not installed here (diffusers, pytorch_lightning),
+  * ~30 lines of stubs for what is not installed here (diffusers, pytorch_lightning; SURVEY §8c;
+    tests/golden/_ref_stubs.py, model / scheduler set-up shared with the planar-loop generators in
+    tests/golden/_ref_fake_t2v.py),
 and records, per UNet call, the digest of the input window and the model output.  The GPU box has no
 reference checkout: there the tests replay the recorded UNet outputs ("replay model") through
 dynamicscaler_b200's fused gather / merge calls and must reproduce the final panoramas bit for bit.
@@ -20,10 +22,8 @@ b*t -- the call the batched driver makes -- next to the per-window results.
 
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_loop.py
 """
-import hashlib
 import os
 import sys
-import types
 
 import numpy as np
 import torch
@@ -31,73 +31,20 @@ import torch
 sys.dont_write_bytecode = True
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-sys.path.insert(0, os.path.dirname(HERE))
-from conftest import randn  # noqa: E402
+import _ref_fake_t2v as rf  # noqa: E402  (reduced reference UNet, scheduler, fake pretrained_t2v, stubs)
+from _ref_fake_t2v import randn, text_embed  # noqa: E402
 
-import _ref_stubs  # noqa: E402,F401  (registers the pytorch_lightning / diffusers stubs)
+with rf.quiet():
+    import pipeline.scheduler as ref_sched  # noqa: E402
+    from pipeline.t2v_sphere_panorama_pipeline import VC2_Pipeline_T2V_SpherePano  # noqa: E402
 
 import builtins  # noqa: E402
 _print = builtins.print
-builtins.print = lambda *a, **k: None          # the reference prints one line per window
-try:
-    from lvdm.models.utils_diffusion import make_beta_schedule  # noqa: E402
-    from lvdm.models.ddpm3d import DiffusionWrapper  # noqa: E402
-    import pipeline.scheduler as ref_sched  # noqa: E402
-    from pipeline.t2v_sphere_panorama_pipeline import VC2_Pipeline_T2V_SpherePano  # noqa: E402
-finally:
-    builtins.print = _print
-
-
-def sha(a):
-    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
-
-
-# ---- reduced-width reference UNet ------------------------------------------------------------
-CTX = 32
-UNET = dict(in_channels=4, out_channels=4, model_channels=32, attention_resolutions=[2, 1], num_res_blocks=1,
-            channel_mult=[1, 2], num_head_channels=16, transformer_depth=1, context_dim=CTX, use_linear=True,
-            use_checkpoint=False, temporal_conv=True, temporal_attention=True, temporal_selfatt_only=True,
-            use_relative_position=False, use_causal_attention=False, temporal_length=4, addition_attention=True,
-            fps_cond=True)
-torch.manual_seed(0)
-torch.set_num_threads(1)
-wrapper = DiffusionWrapper({"target": "lvdm.modules.networks.openaimodel3d.UNetModel", "params": UNET}, "crossattn")
-g = torch.Generator().manual_seed(1)
-for name, p in wrapper.named_parameters():      # zero_module layers would make a random-init UNet output exactly 0
-    if p.abs().max() == 0:
-        p.data = torch.randn(p.shape, generator=g) * 0.05
-wrapper.eval()
-
-# ---- fake pretrained_t2v (only what the loop touches) ---------------------------
-betas = make_beta_schedule("linear", 1000, linear_start=0.00085, linear_end=0.012)
-ac = np.cumprod(1.0 - betas, axis=0)
-calls = []                                        # (input sha, input sample, output)
-
-
-def recording_model(x, t, **kw):
-    y = wrapper(x, t, **kw)
-    calls.append((sha(x.numpy()), x.numpy().reshape(-1)[::97].copy(), y.numpy().copy(), x.numpy().copy()))
-    return y
-
-
-def text_embed(prompts):
-    out = []
-    for pr in prompts:
-        seed = int(hashlib.sha256(pr.encode()).hexdigest()[:8], 16)
-        out.append(torch.from_numpy(randn(seed, 77, CTX)))
-    return torch.stack(out)
-
-
-fake = types.SimpleNamespace(
-    model=recording_model, first_stage_model=None, cond_stage_model=None, uncond_type="empty_seq",
-    temporal_length=4, device=torch.device("cpu"), get_learned_conditioning=text_embed,
-    num_timesteps=1000, betas=torch.tensor(betas, dtype=torch.float32),
-    alphas_cumprod=torch.tensor(ac, dtype=torch.float32),
-    alphas_cumprod_prev=torch.tensor(np.append(1.0, ac[:-1]), dtype=torch.float32), use_scale=False)
-sched = ref_sched.lvdm_DDIM_Scheduler(fake)
+CTX = rf.CTX
+wrapper, calls, fake, sched = rf.build()        # calls: (input sha, input, output) per UNet call
 pipe = VC2_Pipeline_T2V_SpherePano.__new__(VC2_Pipeline_T2V_SpherePano)
 pipe.pretrained_t2v, pipe.scheduler = fake, sched
-pipe.model_config = {"params": {"unet_config": {"params": UNET}}}
+pipe.model_config = {"params": {"unet_config": {"params": rf.UNET}}}
 pipe.vae_scale_factor = 8
 
 # ---- the run ----------------------------------------------------------------------------------
@@ -142,7 +89,7 @@ assert len(calls) == CFG["steps"] * n_views * 2, len(calls)
 out["final_latent"] = videos.numpy()
 out["final_denoised"] = denoised.numpy()
 out["unet_in_sha"] = np.stack([c[0] for c in calls[0::2]])           # cond call of every window (uncond sees the same x)
-out["unet_in_sample"] = np.stack([c[1] for c in calls[0::2]])
+out["unet_in_sample"] = np.stack([c[1].reshape(-1)[::97].copy() for c in calls[0::2]])
 out["eps_cond"] = np.stack([c[2] for c in calls[0::2]])
 out["eps_uncond"] = np.stack([c[2] for c in calls[1::2]])
 out["renoise_draws"] = np.array(draws["n"])
@@ -155,7 +102,7 @@ for k in ("ddim_alphas", "ddim_alphas_prev", "ddim_sigmas", "ddim_sqrt_one_minus
     out[k] = np.asarray(getattr(sched, k), dtype=np.float64)
 
 # ---- P9: one batched UNet call (timesteps of length b*t) == the per-window calls ----------------
-step0 = [c[3] for c in calls[0:2 * n_views:2]]
+step0 = [c[1] for c in calls[0:2 * n_views:2]]
 xb = torch.from_numpy(np.concatenate(step0, axis=0))               # [n, 4, F, h, w]
 t0 = int(np.flip(sched.ddim_timesteps)[0])
 ts = torch.full((xb.shape[0] * CFG["F"],), t0, dtype=torch.long)
