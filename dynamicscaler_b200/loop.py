@@ -120,7 +120,10 @@ def sphere_denoise_step(stepper: PanoramaStepper, state: PanoramaState, views: S
     ddim_sigmas, ddim_sqrt_one_minus_alphas`` (pipeline/scheduler.py:17-57).  ``eps_fn(step_i, job_ids,
     shape, device)`` supplies the re_noise epsilon, ``noise_fn`` the ddim noise when sigma > 0 (the
     reference draws them from the global RNG).  ``on_input(step_i, job_ids, x)``: observer of
-    the model inputs (tests)."""
+    the model inputs (tests).  ``frame_begins``: ordered frame-window begins (I2V temporal loop); the job list
+    is frame windows (outer) x views (inner) and a ``group_size`` group never spans two frame windows.
+    ``cond`` may be a callable ``cond(step_i, job_ids, boxes)`` -> dict with one context row per window
+    (``boxes``: (phi, theta, frame_begin) per job; the I2V loop builds one image embedding per view, i2v :367-395)."""
     total = len(_get(schedule, "ddim_timesteps"))
     index = total - step_i - 1                                          # t2v_sphere_panorama_pipeline.py:263
     coef = ddim_coefficients(_get(schedule, "ddim_alphas")[index], _get(schedule, "ddim_alphas_prev")[index],
@@ -135,13 +138,18 @@ def sphere_denoise_step(stepper: PanoramaStepper, state: PanoramaState, views: S
         rc, rs = renoise_coefficients(_get(schedule, "alphas_cumprod"), _get(schedule, "ddim_timesteps"),
                                       total - step_i - 2, total - step_i - 1) if use_renoise else (1.0, 0.0)
     state.reset_mask()                                                  # :173 fresh mask panorama every step
-    gs = len(views) if group_size is None else int(group_size)
-    fkw = {} if frame_begins is None else dict(frame_begins=frame_begins, frames=frames)
-    for g0 in range(0, len(views), gs):
+    nv = len(views)
+    if group_size is None or frame_begins is None:                      # whole step, or groups of views (no frame windows)
+        gs = nv if group_size is None else int(group_size)
+        groups = [(g0, 0, None if frame_begins is None else list(frame_begins)) for g0 in range(0, nv, gs)]
+    else:                                                               # i2v :284: frame windows outer, views inner
+        gs = int(group_size)
+        groups = [(g0, s, [fb]) for s, fb in enumerate(frame_begins) for g0 in range(0, nv, gs)]
+    for g0, s0, fbs in groups:
+        fkw = {} if fbs is None else dict(frame_begins=fbs, frames=frames)
         plan = stepper.plan_sphere(list(views[g0:g0 + gs]), width, height, fov=fov, mode="nearest", **fkw)
-        n_fw = plan.n_fwin
-        job_ids = [(j // len(plan.extra["vms"])) * len(views) + g0 + j % len(plan.extra["vms"]) for j in plan.job_ids] \
-            if n_fw > 1 else [g0 + j for j in plan.job_ids]            # indices in the step's ordered job list
+        nvp = len(plan.extra["vms"])                                    # views of this group (all ranks)
+        job_ids = [(s0 + j // nvp) * nv + g0 + j % nvp for j in plan.job_ids]   # indices in the step's ordered job list
         raw = mview = None
         if use_renoise or use_prev:
             shape = (plan.n_local, state.shape[0], state.shape[1], plan.f_len, plan.h, plan.w)
@@ -157,10 +165,16 @@ def sphere_denoise_step(stepper: PanoramaStepper, state: PanoramaState, views: S
         if on_input is not None and n > 0:
             on_input(step_i, job_ids, xb)
         if balance_evals and stepper.world > 1 and uncond is not None:
+            assert not callable(cond), "eval balancing takes one shared cond dict"
             ec, eu = _balanced_eval(stepper, plan, model, xb, t, cond, uncond, frames, model_kwargs, cfg_batch)
             ec, eu = ec.view(x.shape), eu.view(x.shape)
         elif n > 0:
-            ec, eu = unet_eval(model, xb, t, cond, frames, model_kwargs, uncond, cfg_batch)
+            c = cond
+            if callable(cond):                  # one context row per window (i2v :367-395: one image embedding per view)
+                boxes = [(views[g0 + j % nvp][0], views[g0 + j % nvp][1], None if fbs is None else fbs[j // nvp])
+                         for j in plan.job_ids]
+                c = cond(step_i, job_ids, boxes)
+            ec, eu = unet_eval(model, xb, t, c, frames, model_kwargs, uncond, cfg_batch)
             ec = ec.view(x.shape)
             eu = None if eu is None else eu.view(x.shape)
         else:

@@ -466,6 +466,55 @@ def test_t2v_ring_loop_oracle_matches_real_pipeline():
     assert np.array_equal(den, g["final_denoised"])
 
 
+def loop_i2v_golden():
+    g = np.load(os.path.join(GOLDEN, "loop_i2v.npz"))
+    names = ("frames", "total_f", "H", "W", "h", "w", "steps", "fov", "loop_step_frame", "loop_step_theta")
+    c = {k: int(v) for k, v in zip(names, g["cfg"])}
+    sched = {k: g[k] for k in ("ddim_timesteps", "alphas_cumprod", "ddim_alphas", "ddim_alphas_prev", "ddim_sigmas",
+                               "ddim_sqrt_one_minus_alphas")}
+    views0 = [(float(p), float(t)) for p, t in g["views"]]
+    views_fn = lambda i: [(p, t + (i % c["loop_step_theta"]) * (c["fov"] // c["loop_step_theta"])) for p, t in views0]
+    fb_fn = lambda i: po.frame_window_begins(i, frames=c["frames"], total_f=c["total_f"], overlap=float(g["overlap_f"]),
+                                             loop_step_frame=c["loop_step_frame"])
+    return g, c, sched, views_fn, fb_fn
+
+
+def test_i2v_sphere_loop_oracle_matches_real_pipeline():
+    """oracle.sphere_denoise_loop with wrapping frame windows, the latent-shaped mask panorama, the re-noise mix and the
+    merge_prev mix == the REAL ``VC2_Pipeline_I2V_SpherePano.basic_sample_shift_shpere_panorama`` run
+    (tests/golden/loop_i2v.npz: 3 DDIM steps x 3 frame windows x 6 views): every UNet input, every condition-image view
+    (``PanoramaTensor`` nearest read of the [3, 128, 256] image) and both returned panoramas, bit for bit."""
+    import hashlib
+    sha = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest(), dtype=np.uint8)
+    g, c, sched, views_fn, fb_fn = loop_i2v_golden()
+    nv = len(g["views"])
+    counts = [len(fb_fn(i)) * nv for i in range(c["steps"])]
+    assert counts == [18, 18, 18] and sum(counts) == len(g["unet_in_sha"])
+    base = np.concatenate([[0], np.cumsum(counts)])
+    image = ((g["image_u8"].astype(np.float32).transpose(2, 0, 1) / np.float32(255.)) - np.float32(0.5)) * np.float32(2)
+    assert np.array_equal(sha(image), g["image_f32_sha"])
+    draws = {"n": 0}
+
+    def eps_fn(i, n, shape):
+        draws["n"] += 1
+        return randn(8000 + draws["n"], *shape)
+
+    def model_fn(i, n, x):
+        j = int(base[i]) + n
+        assert np.array_equal(sha(x), g["unet_in_sha"][j]), (i, n)
+        phi, th = views_fn(i)[n % nv]
+        view, _ = po.sphere_get_nearest(image, c["fov"], th, phi, c["w"] * 8, c["h"] * 8)          # i2v :367-372
+        assert np.array_equal(sha(view), g["img_view_sha"][j]), (i, n)
+        return g["eps_cond"][j], g["eps_uncond"][j]
+
+    lat, den, _, _ = po.sphere_denoise_loop(randn(101, 1, 4, c["total_f"], c["H"], c["W"]), sched, views_fn, model_fn, eps_fn,
+                                            float(g["guidance"]), fov=c["fov"], width=c["w"], height=c["h"],
+                                            renoise_ratio=float(g["ratio"]), prev_ratio_list=[float(v) for v in g["prev_ratios"]],
+                                            group_size=1, frame_begins_fn=fb_fn, frames=c["frames"], full_mask=True)
+    assert draws["n"] == int(g["renoise_draws"])
+    assert np.array_equal(lat, g["final_latent"]) and np.array_equal(den, g["final_denoised"])
+
+
 def test_vae_tiling_oracle_matches_reference():
     """oracle.tiled_encode / wrap_pad / crop_wrap_padded == the reference's tiled_vae_encode_tensor_simple
     and the inline wrap-padded decode of i2v_sphere_panorama_pipeline.py:974-991 (tests/golden/vae.npz)."""
