@@ -298,6 +298,21 @@ class RingPanoramaState:
         return None if self.mask is None else self.mask.clone()
 
 
+class _PlanCache(dict):
+    """Bounded plan cache (oldest entry out first).  A whole-step loop needs one plan per distinct window list
+    (10-16 per stage); the reference's one-window-at-a-time order builds one per window and step offset, and a
+    planar plan holds a dense H*W map (2 MB at 4K scale), so the cache must not grow without bound."""
+
+    def __init__(self, capacity: int = 1024):
+        super().__init__()
+        self.capacity = int(capacity)
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        while len(self) > self.capacity:
+            del self[next(iter(self))]
+
+
 class PanoramaStepper:
     """Plans and runs gather_all / merge_all for one panorama geometry on one device."""
 
@@ -308,7 +323,7 @@ class PanoramaStepper:
         # peer states: NVLS multicast stores win from 4 GPUs up (one store instead of world-1 copies);
         # at 2 GPUs the per-replica TMA row copies are faster (tools/peer_probe.py)
         self.use_multicast = world > 2
-        self._plans = {}
+        self._plans = _PlanCache()
         self._xbuf = {}
 
     @property

@@ -157,3 +157,13 @@ def test_ring_loop_switches_mixes_off_at_the_last_step():
     assert len(gathers) == 4 and len(merges) == 4
     assert all(g[2] is not None and "eps" in g[2] for g in gathers[:3]) and gathers[3][2] is None      # i < total - 1 (:875)
     assert all("prev" in m[2] for m in merges[:3]) and "prev" not in merges[3][2]
+
+
+def test_plan_cache_is_bounded():
+    from dynamicscaler_b200.step import _PlanCache
+    c = _PlanCache(capacity=3)
+    for k in range(5):
+        c[("ring", k)] = k
+    assert list(c) == [("ring", 2), ("ring", 3), ("ring", 4)] and ("ring", 0) not in c and c[("ring", 4)] == 4
+    c[("ring", 3)] = 33                                   # re-insert keeps the size
+    assert len(c) == 3 and c[("ring", 3)] == 33
