@@ -18,6 +18,15 @@ additionally moves single uncond evaluations between ranks so that 44 views x 2 
 evaluations on each of 8 ranks instead of 12 / 10), and the merge kernels push the surviving rows into
 every replica (step.py).
 
+The planar shift-window loops (``basic_sample_shift_multi_windows`` of pipeline/t2v_normal_pipeline.py,
+pipeline/t2v_sphere_panorama_pipeline.py and pipeline/i2v_sphere_panorama_pipeline.py) have the same driver on
+reference-order tensors -- :func:`ring_denoise_loop` with the window schedules :func:`shift_window_schedule`,
+:func:`t2v_planar_schedule`, :func:`i2v_planar_schedule`:
+
+    gather  ds_ring_gather (+ mask windows + ds_renoise_mix)
+    UNet    one call per group
+    merge   ds_merge_nearest_ddim (CFG + ddim_step + merge_prev mix + latent / denoised / mask sets)
+
 The model is called exactly like the reference calls ``self.pretrained_t2v.model`` (:236-254):
 ``model(x, ts, c_crossattn=[ctx], fps=fps, curr_time_steps=ts, temporal_length=frames, **kwargs)``.
 ``UNetModel.forward`` with a batch of b > 1 windows needs ``timesteps`` of length b*t, not b
