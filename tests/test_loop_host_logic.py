@@ -167,3 +167,39 @@ def test_plan_cache_is_bounded():
     assert list(c) == [("ring", 2), ("ring", 3), ("ring", 4)] and ("ring", 0) not in c and c[("ring", 4)] == 4
     c[("ring", 3)] = 33                                   # re-insert keeps the size
     assert len(c) == 3 and c[("ring", 3)] == 33
+
+
+def test_sharded_steps_cover_every_job_exactly_once():
+    """world_size 2 and 3: the ranks' job ids of every group are disjoint and together make up the step's ordered job list
+    (sphere: views dealt round-robin inside each frame window; planar: contiguous blocks), idle ranks call gather / merge
+    with zero windows and never call the model."""
+    views = [(90, 0), (0, 0), (0, 120), (0, 240), (-45, 60)]
+    windows, fbs = [(0, 0), (0, 4), (9, 0), (9, 4)], [1, 5]
+    lat = torch.zeros(1, 4, 8, 16, 30)
+    for world in (2, 3):
+        for group_size in (None, 1, 2):
+            seen_sphere, seen_ring = {}, {}
+            for rank in range(world):
+                st = FakeStepper(8, rank, world)
+                state = types.SimpleNamespace(shape=(1, 4, 8, 16, 32), dtype=torch.float32, device=torch.device("cpu"),
+                                              reset_mask=lambda: None)
+                calls = []
+                model = lambda x, ts, c_crossattn=None, fps=None, **k: calls.append(x.shape[0]) or x
+                cond = {"c_crossattn": [torch.zeros(1, 7, 3)], "fps": 16}
+                ids = []
+                L.sphere_denoise_step(st, state, views, 12, 8, model=model, t=500, step_i=0, schedule=SCHED, cond=cond,
+                                      uncond=None, guidance_scale=1.0, frames=4, group_size=group_size, frame_begins=[1, 3],
+                                      on_input=lambda i, j, x: ids.append(list(j)))
+                assert all(n > 0 for n in calls)
+                n_groups = len([e for e in st.log if e[0] == "plan"])
+                assert len([e for e in st.log if e[0] == "merge"]) == n_groups          # idle ranks still take part in the exchange
+                seen_sphere[rank] = [j for g in ids for j in g]
+                st = FakeStepper(8, rank, world)
+                ids = []
+                L.ring_denoise_step(st, [lat, lat.clone()], windows, fbs, 12, 8, 4, model=model, t=500, index=2, step_i=0,
+                                    schedule=SCHED, cond=cond, uncond=None, guidance_scale=1.0, group_size=group_size,
+                                    on_input=lambda i, j, x: ids.append(list(j)))
+                seen_ring[rank] = [j for g in ids for j in g]
+            for seen, total in ((seen_sphere, 10), (seen_ring, 8)):
+                merged = sorted(j for r in seen.values() for j in r)
+                assert merged == list(range(total)), (world, group_size, seen)
