@@ -1,5 +1,5 @@
 """SASS evidence for the hot kernels: mnemonic histogram + the memory-instruction skeleton of each, taken with
-`cuobjdump -sass` from the in-tree libdynscaler_sm100.so.  usage: python tools/sass_excerpt.py <round-label>"""
+`cuobjdump -sass` from the in-tree libdynscaler_sm100.so.  usage: python tools/sass_excerpt.py <round-label> [planar]"""
 import collections
 import os
 import re
@@ -16,6 +16,14 @@ WANT = [("pm_gather_kernel<float, 4, 16, 4, true>", r"pm_gather_kernelIfLi4ELi16
         ("pm_merge_weighted_tiled_kernel<float, 16, 2, false, true> (exchange mode)", r"pm_merge_weighted_tiled_kernelIfLi16ELi2ELb0ELb1E"),
         ("pm_merge_nearest_kernel<float, 16, true, false> (fused CFG + ddim_step)", r"pm_merge_nearest_kernelIfLi16ELb1ELb0E"),
         ("ring_copy_kernel<float, 4, true, 16>", r"ring_copy_kernelIfLi4ELb1ELi16E")]
+if len(sys.argv) > 2 and sys.argv[2] == "planar":        # the reference-order kernels of the planar loops
+    WANT = [("merge_nearest_ddim_kernel<float, 4, 2, false, false> (planar merge + CFG + ddim_step, 16-byte vectors)",
+             r"merge_nearest_ddim_kernelIfLi4ELi2ELb0ELb0E"),
+            ("merge_nearest_ddim_kernel<float, 4, 2, false, true> (+ merge_prev mix)", r"merge_nearest_ddim_kernelIfLi4ELi2ELb0ELb1E"),
+            ("merge_nearest_ddim_kernel<float, 4, 2, true, false> (exchange mode: peer stores)", r"merge_nearest_ddim_kernelIfLi4ELi2ELb1ELb0E"),
+            ("merge_nearest_kernel<float, 4, 4, 4, false> (plain planar merge)", r"merge_nearest_kernelIfLi4ELi4ELi4ELb0E"),
+            ("renoise_mix_kernel<float, 4>", r"renoise_mix_kernelIfLi4E"),
+            ("ring_copy_kernel<float, 4, true, 16>", r"ring_copy_kernelIfLi4ELb1ELi16E")]
 funcs = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True, check=True).stdout
 blocks = re.split(r"\n\s*Function : ", funcs)
 KEY = ("UBLKCP", "LDGSTS", "LDG", "STG", "LDS", "STS", "MULTIMEM", "MEMBAR", "BAR", "ACQBULK", "DEPBAR", "FFMA", "FMUL", "FADD",
@@ -23,7 +31,7 @@ KEY = ("UBLKCP", "LDGSTS", "LDG", "STG", "LDS", "STS", "MULTIMEM", "MEMBAR", "BA
 out = [f"# {label} -- SASS of the hot kernels (`cuobjdump -sass dynamicscaler_b200/libdynscaler_sm100.so`, sm_100a)\n",
        "Counts are static instruction counts of the function body (all paths); `UBLKCP` = TMA bulk copy shared->global, "
        "`LDGSTS` = cp.async global->shared, `LDG.E.128` = 16-byte loads, `ACQBULK`/`DEPBAR` = griddepcontrol / bulk-group waits, "
-       "`MULTIMEM` = NVLS multicast stores.  The headline fp32 / 16-frame kernels below have no `LDL`/`STL` (no local-memory spills); `-Xptxas -v` shows 4-168 bytes of spill only in rarely used variants (runtime frame count, fused denoise at the 48-register budget).\n"]
+       "`MULTIMEM` = NVLS multicast stores.  " + ("" if len(sys.argv) <= 2 else "Planar (reference-order) kernels: plain 16-byte `LDG`/`STG`, no shared memory.  ") + "The headline fp32 / 16-frame kernels below have no `LDL`/`STL` (no local-memory spills); `-Xptxas -v` shows 4-168 bytes of spill only in rarely used variants (runtime frame count, fused denoise at the 48-register budget).\n"]
 for title, pat in WANT:
     blk = next((b for b in blocks if re.match(r"_ZN2ds\d+" + pat, b)), None)
     if blk is None:
